@@ -1,0 +1,140 @@
+// common.h — shared host/device declarations of the B200 lattice engine.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/snn_b200.h"
+
+namespace snn {
+
+constexpr int kNT = SNN_NUM_NT_TYPES;
+
+// ---- sliced-ELL in-edge storage (slice height = one warp) -------------------------------------
+// col word: bits 0..27 presynaptic node index (local), 28..30 neurotransmitter types the
+// presynaptic node releases, 31 presynaptic node is a spike train.  0xFFFFFFFF = padding.
+constexpr uint32_t kColPad = 0xFFFFFFFFu;
+constexpr uint32_t kColIdxMask = 0x0FFFFFFFu;
+constexpr uint32_t kColNtShift = 28;
+constexpr uint32_t kColTrainBit = 0x80000000u;
+constexpr uint64_t kMaxNodes = 0x0FFFFFFEull;
+
+// ---- per-neuron device field slots (index into StepParams::f) ---------------------------------
+enum NeuronSlot : int {
+    F_GAP = 0, F_DT, F_CM, F_VTH, F_VRESET, F_REFR, F_TREF, F_LEAK, F_INTEG, F_EL, F_GL, F_TAUM,
+    F_ALPHA, F_BETA, F_SLOPE, F_W, F_VC, F_A, F_B, F_C, F_D, F_G, F_E,
+    F_GNA, F_ENA, F_M, F_H, F_GK, F_EK, F_N, F_GKL, F_EKL,
+    // derived (written by the finalize kernel only, never inside the step loop)
+    F_NA_CUR, F_M_ALPHA, F_M_BETA, F_H_ALPHA, F_H_BETA, F_K_CUR, F_N_ALPHA, F_N_BETA, F_KL_CUR,
+    F_COUNT
+};
+
+// per spike-train device field slots
+enum TrainSlot : int { TF_VTH = 0, TF_VREST, TF_DT, TF_K, TF_CHANCE, TF_RATE, TF_STEP, TF_ICLOCK, TF_COUNTER, TF_COUNT };
+
+// per-type (type-major, stride = node/neuron capacity) chemical arrays
+enum NtSlot : int { NTF_TMAX = 0, NTF_P1 /* clearance | v_p | decay */, NTF_P2 /* k_p */, NTF_COUNT };
+enum RcSlot : int { RCF_R = 0, RCF_K1 /* alpha | r_max */, RCF_K2 /* beta | decay */, RCF_G, RCF_E, RCF_MG, RCF_CUR, RCF_COUNT };
+
+struct LatInfo {  // one per neuron lattice, device table
+    uint32_t base;        // first neuron (local neuron number)
+    uint32_t n;
+    float a_plus, a_minus, tau_plus, tau_minus, dt;
+    uint32_t do_plasticity;
+    uint32_t grid_hist;   // record grid voltage history
+    uint32_t spike_hist;
+    uint64_t hist_off;    // float offset of this lattice inside one history step record
+};
+
+constexpr int kMaxLattices = 16;
+
+// halo export of one direction (multi-GPU row strips): owned neurons [first, first+count) are also
+// written into the peer's ghost slots starting at node index peer_node0
+struct HaloDir {
+    uint32_t first, count, peer_node0;
+    uint32_t my_ghost0;          // node index of the ghost slots the peer fills for me
+    float *peer_v[2];            // peer's V ping-pong buffers (device pointers mapped through CUDA IPC)
+    int *peer_lft[2];
+    float *peer_t[2];            // type-major, stride peer_t_stride
+    uint64_t peer_t_stride;
+    unsigned long long *peer_flag;   // peer-side arrival counter for data coming from me
+    unsigned long long *my_flag;     // my arrival counter for data coming from this peer
+    uint32_t active;
+};
+
+struct StepParams {
+    // index space
+    uint32_t own0;        // node index of neuron 0 (multiple of 32)
+    uint32_t n_neurons;   // neurons stepped by this kernel
+    uint32_t n_nodes;     // neurons + ghosts + spike trains
+    uint32_t clock;       // internal clock value stamped on spikes of this step
+    uint32_t apply_pending;  // lazy STDP: apply last step's weight updates while streaming the edges
+    uint32_t electrical, chemical;
+    uint32_t nt_used, rc_used;   // union over nodes of present neurotransmitter / receptor types
+    int ntk, rck, refract;
+    // graph
+    const uint32_t *slice_off;
+    const uint32_t *col;
+    float *wgt;
+    // shared node arrays
+    const float *v_in;  float *v_out;
+    const int *lft_in;  int *lft_out;
+    uint32_t lft_pp;     // lft is ping-ponged (else in == out, written on spike only)
+    const uint32_t *spk_in; uint32_t *spk_out;
+    const float *t_in; float *t_out; uint64_t t_stride;   // type-major [kNT][t_stride]
+    const uint8_t *node_flags;  // per node: nt mask | rc mask << 4
+    // neuron arrays
+    float *f[F_COUNT];
+    uint32_t *was_inc;          // HH bitmask
+    float *nt[NTF_COUNT]; uint64_t nt_stride;   // per node
+    float *rc[RCF_COUNT]; uint64_t rc_stride;   // per neuron
+    // spike trains (nodes [train0, train0+n_trains))
+    uint32_t train0, n_trains;
+    const float *tf[TF_COUNT];
+    // lattices
+    const LatInfo *lat; int n_lat;
+    // histories: this step's record
+    float *grid_hist;           // nullptr = off
+    uint32_t *spike_hist;       // bit words, one per warp of neurons
+    // halos
+    HaloDir halo[2];
+    unsigned long long halo_epoch;   // value the arrival counters must reach before ghosts are read
+    uint32_t out_par;                // parity of the *_out ping-pong buffers (same on every rank)
+    unsigned int *halo_done;         // [2] per-direction CTA completion counters
+};
+
+struct TrainParams {
+    uint32_t train0, n_trains, clock; int kind; int ntk;
+    uint64_t seed;
+    const float *v_in; float *v_out;
+    const int *lft_in; int *lft_out; uint32_t lft_pp;
+    const uint32_t *spk_in; uint32_t *spk_out;
+    const float *t_in; float *t_out; uint64_t t_stride;
+    const uint8_t *node_flags;
+    float *nt[NTF_COUNT]; uint64_t nt_stride;
+    float *tf[TF_COUNT];
+    const uint64_t *ft_off; const float *ft;   // preset firing times CSR
+    // per train-lattice clocks: lattice l covers trains [tl_base[l], tl_base[l+1]) and stamps tl_clock[l]
+    int n_tl; uint32_t tl_base[kMaxLattices + 1]; uint32_t tl_clock[kMaxLattices];
+    float *grid_hist; uint32_t *spike_hist;   // this step's record over all trains (nullptr = off)
+};
+
+// ---- kernel launchers (kernels.cu) ------------------------------------------------------------
+cudaError_t launch_step(const StepParams &p, int model, bool chem, bool stdp, cudaStream_t s);
+cudaError_t launch_trains(const TrainParams &p, cudaStream_t s);
+cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s);
+cudaError_t launch_finalize(const StepParams &p, int model, const float *v_prev, cudaStream_t s);
+cudaError_t launch_sell_from_csr(const uint64_t *row_ptr, const uint32_t *pre, const float *w, const uint8_t *node_flags,
+                                 uint32_t train0, uint32_t n_rows, const uint32_t *slice_off, uint32_t *col, float *wgt,
+                                 cudaStream_t s);
+cudaError_t launch_sell_grid(uint32_t rows_local, uint32_t cols, uint32_t row0_global, uint32_t rows_global,
+                             uint32_t radius, float weight, uint32_t own0, const uint8_t *node_flags, uint32_t width,
+                             uint32_t *slice_off, uint32_t *col, float *wgt, cudaStream_t s);
+cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s);
+cudaError_t launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t s);
+cudaError_t launch_bits_from_u32(const uint32_t *src, uint32_t *words, uint64_t n, uint64_t bit0, cudaStream_t s);
+cudaError_t launch_u32_from_bits(const uint32_t *words, uint32_t *dst, uint64_t n, uint64_t bit0, cudaStream_t s);
+cudaError_t launch_transpose_in(const float *src_nm, float *dst_tm, uint64_t n, uint64_t stride, cudaStream_t s);
+cudaError_t launch_transpose_out(const float *src_tm, float *dst_nm, uint64_t n, uint64_t stride, cudaStream_t s);
+
+}  // namespace snn

@@ -1,0 +1,1319 @@
+// engine.cu — host runtime: device memory layout, named-field I/O, graph ingestion, the step loop.
+#include "engine.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+
+namespace snn {
+
+#define CK(call, status)                                                          \
+    do {                                                                          \
+        cudaError_t _e = (call);                                                  \
+        if (_e != cudaSuccess) return cuda_fail(_e, (status), #call);             \
+    } while (0)
+
+static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
+
+template <class T>
+static cudaError_t dev_alloc(T **p, size_t n) {
+    *p = nullptr;
+    return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+Engine::Engine(int model_, int ntk_, int rck_, int train_kind_, int refract_, int device_)
+    : model(model_), ntk(ntk_), rck(rck_), train_kind(train_kind_), refract(refract_), device(device_) {}
+
+Engine::~Engine() {
+    if (device >= 0) cudaSetDevice(device);
+    for (int d = 0; d < 2; ++d) {
+        if (peer_slab_[d]) cudaIpcCloseMemHandle(peer_slab_[d]);
+        if (peer_flags_[d]) cudaIpcCloseMemHandle(peer_flags_[d]);
+    }
+    free_device();
+    if (flags_) cudaFree(flags_);
+    if (halo_done_) cudaFree(halo_done_);
+    if (scratch_) cudaFree(scratch_);
+    if (ev0_) cudaEventDestroy(ev0_);
+    if (ev1_) cudaEventDestroy(ev1_);
+    if (stream_) cudaStreamDestroy(stream_);
+}
+
+int Engine::cuda_fail(cudaError_t e, int status, const char *what) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    last_error = buf;
+    cudaGetLastError();
+    return status;
+}
+
+int Engine::init() {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(SNN_GPU_GET_DEVICE_FAILURE, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return fail(SNN_GPU_GET_DEVICE_FAILURE, "cudaGetDevice failed");
+    }
+    if (device >= count) return fail(SNN_GPU_GET_DEVICE_FAILURE, "device ordinal out of range");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), SNN_GPU_QUEUE_FAILURE);
+    CK(cudaEventCreate(&ev0_), SNN_GPU_QUEUE_FAILURE);
+    CK(cudaEventCreate(&ev1_), SNN_GPU_QUEUE_FAILURE);
+    CK(dev_alloc(&flags_, 2), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemset(flags_, 0, 2 * sizeof(unsigned long long)), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(dev_alloc(&halo_done_, 2), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemset(halo_done_, 0, 2 * sizeof(unsigned int)), SNN_GPU_BUFFER_WRITE_ERROR);
+    return SNN_OK;
+}
+
+int Engine::ensure_scratch(size_t bytes) {
+    if (bytes <= scratch_bytes_) return SNN_OK;
+    if (scratch_) cudaFree(scratch_);
+    scratch_ = nullptr; scratch_bytes_ = 0;
+    CK(cudaMalloc(&scratch_, bytes), SNN_GPU_BUFFER_CREATE_ERROR);
+    scratch_bytes_ = bytes;
+    return SNN_OK;
+}
+
+Lat *Engine::find(uint64_t id) {
+    for (auto &L : lats_) if (L.id == id) return &L;
+    return nullptr;
+}
+const Lat *Engine::find(uint64_t id) const {
+    for (auto &L : lats_) if (L.id == id) return &L;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout
+// ------------------------------------------------------------------------------------------------
+void Engine::compute_layout() {
+    // canonical order: neuron lattices by ascending id, then spike-train lattices by ascending id
+    std::stable_sort(lats_.begin(), lats_.end(), [](const Lat &a, const Lat &b) {
+        if (a.is_train != b.is_train) return !a.is_train;
+        return a.id < b.id;
+    });
+    n_neurons = n_trains = 0;
+    for (auto &L : lats_) {
+        if (L.is_train) { L.off = n_trains; n_trains += L.n; }
+        else { L.off = n_neurons; n_neurons += L.n; }
+    }
+    const uint32_t halo_lo = (part_world > 1 && part_rank > 0) ? halo_ : 0;
+    const uint32_t halo_hi = (part_world > 1 && part_rank < part_world - 1) ? halo_ : 0;
+    own0_ = (uint32_t)round_up(halo_lo, 32);
+    train0_ = (uint32_t)round_up(own0_ + n_neurons, 32);
+    ghost_hi0_ = train0_;
+    n_nodes_ = (part_world > 1) ? ghost_hi0_ + halo_hi : train0_ + (uint32_t)n_trains;
+    node_cap_ = round_up(std::max<uint64_t>(n_nodes_, 1), 32) + 32;
+    neuron_cap_ = round_up(std::max<uint64_t>(n_neurons, 1), 32);
+    train_cap_ = round_up(std::max<uint64_t>(n_trains, 1), 32);
+}
+
+void Engine::free_device() {
+    auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
+    if (slab_) cudaFree(slab_);
+    slab_ = nullptr;
+    V_[0] = V_[1] = nullptr; LFT_[0] = LFT_[1] = nullptr; T_[0] = T_[1] = nullptr;
+    fr(SPK_[0]); fr(SPK_[1]); fr(node_flags_); fr(was_inc_);
+    for (auto &p : NT_) fr(p);
+    for (auto &p : F_) fr(p);
+    for (auto &p : RC_) fr(p);
+    for (auto &p : TF_) fr(p);
+    fr(ft_off_); fr(ft_); fr(d_lat_);
+    fr(slice_off_); fr(col_); fr(wgt_);
+    chem_alloc_ = false;
+    graph_dirty_ = true;
+    grid_fast_ = false;
+}
+
+static cudaError_t fill_f32(float *p, float v, uint64_t n, cudaStream_t s) {
+    uint32_t b; memcpy(&b, &v, 4);
+    return launch_fill_u32((uint32_t *)p, b, n, s);
+}
+
+int Engine::alloc_device() {
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    // slab: V[2], LFT[2] (+ T[2] once chemistry is touched) in one allocation so that a neighbouring rank can
+    // map all halo-visible arrays with one CUDA IPC handle
+    const size_t vb = round_up(node_cap_ * 4, 256);
+    slab_off_v_[0] = 0; slab_off_v_[1] = vb; slab_off_lft_[0] = 2 * vb; slab_off_lft_[1] = 3 * vb;
+    slab_off_t_[0] = 4 * vb; slab_off_t_[1] = 4 * vb + round_up(node_cap_ * 4 * kNT, 256);
+    slab_bytes_ = 4 * vb;  // T appended by ensure_chem (which reallocates the slab)
+    CK(cudaMalloc(&slab_, slab_bytes_), SNN_GPU_BUFFER_CREATE_ERROR);
+    for (int k = 0; k < 2; ++k) {
+        V_[k] = (float *)((char *)slab_ + slab_off_v_[k]);
+        LFT_[k] = (int *)((char *)slab_ + slab_off_lft_[k]);
+        CK(fill_f32(V_[k], 0.f, node_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(launch_fill_u32((uint32_t *)LFT_[k], 0xFFFFFFFFu, node_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(dev_alloc(&SPK_[k], node_cap_ / 32 + 1), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(launch_fill_u32(SPK_[k], 0u, node_cap_ / 32 + 1, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    }
+    CK(dev_alloc(&node_flags_, node_cap_), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemsetAsync(node_flags_, 0, node_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    h_node_flags_.assign(node_cap_, 0);
+    // neuron fields used by this model
+    for (int i = 0; i < kNumNeuronFields; ++i) {
+        const FieldDef &fd = kNeuronFields[i];
+        if (fd.kind != FK_NEURON_DEV || !(fd.models & SNN_M(model))) continue;
+        CK(dev_alloc(&F_[fd.slot], neuron_cap_), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(fill_f32(F_[fd.slot], neuron_default(model, fd.kind, fd.slot), neuron_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    }
+    if (model == SNN_MODEL_HODGKIN_HUXLEY) {
+        CK(dev_alloc(&was_inc_, neuron_cap_ / 32 + 1), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(launch_fill_u32(was_inc_, 0u, neuron_cap_ / 32 + 1, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    }
+    // neuron voltage default
+    if (n_neurons)
+        CK(fill_f32(V_[0] + own0_, neuron_default(model, FK_V, 0), n_neurons, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (n_neurons) CK(fill_f32(V_[1] + own0_, neuron_default(model, FK_V, 0), n_neurons, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    // trains
+    if (n_trains) {
+        for (int s = 0; s < TF_COUNT; ++s) {
+            CK(dev_alloc(&TF_[s], train_cap_), SNN_GPU_BUFFER_CREATE_ERROR);
+            CK(fill_f32(TF_[s], train_default(s), train_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+        }
+        std::vector<uint64_t> zero(n_trains + 1, 0);
+        CK(dev_alloc(&ft_off_, n_trains + 1), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(cudaMemcpyAsync(ft_off_, zero.data(), (n_trains + 1) * 8, cudaMemcpyHostToDevice, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(dev_alloc(&ft_, 1), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    }
+    CK(dev_alloc(&d_lat_, kMaxLattices), SNN_GPU_BUFFER_CREATE_ERROR);
+    for (auto &L : lats_) {
+        if (L.is_train) continue;
+        if (L.cold[0].size() != L.n) L.cold[0].assign(L.n, neuron_default(model, FK_NEURON_COLD, 0));
+        if (L.cold[1].size() != L.n) L.cold[1].assign(L.n, neuron_default(model, FK_NEURON_COLD, 1));
+    }
+    cur_ = 0; lft_loc_ = 0;
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    return SNN_OK;
+}
+
+int Engine::ensure_chem() {
+    if (chem_alloc_) return SNN_OK;
+    if (peer_slab_[0] || peer_slab_[1]) return fail(SNN_UNSUPPORTED, "chemical fields must be set before the halo slab is exported");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    // grow the slab to hold T[2]
+    const size_t tb = round_up(node_cap_ * 4 * kNT, 256);
+    const size_t new_bytes = slab_off_t_[0] + 2 * tb;
+    void *ns = nullptr;
+    CK(cudaMalloc(&ns, new_bytes), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemcpyAsync(ns, slab_, slab_bytes_, cudaMemcpyDeviceToDevice, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(cudaMemsetAsync((char *)ns + slab_off_t_[0], 0, 2 * tb, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    cudaFree(slab_);
+    slab_ = ns; slab_bytes_ = new_bytes;
+    for (int k = 0; k < 2; ++k) {
+        V_[k] = (float *)((char *)slab_ + slab_off_v_[k]);
+        LFT_[k] = (int *)((char *)slab_ + slab_off_lft_[k]);
+        T_[k] = (float *)((char *)slab_ + slab_off_t_[k]);
+    }
+    for (int s = 0; s < NTF_COUNT; ++s) {
+        CK(dev_alloc(&NT_[s], node_cap_ * kNT), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(fill_f32(NT_[s], nt_default(ntk, s), node_cap_ * kNT, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    }
+    for (int s = 0; s < RCF_COUNT; ++s) {
+        CK(dev_alloc(&RC_[s], neuron_cap_ * kNT), SNN_GPU_BUFFER_CREATE_ERROR);
+        for (int ty = 0; ty < kNT; ++ty)
+            CK(fill_f32(RC_[s] + (size_t)ty * neuron_cap_, rc_default(rck, ty, s), neuron_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    }
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    chem_alloc_ = true;
+    return SNN_OK;
+}
+
+int Engine::set_partition(uint32_t rows_g, uint32_t cols, int rank, int world) {
+    if (!lats_.empty()) return fail(SNN_INVALID_ARGUMENT, "set_partition must precede add_lattice");
+    if (world < 1 || rank < 0 || rank >= world) return fail(SNN_INVALID_ARGUMENT, "bad partition rank/world");
+    part_rank = rank; part_world = world; rows_global = rows_g;
+    row0_global = snn_partition_begin(rows_g, world, rank);
+    halo_ = world > 1 ? cols : 0;  // one grid row; grows with the stencil radius (connect_grid)
+    return SNN_OK;
+}
+
+struct FieldSnap { std::string name; int dtype; std::vector<uint8_t> data; uint64_t count; };
+struct LatSnap { uint64_t id; std::vector<FieldSnap> fields; };
+
+int Engine::add_lattice(uint64_t id, uint32_t rows, uint32_t cols, bool is_train) {
+    // LatticeNetwork::add_lattice / add_spike_train_lattice, neuron/mod.rs:1663-1698
+    if (find(id)) return fail(SNN_NET_GRAPH_ID_ALREADY_PRESENT, "Graph id already present in network, id: " + std::to_string(id));
+    int n_neuron_lat = 0;
+    for (auto &L : lats_) if (!L.is_train) n_neuron_lat++;
+    if (!is_train && n_neuron_lat >= kMaxLattices) return fail(SNN_UNSUPPORTED, "too many lattices");
+    if (part_world > 1 && (!lats_.empty() || is_train)) return fail(SNN_UNSUPPORTED, "a partitioned handle holds exactly one neuron lattice");
+    Lat nl;
+    nl.id = id; nl.rows = rows; nl.cols = cols; nl.n = (uint64_t)rows * cols; nl.is_train = is_train;
+    if ((is_train ? n_trains : n_neurons) + nl.n + 64ull * (part_world > 1 ? cols : 0) > kMaxNodes)
+        return fail(SNN_UNSUPPORTED, "lattice too large for one device (node index is 28 bits)");
+    return relayout_add(nl);
+}
+
+int Engine::relayout_add(const Lat &nl) {
+    // snapshot every existing field through the public get path, rebuild the device layout, restore.
+    // Lattices are added at set-up time; the single-lattice (large) case never has anything to snapshot.
+    if (dev_weights_newer_) { int r = sync_weights_to_host(); if (r) return r; }
+    std::vector<LatSnap> snaps;
+    const bool had_chem = chem_alloc_;
+    for (auto &L : lats_) {
+        LatSnap s; s.id = L.id;
+        uint32_t cnt = 0; field_count(L.id, &cnt);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const char *name; int32_t dt; uint32_t per;
+            field_info(L.id, i, &name, &dt, &per);
+            FieldDef fd;
+            if (lookup_field(L, name, &fd)) continue;
+            const bool is_chem = fd.kind == FK_NT_FLAGS || fd.kind == FK_NT_T || fd.kind == FK_NT || fd.kind == FK_RC_FLAGS || fd.kind == FK_RC;
+            if (is_chem && !had_chem) continue;
+            FieldSnap f; f.name = name; f.dtype = dt; f.count = L.n * per; f.data.resize(std::max<uint64_t>(f.count, 1) * 4);
+            int r = get_field(L.id, name, f.data.data(), f.count, dt);
+            if (r) return r;
+            s.fields.push_back(std::move(f));
+        }
+        snaps.push_back(std::move(s));
+    }
+    const uint64_t saved_clock = internal_clock;
+    free_device();
+    lats_.push_back(nl);
+    compute_layout();
+    int r = alloc_device();
+    if (r) return r;
+    if (had_chem) { r = ensure_chem(); if (r) return r; }
+    for (auto &s : snaps)
+        for (auto &f : s.fields) {
+            r = set_field(s.id, f.name.c_str(), f.data.data(), f.count, f.dtype);
+            if (r) return r;
+        }
+    // re-upload preset firing times
+    for (auto &L : lats_)
+        if (L.is_train && !L.ft_off.empty()) {
+            std::vector<uint64_t> off = L.ft_off; std::vector<float> t = L.ft;
+            r = set_preset_firing_times(L.id, off.data(), t.data(), L.n, t.size());
+            if (r) return r;
+        }
+    internal_clock = saved_clock;
+    graph_dirty_ = true;
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// field directory
+// ------------------------------------------------------------------------------------------------
+static bool field_visible(const FieldDef &fd, int kind_bit, int ntk_, int rck_) {
+    if (!(fd.models & SNN_M(kind_bit))) return false;
+    if (fd.kind == FK_NT && fd.aux && !(fd.aux & SNN_M(ntk_))) return false;
+    (void)rck_;
+    return true;
+}
+
+int Engine::field_count(uint64_t id, uint32_t *count) const {
+    const Lat *L = find(id);
+    if (!L) return SNN_NET_ID_NOT_FOUND_IN_LATTICES;
+    uint32_t c = 0;
+    if (L->is_train) {
+        for (int i = 0; i < kNumTrainFields; ++i) if (field_visible(kTrainFields[i], train_kind, ntk, rck)) c++;
+    } else {
+        for (int i = 0; i < kNumNeuronFields; ++i) if (field_visible(kNeuronFields[i], model, ntk, rck)) c++;
+        for (int ty = 0; ty < kNT; ++ty)
+            for (int i = 0; i < kNumRcFields; ++i) {
+                if (kRcFields[i].nmda_only && ty != SNN_NT_NMDA) continue;
+                if (kRcFields[i].kinetics_mask && !(kRcFields[i].kinetics_mask & SNN_M(rck))) continue;
+                c++;
+            }
+    }
+    *count = c;
+    return SNN_OK;
+}
+
+static thread_local char g_name_buf[128];
+
+int Engine::field_info(uint64_t id, uint32_t index, const char **name, int32_t *dtype, uint32_t *per) const {
+    const Lat *L = find(id);
+    if (!L) return SNN_NET_ID_NOT_FOUND_IN_LATTICES;
+    uint32_t c = 0;
+    if (L->is_train) {
+        for (int i = 0; i < kNumTrainFields; ++i)
+            if (field_visible(kTrainFields[i], train_kind, ntk, rck)) {
+                if (c == index) { *name = kTrainFields[i].name; *dtype = kTrainFields[i].dtype; *per = kTrainFields[i].per; return SNN_OK; }
+                c++;
+            }
+    } else {
+        for (int i = 0; i < kNumNeuronFields; ++i)
+            if (field_visible(kNeuronFields[i], model, ntk, rck)) {
+                if (c == index) { *name = kNeuronFields[i].name; *dtype = kNeuronFields[i].dtype; *per = kNeuronFields[i].per; return SNN_OK; }
+                c++;
+            }
+        for (int ty = 0; ty < kNT; ++ty)
+            for (int i = 0; i < kNumRcFields; ++i) {
+                if (kRcFields[i].nmda_only && ty != SNN_NT_NMDA) continue;
+                if (kRcFields[i].kinetics_mask && !(kRcFields[i].kinetics_mask & SNN_M(rck))) continue;
+                if (c == index) {
+                    snprintf(g_name_buf, sizeof g_name_buf, "receptors$%s%s", kRcTypeNames[ty], kRcFields[i].suffix);
+                    *name = g_name_buf; *dtype = SNN_F32; *per = 1;
+                    return SNN_OK;
+                }
+                c++;
+            }
+    }
+    return SNN_INVALID_ARGUMENT;
+}
+
+int Engine::lookup_field(const Lat &L, const char *name, FieldDef *out) const {
+    if (L.is_train) {
+        for (int i = 0; i < kNumTrainFields; ++i)
+            if (field_visible(kTrainFields[i], train_kind, ntk, rck) && !strcmp(kTrainFields[i].name, name)) { *out = kTrainFields[i]; return SNN_OK; }
+        return SNN_UNKNOWN_FIELD;
+    }
+    for (int i = 0; i < kNumNeuronFields; ++i)
+        if (field_visible(kNeuronFields[i], model, ntk, rck) && !strcmp(kNeuronFields[i].name, name)) { *out = kNeuronFields[i]; return SNN_OK; }
+    if (!strncmp(name, "receptors$", 10)) {
+        for (int ty = 0; ty < kNT; ++ty) {
+            const size_t tl = strlen(kRcTypeNames[ty]);
+            if (strncmp(name + 10, kRcTypeNames[ty], tl)) continue;
+            for (int i = 0; i < kNumRcFields; ++i) {
+                if (kRcFields[i].nmda_only && ty != SNN_NT_NMDA) continue;
+                if (kRcFields[i].kinetics_mask && !(kRcFields[i].kinetics_mask & SNN_M(rck))) continue;
+                if (!strcmp(name + 10 + tl, kRcFields[i].suffix)) {
+                    *out = FieldDef{nullptr, SNN_F32, 1, FK_RC, kRcFields[i].slot, ty, kAllModels};
+                    return SNN_OK;
+                }
+            }
+        }
+    }
+    return SNN_UNKNOWN_FIELD;
+}
+
+// ------------------------------------------------------------------------------------------------
+// field I/O
+// ------------------------------------------------------------------------------------------------
+int Engine::set_bits(uint32_t *words, const uint32_t *host_u32, uint64_t n, uint64_t bit0) {
+    int r = ensure_scratch(n * 4);
+    if (r) return r;
+    CK(cudaMemcpyAsync(scratch_, host_u32, n * 4, cudaMemcpyHostToDevice, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(launch_bits_from_u32((const uint32_t *)scratch_, words, n, bit0, stream_), SNN_GPU_QUEUE_FAILURE);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    return SNN_OK;
+}
+
+int Engine::get_bits(const uint32_t *words, uint32_t *host_u32, uint64_t n, uint64_t bit0) {
+    int r = ensure_scratch(n * 4);
+    if (r) return r;
+    CK(launch_u32_from_bits(words, (uint32_t *)scratch_, n, bit0, stream_), SNN_GPU_QUEUE_FAILURE);
+    CK(cudaMemcpyAsync(host_u32, scratch_, n * 4, cudaMemcpyDeviceToHost, stream_), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    return SNN_OK;
+}
+
+int Engine::field_io(Lat &L, const FieldDef &fd, void *data, uint64_t count, bool set) {
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    const uint64_t n = L.n;
+    if (n == 0) return SNN_OK;
+    const uint32_t no = node_off(L);
+    const cudaMemcpyKind dir = set ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    const int wr = set ? SNN_GPU_BUFFER_WRITE_ERROR : SNN_GPU_BUFFER_READ_ERROR;
+    auto plain = [&](void *dev, uint64_t elems) -> int {
+        if (set) CK(cudaMemcpyAsync(dev, data, elems * 4, dir, stream_), wr);
+        else CK(cudaMemcpyAsync(data, dev, elems * 4, dir, stream_), wr);
+        CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+        return SNN_OK;
+    };
+    // neuron-major [n][3] host <-> type-major device [3][stride] at element offset `o`
+    auto typed = [&](float *dev_tm, uint64_t stride, uint64_t o) -> int {
+        int r = ensure_scratch(n * kNT * 4);
+        if (r) return r;
+        if (set) {
+            CK(cudaMemcpyAsync(scratch_, data, n * kNT * 4, cudaMemcpyHostToDevice, stream_), wr);
+            CK(launch_transpose_in((const float *)scratch_, dev_tm + o, n, stride, stream_), SNN_GPU_QUEUE_FAILURE);
+        } else {
+            CK(launch_transpose_out(dev_tm + o, (float *)scratch_, n, stride, stream_), SNN_GPU_QUEUE_FAILURE);
+            CK(cudaMemcpyAsync(data, scratch_, n * kNT * 4, cudaMemcpyDeviceToHost, stream_), wr);
+        }
+        CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+        return SNN_OK;
+    };
+    switch (fd.kind) {
+    case FK_NEURON_DEV:
+        return plain(F_[fd.slot] + L.off, n);
+    case FK_NEURON_COLD:
+        if (set) memcpy(L.cold[fd.slot].data(), data, n * 4); else memcpy(data, L.cold[fd.slot].data(), n * 4);
+        return SNN_OK;
+    case FK_V:
+        return plain(V_[cur_] + no, n);
+    case FK_LFT: {
+        int r = plain(LFT_[lft_loc_] + no, n);
+        if (r) return r;
+        if (set && part_world > 1)  // keep both parities coherent for the halo protocol
+            CK(cudaMemcpy(LFT_[lft_loc_ ^ 1] + no, LFT_[lft_loc_] + no, n * 4, cudaMemcpyDeviceToDevice), wr);
+        return SNN_OK;
+    }
+    case FK_SPIKING:
+        return set ? set_bits(SPK_[cur_], (const uint32_t *)data, n, no) : get_bits(SPK_[cur_], (uint32_t *)data, n, no);
+    case FK_WAS_INC:
+        return set ? set_bits(was_inc_, (const uint32_t *)data, n, L.off) : get_bits(was_inc_, (uint32_t *)data, n, L.off);
+    case FK_NT_FLAGS:
+    case FK_RC_FLAGS: {
+        const int shift = fd.kind == FK_NT_FLAGS ? 0 : 4;
+        uint32_t *h = (uint32_t *)data;
+        if (set) {
+            int r = ensure_chem();
+            if (r) return r;
+            for (uint64_t i = 0; i < n; ++i) {
+                uint8_t m = 0;
+                for (int ty = 0; ty < kNT; ++ty) if (h[i * kNT + ty]) m |= (uint8_t)(1u << ty);
+                uint8_t &f = h_node_flags_[no + i];
+                f = (uint8_t)((f & ~(0xFu << shift)) | (m << shift));
+            }
+            CK(cudaMemcpyAsync(node_flags_ + no, h_node_flags_.data() + no, n, cudaMemcpyHostToDevice, stream_), wr);
+            CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+            if (part_world > 1) {  // ghost rows inherit the type sets of the strip's edge rows (uniform-across-boundary assumption)
+                // handled when the graph is finalised
+            }
+            if (shift == 0) {
+                if (dev_weights_newer_) { r = sync_weights_to_host(); if (r) return r; }
+                graph_dirty_ = true;  // type bits are baked into the edge words
+            }
+        } else {
+            for (uint64_t i = 0; i < n; ++i)
+                for (int ty = 0; ty < kNT; ++ty) h[i * kNT + ty] = (h_node_flags_[no + i] >> (shift + ty)) & 1u;
+        }
+        return SNN_OK;
+    }
+    case FK_NT_T: {
+        if (set) { int r = ensure_chem(); if (r) return r; }
+        if (!chem_alloc_) { memset(data, 0, n * kNT * 4); return SNN_OK; }
+        return typed(T_[cur_], node_cap_, no);
+    }
+    case FK_NT: {
+        if (set) { int r = ensure_chem(); if (r) return r; }
+        if (!chem_alloc_) {
+            float *o = (float *)data;
+            for (uint64_t i = 0; i < n * kNT; ++i) o[i] = nt_default(ntk, fd.slot);
+            return SNN_OK;
+        }
+        return typed(NT_[fd.slot], node_cap_, no);
+    }
+    case FK_RC: {
+        if (set) { int r = ensure_chem(); if (r) return r; }
+        if (!chem_alloc_) {
+            float *o = (float *)data;
+            for (uint64_t i = 0; i < n; ++i) o[i] = rc_default(rck, fd.aux, fd.slot);
+            return SNN_OK;
+        }
+        return plain(RC_[fd.slot] + (size_t)fd.aux * neuron_cap_ + L.off, n);
+    }
+    case FK_TRAIN_DEV:
+    case FK_TRAIN_COUNTER:
+        return plain(TF_[fd.slot] + L.off, n);
+    }
+    (void)count;
+    return SNN_UNKNOWN_FIELD;
+}
+
+int Engine::set_field(uint64_t id, const char *name, const void *data, uint64_t count, int dtype) {
+    Lat *L = find(id);
+    if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices, id: " + std::to_string(id));
+    if (!name || (!data && L->n)) return fail(SNN_INVALID_ARGUMENT, "null argument");
+    FieldDef fd;
+    if (lookup_field(*L, name, &fd)) return fail(SNN_UNKNOWN_FIELD, std::string("unknown field: ") + name);
+    if (dtype != fd.dtype) return fail(SNN_DTYPE_MISMATCH, std::string("dtype mismatch for field: ") + name);
+    if (count != L->n * (uint64_t)fd.per) return fail(SNN_SIZE_MISMATCH, std::string("size mismatch for field: ") + name);
+    return field_io(*L, fd, const_cast<void *>(data), count, true);
+}
+
+int Engine::get_field(uint64_t id, const char *name, void *out, uint64_t count, int dtype) {
+    Lat *L = find(id);
+    if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices, id: " + std::to_string(id));
+    if (!name || (!out && L->n)) return fail(SNN_INVALID_ARGUMENT, "null argument");
+    FieldDef fd;
+    if (lookup_field(*L, name, &fd)) return fail(SNN_UNKNOWN_FIELD, std::string("unknown field: ") + name);
+    if (dtype != fd.dtype) return fail(SNN_DTYPE_MISMATCH, std::string("dtype mismatch for field: ") + name);
+    if (count != L->n * (uint64_t)fd.per) return fail(SNN_SIZE_MISMATCH, std::string("size mismatch for field: ") + name);
+    return field_io(*L, fd, out, count, false);
+}
+
+int Engine::fill_field(uint64_t id, const char *name, uint32_t bits, int dtype) {
+    Lat *L = find(id);
+    if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices, id: " + std::to_string(id));
+    FieldDef fd;
+    if (!name || lookup_field(*L, name, &fd)) return fail(SNN_UNKNOWN_FIELD, std::string("unknown field: ") + (name ? name : "(null)"));
+    if (dtype != fd.dtype) return fail(SNN_DTYPE_MISMATCH, std::string("dtype mismatch for field: ") + name);
+    if (L->n == 0) return SNN_OK;
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    // fast device-side fills for the plain arrays; everything else goes through the host path
+    uint32_t *dev = nullptr;
+    switch (fd.kind) {
+    case FK_NEURON_DEV: dev = (uint32_t *)(F_[fd.slot] + L->off); break;
+    case FK_V: dev = (uint32_t *)(V_[cur_] + node_off(*L)); break;
+    case FK_TRAIN_DEV: case FK_TRAIN_COUNTER: dev = (uint32_t *)(TF_[fd.slot] + L->off); break;
+    case FK_RC: { int r = ensure_chem(); if (r) return r; dev = (uint32_t *)(RC_[fd.slot] + (size_t)fd.aux * neuron_cap_ + L->off); break; }
+    default: break;
+    }
+    if (dev) {
+        CK(launch_fill_u32(dev, bits, L->n, stream_), SNN_GPU_QUEUE_FAILURE);
+        CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+        return SNN_OK;
+    }
+    std::vector<uint32_t> tmp(L->n * fd.per, bits);
+    return field_io(*L, fd, tmp.data(), tmp.size(), true);
+}
+
+int Engine::set_preset_firing_times(uint64_t id, const uint64_t *offsets, const float *times, uint64_t nt, uint64_t n_times) {
+    Lat *L = find(id);
+    if (!L || !L->is_train) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in spike train lattices");
+    if (train_kind != SNN_TRAIN_PRESET) return fail(SNN_UNSUPPORTED, "spike train type has no firing_times");
+    if (nt != L->n || !offsets || offsets[nt] != n_times) return fail(SNN_SIZE_MISMATCH, "firing_times size mismatch");
+    L->ft_off.assign(offsets, offsets + nt + 1);
+    L->ft.assign(times, times + n_times);
+    // rebuild the concatenated CSR over all train lattices
+    std::vector<uint64_t> off(n_trains + 1, 0);
+    std::vector<float> all;
+    for (auto &X : lats_) {
+        if (!X.is_train) continue;
+        for (uint64_t i = 0; i < X.n; ++i) {
+            off[X.off + i] = all.size();
+            if (!X.ft_off.empty()) all.insert(all.end(), X.ft.begin() + X.ft_off[i], X.ft.begin() + X.ft_off[i + 1]);
+        }
+    }
+    off[n_trains] = all.size();
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    if (ft_) cudaFree(ft_);
+    CK(dev_alloc(&ft_, all.size()), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemcpy(ft_off_, off.data(), off.size() * 8, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (!all.empty()) CK(cudaMemcpy(ft_, all.data(), all.size() * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// graph ingestion
+// ------------------------------------------------------------------------------------------------
+static int check_connect(Engine &E, uint64_t pre_id, uint64_t post_id, Lat **A, Lat **B) {
+    // LatticeNetwork::connect preconditions, neuron/mod.rs:1852-1862
+    Lat *pre = E.find(pre_id), *post = E.find(post_id);
+    if (post && post->is_train)
+        return E.fail(SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN,
+                      "Postsynaptic lattice cannot be a spike train lattice because spike trains cannot take inputs");
+    if (!pre) return E.fail(SNN_NET_PRESYNAPTIC_ID_NOT_FOUND, "Presynaptic id not present in network, id: " + std::to_string(pre_id));
+    if (!post) return E.fail(SNN_NET_POSTSYNAPTIC_ID_NOT_FOUND, "Postsynaptic id not present in network, id: " + std::to_string(post_id));
+    *A = pre; *B = post;
+    return SNN_OK;
+}
+
+static void sort_rows(Block &b) {
+    const uint64_t n = b.row_ptr.size() - 1;
+    std::vector<std::pair<uint32_t, float>> tmp;
+    for (uint64_t q = 0; q < n; ++q) {
+        const uint64_t s = b.row_ptr[q], e = b.row_ptr[q + 1];
+        bool sorted = true;
+        for (uint64_t k = s + 1; k < e; ++k) if (b.pre[k - 1] > b.pre[k]) { sorted = false; break; }
+        if (sorted) continue;
+        tmp.clear();
+        for (uint64_t k = s; k < e; ++k) tmp.emplace_back(b.pre[k], b.w[k]);
+        std::stable_sort(tmp.begin(), tmp.end(), [](auto &x, auto &y) { return x.first < y.first; });
+        for (uint64_t k = s; k < e; ++k) { b.pre[k] = tmp[k - s].first; b.w[k] = tmp[k - s].second; }
+    }
+}
+
+int Engine::connect_dense(uint64_t pre_id, uint64_t post_id, const uint32_t *connections, const float *weights,
+                          const uint32_t *itp, uint64_t n_pre, uint64_t n_post) {
+    Lat *A, *B;
+    int r = check_connect(*this, pre_id, post_id, &A, &B);
+    if (r) return r;
+    if (n_pre != A->n || n_post != B->n) return fail(SNN_GRAPH_DIMENSIONS_DO_NOT_MATCH, "Dimensions do not match");
+    if ((n_pre * n_post) && (!connections || !weights)) return fail(SNN_INVALID_ARGUMENT, "null graph pointers");
+    if (part_world > 1) return fail(SNN_UNSUPPORTED, "dense graphs are not supported on partitioned handles");
+    if (itp) {
+        if (pre_id != post_id) return fail(SNN_INVALID_ARGUMENT, "index_to_position only applies to an internal graph");
+        for (uint64_t i = 0; i < n_pre; ++i)
+            if (itp[i] >= n_pre) return fail(SNN_GRAPH_POSITION_NOT_FOUND, "Position not found, position: " + std::to_string(itp[i]));
+    }
+    if (dev_weights_newer_) { r = sync_weights_to_host(); if (r) return r; }
+    Block b;
+    b.kind = Block::CSR;
+    b.row_ptr.assign(n_post + 1, 0);
+    // rows are indexed by cell position; graph index g maps to position itp[g]
+    std::vector<uint64_t> cnt(n_post + 1, 0);
+    for (uint64_t q = 0; q < n_post; ++q) {
+        const uint64_t qp = itp ? itp[q] : q;
+        uint64_t c = 0;
+        for (uint64_t p = 0; p < n_pre; ++p) if (connections[p * n_post + q]) c++;
+        cnt[qp] = c;
+    }
+    for (uint64_t q = 0; q < n_post; ++q) b.row_ptr[q + 1] = b.row_ptr[q] + cnt[q];
+    b.pre.resize(b.row_ptr[n_post]); b.w.resize(b.row_ptr[n_post]);
+    for (uint64_t q = 0; q < n_post; ++q) {
+        const uint64_t qp = itp ? itp[q] : q;
+        uint64_t o = b.row_ptr[qp];
+        for (uint64_t p = 0; p < n_pre; ++p)
+            if (connections[p * n_post + q]) { b.pre[o] = (uint32_t)(itp ? itp[p] : p); b.w[o] = weights[p * n_post + q]; ++o; }
+    }
+    if (itp) sort_rows(b);
+    blocks_[{pre_id, post_id}] = std::move(b);
+    graph_dirty_ = true;
+    return SNN_OK;
+}
+
+int Engine::connect_csr(uint64_t pre_id, uint64_t post_id, const uint64_t *row_ptr, const uint32_t *pre, const float *weights,
+                        uint64_t n_post, uint64_t nnz) {
+    Lat *A, *B;
+    int r = check_connect(*this, pre_id, post_id, &A, &B);
+    if (r) return r;
+    if (n_post != B->n) return fail(SNN_GRAPH_DIMENSIONS_DO_NOT_MATCH, "Dimensions do not match");
+    if (!row_ptr || (nnz && (!pre || !weights))) return fail(SNN_INVALID_ARGUMENT, "null graph pointers");
+    if (row_ptr[0] != 0 || row_ptr[n_post] != nnz) return fail(SNN_SIZE_MISMATCH, "row_ptr does not match nnz");
+    const uint64_t pre_limit = part_world > 1 ? (uint64_t)rows_global * A->cols : A->n;
+    for (uint64_t k = 0; k < nnz; ++k)
+        if (pre[k] >= pre_limit) return fail(SNN_GRAPH_PRESYNAPTIC_NOT_FOUND, "Presynaptic position not found, position: " + std::to_string(pre[k]));
+    for (uint64_t q = 0; q < n_post; ++q)
+        if (row_ptr[q + 1] < row_ptr[q]) return fail(SNN_INVALID_ARGUMENT, "row_ptr must be non-decreasing");
+    if (dev_weights_newer_) { r = sync_weights_to_host(); if (r) return r; }
+    Block b;
+    b.kind = Block::CSR;
+    b.row_ptr.assign(row_ptr, row_ptr + n_post + 1);
+    b.pre.assign(pre, pre + nnz);
+    b.w.assign(weights, weights + nnz);
+    sort_rows(b);
+    blocks_[{pre_id, post_id}] = std::move(b);
+    graph_dirty_ = true;
+    return SNN_OK;
+}
+
+int Engine::connect_grid(uint64_t id, uint32_t radius, float weight) {
+    Lat *A, *B;
+    int r = check_connect(*this, id, id, &A, &B);
+    if (r) return r;
+    if (radius > 7) return fail(SNN_UNSUPPORTED, "stencil radius too large");
+    if (part_world > 1) {
+        const uint32_t need = radius * A->cols;
+        if (need > A->n && A->n) return fail(SNN_UNSUPPORTED, "strip is thinner than the stencil radius");
+        if (need != halo_) {
+            // re-layout with a halo of `radius` rows (snapshot/restore through the field path)
+            if (peer_slab_[0] || peer_slab_[1]) return fail(SNN_UNSUPPORTED, "cannot change the stencil after the halo slab was exported");
+            Lat copy = *A;
+            std::vector<LatSnap> unused;
+            // temporarily remove the lattice and add it back with the new halo
+            std::vector<FieldSnap> fields;
+            uint32_t cnt = 0; field_count(id, &cnt);
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const char *name; int32_t dt; uint32_t per;
+                field_info(id, i, &name, &dt, &per);
+                FieldDef fd;
+                if (lookup_field(*A, name, &fd)) continue;
+                const bool is_chem = fd.kind == FK_NT_FLAGS || fd.kind == FK_NT_T || fd.kind == FK_NT || fd.kind == FK_RC_FLAGS || fd.kind == FK_RC;
+                if (is_chem && !chem_alloc_) continue;
+                FieldSnap f; f.name = name; f.dtype = dt; f.count = A->n * per; f.data.resize(std::max<uint64_t>(f.count, 1) * 4);
+                r = get_field(id, name, f.data.data(), f.count, dt);
+                if (r) return r;
+                fields.push_back(std::move(f));
+            }
+            const bool had_chem = chem_alloc_;
+            free_device();
+            halo_ = need;
+            compute_layout();
+            r = alloc_device();
+            if (r) return r;
+            if (had_chem) { r = ensure_chem(); if (r) return r; }
+            for (auto &f : fields) { r = set_field(id, f.name.c_str(), f.data.data(), f.count, f.dtype); if (r) return r; }
+            A = B = find(id);
+        }
+    }
+    Block b;
+    b.kind = Block::GRID;
+    b.radius = radius; b.weight = weight;
+    blocks_[{id, id}] = std::move(b);
+    dev_weights_newer_ = false;
+    graph_dirty_ = true;
+    return SNN_OK;
+}
+
+int Engine::materialize_grid(Block &b, const Lat &L) {
+    // host CSR of the Moore stencil (same enumeration order as sell_grid_kernel: ascending flat index)
+    const int64_t R = b.radius, rows_g = part_world > 1 ? rows_global : L.rows, cols = L.cols;
+    const int64_t r0 = part_world > 1 ? row0_global : 0;
+    b.row_ptr.assign(L.n + 1, 0);
+    b.pre.clear(); b.w.clear();
+    for (int64_t i = 0; i < (int64_t)L.rows; ++i)
+        for (int64_t j = 0; j < cols; ++j) {
+            for (int64_t di = -R; di <= R; ++di)
+                for (int64_t dj = -R; dj <= R; ++dj) {
+                    const int64_t a = r0 + i + di, c = j + dj;
+                    if ((di == 0 && dj == 0) || a < 0 || c < 0 || a >= rows_g || c >= cols) continue;
+                    // pre index: global flat index on partitioned handles, local otherwise
+                    b.pre.push_back((uint32_t)(a * cols + c));
+                    b.w.push_back(b.weight);
+                }
+            b.row_ptr[i * cols + j + 1] = b.pre.size();
+        }
+    b.kind = Block::CSR;
+    return SNN_OK;
+}
+
+uint32_t Engine::nt_used() const {
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n_nodes_; ++i) m |= h_node_flags_[i] & 0x7u;
+    return m;
+}
+uint32_t Engine::rc_used() const {
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n_nodes_; ++i) m |= (h_node_flags_[i] >> 4) & 0x7u;
+    return m;
+}
+
+int Engine::finalize_graph() {
+    if (!graph_dirty_) return SNN_OK;
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    if (slice_off_) cudaFree(slice_off_);
+    if (col_) cudaFree(col_);
+    if (wgt_) cudaFree(wgt_);
+    slice_off_ = col_ = nullptr; wgt_ = nullptr;
+    grid_fast_ = false;
+    n_slices_ = (uint32_t)((n_neurons + 31) / 32);
+    CK(dev_alloc(&slice_off_, (size_t)n_slices_ + 1), SNN_GPU_BUFFER_CREATE_ERROR);
+    // partitioned handles: ghost rows inherit the neurotransmitter type sets of the adjacent owned rows
+    if (part_world > 1 && n_neurons) {
+        for (uint32_t g = 0; g < halo_; ++g) {
+            if (part_rank > 0) h_node_flags_[own0_ - halo_ + g] = h_node_flags_[own0_ + (g % std::max<uint64_t>(n_neurons, 1))];
+            if (part_rank < part_world - 1) h_node_flags_[ghost_hi0_ + g] = h_node_flags_[own0_ + n_neurons - halo_ + g];
+        }
+        CK(cudaMemcpy(node_flags_, h_node_flags_.data(), node_cap_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    }
+    int n_neuron_lat = 0;
+    const Lat *only = nullptr;
+    for (auto &L : lats_) if (!L.is_train) { n_neuron_lat++; only = &L; }
+    // fast path: one lattice whose only block is a grid stencil -> built directly in sliced-ELL form on the device
+    if (n_neuron_lat == 1 && blocks_.size() == 1 && blocks_.begin()->second.kind == Block::GRID &&
+        blocks_.begin()->first == std::make_pair(only->id, only->id)) {
+        const Block &b = blocks_.begin()->second;
+        const uint32_t width = (2 * b.radius + 1) * (2 * b.radius + 1) - 1;
+        sell_krows_ = (uint64_t)n_slices_ * width;
+        CK(dev_alloc(&col_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(dev_alloc(&wgt_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+        if (n_neurons == 0) CK(cudaMemset(slice_off_, 0, 4), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(launch_sell_grid(only->rows, only->cols, part_world > 1 ? row0_global : 0, part_world > 1 ? rows_global : only->rows,
+                            b.radius, b.weight, own0_, node_flags_, width, slice_off_, col_, wgt_, stream_), SNN_GPU_QUEUE_FAILURE);
+        CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+        grid_fast_ = true;
+        graph_dirty_ = false;
+        dev_weights_newer_ = false;
+        return SNN_OK;
+    }
+    // general path: merge every block into one CSR over canonical node indices
+    for (auto &kv : blocks_)
+        if (kv.second.kind == Block::GRID) materialize_grid(kv.second, *find(kv.first.first));
+    std::vector<uint64_t> row_ptr(n_neurons + 1, 0);
+    // blocks into each post lattice ordered by the pre lattice's node offset => rows stay sorted by node index
+    std::vector<std::vector<std::pair<const Lat *, const Block *>>> into(lats_.size());
+    for (size_t li = 0; li < lats_.size(); ++li) {
+        if (lats_[li].is_train) continue;
+        for (auto &kv : blocks_)
+            if (kv.first.second == lats_[li].id) {
+                const Lat *A = find(kv.first.first);
+                if (A) into[li].emplace_back(A, &kv.second);
+            }
+        std::sort(into[li].begin(), into[li].end(), [&](auto &x, auto &y) { return node_off(*x.first) < node_off(*y.first); });
+        for (uint64_t q = 0; q < lats_[li].n; ++q) {
+            uint64_t c = 0;
+            for (auto &ab : into[li]) c += ab.second->row_ptr[q + 1] - ab.second->row_ptr[q];
+            row_ptr[lats_[li].off + q + 1] = c;
+        }
+    }
+    for (uint64_t i = 0; i < n_neurons; ++i) row_ptr[i + 1] += row_ptr[i];
+    const uint64_t nnz = row_ptr[n_neurons];
+    std::vector<uint32_t> pre(std::max<uint64_t>(nnz, 1));
+    std::vector<float> w(std::max<uint64_t>(nnz, 1));
+    const int64_t node_shift = part_world > 1 ? (int64_t)own0_ - (int64_t)row0_global * (only ? only->cols : 0) : 0;
+    for (size_t li = 0; li < lats_.size(); ++li) {
+        if (lats_[li].is_train) continue;
+        for (uint64_t q = 0; q < lats_[li].n; ++q) {
+            uint64_t o = row_ptr[lats_[li].off + q];
+            for (auto &ab : into[li]) {
+                const Block &b = *ab.second;
+                const uint32_t base = node_off(*ab.first);
+                for (uint64_t k = b.row_ptr[q]; k < b.row_ptr[q + 1]; ++k) {
+                    int64_t node = part_world > 1 ? (int64_t)b.pre[k] + node_shift : (int64_t)base + b.pre[k];
+                    if (node < 0 || node >= (int64_t)n_nodes_)
+                        return fail(SNN_UNSUPPORTED, "edge reaches beyond the halo of this strip");
+                    pre[o] = (uint32_t)node; w[o] = b.w[k]; ++o;
+                }
+            }
+        }
+    }
+    std::vector<uint32_t> slice_off(n_slices_ + 1, 0);
+    for (uint32_t s = 0; s < n_slices_; ++s) {
+        uint64_t mx = 0;
+        for (uint64_t r = (uint64_t)s * 32; r < std::min<uint64_t>((uint64_t)s * 32 + 32, n_neurons); ++r)
+            mx = std::max(mx, row_ptr[r + 1] - row_ptr[r]);
+        const uint64_t next = (uint64_t)slice_off[s] + mx;
+        if (next > 0xFFFFFFF0ull / 32) return fail(SNN_UNSUPPORTED, "graph too large");
+        slice_off[s + 1] = (uint32_t)next;
+    }
+    sell_krows_ = slice_off[n_slices_];
+    CK(dev_alloc(&col_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&wgt_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemcpy(slice_off_, slice_off.data(), ((size_t)n_slices_ + 1) * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    uint64_t *d_rp = nullptr; uint32_t *d_pre = nullptr; float *d_w = nullptr;
+    CK(dev_alloc(&d_rp, n_neurons + 1), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&d_pre, nnz), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&d_w, nnz), SNN_GPU_BUFFER_CREATE_ERROR);
+    cudaMemcpy(d_rp, row_ptr.data(), (n_neurons + 1) * 8, cudaMemcpyHostToDevice);
+    if (nnz) { cudaMemcpy(d_pre, pre.data(), nnz * 4, cudaMemcpyHostToDevice); cudaMemcpy(d_w, w.data(), nnz * 4, cudaMemcpyHostToDevice); }
+    cudaError_t e = launch_sell_from_csr(d_rp, d_pre, d_w, node_flags_, part_world > 1 ? 0xFFFFFFFFu : train0_, (uint32_t)n_neurons,
+                                         slice_off_, col_, wgt_, stream_);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
+    cudaFree(d_rp); cudaFree(d_pre); cudaFree(d_w);
+    if (e != cudaSuccess) return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "sell_from_csr");
+    graph_dirty_ = false;
+    dev_weights_newer_ = false;
+    return SNN_OK;
+}
+
+int Engine::sync_weights_to_host() {
+    if (!dev_weights_newer_) return SNN_OK;
+    if (graph_dirty_ || !col_) { dev_weights_newer_ = false; return SNN_OK; }
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    std::vector<uint32_t> so((size_t)n_slices_ + 1), col(std::max<uint64_t>(sell_krows_ * 32, 1));
+    std::vector<float> wg(std::max<uint64_t>(sell_krows_ * 32, 1));
+    CK(cudaMemcpy(so.data(), slice_off_, so.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    if (sell_krows_) {
+        CK(cudaMemcpy(col.data(), col_, sell_krows_ * 32 * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+        CK(cudaMemcpy(wg.data(), wgt_, sell_krows_ * 32 * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    }
+    for (auto &kv : blocks_)
+        if (kv.second.kind == Block::GRID) materialize_grid(kv.second, *find(kv.first.first));
+    // walk every row in the same order finalize_graph wrote it
+    for (auto &L : lats_) {
+        if (L.is_train) continue;
+        std::vector<std::pair<const Lat *, Block *>> into;
+        for (auto &kv : blocks_)
+            if (kv.first.second == L.id) { const Lat *A = find(kv.first.first); if (A) into.emplace_back(A, &kv.second); }
+        std::sort(into.begin(), into.end(), [&](auto &x, auto &y) { return node_off(*x.first) < node_off(*y.first); });
+        for (uint64_t q = 0; q < L.n; ++q) {
+            const uint64_t row = L.off + q;
+            const uint32_t s = (uint32_t)(row / 32), lane = (uint32_t)(row % 32);
+            uint32_t k = so[s];
+            for (auto &ab : into) {
+                Block &b = *ab.second;
+                for (uint64_t e = b.row_ptr[q]; e < b.row_ptr[q + 1]; ++e, ++k) b.w[e] = wg[(size_t)k * 32 + lane];
+            }
+        }
+    }
+    dev_weights_newer_ = false;
+    return SNN_OK;
+}
+
+int Engine::connection_nnz(uint64_t pre_id, uint64_t post_id, uint64_t *nnz) {
+    Lat *A = find(pre_id), *B = find(post_id);
+    if (!A || !B) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    auto it = blocks_.find({pre_id, post_id});
+    if (it == blocks_.end()) { *nnz = 0; return SNN_OK; }
+    if (it->second.kind == Block::GRID) {
+        int r = sync_weights_to_host();
+        if (r) return r;
+        if (it->second.kind == Block::GRID) materialize_grid(it->second, *A);
+    }
+    *nnz = it->second.pre.size();
+    return SNN_OK;
+}
+
+int Engine::get_connection_csr(uint64_t pre_id, uint64_t post_id, uint64_t *row_ptr, uint32_t *pre, float *weights,
+                               uint64_t n_post, uint64_t nnz) {
+    Lat *A = find(pre_id), *B = find(post_id);
+    if (!A || !B || B->is_train) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    if (n_post != B->n) return fail(SNN_GRAPH_DIMENSIONS_DO_NOT_MATCH, "Dimensions do not match");
+    int r = sync_weights_to_host();
+    if (r) return r;
+    auto it = blocks_.find({pre_id, post_id});
+    if (it == blocks_.end()) {
+        if (nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
+        if (row_ptr) std::fill(row_ptr, row_ptr + n_post + 1, 0);
+        return SNN_OK;
+    }
+    Block &b = it->second;
+    if (b.kind == Block::GRID) {
+        // materialise on a copy so that the device fast path stays available
+        Block tmp = b;
+        materialize_grid(tmp, *A);
+        if (tmp.pre.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
+        if (row_ptr) memcpy(row_ptr, tmp.row_ptr.data(), (n_post + 1) * 8);
+        if (pre) memcpy(pre, tmp.pre.data(), nnz * 4);
+        if (weights) memcpy(weights, tmp.w.data(), nnz * 4);
+        return SNN_OK;
+    }
+    if (b.pre.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
+    if (row_ptr) memcpy(row_ptr, b.row_ptr.data(), (n_post + 1) * 8);
+    if (pre && nnz) memcpy(pre, b.pre.data(), nnz * 4);
+    if (weights && nnz) memcpy(weights, b.w.data(), nnz * 4);
+    return SNN_OK;
+}
+
+int Engine::get_connection_dense(uint64_t pre_id, uint64_t post_id, uint32_t *connections, float *weights, uint64_t n_pre,
+                                 uint64_t n_post) {
+    Lat *A = find(pre_id), *B = find(post_id);
+    if (!A || !B || B->is_train) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    if (n_pre != A->n || n_post != B->n) return fail(SNN_GRAPH_DIMENSIONS_DO_NOT_MATCH, "Dimensions do not match");
+    if (part_world > 1) return fail(SNN_UNSUPPORTED, "dense graphs are not supported on partitioned handles");
+    int r = sync_weights_to_host();
+    if (r) return r;
+    if (connections) std::fill(connections, connections + n_pre * n_post, 0u);
+    if (weights) std::fill(weights, weights + n_pre * n_post, 0.f);
+    auto it = blocks_.find({pre_id, post_id});
+    if (it == blocks_.end()) return SNN_OK;
+    Block tmp;
+    const Block *b = &it->second;
+    if (b->kind == Block::GRID) { tmp = *b; materialize_grid(tmp, *A); b = &tmp; }
+    for (uint64_t q = 0; q < n_post; ++q)
+        for (uint64_t k = b->row_ptr[q]; k < b->row_ptr[q + 1]; ++k) {
+            const uint64_t idx = (uint64_t)b->pre[k] * n_post + q;
+            if (connections) connections[idx] = 1;
+            if (weights) weights[idx] = b->w[k];
+        }
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// options
+// ------------------------------------------------------------------------------------------------
+int Engine::set_dt(float dt) {
+    // LatticeNetwork::set_dt neuron/mod.rs:1655-1660; Lattice::set_dt :649-652; PoissonNeuron::set_dt
+    // rescales chance_of_firing (spike_train/mod.rs:345-349)
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    for (auto &L : lats_) {
+        if (L.n == 0) { if (!L.is_train) L.stdp.dt = dt; continue; }
+        if (L.is_train) {
+            std::vector<float> old(L.n), ch(L.n);
+            CK(cudaMemcpy(old.data(), TF_[TF_DT] + L.off, L.n * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+            if (train_kind == SNN_TRAIN_POISSON) {
+                CK(cudaMemcpy(ch.data(), TF_[TF_CHANCE] + L.off, L.n * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+                for (uint64_t i = 0; i < L.n; ++i) { const float scalar = dt / old[i]; ch[i] *= scalar; }
+                CK(cudaMemcpy(TF_[TF_CHANCE] + L.off, ch.data(), L.n * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+            }
+            CK(fill_f32(TF_[TF_DT] + L.off, dt, L.n, stream_), SNN_GPU_QUEUE_FAILURE);
+        } else {
+            CK(fill_f32(F_[F_DT] + L.off, dt, L.n, stream_), SNN_GPU_QUEUE_FAILURE);
+            L.stdp.dt = dt;
+        }
+    }
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    return SNN_OK;
+}
+
+int Engine::reset_timing() {
+    // neuron/mod.rs:405-420, 1710-1717
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    internal_clock = 0;
+    for (auto &L : lats_) L.clock = 0;
+    for (int k = 0; k < 2; ++k)
+        if (LFT_[k]) CK(launch_fill_u32((uint32_t *)LFT_[k], 0xFFFFFFFFu, node_cap_, stream_), SNN_GPU_QUEUE_FAILURE);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    return SNN_OK;
+}
+
+int Engine::reset_history() {
+    for (auto &L : lats_) { L.grid_history.clear(); L.spike_history.clear(); L.hist_len = 0; }
+    return SNN_OK;
+}
+
+int Engine::history_len(uint64_t id, uint64_t *steps) const {
+    const Lat *L = find(id);
+    if (!L) return SNN_NET_ID_NOT_FOUND_IN_LATTICES;
+    *steps = L->hist_len;
+    return SNN_OK;
+}
+
+int Engine::get_grid_history(uint64_t id, float *out, uint64_t capacity) {
+    Lat *L = find(id);
+    if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    if (capacity < L->grid_history.size()) return fail(SNN_SIZE_MISMATCH, "history buffer too small");
+    if (!L->grid_history.empty()) memcpy(out, L->grid_history.data(), L->grid_history.size() * 4);
+    return SNN_OK;
+}
+
+int Engine::get_spike_history(uint64_t id, uint8_t *out, uint64_t capacity) {
+    Lat *L = find(id);
+    if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    if (capacity < L->spike_history.size()) return fail(SNN_SIZE_MISMATCH, "history buffer too small");
+    if (!L->spike_history.empty()) memcpy(out, L->spike_history.data(), L->spike_history.size());
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step loop
+// ------------------------------------------------------------------------------------------------
+int Engine::upload_lat_table() {
+    LatInfo tab[kMaxLattices];
+    memset(tab, 0, sizeof tab);
+    int k = 0;
+    for (auto &L : lats_) {
+        if (L.is_train) continue;
+        tab[k].base = (uint32_t)L.off; tab[k].n = (uint32_t)L.n;
+        tab[k].a_plus = L.stdp.a_plus; tab[k].a_minus = L.stdp.a_minus; tab[k].tau_plus = L.stdp.tau_plus;
+        tab[k].tau_minus = L.stdp.tau_minus; tab[k].dt = L.stdp.dt;
+        tab[k].do_plasticity = L.do_plasticity; tab[k].grid_hist = L.grid_hist; tab[k].spike_hist = L.spike_hist;
+        ++k;
+    }
+    if (k == 0) k = 1;
+    CK(cudaMemcpyAsync(d_lat_, tab, sizeof(LatInfo) * kMaxLattices, cudaMemcpyHostToDevice, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    return SNN_OK;
+}
+
+void Engine::fill_step_params(StepParams &p) {
+    memset(&p, 0, sizeof p);
+    p.own0 = own0_; p.n_neurons = (uint32_t)n_neurons; p.n_nodes = n_nodes_;
+    p.electrical = electrical; p.chemical = chemical;
+    p.nt_used = nt_used(); p.rc_used = rc_used();
+    p.ntk = ntk; p.rck = rck; p.refract = refract;
+    p.slice_off = slice_off_; p.col = col_; p.wgt = wgt_;
+    p.t_stride = node_cap_; p.node_flags = node_flags_;
+    for (int s = 0; s < F_COUNT; ++s) p.f[s] = F_[s];
+    p.was_inc = was_inc_;
+    for (int s = 0; s < NTF_COUNT; ++s) p.nt[s] = NT_[s];
+    p.nt_stride = node_cap_;
+    for (int s = 0; s < RCF_COUNT; ++s) p.rc[s] = RC_[s];
+    p.rc_stride = neuron_cap_;
+    p.train0 = train0_; p.n_trains = (uint32_t)n_trains;
+    for (int s = 0; s < TF_COUNT; ++s) p.tf[s] = TF_[s];
+    p.lat = d_lat_;
+    int nl = 0;
+    for (auto &L : lats_) if (!L.is_train) nl++;
+    p.n_lat = std::max(nl, 1);
+    p.halo[0] = halo_dir_[0]; p.halo[1] = halo_dir_[1];
+    p.halo_done = halo_done_;
+}
+
+int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
+    if (elapsed_ms) *elapsed_ms = 0.f;
+    if (launches) *launches = 0;
+    // gpu_lattices/mod.rs:1089-1091: empty lattice or zero iterations -> Ok(()); neuron/mod.rs:1217: both flags off -> Ok(())
+    if (iterations == 0 || (n_neurons == 0 && n_trains == 0)) return SNN_OK;
+    if (!electrical && !chemical) return SNN_OK;
+    if (internal_clock + iterations > 0x7FFFFFF0ull) return fail(SNN_UNSUPPORTED, "internal clock would overflow the i32 last_firing_time");
+    if (part_world > 1) {
+        if ((part_rank > 0 && !halo_dir_[0].active) || (part_rank < part_world - 1 && !halo_dir_[1].active))
+            return fail(SNN_INVALID_ARGUMENT, "partitioned handle: neighbouring strips are not attached");
+    }
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    if (chemical) { int r = ensure_chem(); if (r) return r; }
+    int r = finalize_graph();
+    if (r) return r;
+    r = upload_lat_table();
+    if (r) return r;
+
+    bool stdp = false, want_grid = false, want_spk = false, want_tgrid = false, want_tspk = false;
+    for (auto &L : lats_) {
+        if (!L.is_train) { stdp |= L.do_plasticity; want_grid |= L.grid_hist; want_spk |= L.spike_hist; }
+        else { want_tgrid |= L.grid_hist; want_tspk |= L.spike_hist; }
+    }
+    const bool chem_tpl = chem_alloc_ && (chemical || nt_used() != 0 || (model == SNN_MODEL_HODGKIN_HUXLEY && rc_used() != 0));
+    const bool lft_pp = stdp || (n_trains && electrical) || part_world > 1;
+
+    StepParams sp;
+    fill_step_params(sp);
+    sp.lft_pp = lft_pp;
+    TrainParams tp;
+    memset(&tp, 0, sizeof tp);
+    if (n_trains) {
+        tp.train0 = train0_; tp.n_trains = (uint32_t)n_trains; tp.kind = train_kind; tp.ntk = ntk; tp.seed = seed;
+        tp.t_stride = node_cap_; tp.node_flags = node_flags_; tp.nt_stride = node_cap_;
+        for (int s = 0; s < NTF_COUNT; ++s) tp.nt[s] = NT_[s];
+        for (int s = 0; s < TF_COUNT; ++s) tp.tf[s] = TF_[s];
+        tp.ft_off = ft_off_; tp.ft = ft_; tp.lft_pp = lft_pp;
+        if (!chem_alloc_) {  // train kernel reads node_flags only; nt pointers unused when no types are present
+        }
+    }
+
+    // history staging: chunks of steps recorded on the device, drained to the host between chunks
+    const uint64_t n_words = (n_neurons + 31) / 32, t_words = (n_trains + 31) / 32;
+    uint64_t per_step_bytes = 0;
+    if (want_grid) per_step_bytes += n_neurons * 4;
+    if (want_spk) per_step_bytes += n_words * 4;
+    if (want_tgrid) per_step_bytes += n_trains * 4;
+    if (want_tspk) per_step_bytes += t_words * 4;
+    uint64_t chunk = iterations;
+    if (per_step_bytes) chunk = std::max<uint64_t>(1, std::min<uint64_t>(iterations, (256ull << 20) / per_step_bytes));
+    float *d_grid = nullptr, *d_tgrid = nullptr; uint32_t *d_spk = nullptr, *d_tspk = nullptr;
+    if (want_grid) CK(dev_alloc(&d_grid, chunk * n_neurons), SNN_GPU_BUFFER_CREATE_ERROR);
+    if (want_spk) CK(dev_alloc(&d_spk, chunk * n_words), SNN_GPU_BUFFER_CREATE_ERROR);
+    if (want_tgrid) CK(dev_alloc(&d_tgrid, chunk * n_trains), SNN_GPU_BUFFER_CREATE_ERROR);
+    if (want_tspk) CK(dev_alloc(&d_tspk, chunk * t_words), SNN_GPU_BUFFER_CREATE_ERROR);
+    auto free_hist = [&]() { cudaFree(d_grid); cudaFree(d_spk); cudaFree(d_tgrid); cudaFree(d_tspk); };
+
+    uint64_t n_launch = 0;
+    float total_ms = 0.f;
+    int status = SNN_OK;
+    auto bail = [&](cudaError_t e, int st, const char *what) { status = cuda_fail(e, st, what); };
+
+    // multi-GPU: push the current boundary state into the neighbours' ghost slots
+    if (part_world > 1) {
+        StepParams hp = sp;
+        hp.v_in = V_[cur_]; hp.lft_in = LFT_[lft_loc_]; hp.t_in = T_[cur_]; hp.out_par = (uint32_t)cur_;
+        hp.halo_epoch = halo_epoch_;
+        if (lft_loc_ != cur_) {  // keep lft parity aligned with the V parity on partitioned handles
+            cudaMemcpyAsync(LFT_[cur_], LFT_[lft_loc_], node_cap_ * 4, cudaMemcpyDeviceToDevice, stream_);
+            lft_loc_ = cur_; hp.lft_in = LFT_[lft_loc_];
+        }
+        cudaError_t e = launch_halo_push(hp, stream_);
+        if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "halo_push"); }
+        halo_epoch_ += 1;
+        n_launch++;
+    }
+
+    uint64_t done = 0;
+    bool first_step = true;
+    while (done < iterations && status == SNN_OK) {
+        const uint64_t steps = std::min(chunk, iterations - done);
+        cudaEventRecord(ev0_, stream_);
+        for (uint64_t s = 0; s < steps; ++s) {
+            const int in = cur_, out = cur_ ^ 1;
+            sp.clock = (uint32_t)internal_clock;
+            sp.apply_pending = (stdp && !first_step) ? 1u : 0u;
+            sp.v_in = V_[in]; sp.v_out = V_[out];
+            sp.spk_in = SPK_[in]; sp.spk_out = SPK_[out];
+            sp.t_in = T_[in]; sp.t_out = T_[out];
+            if (lft_pp) { sp.lft_in = LFT_[lft_loc_]; sp.lft_out = LFT_[lft_loc_ ^ 1]; }
+            else { sp.lft_in = LFT_[lft_loc_]; sp.lft_out = LFT_[lft_loc_]; }
+            sp.grid_hist = want_grid ? d_grid + s * n_neurons : nullptr;
+            sp.spike_hist = want_spk ? d_spk + s * n_words : nullptr;
+            sp.out_par = (uint32_t)out;
+            sp.halo_epoch = halo_epoch_;
+            if (n_neurons) {
+                cudaError_t e = launch_step(sp, model, chem_tpl, stdp, stream_);
+                if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step"); break; }
+                n_launch++;
+            }
+            if (part_world > 1) halo_epoch_ += 1;
+            // LatticeNetwork::iterate: clock += 1, then the spike trains step with their own clocks
+            // (neuron/mod.rs:2582-2591)
+            if (n_trains) {
+                tp.v_in = V_[in]; tp.v_out = V_[out]; tp.spk_in = SPK_[in]; tp.spk_out = SPK_[out];
+                tp.t_in = T_[in]; tp.t_out = T_[out];
+                tp.lft_in = sp.lft_in; tp.lft_out = sp.lft_out;
+                tp.n_tl = 0;
+                for (auto &L : lats_)
+                    if (L.is_train) { tp.tl_base[tp.n_tl] = (uint32_t)L.off; tp.tl_clock[tp.n_tl] = (uint32_t)L.clock; tp.n_tl++; }
+                tp.tl_base[tp.n_tl] = (uint32_t)n_trains;
+                tp.grid_hist = want_tgrid ? d_tgrid + s * n_trains : nullptr;
+                tp.spike_hist = want_tspk ? d_tspk + s * t_words : nullptr;
+                cudaError_t e = launch_trains(tp, stream_);
+                if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_trains"); break; }
+                n_launch++;
+                for (auto &L : lats_) if (L.is_train) L.clock += 1;
+            }
+            internal_clock += 1;
+            cur_ = out;
+            if (lft_pp) lft_loc_ ^= 1;
+            first_step = false;
+        }
+        if (status != SNN_OK) break;
+        done += steps;
+        if (done == iterations && stdp) {
+            // the last step's STDP is still pending: apply it now so that weights are final at the API boundary
+            StepParams fp = sp;
+            fp.clock = (uint32_t)internal_clock;
+            fp.lft_in = LFT_[lft_loc_];
+            cudaError_t e = launch_flush_stdp(fp, stream_);
+            if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "flush_stdp"); break; }
+            n_launch++;
+        }
+        cudaEventRecord(ev1_, stream_);
+        cudaError_t e = cudaStreamSynchronize(stream_);
+        if (e != cudaSuccess) { bail(e, SNN_GPU_WAIT_ERROR, "cudaStreamSynchronize(step loop)"); break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev0_, ev1_);
+        total_ms += ms;
+        // drain histories
+        if (per_step_bytes) {
+            std::vector<float> hg, htg; std::vector<uint32_t> hs, hts;
+            if (want_grid) { hg.resize(steps * n_neurons); cudaMemcpy(hg.data(), d_grid, hg.size() * 4, cudaMemcpyDeviceToHost); }
+            if (want_spk) { hs.resize(steps * n_words); cudaMemcpy(hs.data(), d_spk, hs.size() * 4, cudaMemcpyDeviceToHost); }
+            if (want_tgrid) { htg.resize(steps * n_trains); cudaMemcpy(htg.data(), d_tgrid, htg.size() * 4, cudaMemcpyDeviceToHost); }
+            if (want_tspk) { hts.resize(steps * t_words); cudaMemcpy(hts.data(), d_tspk, hts.size() * 4, cudaMemcpyDeviceToHost); }
+            for (auto &L : lats_) {
+                if (!L.grid_hist && !L.spike_hist) continue;
+                const uint64_t dom_n = L.is_train ? n_trains : n_neurons, dom_w = L.is_train ? t_words : n_words;
+                const std::vector<float> &G = L.is_train ? htg : hg;
+                const std::vector<uint32_t> &S = L.is_train ? hts : hs;
+                for (uint64_t s = 0; s < steps; ++s) {
+                    if (L.grid_hist) L.grid_history.insert(L.grid_history.end(), G.begin() + s * dom_n + L.off, G.begin() + s * dom_n + L.off + L.n);
+                    if (L.spike_hist) {
+                        const size_t o = L.spike_history.size();
+                        L.spike_history.resize(o + L.n);
+                        for (uint64_t j = 0; j < L.n; ++j) {
+                            const uint64_t b = L.off + j;
+                            L.spike_history[o + j] = (uint8_t)((S[s * dom_w + (b >> 5)] >> (b & 31)) & 1u);
+                        }
+                    }
+                }
+                L.hist_len += steps;
+            }
+        }
+    }
+    free_hist();
+    if (status != SNN_OK) return status;
+    if (stdp) dev_weights_newer_ = true;
+    // derived fields (receptor currents, HH gate rates / channel currents) from the retained pre-update V
+    if ((chemical && chem_alloc_) || model == SNN_MODEL_HODGKIN_HUXLEY) {
+        StepParams fp = sp;
+        fp.chemical = chemical && chem_alloc_;
+        CK(launch_finalize(fp, model, V_[cur_ ^ 1], stream_), SNN_GPU_QUEUE_FAILURE);
+        CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    }
+    if (elapsed_ms) *elapsed_ms = total_ms;
+    if (launches) *launches = n_launch;
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU halo plumbing (CUDA IPC; the caller moves the blobs between ranks)
+// ------------------------------------------------------------------------------------------------
+int Engine::ipc_export(IpcBlob *blob) {
+    if (part_world <= 1) return fail(SNN_INVALID_ARGUMENT, "handle is not partitioned");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    memset(blob, 0, sizeof *blob);
+    blob->magic = 0x534E4E42u; blob->version = SNN_B200_ABI_VERSION;
+    CK(cudaIpcGetMemHandle(&blob->slab, slab_), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaIpcGetMemHandle(&blob->flags, flags_), SNN_GPU_BUFFER_CREATE_ERROR);
+    for (int k = 0; k < 2; ++k) { blob->off_v[k] = slab_off_v_[k]; blob->off_lft[k] = slab_off_lft_[k]; blob->off_t[k] = slab_off_t_[k]; }
+    blob->t_stride = node_cap_;
+    blob->own0 = own0_; blob->n_neurons = (uint32_t)n_neurons; blob->ghost_hi0 = ghost_hi0_; blob->halo = halo_;
+    blob->cols = lats_.empty() ? 0 : lats_[0].cols; blob->chem = chem_alloc_;
+    blob->rank = part_rank; blob->world = part_world;
+    return SNN_OK;
+}
+
+int Engine::ipc_attach(int direction, const IpcBlob *blob) {
+    if (part_world <= 1) return fail(SNN_INVALID_ARGUMENT, "handle is not partitioned");
+    if (direction != -1 && direction != 1) return fail(SNN_INVALID_ARGUMENT, "direction must be -1 or +1");
+    if (blob->magic != 0x534E4E42u || blob->version != SNN_B200_ABI_VERSION) return fail(SNN_INVALID_ARGUMENT, "bad ipc blob");
+    if (blob->rank != part_rank + direction || blob->world != part_world) return fail(SNN_INVALID_ARGUMENT, "ipc blob is not from the neighbouring rank");
+    if (blob->halo != halo_ || (blob->chem != 0) != chem_alloc_) return fail(SNN_INVALID_ARGUMENT, "neighbouring strips disagree on halo width / chemistry");
+    if (halo_ > n_neurons || halo_ > blob->n_neurons) return fail(SNN_UNSUPPORTED, "strip thinner than the halo");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    const int d = direction < 0 ? 0 : 1;
+    if (peer_slab_[d]) return fail(SNN_INVALID_ARGUMENT, "direction already attached");
+    CK(cudaIpcOpenMemHandle(&peer_slab_[d], blob->slab, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaIpcOpenMemHandle(&peer_flags_[d], blob->flags, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
+    HaloDir &H = halo_dir_[d];
+    memset(&H, 0, sizeof H);
+    H.count = halo_;
+    // d == 0: my first `halo` neurons go to the upper ghost slots of rank-1; d == 1: my last `halo` neurons go to
+    // the lower ghost slots of rank+1
+    H.first = d == 0 ? 0 : (uint32_t)n_neurons - halo_;
+    H.peer_node0 = d == 0 ? blob->ghost_hi0 : blob->own0 - blob->halo;
+    H.my_ghost0 = d == 0 ? own0_ - halo_ : ghost_hi0_;
+    for (int k = 0; k < 2; ++k) {
+        H.peer_v[k] = (float *)((char *)peer_slab_[d] + blob->off_v[k]);
+        H.peer_lft[k] = (int *)((char *)peer_slab_[d] + blob->off_lft[k]);
+        H.peer_t[k] = (float *)((char *)peer_slab_[d] + blob->off_t[k]);
+    }
+    H.peer_t_stride = blob->t_stride;
+    // the neighbour's arrival counter for data coming from me: I am its rank+1 when d == 0 (slot 1), its rank-1 when d == 1 (slot 0)
+    H.peer_flag = (unsigned long long *)peer_flags_[d] + (d == 0 ? 1 : 0);
+    H.my_flag = flags_ + d;
+    H.active = 1;
+    return SNN_OK;
+}
+
+}  // namespace snn

@@ -1,0 +1,181 @@
+// engine.h — host-side runtime of the lattice stepping engine (one CUDA device, one stream).
+//
+// An Engine is the device-resident twin of a reference `LatticeNetwork` (neuron/mod.rs:1538-1564):
+// neuron lattices in ascending id order, then spike-train lattices, one canonical node index space,
+// one in-edge table.  A reference `Lattice` is an Engine with a single lattice.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "common.h"
+#include "fields.h"
+
+namespace snn {
+
+struct Lat {
+    uint64_t id = 0;
+    uint32_t rows = 0, cols = 0;
+    uint64_t n = 0;
+    bool is_train = false;
+    uint64_t off = 0;  // offset inside its domain (local neuron number / local train number)
+    bool do_plasticity = false, grid_hist = false, spike_hist = false;
+    snn_stdp_t stdp{2.f, 2.f, 4.5f, 4.5f, 0.1f};  // STDP::default, plasticity/mod.rs:29-39
+    uint64_t clock = 0;                           // SpikeTrainLattice::internal_clock
+    std::vector<float> cold[2];                   // v_init, w_init
+    std::vector<float> grid_history;
+    std::vector<uint8_t> spike_history;
+    uint64_t hist_len = 0;
+    std::vector<uint64_t> ft_off;                 // preset firing times (CSR) of a train lattice
+    std::vector<float> ft;
+};
+
+struct Block {  // connections pre lattice -> post lattice, CSR by post (pre ascending), or a grid stencil
+    enum Kind { CSR, GRID } kind = CSR;
+    std::vector<uint64_t> row_ptr;
+    std::vector<uint32_t> pre;
+    std::vector<float> w;
+    uint32_t radius = 0;
+    float weight = 1.f;
+};
+
+struct IpcBlob {  // exchanged between neighbouring ranks by the caller (e.g. torch.distributed all_gather)
+    uint32_t magic, version;
+    cudaIpcMemHandle_t slab, flags;
+    uint64_t off_v[2], off_lft[2], off_t[2];
+    uint64_t t_stride;
+    uint32_t own0, n_neurons, ghost_hi0, halo, cols, chem;
+    int32_t rank, world;
+};
+
+class Engine {
+public:
+    Engine(int model, int ntk, int rck, int train_kind, int refract, int device);
+    ~Engine();
+    int init();  // device selection + stream; returns snn_status
+
+    // topology
+    int add_lattice(uint64_t id, uint32_t rows, uint32_t cols, bool is_train);
+    int set_partition(uint32_t rows_global, uint32_t cols, int rank, int world);  // before add_lattice
+    Lat *find(uint64_t id);
+    const Lat *find(uint64_t id) const;
+
+    // fields
+    int field_count(uint64_t id, uint32_t *count) const;
+    int field_info(uint64_t id, uint32_t index, const char **name, int32_t *dtype, uint32_t *per) const;
+    int set_field(uint64_t id, const char *name, const void *data, uint64_t count, int dtype);
+    int get_field(uint64_t id, const char *name, void *out, uint64_t count, int dtype);
+    int fill_field(uint64_t id, const char *name, uint32_t bits, int dtype);
+    int set_preset_firing_times(uint64_t id, const uint64_t *offsets, const float *times, uint64_t n_trains, uint64_t n_times);
+
+    // graph
+    int connect_dense(uint64_t pre_id, uint64_t post_id, const uint32_t *connections, const float *weights,
+                      const uint32_t *index_to_position, uint64_t n_pre, uint64_t n_post);
+    int connect_csr(uint64_t pre_id, uint64_t post_id, const uint64_t *row_ptr, const uint32_t *pre, const float *weights,
+                    uint64_t n_post, uint64_t nnz);
+    int connect_grid(uint64_t id, uint32_t radius, float weight);
+    int connection_nnz(uint64_t pre_id, uint64_t post_id, uint64_t *nnz);
+    int get_connection_csr(uint64_t pre_id, uint64_t post_id, uint64_t *row_ptr, uint32_t *pre, float *weights,
+                           uint64_t n_post, uint64_t nnz);
+    int get_connection_dense(uint64_t pre_id, uint64_t post_id, uint32_t *connections, float *weights, uint64_t n_pre,
+                             uint64_t n_post);
+
+    // options
+    int set_dt(float dt);
+    int reset_timing();
+    int reset_history();
+
+    // run
+    int run(uint64_t iterations, float *elapsed_ms, uint64_t *launches);
+
+    // histories
+    int history_len(uint64_t id, uint64_t *steps) const;
+    int get_grid_history(uint64_t id, float *out, uint64_t capacity);
+    int get_spike_history(uint64_t id, uint8_t *out, uint64_t capacity);
+
+    // multi-GPU
+    int ipc_export(IpcBlob *blob);
+    int ipc_attach(int direction, const IpcBlob *blob);
+
+    // public knobs (Lattice / LatticeNetwork pub fields, neuron/mod.rs:556-587, 1554-1563)
+    bool electrical = true, chemical = false, parallel = false;
+    uint64_t internal_clock = 0;
+    uint64_t seed = 0x5EED5EEDull;
+    uint32_t steps_per_graph = 0;
+    std::string last_error;
+
+    int model, ntk, rck, train_kind, refract, device;
+    uint64_t n_neurons = 0, n_trains = 0;
+    // partition
+    int part_rank = 0, part_world = 1;
+    uint32_t rows_global = 0, row0_global = 0;
+
+    int fail(int status, const std::string &msg) { last_error = msg; return status; }
+
+private:
+    // layout
+    std::vector<Lat> lats_;
+    uint32_t own0_ = 0, train0_ = 0, ghost_hi0_ = 0, n_nodes_ = 0, halo_ = 0;
+    uint64_t node_cap_ = 0, neuron_cap_ = 0, train_cap_ = 0;
+    // device arrays
+    cudaStream_t stream_ = nullptr;
+    cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
+    void *slab_ = nullptr; size_t slab_bytes_ = 0;
+    float *V_[2] = {nullptr, nullptr};
+    int *LFT_[2] = {nullptr, nullptr};
+    float *T_[2] = {nullptr, nullptr};
+    uint64_t slab_off_v_[2] = {0, 0}, slab_off_lft_[2] = {0, 0}, slab_off_t_[2] = {0, 0};
+    uint32_t *SPK_[2] = {nullptr, nullptr};
+    uint8_t *node_flags_ = nullptr;
+    std::vector<uint8_t> h_node_flags_;
+    float *NT_[NTF_COUNT] = {};
+    float *F_[F_COUNT] = {};
+    uint32_t *was_inc_ = nullptr;
+    float *RC_[RCF_COUNT] = {};
+    float *TF_[TF_COUNT] = {};
+    uint64_t *ft_off_ = nullptr; float *ft_ = nullptr;
+    LatInfo *d_lat_ = nullptr;
+    bool chem_alloc_ = false;
+    int cur_ = 0;       // parity holding the current V / T / SPK state
+    int lft_loc_ = 0;   // buffer holding the current last_firing_time
+    bool derived_stale_ = false;
+    // graph
+    std::map<std::pair<uint64_t, uint64_t>, Block> blocks_;
+    bool graph_dirty_ = true;
+    bool dev_weights_newer_ = false;
+    bool grid_fast_ = false;
+    uint32_t *slice_off_ = nullptr, *col_ = nullptr; float *wgt_ = nullptr;
+    uint64_t sell_krows_ = 0; uint32_t n_slices_ = 0;
+    // halo
+    unsigned long long *flags_ = nullptr;  // [0] arrivals from rank-1, [1] arrivals from rank+1
+    unsigned int *halo_done_ = nullptr;
+    HaloDir halo_dir_[2] = {};
+    void *peer_slab_[2] = {nullptr, nullptr};
+    void *peer_flags_[2] = {nullptr, nullptr};
+    unsigned long long halo_epoch_ = 0;
+    // scratch
+    void *scratch_ = nullptr; size_t scratch_bytes_ = 0;
+
+    int cuda_fail(cudaError_t e, int status, const char *what);
+    int ensure_scratch(size_t bytes);
+    void free_device();
+    int alloc_device();
+    int ensure_chem();
+    int relayout_add(const Lat &nl);
+    void compute_layout();
+    uint32_t node_off(const Lat &L) const { return (L.is_train ? train0_ : own0_) + (uint32_t)L.off; }
+    int lookup_field(const Lat &L, const char *name, FieldDef *out) const;
+    int field_io(Lat &L, const FieldDef &fd, void *data, uint64_t count, bool set);
+    int set_bits(uint32_t *words, const uint32_t *host_u32, uint64_t n, uint64_t bit0);
+    int get_bits(const uint32_t *words, uint32_t *host_u32, uint64_t n, uint64_t bit0);
+    int finalize_graph();
+    int sync_weights_to_host();
+    int materialize_grid(Block &b, const Lat &L);
+    uint32_t nt_used() const; uint32_t rc_used() const;
+    void fill_step_params(StepParams &p);
+    int upload_lat_table();
+};
+
+}  // namespace snn

@@ -321,14 +321,27 @@ static o_lattice *find_lat(orc_network *net, uint64_t id) {
     return NULL;
 }
 
-/* re-derive canonical bases; graph must be empty (tests add all lattices before connecting, as
- * generate_network does: neuron/mod.rs:1625-1640) */
+static void ensure_graph(orc_network *net);
+
+/* Insert a lattice keeping the canonical order and re-index any edges that already exist (a lattice that
+ * was connected internally before joining the network keeps its graph: neuron/mod.rs:1663-1678 moves the whole
+ * Lattice, graph included). */
 static int add_lat(orc_network *net, uint64_t id, uint32_t rows, uint32_t cols, int is_train) {
     if (find_lat(net, id)) return 32; /* GraphIDAlreadyPresent neuron/mod.rs:1669-1671 */
-    int has_edges = 0;
-    if (net->in) for (uint64_t i = 0; i < net->n_neurons; i++) if (net->in_len[i]) has_edges = 1;
-    if (has_edges) return 68;
-    free_graph(net);
+    /* remember the old index space */
+    int old_n_lat = net->n_lat;
+    uint64_t old_n_neurons = net->n_neurons;
+    uint64_t *old_base = malloc(sizeof(uint64_t) * (old_n_lat + 1));
+    for (int i = 0; i < old_n_lat; i++) old_base[i] = net->lat[i]->base;
+    o_lattice **old_order = malloc(sizeof(o_lattice *) * (old_n_lat + 1));
+    for (int i = 0; i < old_n_lat; i++) old_order[i] = net->lat[i];
+    o_edge **old_in = net->in; uint32_t *old_len = net->in_len, *old_cap = net->in_cap;
+    net->in = NULL; net->in_len = net->in_cap = NULL;
+    free(net->out_ptr); free(net->out_post); free(net->out_pos);
+    net->out_ptr = NULL; net->out_post = net->out_pos = NULL; net->out_valid = 0;
+    free(net->inp_e); free(net->inp_t); free(net->inp_has);
+    net->inp_e = net->inp_t = NULL; net->inp_has = NULL;
+
     o_lattice *L = calloc(1, sizeof *L);
     L->id = id; L->rows = rows; L->cols = cols; L->n = (uint64_t)rows * cols; L->is_train = is_train;
     L->plasticity = (orc_stdp){2.f, 2.f, 4.5f, 4.5f, 0.1f}; /* STDP::default plasticity/mod.rs:29-39 */
@@ -356,6 +369,29 @@ static int add_lat(orc_network *net, uint64_t id, uint32_t rows, uint32_t cols, 
         if (!net->lat[i]->is_train) net->n_neurons = base;
     }
     net->n_nodes = base;
+    /* carry the existing edges over to the new index space */
+    if (old_in) {
+        ensure_graph(net);
+        for (int i = 0; i < old_n_lat; i++) {
+            o_lattice *B = old_order[i];
+            if (B->is_train) continue;
+            for (uint64_t q = 0; q < B->n; q++) {
+                uint64_t orow = old_base[i] + q, nrow = B->base + q;
+                net->in[nrow] = old_in[orow]; net->in_len[nrow] = old_len[orow]; net->in_cap[nrow] = old_cap[orow];
+                for (uint32_t k = 0; k < old_len[orow]; k++) {
+                    uint32_t p = net->in[nrow][k].pre;
+                    for (int a = 0; a < old_n_lat; a++)
+                        if (p >= old_base[a] && p < old_base[a] + old_order[a]->n) {
+                            net->in[nrow][k].pre = (uint32_t)(p - old_base[a] + old_order[a]->base);
+                            break;
+                        }
+                }
+            }
+        }
+        (void)old_n_neurons;
+        free(old_in); free(old_len); free(old_cap);
+    }
+    free(old_base); free(old_order);
     return 0;
 }
 

@@ -65,8 +65,8 @@ int Engine::init() {
     CK(cudaEventCreate(&ev1_), SNN_GPU_QUEUE_FAILURE);
     CK(dev_alloc(&flags_, 2), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(cudaMemset(flags_, 0, 2 * sizeof(unsigned long long)), SNN_GPU_BUFFER_WRITE_ERROR);
-    CK(dev_alloc(&halo_done_, 2), SNN_GPU_BUFFER_CREATE_ERROR);
-    CK(cudaMemset(halo_done_, 0, 2 * sizeof(unsigned int)), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(dev_alloc(&halo_done_, 4), SNN_GPU_BUFFER_CREATE_ERROR);  // [0],[1] completion counters, [2] halo time-out flag
+    CK(cudaMemset(halo_done_, 0, 4 * sizeof(unsigned int)), SNN_GPU_BUFFER_WRITE_ERROR);
     return SNN_OK;
 }
 
@@ -1252,6 +1252,14 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     }
     free_hist();
     if (status != SNN_OK) return status;
+    if (part_world > 1) {
+        unsigned int err = 0;
+        CK(cudaMemcpy(&err, halo_done_ + 2, 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+        if (err) {
+            cudaMemset(halo_done_, 0, 4 * sizeof(unsigned int));
+            return fail(SNN_GPU_WAIT_ERROR, "timed out waiting for a neighbouring strip's halo (is every rank running the same number of steps?)");
+        }
+    }
     if (stdp) dev_weights_newer_ = true;
     // derived fields (receptor currents, HH gate rates / channel currents) from the retained pre-update V
     if ((chemical && chem_alloc_) || model == SNN_MODEL_HODGKIN_HUXLEY) {

@@ -122,6 +122,16 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// Spin until the neighbour's arrival counter reaches `epoch`.  Bounded (~4e9 SM cycles, about two seconds): a
+// neighbour that died must not hang this GPU; the host turns the error flag into SNN_GPU_WAIT_ERROR.
+__device__ __forceinline__ void halo_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // the fused step kernel
 // ------------------------------------------------------------------------------------------------
@@ -143,11 +153,11 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
         const bool near_lo = p.halo[0].active && w0 < p.halo[0].first + p.halo[0].count;
         const bool near_hi = p.halo[1].active && w1 > p.halo[1].first;
         if (near_lo) {
-            if (lane == 0) while (ld_acquire_sys(p.halo[0].my_flag) < p.halo_epoch) __nanosleep(64);
+            if (lane == 0) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2);
             __syncwarp();
         }
         if (near_hi) {
-            if (lane == 0) while (ld_acquire_sys(p.halo[1].my_flag) < p.halo_epoch) __nanosleep(64);
+            if (lane == 0) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
             __syncwarp();
         }
         export_lo = near_lo && valid && ln >= p.halo[0].first && ln < p.halo[0].first + p.halo[0].count;

@@ -1,0 +1,164 @@
+"""Scenario builders shared by the CPU and GPU parity tests: one description, any back end."""
+from __future__ import annotations
+
+import numpy as np
+
+import snn_b200 as S
+from snn_b200 import _capi as K
+
+f32 = np.float32
+
+MODELS = {
+    "lif": S.LeakyIntegrateAndFireNeuron,
+    "qif": S.QuadraticIntegrateAndFireNeuron,
+    "adlif": S.AdaptiveLeakyIntegrateAndFireNeuron,
+    "adex": S.AdaptiveExpLeakyIntegrateAndFireNeuron,
+    "izh": S.IzhikevichNeuron,
+    "leaky_izh": S.LeakyIzhikevichNeuron,
+    "simple_lif": S.SimpleLeakyIntegrateAndFire,
+    "hh": S.HodgkinHuxleyNeuron,
+}
+# models whose step uses only + - * / and comparisons: rasters and voltages must match the oracle bit for bit
+EXACT_MODELS = ["lif", "qif", "adlif", "izh", "leaky_izh", "simple_lif"]
+
+
+def random_graph(rows, cols, seed, radius=2.0, p=0.8, weights="ones"):
+    """tests/gpu_accuracy.rs:28-32 style: connect within `radius` with probability p, x != y."""
+    rng = np.random.default_rng(seed)
+    n = rows * cols
+    pos = [(i, j) for i in range(rows) for j in range(cols)]
+    conn = np.zeros((n, n), np.uint32)
+    for a, x in enumerate(pos):
+        for b, y in enumerate(pos):
+            if a != b and np.hypot(x[0] - y[0], x[1] - y[1]) <= radius and rng.random() <= p:
+                conn[a, b] = 1
+    if weights == "ones":
+        w = conn.astype(f32)
+    else:
+        w = (rng.uniform(0.2, 2.0, (n, n)).astype(f32)) * conn
+    return conn, w
+
+
+def dense_to_csr(conn, w):
+    n_pre, n_post = conn.shape
+    row_ptr = np.zeros(n_post + 1, np.uint64)
+    pre, ww = [], []
+    for q in range(n_post):
+        idx = np.nonzero(conn[:, q])[0]
+        pre.extend(idx.tolist())
+        ww.extend(w[idx, q].tolist())
+        row_ptr[q + 1] = len(pre)
+    return row_ptr, np.array(pre, np.uint32), np.array(ww, f32)
+
+
+def add_chemistry(neuron, chem):
+    """chem: None | 'approx_ampa' | 'approx_all' | 'destexhe_all' | 'expdecay_all' | 'discrete_ampa'."""
+    T = S.IonotropicNeurotransmitterType
+    if chem is None:
+        return
+    kind, which = chem.split("_")
+    types = [T.AMPA] if which == "ampa" else [T.AMPA, T.NMDA, T.GABA]
+    nt_cls = {"approx": S.ApproximateNeurotransmitter, "destexhe": S.DestexheNeurotransmitter,
+              "expdecay": S.ExponentialDecayNeurotransmitter, "discrete": S.DiscreteSpikeNeurotransmitter}[kind]
+    rc_cls = {"approx": S.ApproximateReceptor, "destexhe": S.DestexheReceptor, "expdecay": S.ExponentialDecayReceptor,
+              "discrete": S.ApproximateReceptor}[kind]
+    rec = {T.AMPA: S.AMPAReceptor, T.NMDA: S.NMDAReceptor, T.GABA: S.GABAReceptor}
+    for ty in types:
+        neuron.synaptic_neurotransmitters[ty] = nt_cls()
+        neuron.receptors[ty] = rec[ty](r=rc_cls())
+
+
+def build_lattice(factory, model="izh", rows=6, cols=7, seed=1, graph="grid", chem=None, stdp=False,
+                  electrical=True, chemical=None, gap=10.0, hetero=True, history=True, c_m=None):
+    cls = MODELS[model]
+    base = cls(gap_conductance=gap)
+    if c_m is not None:
+        base.c_m = c_m
+    add_chemistry(base, chem)
+    lat = S.Lattice(cls, backend_factory=factory)
+    lat.populate(base, rows, cols)
+    n = rows * cols
+    rng = np.random.default_rng(seed)
+    if n:
+        lo = -65.0 if model in ("izh", "leaky_izh", "hh") else -75.0
+        hi = {"izh": 30.0, "leaky_izh": 30.0, "hh": -50.0}.get(model, -55.0)
+        lat.set_field("current_voltage", rng.uniform(lo, hi, n).astype(f32))
+        if hetero:
+            lat.set_field("gap_conductance", (gap * rng.uniform(0.5, 1.5, n)).astype(f32))
+            # tonic firing without an external current: Izhikevich b > 0.27 removes the fixed point; leak reversal
+            # above threshold; QIF reset above the critical voltage (same recipe as tests/golden/make_golden.py)
+            if model in ("izh", "leaky_izh"):
+                lat.set_field("a", rng.uniform(0.015, 0.03, n).astype(f32))
+                lat.set_field("b", rng.uniform(0.25, 0.36, n).astype(f32))
+                lat.set_field("d", rng.uniform(6.0, 9.0, n).astype(f32))
+                if c_m is None:
+                    lat.fill_field("c_m", 2.0)
+            if model == "leaky_izh":
+                lat.set_field("w_value", rng.uniform(0.0, 1.0, n).astype(f32))
+            if model in ("lif", "adlif", "adex"):
+                lat.set_field("e_l", rng.uniform(-62, -42, n).astype(f32))
+                if c_m is None:
+                    lat.fill_field("c_m", 10.0)
+            if model in ("lif", "qif", "adlif", "adex"):
+                lat.set_field("tref", rng.choice([0.5, 1.0, 2.0], n).astype(f32))
+            if model == "qif":
+                # reset above a lowered threshold: fires whenever it is not refractory
+                lat.fill_field("v_th", -58.0)
+                lat.set_field("v_reset", rng.uniform(-57.5, -56, n).astype(f32))
+                lat.set_field("current_voltage", rng.uniform(-62, -56, n).astype(f32))
+                lat.fill_field("tau_m", 10.0)
+    if graph == "grid":
+        lat.connect_grid(1, 1.0)
+    elif graph == "grid2":
+        lat.connect_grid(2, 0.5)
+    elif graph == "random":
+        conn, w = random_graph(rows, cols, seed + 100, weights="rand")
+        lat._be.connect_dense(lat._bid, lat._bid, conn, w)
+        lat._graph_spec = ("dense", conn, w)
+    elif graph == "csr":
+        conn, w = random_graph(rows, cols, seed + 100, weights="rand")
+        lat.connect_csr(*dense_to_csr(conn, w))
+    elif graph == "all":
+        lat.connect(lambda x, y: x != y, lambda x, y: 2.0)
+    elif graph == "none":
+        pass
+    else:
+        raise ValueError(graph)
+    lat.electrical_synapse = electrical
+    lat.chemical_synapse = (chem is not None) if chemical is None else chemical
+    lat.do_plasticity = stdp
+    lat.update_grid_history = history
+    lat.update_spike_history = history
+    return lat
+
+
+def drive_current(model):
+    """A gap conductance that makes each model spike within a few hundred steps from random initial V."""
+    return {"hh": 2.0}.get(model, 10.0)
+
+
+def compare_lattices(a, b, exact=True, rtol=1e-4, atol=1e-3, fields=("current_voltage",), check_raster=True):
+    """a = device under test, b = oracle."""
+    if a.update_grid_history:
+        ha, hb = a.grid_history.history, b.grid_history.history
+        assert ha.shape == hb.shape
+        if exact:
+            bad = np.nonzero(ha != hb)
+            assert bad[0].size == 0, f"first voltage mismatch at step {bad[0][0]} cell ({bad[1][0]},{bad[2][0]}): {ha[bad][0]!r} vs {hb[bad][0]!r}"
+        else:
+            np.testing.assert_allclose(ha, hb, rtol=rtol, atol=atol)
+    if check_raster and a.update_spike_history:
+        sa, sb = a.spike_history.history, b.spike_history.history
+        assert sa.shape == sb.shape
+        assert (sa == sb).all(), f"raster differs at steps {np.unique(np.nonzero(sa != sb)[0])[:5]}"
+    for name in fields:
+        fa, fb = a.get_field(name), b.get_field(name)
+        if exact or fa.dtype.kind in "iu":
+            assert (fa == fb).all(), name
+        else:
+            np.testing.assert_allclose(fa, fb, rtol=rtol, atol=atol, err_msg=name)
+
+
+def all_field_names(lat):
+    names = list(lat.neuron_type().scalar_fields())
+    return names

@@ -1,0 +1,84 @@
+"""Host-side logic of the reference-shaped front end (populate / connect / apply / network assembly / error
+behaviour), exercised on CPU with the oracle back end injected.  No product compute is involved."""
+import numpy as np
+import pytest
+
+import scenarios as SC
+import snn_b200 as S
+from snn_b200 import _capi as K
+from test_gpu_parity import build_network
+
+f32 = np.float32
+
+
+def test_populate_connect_apply_cell_grid(oracle_lattice_factory):
+    base = S.IzhikevichNeuron(gap_conductance=10.0, c_m=25.0)
+    lat = S.Lattice(S.IzhikevichNeuron, backend_factory=oracle_lattice_factory)
+    lat.populate(base, 3, 4)
+    lat.connect(lambda x, y: x != y, lambda x, y: 5.0)
+    assert lat.get_weight((0, 0), (2, 3)) == 5.0 and lat.get_weight((1, 1), (1, 1)) is None
+    with pytest.raises(S.SnnError) as ei:
+        lat.get_weight((0, 0), (9, 9))
+    assert ei.value.status == K.SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND
+    lat.apply_given_position(lambda pos, n: setattr(n, "current_voltage", -60.0 + pos[0] * 4 + pos[1]))
+    assert (lat.get_field("current_voltage") == -60.0 + np.arange(12, dtype=f32)).all()
+    grid = lat.cell_grid()
+    assert grid[2][3].c_m == 25.0 and grid[2][3].gap_conductance == 10.0 and grid[0][0].last_firing_time is None
+    with pytest.raises(S.SnnError):
+        lat.set_cell_grid(grid[:2])
+    lat.update_grid_history = True
+    lat.run_lattice(20)
+    assert lat.grid_history.history.shape == (20, 3, 4) and lat.internal_clock == 20
+
+
+def test_chemistry_objects_round_trip(oracle_lattice_factory):
+    T = S.IonotropicNeurotransmitterType
+    base = S.HodgkinHuxleyNeuron()
+    SC.add_chemistry(base, "destexhe_all")
+    base.receptors[T.NMDA].mg = 0.5
+    base.synaptic_neurotransmitters[T.GABA].k_p = 7.0
+    lat = S.Lattice(S.HodgkinHuxleyNeuron, backend_factory=oracle_lattice_factory)
+    lat.populate(base, 2, 2)
+    cell = lat.cell_grid()[1][1]
+    assert cell.receptors[T.NMDA].mg == 0.5 and isinstance(cell.receptors[T.AMPA].r, S.DestexheReceptor)
+    assert cell.synaptic_neurotransmitters[T.GABA].k_p == 7.0 and cell.synaptic_neurotransmitters[T.AMPA].v_p == 2.0
+    assert cell.na_channel_g_na == 120.0 and cell["k_channel$e_k"] == -77.0
+    with pytest.raises(TypeError):
+        bad = S.IzhikevichNeuron()
+        bad.receptors[T.AMPA] = S.GABAReceptor()
+        S.Lattice(S.IzhikevichNeuron, backend_factory=oracle_lattice_factory).populate(bad, 1, 1)
+
+
+def test_network_assembly_and_errors(oracle_lattice_factory, oracle_network_factory):
+    net = build_network(oracle_lattice_factory, oracle_network_factory, train="rate")
+    assert net.get_all_ids() == {0, 1, 2}
+    with pytest.raises(S.SnnError) as ei:
+        net.connect(1, 0, lambda x, y: True)
+    assert ei.value.status == K.SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN
+    with pytest.raises(S.SnnError) as ei:
+        net.connect(9, 1, lambda x, y: True)
+    assert ei.value.status == K.SNN_NET_PRESYNAPTIC_ID_NOT_FOUND
+    with pytest.raises(S.SnnError) as ei:
+        net.connect(1, 9, lambda x, y: True)
+    assert ei.value.status == K.SNN_NET_POSTSYNAPTIC_ID_NOT_FOUND
+    dup = S.Lattice(S.IzhikevichNeuron, id=2, backend_factory=oracle_lattice_factory)
+    dup.populate(S.IzhikevichNeuron(), 1, 1)
+    with pytest.raises(S.SnnError) as ei:
+        net.add_lattice(dup)
+    assert ei.value.status == K.SNN_NET_GRAPH_ID_ALREADY_PRESENT
+    c, w = net.connection_dense(2, 1)
+    assert c.sum() == 20 * 19 and (w[c == 1] == -1.0).all()
+    # the internal graph and per-cell state moved into the network with the lattice
+    ci, wi = net.connection_dense(1, 1)
+    assert ci.sum() > 0 and (wi[ci == 1] == 0.5).all()
+    net.run_lattices(50)
+    assert net.internal_clock == 50
+    assert net.get_lattice(1).grid_history.history.shape == (50, 4, 5)
+    assert net.get_spike_train_lattice(0).spike_history.history.sum() > 0
+    with pytest.raises(RuntimeError):
+        net.get_lattice(1).run_lattice(1)
+
+
+def test_poisson_from_firing_rate_matches_reference_formula():
+    p = S.PoissonNeuron.from_firing_rate(20.0, 0.1)
+    assert p.chance_of_firing == float(f32(1.0) / ((f32(1000.0) / f32(0.1)) / f32(20.0)))

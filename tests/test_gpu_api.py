@@ -1,0 +1,231 @@
+"""Boundary behaviour of the C ABI on the device: SoA conversion round trips, graph ingestion, error codes, empty
+lattices.  Mirrors the reference's conversion / edge-case tests (backend/tests/{neuron,neurotransmitter,ligand_gates,
+spike_train}_conversion.rs, size_zero_cases.rs, grid_formation_invariant.rs)."""
+import numpy as np
+import pytest
+
+import scenarios as SC
+import snn_b200 as S
+from snn_b200 import _capi as K
+from snn_b200.backend import CudaLatticeBackend, CudaNetworkBackend
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+_NP = {K.F32: np.float32, K.U32: np.uint32, K.I32: np.int32}
+
+
+def _random_for(name, dt, count, rng):
+    if dt == K.F32:
+        return rng.uniform(-3, 3, count).astype(f32)
+    if dt == K.U32:
+        return rng.integers(0, 2, count).astype(np.uint32)
+    return rng.integers(-1, 1000, count).astype(np.int32)
+
+
+@pytest.mark.parametrize("model", range(8))
+@pytest.mark.parametrize("kin", [(0, 0), (1, 1), (3, 2), (2, 0)])
+def test_every_field_round_trips(model, kin):
+    """neuron_conversion.rs / neurotransmitter_conversion.rs / ligand_gates_conversion.rs: to-device then back equals
+    the original, for every named field, including lattices that are not a multiple of the warp size."""
+    be = CudaLatticeBackend(model, kin[0], kin[1], 5, 7)
+    rng = np.random.default_rng(model * 10 + kin[0])
+    vals = {}
+    fields = be.fields(0)
+    assert {"current_voltage", "gap_conductance", "dt", "is_spiking", "last_firing_time"} <= {f[0] for f in fields}
+    for name, dt, per in fields:
+        vals[name] = _random_for(name, dt, 35 * per, rng)
+        be.set_field(0, name, vals[name])
+    for name, dt, per in fields:
+        got = be.get_field(0, name)
+        assert got.dtype == _NP[dt] and (got == vals[name]).all(), name
+
+
+def test_defaults_match_reference_default_impl(oracle_lattice_factory):
+    """populate() with default_impl(): every field equals the Rust Default (and the oracle's independent table)."""
+    for name, cls in SC.MODELS.items():
+        be = CudaLatticeBackend(cls.model, cls.default_nt.kind, cls.default_rc.kind, 2, 3)
+        ob = oracle_lattice_factory(cls.model, cls.default_nt.kind, cls.default_rc.kind, 2, 3)
+        proto = cls()
+        for fname, v in proto.scalar_fields().items():
+            got = be.get_field(0, fname)
+            want = -1 if v is None else v
+            assert np.allclose(got, f32(want)), (name, fname)
+            assert (got == ob.get_field(0, fname)).all(), (name, fname)
+        for fname in ("receptors$AMPA_g", "receptors$NMDA_g", "receptors$NMDA_mg", "receptors$GABA_e", "neurotransmitters$t_max"):
+            assert (be.get_field(0, fname) == ob.get_field(0, fname)).all(), (name, fname)
+
+
+def test_field_errors():
+    be = CudaLatticeBackend(K.MODEL_IZH, 0, 0, 3, 3)
+    lib = be.lib
+    a = np.zeros(9, f32)
+    p = a.ctypes.data
+    assert lib.snn_lattice_set_field(be.h, b"nonsense", p, 9, K.F32) == K.SNN_UNKNOWN_FIELD
+    assert lib.snn_lattice_set_field(be.h, b"refractory_count", p, 9, K.F32) == K.SNN_UNKNOWN_FIELD  # not an Izhikevich field
+    assert lib.snn_lattice_set_field(be.h, b"current_voltage", p, 8, K.F32) == K.SNN_SIZE_MISMATCH
+    assert lib.snn_lattice_set_field(be.h, b"current_voltage", p, 9, K.U32) == K.SNN_DTYPE_MISMATCH
+    assert lib.snn_lattice_set_field(be.h, b"neurotransmitters$t", p, 9, K.F32) == K.SNN_SIZE_MISMATCH
+    assert b"current_voltage" in lib.snn_lattice_last_error(be.h) or b"neurotransmitters" in lib.snn_lattice_last_error(be.h)
+    assert lib.snn_lattice_set_option(be.h, 1234, 1) == K.SNN_INVALID_ARGUMENT
+
+
+def test_graph_ingestion_round_trips():
+    rows, cols = 4, 5
+    n = rows * cols
+    conn, w = SC.random_graph(rows, cols, 5, weights="rand")
+    be = CudaLatticeBackend(K.MODEL_IZH, 0, 0, rows, cols)
+    be.connect_dense(0, 0, conn, w)
+    c2, w2 = be.get_connection_dense()
+    assert (c2 == conn).all() and (w2 == w).all()
+    rp, pre, ww = SC.dense_to_csr(conn, w)
+    # shuffled rows must come back canonical (presynaptic ascending)
+    rng = np.random.default_rng(0)
+    pre_s, ww_s = pre.copy(), ww.copy()
+    for q in range(n):
+        s, e = int(rp[q]), int(rp[q + 1])
+        perm = rng.permutation(e - s)
+        pre_s[s:e], ww_s[s:e] = pre[s:e][perm], ww[s:e][perm]
+    be2 = CudaLatticeBackend(K.MODEL_IZH, 0, 0, rows, cols)
+    be2.connect_csr(0, 0, rp, pre_s, ww_s)
+    rp2, pre2, ww2 = be2.get_connection_csr()
+    assert (rp2 == rp).all() and (pre2 == pre).all() and (ww2 == ww).all()
+    assert be2.connection_nnz() == pre.size
+    # GraphGPU index_to_position (graph/mod.rs:300-361): a permuted graph index space lands on the same cells
+    itp = rng.permutation(n).astype(np.uint32)
+    inv = np.argsort(itp)
+    be3 = CudaLatticeBackend(K.MODEL_IZH, 0, 0, rows, cols)
+    be3.connect_dense(0, 0, conn[np.ix_(itp, itp)], w[np.ix_(itp, itp)], index_to_position=itp)
+    c3, w3 = be3.get_connection_dense()
+    assert (c3 == conn).all() and (w3 == w).all()
+    del inv
+    # lookup_weight / None vs Some(0.0)
+    a, b = np.argwhere(conn == 1)[0]
+    assert be.lookup_weight(a, b) == pytest.approx(float(w[a, b]))
+    z = np.argwhere(conn == 0)[0]
+    assert be.lookup_weight(z[0], z[1]) is None
+    with pytest.raises(S.SnnError) as ei:
+        be.lookup_weight(0, n)
+    assert ei.value.status == K.SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND
+    with pytest.raises(S.SnnError) as ei:
+        be.lookup_weight(n, 0)
+    assert ei.value.status == K.SNN_GRAPH_PRESYNAPTIC_NOT_FOUND
+    with pytest.raises(S.SnnError) as ei:
+        be.connect_dense(0, 0, np.zeros((3, 3), np.uint32), np.zeros((3, 3), f32))
+    assert ei.value.status == K.SNN_GRAPH_DIMENSIONS_DO_NOT_MATCH
+    with pytest.raises(S.SnnError) as ei:
+        be.connect_csr(0, 0, np.array([0] * n + [1], np.uint64), np.array([n + 3], np.uint32), np.ones(1, f32))
+    assert ei.value.status == K.SNN_GRAPH_PRESYNAPTIC_NOT_FOUND
+
+
+def test_grid_generator_equals_connect_predicate(oracle_lattice_factory):
+    """set_graph_grid(radius) == Lattice::connect(|x,y| max(|dr|,|dc|) <= radius && x != y, None) (neuron/mod.rs:1134-1157)."""
+    for radius in (1, 2):
+        lat = S.Lattice(S.IzhikevichNeuron)
+        lat.populate(S.IzhikevichNeuron(), 5, 6)
+        lat.connect_grid(radius, 1.0)
+        ref = S.Lattice(S.IzhikevichNeuron, backend_factory=oracle_lattice_factory)
+        ref.populate(S.IzhikevichNeuron(), 5, 6)
+        ref.connect(lambda x, y: x != y and max(abs(x[0] - y[0]), abs(x[1] - y[1])) <= radius)
+        (ca, wa), (cb, wb) = lat.graph_dense(), ref.graph_dense()
+        assert (ca == cb).all() and (wa == wb).all()
+        assert lat.get_weight((0, 0), (1, 1)) == 1.0 and lat.get_weight((0, 0), (4, 5)) is None
+
+
+def test_size_zero_and_noop_cases():
+    """tests/size_zero_cases.rs: 0x0 lattices return Ok; zero iterations and both synapse flags off are no-ops."""
+    for rows, cols in [(0, 0), (0, 4), (3, 0)]:
+        lat = S.Lattice(S.IzhikevichNeuron)
+        lat.populate(S.IzhikevichNeuron(), rows, cols)
+        lat.connect(lambda x, y: True)
+        lat.run_lattice(10)
+        assert lat.cell_grid() == [[]] * rows or lat.cell_grid() == []
+    never = S.Lattice(S.IzhikevichNeuron)
+    never.run_lattice(5)
+    lat = SC.build_lattice(None, model="izh", rows=3, cols=3, history=False)
+    v0 = lat.get_field("current_voltage")
+    lat.run_lattice(0)
+    assert (lat.get_field("current_voltage") == v0).all() and lat.internal_clock == 0
+    lat.electrical_synapse = False
+    lat.chemical_synapse = False
+    lat.run_lattice(50)
+    assert (lat.get_field("current_voltage") == v0).all() and lat.internal_clock == 0
+    net = S.LatticeNetwork()
+    net.run_lattices(3)
+
+
+def test_set_cell_grid_dimension_invariant():
+    """tests/grid_formation_invariant.rs: set_cell_grid rejects a grid of different dimensions."""
+    lat = S.Lattice(S.IzhikevichNeuron)
+    lat.populate(S.IzhikevichNeuron(), 2, 3)
+    grid = lat.cell_grid()
+    with pytest.raises(S.SnnError) as ei:
+        lat.set_cell_grid(grid[:1])
+    assert ei.value.status == K.SNN_GRAPH_POSITION_NOT_FOUND
+    with pytest.raises(S.SnnError):
+        lat.set_cell_grid([row[:2] for row in grid])
+    grid[1][2].current_voltage = -12.5
+    grid[0][1].last_firing_time = 17
+    lat.set_cell_grid(grid)
+    g2 = lat.cell_grid()
+    assert g2[1][2].current_voltage == -12.5 and g2[0][1].last_firing_time == 17 and g2[0][0].last_firing_time is None
+
+
+def test_apply_and_timing_controls():
+    lat = S.Lattice(S.IzhikevichNeuron)
+    lat.populate(S.IzhikevichNeuron(gap_conductance=10.0), 3, 3)
+    lat.apply(lambda nrn: setattr(nrn, "current_voltage", 29.99))
+    lat.apply_given_position(lambda pos, nrn: setattr(nrn, "d", float(pos[0] * 3 + pos[1])))
+    assert (lat.get_field("d") == np.arange(9, dtype=f32)).all()
+    lat.connect_grid()
+    lat.run_lattice(1)
+    assert (lat.get_field("last_firing_time") == 0).all() and lat.internal_clock == 1
+    assert (lat.get_field("is_spiking") == 1).all()
+    lat.run_lattice(2)
+    assert lat.internal_clock == 3
+    lat.reset_timing()
+    assert lat.internal_clock == 0 and (lat.get_field("last_firing_time") == -1).all()
+    lat.set_dt(0.05)
+    assert (lat.get_field("dt") == f32(0.05)).all() and lat.plasticity.dt == 0.05
+    assert lat._be.get_plasticity()[4] == pytest.approx(0.05)
+
+
+def test_network_error_codes_and_ids():
+    """LatticeNetwork::add_lattice / connect error behaviour (neuron/mod.rs:1663-1698, 1852-1862)."""
+    be = CudaNetworkBackend(K.MODEL_IZH)
+    be.add_lattice(1, 2, 2)
+    be.add_train_lattice(0, 1, 2)
+    with pytest.raises(S.SnnError) as ei:
+        be.add_lattice(1, 3, 3)
+    assert ei.value.status == K.SNN_NET_GRAPH_ID_ALREADY_PRESENT
+    with pytest.raises(S.SnnError) as ei:
+        be.add_train_lattice(1, 1, 1)
+    assert ei.value.status == K.SNN_NET_GRAPH_ID_ALREADY_PRESENT
+    lib, h = be.lib, be.h
+    c, w = np.ones(4, np.uint32), np.ones(4, f32)
+    assert lib.snn_network_connect_dense(h, 1, 0, c.ctypes.data, w.ctypes.data, 4, 2) == K.SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN
+    assert lib.snn_network_connect_dense(h, 7, 1, c.ctypes.data, w.ctypes.data, 4, 4) == K.SNN_NET_PRESYNAPTIC_ID_NOT_FOUND
+    assert lib.snn_network_connect_dense(h, 1, 9, c.ctypes.data, w.ctypes.data, 4, 4) == K.SNN_NET_POSTSYNAPTIC_ID_NOT_FOUND
+    assert lib.snn_network_connect_dense(h, 0, 1, c.ctypes.data, w.ctypes.data, 3, 4) == K.SNN_GRAPH_DIMENSIONS_DO_NOT_MATCH
+    be.connect_dense(0, 1, np.ones((2, 4), np.uint32), np.full((2, 4), 0.25, f32))
+    assert be.connection_nnz(0, 1) == 8
+    # fields set before a later lattice is added survive the re-layout
+    be.set_field(1, "current_voltage", [1.0, 2.0, 3.0, 4.0])
+    be.add_lattice(0 + 5, 3, 3)
+    be.add_train_lattice(3, 2, 2)
+    assert (be.get_field(1, "current_voltage") == f32([1, 2, 3, 4])).all()
+    c2, w2 = be.get_connection_dense(0, 1)
+    assert (c2 == 1).all() and (w2 == 0.25).all()
+
+
+def test_spike_train_lattice_alone_and_rate_kat():
+    """RunSpikeTrainLattice (neuron/mod.rs:1419-1428) + tests/rate_spike_train.rs:54-72 on the device."""
+    st = S.SpikeTrainLattice(S.RateSpikeTrain, id=4)
+    st.populate(S.RateSpikeTrain(rate=100.0, dt=1.0), 2, 3)
+    st.update_spike_history = True
+    st.run_lattice(1001)
+    s = st.spike_history.history.reshape(1001, 6)
+    for i in range(1001):
+        assert bool(s[i].all()) == bool(s[i].any()) == (i != 0 and (i + 1) % 100 == 0)
+    assert (st.get_field("last_firing_time") == 999).all() and st.internal_clock == 1001
+    cells = st.spike_train_grid()
+    assert cells[0][0].rate == 100.0 and cells[1][2].last_firing_time == 999

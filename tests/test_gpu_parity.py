@@ -1,0 +1,349 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.
+
+Bar (BASELINE.json north_star / SURVEY.md §8c): adjacency and spike rasters bit-exact for the deterministic
+models; state within rel. 1e-4 for models that call expf/powf; Poisson runs by firing statistics.
+"""
+import numpy as np
+import pytest
+
+import golden_util as G
+import scenarios as SC
+import snn_b200 as S
+from snn_b200 import _capi as K
+
+pytestmark = pytest.mark.gpu
+f32 = np.float32
+
+
+def pair(oracle_factory, **kw):
+    return SC.build_lattice(None, **kw), SC.build_lattice(oracle_factory, **kw)
+
+
+def state_fields(model):
+    return list(SC.MODELS[model]().scalar_fields())
+
+
+# ------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("name", G.NAMES)
+def test_cuda_matches_golden(name):
+    from snn_b200.backend import CudaLatticeBackend
+    g = G.load(name)
+    be = G.replay(g, lambda m, n, r, rows, cols: CudaLatticeBackend(m, n, r, rows, cols))
+    G.check(name, be, g)
+
+
+# ------------------------------------------------------------------ deterministic models: bit exact
+@pytest.mark.parametrize("graph", ["grid", "grid2", "random", "csr", "all", "none"])
+@pytest.mark.parametrize("model", SC.EXACT_MODELS)
+def test_electrical_bit_exact(model, graph, oracle_lattice_factory):
+    a, b = pair(oracle_lattice_factory, model=model, rows=7, cols=9, seed=3, graph=graph)
+    a.run_lattice(500)
+    b.run_lattice(500)
+    assert b.spike_history.history.sum() > 0, "scenario must spike to be a meaningful raster test"
+    SC.compare_lattices(a, b, exact=True, fields=state_fields(model))
+    ca, wa = a.graph_dense()
+    cb, wb = b.graph_dense()
+    assert (ca == cb).all() and (wa == wb).all()
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 33), (33, 1), (5, 13), (32, 32), (31, 33)])
+def test_ragged_shapes_bit_exact(shape, oracle_lattice_factory):
+    a, b = pair(oracle_lattice_factory, model="izh", rows=shape[0], cols=shape[1], seed=5, graph="grid")
+    a.run_lattice(300)
+    b.run_lattice(300)
+    SC.compare_lattices(a, b, exact=True, fields=state_fields("izh"))
+
+
+def test_config1_izhikevich_100x100_first_steps(oracle_lattice_factory):
+    """BASELINE.json configs[0]: Izhikevich 100x100, electrical, 8-neighbour grid, dt=0.1 (raster bit-exact)."""
+    a, b = pair(oracle_lattice_factory, model="izh", rows=100, cols=100, seed=11, graph="grid", hetero=False, c_m=5.0)
+    a.run_lattice(1000)
+    b.run_lattice(1000)
+    assert b.spike_history.history.sum() > 100
+    SC.compare_lattices(a, b, exact=True, fields=state_fields("izh"))
+
+
+# ------------------------------------------------------------------ transcendental models: tolerance
+@pytest.mark.parametrize("model,graph,steps", [("adex", "grid", 500), ("adex", "random", 500), ("hh", "grid", 2000),
+                                               ("hh", "random", 2000)])
+def test_electrical_tolerance_models(model, graph, steps, oracle_lattice_factory):
+    a, b = pair(oracle_lattice_factory, model=model, rows=6, cols=7, seed=4, graph=graph, gap=SC.drive_current(model))
+    a.run_lattice(steps)
+    b.run_lattice(steps)
+    ha, hb = a.grid_history.history, b.grid_history.history
+    np.testing.assert_allclose(ha[:100], hb[:100], rtol=1e-4, atol=1e-3)
+    assert np.abs(ha - hb).max() <= 2.0  # tests/gpu_accuracy.rs:73
+    assert G.raster_close(a.spike_history.history.reshape(steps, -1), b.spike_history.history.reshape(steps, -1))
+
+
+# ------------------------------------------------------------------ chemical synapses
+@pytest.mark.parametrize("electrical", [True, False])
+@pytest.mark.parametrize("graph", ["grid", "random"])
+def test_chemical_approximate_ampa_bit_exact(graph, electrical, oracle_lattice_factory):
+    """Izhikevich + ApproximateNeurotransmitter/ApproximateReceptor AMPA: no transcendental -> exact."""
+    a, b = pair(oracle_lattice_factory, model="izh", rows=6, cols=8, seed=7, graph=graph, chem="approx_ampa",
+                electrical=electrical)
+    a.run_lattice(600)
+    b.run_lattice(600)
+    assert b.spike_history.history.sum() > 0
+    SC.compare_lattices(a, b, exact=True, fields=state_fields("izh") + [
+        "neurotransmitters$t", "receptors$AMPA$r$kinetics$r", "receptors$AMPA_current"])
+
+
+@pytest.mark.parametrize("model,chem,steps", [("izh", "approx_all", 400), ("lif", "expdecay_all", 400), ("qif", "discrete_ampa", 400),
+                                              ("hh", "destexhe_all", 2000), ("izh", "destexhe_all", 400)])
+def test_chemical_tolerance(model, chem, steps, oracle_lattice_factory):
+    a, b = pair(oracle_lattice_factory, model=model, rows=5, cols=6, seed=8, graph="grid", chem=chem,
+                gap=SC.drive_current(model), c_m=(20.0 if model == "izh" else None))
+    a.run_lattice(steps)
+    b.run_lattice(steps)
+    ha, hb = a.grid_history.history, b.grid_history.history
+    np.testing.assert_allclose(ha[:50], hb[:50], rtol=1e-4, atol=1e-3)
+    assert np.abs(ha - hb).max() <= 5.0  # tests/gpu_accuracy.rs:163
+    assert G.raster_close(a.spike_history.history.reshape(steps, -1), b.spike_history.history.reshape(steps, -1))
+    for ty in ("AMPA",) if chem.endswith("ampa") else ("AMPA", "NMDA", "GABA"):
+        np.testing.assert_allclose(a.get_field(f"receptors${ty}$r$kinetics$r"), b.get_field(f"receptors${ty}$r$kinetics$r"),
+                                   rtol=1e-3, atol=1e-4)
+
+
+def test_heterogeneous_neurotransmitter_types(oracle_lattice_factory):
+    """Per-neuron type sets: the per-type averaging denominator counts only presynaptic neurons that have the type
+    (iterate_and_spike/mod.rs:2852-2863); inhibition is a negative weight."""
+    lat = []
+    for fac in (None, oracle_lattice_factory):
+        L = SC.build_lattice(fac, model="izh", rows=5, cols=5, seed=9, graph="random", chem="approx_all")
+        rng = np.random.default_rng(3)
+        L.set_field("neurotransmitters$flags", (rng.random((25, 3)) < 0.6).astype(np.uint32))
+        L.set_field("receptors$flags", (rng.random((25, 3)) < 0.7).astype(np.uint32))
+        c, w = L.graph_dense()
+        w = w * np.where(rng.random(w.shape) < 0.3, -1.0, 1.0).astype(f32)
+        L._be.connect_dense(L._bid, L._bid, c, w)
+        lat.append(L)
+    a, b = lat
+    a.run_lattice(300)
+    b.run_lattice(300)
+    ha, hb = a.grid_history.history, b.grid_history.history
+    np.testing.assert_allclose(ha[:50], hb[:50], rtol=1e-4, atol=1e-3)
+    assert np.abs(ha - hb).max() <= 5.0
+    assert (a.get_field("neurotransmitters$flags") == b.get_field("neurotransmitters$flags")).all()
+
+
+# ------------------------------------------------------------------ STDP
+@pytest.mark.parametrize("model,graph", [("izh", "grid"), ("izh", "random"), ("lif", "grid"), ("lif", "all")])
+def test_stdp_weights(model, graph, oracle_lattice_factory):
+    a, b = pair(oracle_lattice_factory, model=model, rows=6, cols=6, seed=12, graph=graph, stdp=True)
+    for L in (a, b):
+        L.plasticity = S.STDP(a_plus=0.05, a_minus=0.04, tau_plus=4.5, tau_minus=3.0, dt=0.1)
+    a.run_lattice(500)
+    b.run_lattice(500)
+    assert b.spike_history.history.sum() > 10
+    (ca, wa), (cb, wb) = a.graph_dense(), b.graph_dense()
+    assert (ca == cb).all()
+    assert np.abs(wb - SC.build_lattice(oracle_lattice_factory, model=model, rows=6, cols=6, seed=12, graph=graph).graph_dense()[1]).max() > 0
+    np.testing.assert_allclose(wa, wb, rtol=1e-4, atol=1e-5)
+    ha, hb = a.grid_history.history, b.grid_history.history
+    np.testing.assert_allclose(ha[:100], hb[:100], rtol=1e-4, atol=1e-3)
+    assert G.raster_close(a.spike_history.history.reshape(500, -1), b.spike_history.history.reshape(500, -1))
+
+
+def test_stdp_run_continuity(oracle_lattice_factory):
+    """Two run calls == one run call: the lazily applied last-step STDP is flushed at every API boundary and the
+    clock / last_firing_time persist (SURVEY §5 checkpoint/resume)."""
+    one = SC.build_lattice(None, model="izh", rows=6, cols=6, seed=13, graph="grid", stdp=True, history=False)
+    two = SC.build_lattice(None, model="izh", rows=6, cols=6, seed=13, graph="grid", stdp=True, history=False)
+    one.run_lattice(400)
+    two.run_lattice(137)
+    w_mid = two.graph_dense()[1].copy()
+    two.run_lattice(263)
+    assert one.internal_clock == two.internal_clock == 400
+    assert (one.graph_dense()[1] == two.graph_dense()[1]).all()
+    assert (one.get_field("current_voltage") == two.get_field("current_voltage")).all()
+    assert (one.get_field("last_firing_time") == two.get_field("last_firing_time")).all()
+    ref = SC.build_lattice(oracle_lattice_factory, model="izh", rows=6, cols=6, seed=13, graph="grid", stdp=True, history=False)
+    ref.run_lattice(137)
+    np.testing.assert_allclose(w_mid, ref.graph_dense()[1], rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ networks
+def build_network(lattice_factory, network_factory, train="rate", stdp=True, chemical=True, electrical=True, seed=21):
+    """MNIST-shaped miniature of BASELINE.json configs[3]: spike trains -> excitatory <-> inhibitory."""
+    rng = np.random.default_rng(seed)
+    T = S.IonotropicNeurotransmitterType
+    exc_base = S.IzhikevichNeuron(gap_conductance=5.0, c_m=10.0)
+    exc_base.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
+    exc_base.receptors[T.AMPA] = S.AMPAReceptor()
+    exc_base.receptors[T.GABA] = S.GABAReceptor()
+    inh_base = exc_base.clone()
+    inh_base.synaptic_neurotransmitters = {T.GABA: S.ApproximateNeurotransmitter(clearance_constant=0.02)}
+    exc = S.Lattice(S.IzhikevichNeuron, id=1, backend_factory=lattice_factory)
+    exc.populate(exc_base, 4, 5)
+    inh = S.Lattice(S.IzhikevichNeuron, id=2, backend_factory=lattice_factory)
+    inh.populate(inh_base, 4, 5)
+    for L in (exc, inh):
+        L.set_field("current_voltage", rng.uniform(-65, 20, 20).astype(f32))
+        L.set_field("b", rng.uniform(0.25, 0.33, 20).astype(f32))
+        L.update_grid_history = L.update_spike_history = True
+        L.do_plasticity = stdp
+        L.plasticity = S.STDP(a_plus=0.03, a_minus=0.03)
+    exc.connect(lambda x, y: x != y and abs(x[0] - y[0]) + abs(x[1] - y[1]) <= 1, lambda x, y: 0.5)
+    if train == "rate":
+        st_cls, base = S.RateSpikeTrain, S.RateSpikeTrain(rate=2.0)
+    elif train == "poisson":
+        st_cls, base = S.PoissonNeuron, S.PoissonNeuron.from_firing_rate(200.0, 0.1)
+    else:
+        st_cls, base = S.PresetSpikeTrain, S.PresetSpikeTrain(firing_times=[1.0, 2.5, 0.7])
+    base.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
+    st = S.SpikeTrainLattice(st_cls, id=0, network_backend_factory=network_factory)
+    st.populate(base, 3, 4)
+    if train == "rate":
+        st.set_field("rate", rng.choice([0.0, 1.5, 2.0, 3.0], 12).astype(f32))
+    st.update_spike_history = True
+    net = S.LatticeNetwork.generate_network([exc, inh], [st], backend_factory=network_factory)
+    wmat = rng.uniform(0, 1, (12, 20)).astype(f32)
+    net.connect(0, 1, lambda x, y: True, lambda x, y: float(wmat[x[0] * 4 + x[1], y[0] * 5 + y[1]]))
+    net.connect(1, 2, lambda x, y: x == y, lambda x, y: 1.0)
+    net.connect(2, 1, lambda x, y: x != y, lambda x, y: -1.0)
+    net.electrical_synapse, net.chemical_synapse = electrical, chemical
+    return net
+
+
+@pytest.mark.parametrize("train", ["rate", "preset"])
+@pytest.mark.parametrize("mode", [(True, True), (True, False), (False, True)])
+def test_network_deterministic_trains(train, mode, oracle_lattice_factory, oracle_network_factory):
+    a = build_network(None, None, train=train, electrical=mode[0], chemical=mode[1])
+    b = build_network(oracle_lattice_factory, oracle_network_factory, train=train, electrical=mode[0], chemical=mode[1])
+    a.run_lattices(400)
+    b.run_lattices(400)
+    sa, sb = a.get_spike_train_lattice(0).spike_history.history, b.get_spike_train_lattice(0).spike_history.history
+    assert (sa == sb).all() and sb.sum() > 0
+    for lid in (1, 2):
+        ha, hb = a.get_lattice(lid).grid_history.history, b.get_lattice(lid).grid_history.history
+        np.testing.assert_allclose(ha[:60], hb[:60], rtol=1e-4, atol=1e-3)
+        assert np.abs(ha - hb).max() <= 5.0
+        assert G.raster_close(a.get_lattice(lid).spike_history.history.reshape(400, -1),
+                              b.get_lattice(lid).spike_history.history.reshape(400, -1))
+    for pre, post in ((0, 1), (1, 2), (2, 1), (1, 1)):
+        (ca, wa), (cb, wb) = a._be.get_connection_dense(pre, post), b._be.get_connection_dense(pre, post)
+        assert (ca == cb).all()
+        np.testing.assert_allclose(wa, wb, rtol=2e-3, atol=2e-3)
+    assert a.internal_clock == b.internal_clock == 400
+    assert (a.get_spike_train_lattice(0).get_field("last_firing_time") == b.get_spike_train_lattice(0).get_field("last_firing_time")).all()
+
+
+def test_network_electrical_rate_trains_bit_exact(oracle_lattice_factory, oracle_network_factory):
+    """No plasticity, electrical only: the only transcendental is the spike-train refractoriness expf."""
+    a = build_network(None, None, train="rate", stdp=False, electrical=True, chemical=False)
+    b = build_network(oracle_lattice_factory, oracle_network_factory, train="rate", stdp=False, electrical=True, chemical=False)
+    a.run_lattices(300)
+    b.run_lattices(300)
+    for lid in (1, 2):
+        ha, hb = a.get_lattice(lid).grid_history.history, b.get_lattice(lid).grid_history.history
+        np.testing.assert_allclose(ha, hb, rtol=1e-4, atol=1e-3)
+        assert (a.get_lattice(lid).spike_history.history == b.get_lattice(lid).spike_history.history).all()
+
+
+def test_poisson_network_firing_statistics():
+    """Poisson parity is statistical (reference RNG is unseeded thread_rng): the empirical rate of each train must
+    sit inside a 5-sigma binomial interval around chance_of_firing, and runs must be reproducible per seed."""
+    steps = 4000
+    nets = [build_network(None, None, train="poisson", stdp=False) for _ in range(2)]
+    for n in nets:
+        n._be.set_option(K.OPT_RNG_SEED, 1234)
+        n.run_lattices(steps)
+    s0 = nets[0].get_spike_train_lattice(0).spike_history.history
+    s1 = nets[1].get_spike_train_lattice(0).spike_history.history
+    assert (s0 == s1).all()
+    p = float(nets[0].get_spike_train_lattice(0).get_field("chance_of_firing")[0])
+    assert p == pytest.approx(0.02, rel=1e-5)
+    counts = s0.reshape(steps, -1).sum(axis=0)
+    sigma = np.sqrt(steps * p * (1 - p))
+    assert (np.abs(counts - steps * p) < 5 * sigma).all(), counts
+    total = counts.sum()
+    assert abs(total - 12 * steps * p) < 5 * np.sqrt(12) * sigma
+    other = build_network(None, None, train="poisson", stdp=False)
+    other._be.set_option(K.OPT_RNG_SEED, 99)
+    other.run_lattices(steps)
+    assert (other.get_spike_train_lattice(0).spike_history.history != s0).any()
+
+
+@pytest.mark.parametrize("synapses", [(True, False), (False, True)])
+def test_reference_poisson_to_izhikevich_behaviour(synapses):
+    """tests/spike_train_neuron_interaction.rs:90-157 re-stated on the CUDA path."""
+    T = S.IonotropicNeurotransmitterType
+    iterations = 2500
+    neuron = S.IzhikevichNeuron(gap_conductance=10.0)
+    neuron.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
+    neuron.receptors[T.AMPA] = S.AMPAReceptor()
+    poisson = S.PoissonNeuron()
+    poisson.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
+    st = S.SpikeTrainLattice(S.PoissonNeuron, id=0)
+    st.populate(poisson, 1, 1)
+    lat = S.Lattice(S.IzhikevichNeuron, id=1)
+    lat.populate(neuron, 1, 1)
+    lat.update_spike_history = True
+    net = S.LatticeNetwork.generate_network([lat], [st])
+    net.connect(0, 1, lambda x, y: x == y, lambda x, y: 1.0)
+    net.parallel = True
+    net.electrical_synapse, net.chemical_synapse = synapses
+    net.set_dt(1.0)
+    net.run_lattices(iterations)
+    assert net.get_lattice(1).spike_history.history.sum() <= 1
+    net.get_spike_train_lattice(0).apply(lambda s: setattr(s, "chance_of_firing", (1.0 / 1.0) * 0.01))
+    net.run_lattices(iterations)
+    after = net.get_lattice(1).spike_history.history[iterations:].sum()
+    assert after > 2, after
+
+
+# ------------------------------------------------------------------ full size (BASELINE.json configs[4] shape)
+def _window_check(big, rows, cols, r0, c0, h, w, k, oracle_lattice_factory, init, extra_fields=()):
+    """The state of a neuron after k steps depends only on cells within Chebyshev distance k (radius-1 stencil), so a
+    (h+2k)x(w+2k) patch stepped by the oracle must reproduce the big lattice's window exactly."""
+    ra, rb = max(0, r0 - k), min(rows, r0 + h + k)
+    ca, cb = max(0, c0 - k), min(cols, c0 + w + k)
+    # a patch edge that is not a lattice edge gets wrong neighbours: keep only cells at distance >= k from such edges
+    patch = SC.build_lattice(oracle_lattice_factory, model="izh", rows=rb - ra, cols=cb - ca, seed=0, graph="grid", hetero=False,
+                             history=False)
+    for name, arr in init.items():
+        patch.set_field(name, arr.reshape(rows, cols)[ra:rb, ca:cb])
+    patch.run_lattice(k)
+    for name in ("current_voltage", "w_value", "last_firing_time") + tuple(extra_fields):
+        got = big.get_field(name).reshape(rows, cols)[r0:r0 + h, c0:c0 + w]
+        want = patch.get_field(name).reshape(rb - ra, cb - ca)[r0 - ra:r0 - ra + h, c0 - ca:c0 - ca + w]
+        assert (got == want).all(), name
+
+
+def test_full_size_10m_izhikevich_window_property(oracle_lattice_factory):
+    rows = cols = 3163
+    n = rows * cols
+    rng = np.random.default_rng(2024)
+    init = {"current_voltage": rng.uniform(-65, 30, n).astype(f32), "b": rng.uniform(0.25, 0.36, n).astype(f32)}
+    big = SC.build_lattice(None, model="izh", rows=rows, cols=cols, seed=0, graph="grid", hetero=False, history=False)
+    big.fill_field("c_m", 2.0)
+    for name, arr in init.items():
+        big.set_field(name, arr)
+    k = 24
+    big.run_lattice(k)
+    assert big.internal_clock == k
+    init["c_m"] = np.full(n, 2.0, f32)
+    for (r0, c0) in [(0, 0), (1500, 1700), (rows - 16, cols - 16), (0, cols - 16), (3000, 0)]:
+        _window_check(big, rows, cols, r0, c0, 16, 16, k, oracle_lattice_factory, init)
+    spikes = (big.get_field("last_firing_time") >= 0).sum()
+    assert spikes > 1000
+
+
+def test_full_size_uniform_state_follows_isolated_neuron(oracle_lattice_factory):
+    """Identical neurons => zero gap current => every one of the 10^7 neurons follows the isolated trajectory
+    (the size-independent form of tests/gpu_connection_behavior.rs:51-95)."""
+    rows = cols = 3163
+    big = SC.build_lattice(None, model="izh", rows=rows, cols=cols, seed=0, graph="grid", hetero=False, history=False)
+    iso = SC.build_lattice(oracle_lattice_factory, model="izh", rows=1, cols=1, seed=0, graph="none", hetero=False, history=False)
+    for L in (big, iso):
+        L.fill_field("current_voltage", -40.0)
+        L.fill_field("b", 0.3)
+        L.fill_field("c_m", 2.0)
+    big.run_lattice(300)
+    iso.run_lattice(300)
+    v = big.get_field("current_voltage")
+    assert (v == iso.get_field("current_voltage")[0]).all()
+    assert (big.get_field("last_firing_time") == iso.get_field("last_firing_time")[0]).all()
+    assert iso.get_field("last_firing_time")[0] >= 0

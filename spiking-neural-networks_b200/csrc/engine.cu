@@ -155,6 +155,7 @@ int Engine::alloc_device() {
     CK(dev_alloc(&node_flags_, node_cap_), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(cudaMemsetAsync(node_flags_, 0, node_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     h_node_flags_.assign(node_cap_, 0);
+    flags_cache_valid_ = false;
     // neuron fields used by this model
     for (int i = 0; i < kNumNeuronFields; ++i) {
         const FieldDef &fd = kNeuronFields[i];
@@ -460,20 +461,23 @@ int Engine::field_io(Lat &L, const FieldDef &fd, void *data, uint64_t count, boo
         if (set) {
             int r = ensure_chem();
             if (r) return r;
+            bool changed = false;
             for (uint64_t i = 0; i < n; ++i) {
                 uint8_t m = 0;
                 for (int ty = 0; ty < kNT; ++ty) if (h[i * kNT + ty]) m |= (uint8_t)(1u << ty);
                 uint8_t &f = h_node_flags_[no + i];
-                f = (uint8_t)((f & ~(0xFu << shift)) | (m << shift));
+                const uint8_t nf = (uint8_t)((f & ~(0xFu << shift)) | (m << shift));
+                changed |= nf != f;
+                f = nf;
             }
+            if (!changed) return SNN_OK;
+            flags_cache_valid_ = false;
             CK(cudaMemcpyAsync(node_flags_ + no, h_node_flags_.data() + no, n, cudaMemcpyHostToDevice, stream_), wr);
             CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
-            if (part_world > 1) {  // ghost rows inherit the type sets of the strip's edge rows (uniform-across-boundary assumption)
-                // handled when the graph is finalised
-            }
             if (shift == 0) {
+                // the presynaptic type bits are baked into the edge words: re-encode at the next run
                 if (dev_weights_newer_) { r = sync_weights_to_host(); if (r) return r; }
-                graph_dirty_ = true;  // type bits are baked into the edge words
+                graph_dirty_ = true;
             }
         } else {
             for (uint64_t i = 0; i < n; ++i)
@@ -750,16 +754,15 @@ int Engine::materialize_grid(Block &b, const Lat &L) {
     return SNN_OK;
 }
 
-uint32_t Engine::nt_used() const {
-    uint32_t m = 0;
-    for (uint32_t i = 0; i < n_nodes_; ++i) m |= h_node_flags_[i] & 0x7u;
-    return m;
+void Engine::refresh_flag_cache() const {
+    if (flags_cache_valid_) return;
+    uint32_t a = 0;
+    for (uint32_t i = 0; i < n_nodes_; ++i) a |= h_node_flags_[i];
+    nt_used_ = a & 0x7u; rc_used_ = (a >> 4) & 0x7u;
+    flags_cache_valid_ = true;
 }
-uint32_t Engine::rc_used() const {
-    uint32_t m = 0;
-    for (uint32_t i = 0; i < n_nodes_; ++i) m |= (h_node_flags_[i] >> 4) & 0x7u;
-    return m;
-}
+uint32_t Engine::nt_used() const { refresh_flag_cache(); return nt_used_; }
+uint32_t Engine::rc_used() const { refresh_flag_cache(); return rc_used_; }
 
 int Engine::finalize_graph() {
     if (!graph_dirty_) return SNN_OK;
@@ -778,6 +781,7 @@ int Engine::finalize_graph() {
             if (part_rank < part_world - 1) h_node_flags_[ghost_hi0_ + g] = h_node_flags_[own0_ + n_neurons - halo_ + g];
         }
         CK(cudaMemcpy(node_flags_, h_node_flags_.data(), node_cap_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+        flags_cache_valid_ = false;
     }
     int n_neuron_lat = 0;
     const Lat *only = nullptr;

@@ -174,6 +174,9 @@ private:
     int sync_weights_to_host();
     int materialize_grid(Block &b, const Lat &L);
     uint32_t nt_used() const; uint32_t rc_used() const;
+    void refresh_flag_cache() const;
+    mutable bool flags_cache_valid_ = false;
+    mutable uint32_t nt_used_ = 0, rc_used_ = 0;
     void fill_step_params(StepParams &p);
     int upload_lat_table();
 };

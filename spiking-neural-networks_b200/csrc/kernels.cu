@@ -188,59 +188,90 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     const bool do_e = p.electrical != 0;
     const bool do_c = CHEM && p.chemical != 0;
     {
+        // Edges are consumed in chunks of U: first all (coalesced) col/weight loads of the chunk, then all neighbour
+        // gathers, then the strictly ordered accumulation.  U independent requests per thread keep enough bytes in
+        // flight to cover HBM latency; the arithmetic order is unchanged.
+        constexpr int U = 8;
         const uint32_t k0 = p.slice_off[warp_global], k1 = p.slice_off[warp_global + 1];
-        for (uint32_t k = k0; k < k1; ++k) {
-            const size_t e = (size_t)k * 32u + lane;
-            const uint32_t c = __ldg(p.col + e);
-            if (c == kColPad || !valid) continue;
-            float w = p.wgt[e];
-            const uint32_t j = c & kColIdxMask;
-            if (STDP) {
-                if (p.apply_pending) {
-                    // lazy application of the previous step's STDP while the edge streams by:
-                    // in-edge rule if the post neuron spiked last step, out-edge rule if the pre neuron did
-                    // (update_weights_from_neurons, neuron/mod.rs:849-881, 2308-2417); both use the post
-                    // lattice's rule.  No edge can get two non-zero updates in one step.
-                    const int lft_pre = p.lft_in[j];
-                    bool pre_trig = !(c & kColTrainBit) && lft_pre == (int)p.clock - 1;
-                    if (pre_trig && p.n_lat > 1) pre_trig = p.lat[lat_index(p, j - p.own0)].do_plasticity != 0;
-                    else if (pre_trig) pre_trig = p.lat[0].do_plasticity != 0;
+        const bool pending = STDP && p.apply_pending;
+        for (uint32_t k = k0; k < k1; k += U) {
+            uint32_t c[U];
+            float w[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool in = valid && (k + u) < k1;
+                const size_t e = (size_t)(k + u) * 32u + lane;
+                c[u] = in ? __ldg(p.col + e) : kColPad;
+                w[u] = in ? p.wgt[e] : 0.f;
+            }
+            float vj[U];
+            int lj[U];
+            float tj[U][kNT];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                vj[u] = 0.f; lj[u] = -1;
+#pragma unroll
+                for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = 0.f;
+                if (c[u] == kColPad) continue;
+                const uint32_t j = c[u] & kColIdxMask;
+                if (do_e && !(c[u] & kColTrainBit)) vj[u] = p.v_in[j];
+                if (pending || (do_e && (c[u] & kColTrainBit))) lj[u] = p.lft_in[j];
+                if (do_c) {
+                    const uint32_t m = c[u] >> kColNtShift;
+#pragma unroll
+                    for (int ty = 0; ty < kNT; ++ty)
+                        if (m & (1u << ty)) tj[u][ty] = p.t_in[(size_t)ty * p.t_stride + j];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (c[u] == kColPad) continue;
+                const uint32_t j = c[u] & kColIdxMask;
+                float wu = w[u];
+                if (pending) {
+                    // lazy application of the previous step's STDP while the edge streams by: in-edge rule if the
+                    // post neuron spiked last step, out-edge rule if the pre neuron did (update_weights_from_neurons,
+                    // neuron/mod.rs:849-881, 2308-2417); both use the post lattice's rule.  No edge can get two
+                    // non-zero updates in one step.
+                    const int lft_pre = lj[u];
+                    bool pre_trig = !(c[u] & kColTrainBit) && lft_pre == (int)p.clock - 1;
+                    if (pre_trig) pre_trig = p.lat[p.n_lat > 1 ? lat_index(p, j - p.own0) : 0].do_plasticity != 0;
                     if (post_trig | pre_trig) {
                         const float d = stdp_delta(p.lat[li], lft_pre, lft_me);
-                        w = w + d;
-                        if (post_trig & pre_trig) w = w + d;
-                        p.wgt[e] = w;
+                        wu = wu + d;
+                        if (post_trig & pre_trig) wu = wu + d;
+                        p.wgt[(size_t)(k + u) * 32u + lane] = wu;
                     }
                 }
-            }
-            if (do_e) {
-                float final_input;
-                if (!(c & kColTrainBit)) {
-                    // gap_junction, neuron/mod.rs:54-60
-                    final_input = gap * (p.v_in[j] - v);
-                } else {
-                    // spike_train_gap_junction, neuron/mod.rs:119-137
-                    const uint32_t tj = j - p.train0;
-                    const int lt = p.lft_in[j];
-                    const float v_rest = ldf(p.tf[TF_VREST], tj);
-                    if (lt < 0) final_input = v_rest;
-                    else
-                        final_input = gap * refract_effect(p.refract, ldf(p.tf[TF_K], tj), p.clock, (uint32_t)lt,
-                                                           ldf(p.tf[TF_VTH], tj), v_rest, ldf(p.tf[TF_DT], tj));
+                if (do_e) {
+                    float final_input;
+                    if (!(c[u] & kColTrainBit)) {
+                        // gap_junction, neuron/mod.rs:54-60
+                        final_input = gap * (vj[u] - v);
+                    } else {
+                        // spike_train_gap_junction, neuron/mod.rs:119-137
+                        const uint32_t tjx = j - p.train0;
+                        const int lt = lj[u];
+                        const float v_rest = ldf(p.tf[TF_VREST], tjx);
+                        if (lt < 0) final_input = v_rest;
+                        else
+                            final_input = gap * refract_effect(p.refract, ldf(p.tf[TF_K], tjx), p.clock, (uint32_t)lt,
+                                                               ldf(p.tf[TF_VTH], tjx), v_rest, ldf(p.tf[TF_DT], tjx));
+                    }
+                    acc_e = acc_e + final_input * wu;
                 }
-                acc_e = acc_e + final_input * w;
-            }
-            if (do_c) {
-                const uint32_t m = c >> kColNtShift;
+                if (do_c) {
+                    const uint32_t m = c[u] >> kColNtShift;
 #pragma unroll
-                for (int ty = 0; ty < kNT; ++ty)
-                    if (m & (1u << ty)) {
-                        // weight_neurotransmitter_concentration + aggregate, iterate_and_spike/mod.rs:2837-2866
-                        acc_t[ty] = acc_t[ty] + p.t_in[(size_t)ty * p.t_stride + j] * w;
-                        cnt[ty]++;
-                    }
+                    for (int ty = 0; ty < kNT; ++ty)
+                        if (m & (1u << ty)) {
+                            // weight_neurotransmitter_concentration + aggregate, iterate_and_spike/mod.rs:2837-2866
+                            acc_t[ty] = acc_t[ty] + tj[u][ty] * wu;
+                            cnt[ty]++;
+                        }
+                }
+                n_in++;
             }
-            n_in++;
         }
     }
     // neuron/mod.rs:722-729: divide by the number of incoming edges (1 if none)

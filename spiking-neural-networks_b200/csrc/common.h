@@ -120,7 +120,9 @@ struct TrainParams {
 };
 
 // ---- kernel launchers (kernels.cu) ------------------------------------------------------------
-cudaError_t launch_step(const StepParams &p, int model, bool chem, bool stdp, cudaStream_t s);
+// chemg: 0 no chemical gather, 1 one neurotransmitter type in the whole node array, 3 general; ntrel: neurotransmitter /
+// receptor state is present and must be stepped; net: several lattices and/or spike trains share the node array
+cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, cudaStream_t s);
 cudaError_t launch_trains(const TrainParams &p, cudaStream_t s);
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s);
 cudaError_t launch_finalize(const StepParams &p, int model, const float *v_prev, cudaStream_t s);

@@ -849,6 +849,7 @@ int Engine::finalize_graph() {
         uint64_t mx = 0;
         for (uint64_t r = (uint64_t)s * 32; r < std::min<uint64_t>((uint64_t)s * 32 + 32, n_neurons); ++r)
             mx = std::max(mx, row_ptr[r + 1] - row_ptr[r]);
+        mx = round_up(mx, 4);  // the step kernel consumes edges in chunks of 4/8 without tail checks
         const uint64_t next = (uint64_t)slice_off[s] + mx;
         if (next > 0xFFFFFFF0ull / 32) return fail(SNN_UNSUPPORTED, "graph too large");
         slice_off[s + 1] = (uint32_t)next;
@@ -1110,7 +1111,15 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
         if (!L.is_train) { stdp |= L.do_plasticity; want_grid |= L.grid_hist; want_spk |= L.spike_hist; }
         else { want_tgrid |= L.grid_hist; want_tspk |= L.spike_hist; }
     }
-    const bool chem_tpl = chem_alloc_ && (chemical || nt_used() != 0 || (model == SNN_MODEL_HODGKIN_HUXLEY && rc_used() != 0));
+    // kernel specialisation: ntrel = neurotransmitter / receptor state must be stepped; chemg = how the chemical gather
+    // reads presynaptic types (0 none, 1 a single type in the whole node array, 3 per-edge masks); net = several
+    // lattices and/or spike trains share the node array
+    const bool ntrel = chem_alloc_ && (chemical || nt_used() != 0 || (model == SNN_MODEL_HODGKIN_HUXLEY && rc_used() != 0));
+    int n_neuron_lat = 0;
+    for (auto &L : lats_) if (!L.is_train) n_neuron_lat++;
+    const bool net = n_neuron_lat > 1 || n_trains > 0;
+    int chemg = 0;
+    if (chemical && ntrel && nt_used() != 0) chemg = (!net && __builtin_popcount(nt_used()) == 1) ? 1 : 3;
     const bool lft_pp = stdp || (n_trains && electrical) || part_world > 1;
 
     StepParams sp;
@@ -1183,7 +1192,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             sp.out_par = (uint32_t)out;
             sp.halo_epoch = halo_epoch_;
             if (n_neurons) {
-                cudaError_t e = launch_step(sp, model, chem_tpl, stdp, stream_);
+                cudaError_t e = launch_step(sp, model, chemg, ntrel, stdp, net, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step"); break; }
                 n_launch++;
             }
@@ -1217,6 +1226,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             StepParams fp = sp;
             fp.clock = (uint32_t)internal_clock;
             fp.lft_in = LFT_[lft_loc_];
+            fp.lft_out = LFT_[lft_loc_ ^ 1];  // spike trains: last_firing_time from before their last iterate
             cudaError_t e = launch_flush_stdp(fp, stream_);
             if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "flush_stdp"); break; }
             n_launch++;

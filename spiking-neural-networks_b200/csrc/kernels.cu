@@ -133,9 +133,140 @@ __device__ __forceinline__ void halo_wait(const unsigned long long *flag, unsign
 }
 
 // ------------------------------------------------------------------------------------------------
+// in-edge gather
+// ------------------------------------------------------------------------------------------------
+struct EdgeAcc {
+    float acc_e;
+    uint32_t n_in;
+    float acc_t[kNT];
+    uint32_t cnt[kNT];
+};
+
+// CHEMG: 0 = no chemical gather, 1 = exactly one neurotransmitter type in the whole node array (type index ty0),
+//        3 = general per-edge type masks.  NET: the node array holds several lattices and/or spike trains.
+//
+// Edges are consumed in chunks of 8 (slice widths are padded to a multiple of 4): first all coalesced col/weight
+// loads of the chunk, then all neighbour gathers, then the strictly ordered accumulation.  Eight independent
+// requests per thread keep enough bytes in flight to cover HBM latency; the arithmetic order is the canonical one
+// (ascending presynaptic index).  Padding slots carry weight 0 and gather the neuron itself, so they add an exact
+// +0 and need no branch.
+template <int CHEMG, bool STDP, bool NET>
+__device__ __forceinline__ void gather_edges(const StepParams &p, uint32_t warp_global, uint32_t lane, uint32_t i, float v,
+                                             float gap, int lft_me, bool post_trig, int li, uint32_t ty0, EdgeAcc &A) {
+    constexpr int U = 8;
+    const uint32_t k0 = __ldg(p.slice_off + warp_global), k1 = __ldg(p.slice_off + warp_global + 1);
+    const bool pending = STDP && p.apply_pending;
+    const bool do_e = p.electrical != 0;
+    const int prev = (int)p.clock - 1;
+    const float *t0 = (CHEMG == 1) ? p.t_in + (size_t)ty0 * p.t_stride : nullptr;
+    for (uint32_t k = k0; k < k1; k += U) {
+        const bool full = k + U <= k1;
+        const uint32_t *cp = p.col + (size_t)k * 32u + lane;
+        float *wp = p.wgt + (size_t)k * 32u + lane;
+        uint32_t c[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u < 4 || full) { c[u] = __ldg(cp + u * 32); w[u] = wp[u * 32]; }
+            else { c[u] = kColPad; w[u] = 0.f; }
+        }
+        uint32_t j[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = (c[u] == kColPad) ? i : (c[u] & kColIdxMask);
+        float vj[U];
+        if (do_e) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) vj[u] = p.v_in[j[u]];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) vj[u] = v;
+        }
+        int lj[U];
+        if (pending) {
+            // a spike train steps AFTER the neurons and their STDP (neuron/mod.rs:2573-2591): the rule of step s must
+            // see the train's last_firing_time from before its step-s iterate, which still sits in the other
+            // ping-pong buffer (the train kernel of this step has not run yet)
+#pragma unroll
+            for (int u = 0; u < U; ++u) lj[u] = (NET && (c[u] & kColTrainBit) && c[u] != kColPad) ? p.lft_out[j[u]] : p.lft_in[j[u]];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) lj[u] = -1;
+        }
+        float tj[U][CHEMG == 3 ? kNT : 1];
+        if (CHEMG == 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) tj[u][0] = t0[j[u]];
+        } else if (CHEMG == 3) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t m = (c[u] == kColPad) ? 0u : (c[u] >> kColNtShift);
+#pragma unroll
+                for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? p.t_in[(size_t)ty * p.t_stride + j[u]] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = c[u] != kColPad;
+            float wu = w[u];
+            if (pending) {
+                // lazy application of the previous step's STDP while the edge streams by: in-edge rule if the post
+                // neuron spiked last step, out-edge rule if the pre neuron did (update_weights_from_neurons,
+                // neuron/mod.rs:849-881, 2308-2417); both use the post lattice's rule.  No edge can get two non-zero
+                // updates in one step.
+                bool pre_trig = ok && lj[u] == prev;
+                if (NET) {
+                    if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
+                } else {
+                    pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
+                }
+                if ((post_trig && ok) || pre_trig) {
+                    const float d = stdp_delta(p.lat[li], lj[u], lft_me);
+                    wu = wu + d;
+                    if (post_trig && pre_trig) wu = wu + d;
+                    wp[u * 32] = wu;
+                }
+            }
+            if (do_e) {
+                float final_input = gap * (vj[u] - v);  // gap_junction, neuron/mod.rs:54-60
+                if (NET) {
+                    if (ok && (c[u] & kColTrainBit)) {
+                        // spike_train_gap_junction, neuron/mod.rs:119-137
+                        const uint32_t tjx = j[u] - p.train0;
+                        const int lt = p.lft_in[j[u]];
+                        const float v_rest = ldf(p.tf[TF_VREST], tjx);
+                        if (lt < 0) final_input = v_rest;
+                        else
+                            final_input = gap * refract_effect(p.refract, ldf(p.tf[TF_K], tjx), p.clock, (uint32_t)lt,
+                                                               ldf(p.tf[TF_VTH], tjx), v_rest, ldf(p.tf[TF_DT], tjx));
+                    }
+                }
+                A.acc_e = A.acc_e + final_input * wu;
+            }
+            if (CHEMG == 1) {
+                // weight_neurotransmitter_concentration + aggregate, iterate_and_spike/mod.rs:2837-2866
+                const bool has = ok && ((c[u] >> (kColNtShift + ty0)) & 1u);
+                const float term = tj[u][0] * wu;
+                A.acc_t[0] = A.acc_t[0] + (has ? term : 0.f);
+                A.cnt[0] += has ? 1u : 0u;
+            } else if (CHEMG == 3) {
+                const uint32_t m = ok ? (c[u] >> kColNtShift) : 0u;
+#pragma unroll
+                for (int ty = 0; ty < kNT; ++ty) {
+                    const bool has = (m >> ty) & 1u;
+                    const float term = tj[u][ty] * wu;
+                    A.acc_t[ty] = A.acc_t[ty] + (has ? term : 0.f);
+                    A.cnt[ty] += has ? 1u : 0u;
+                }
+            }
+            A.n_in += ok ? 1u : 0u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // the fused step kernel
 // ------------------------------------------------------------------------------------------------
-template <int MODEL, bool CHEM, bool STDP>
+template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p) {
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
@@ -148,7 +279,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     // ---- multi-GPU: warps whose in-edges can reach ghost nodes wait for the neighbour's boundary
     // values of the previous step (pushed over NVLink by the neighbour's own step kernel)
     bool export_lo = false, export_hi = false;
-    if (p.halo[0].active | p.halo[1].active) {
+    if (!NET && (p.halo[0].active | p.halo[1].active)) {
         const uint32_t w0 = warp_global * 32u, w1 = min(w0 + 32u, p.n_neurons);
         const bool near_lo = p.halo[0].active && w0 < p.halo[0].first + p.halo[0].count;
         const bool near_hi = p.halo[1].active && w1 > p.halo[1].first;
@@ -164,126 +295,63 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
         export_hi = near_hi && valid && ln >= p.halo[1].first && ln < p.halo[1].first + p.halo[1].count;
     }
 
-    // ---- own state ------------------------------------------------------------------------------
+    // ---- own state and parameters: every load is issued before the edge loop so that it overlaps with it
     float v = p.v_in[i];
     const float gap = ldf(p.f[F_GAP], lnc);
     const float dt = ldf(p.f[F_DT], lnc);
+    const float v_th = ldf(p.f[F_VTH], lnc);
+    constexpr bool NEEDS_CM = NTREL || MODEL == SNN_MODEL_HODGKIN_HUXLEY || MODEL == SNN_MODEL_IZHIKEVICH ||
+                              MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
+                              MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    const float c_m = NEEDS_CM ? ldf(p.f[F_CM], lnc) : 1.f;
     const int lft_me = (STDP || p.lft_pp) ? p.lft_in[i] : 0;
-    const uint32_t spk_word_in = p.spk_in[(p.own0 >> 5) + warp_global];
+    const uint32_t spk_word_in = __ldg(p.spk_in + (p.own0 >> 5) + warp_global);
     const bool spiking_prev = (spk_word_in >> lane) & 1u;
-    const uint32_t flags = (CHEM) ? p.node_flags[i] : 0u;
+    const uint32_t flags = NTREL ? p.node_flags[i] : 0u;
+    constexpr bool IZH = MODEL == SNN_MODEL_IZHIKEVICH || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH;
+    constexpr bool IF4 = MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE ||
+                         MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    constexpr bool ADAPT = MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    constexpr bool LEAKY = MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || ADAPT;
+    // model parameters (only the ones this model reads are loaded; the rest fold away)
+    float w_adapt = (IZH || ADAPT) ? p.f[F_W][lnc] : 0.f;
+    const float pa = IZH ? ldf(p.f[F_A], lnc) : 0.f, pb = IZH ? ldf(p.f[F_B], lnc) : 0.f;
+    const float pc = IZH ? ldf(p.f[F_C], lnc) : 0.f, pd = IZH ? ldf(p.f[F_D], lnc) : 0.f;
+    const float tau_m = (IZH || IF4) ? ldf(p.f[F_TAUM], lnc) : 1.f;
+    const float e_l = (LEAKY || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH) ? ldf(p.f[F_EL], lnc) : 0.f;
+    const float v_reset = (IF4 || MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) ? ldf(p.f[F_VRESET], lnc) : 0.f;
+    const float integ = IF4 ? ldf(p.f[F_INTEG], lnc) : 0.f;
+    float refr = IF4 ? p.f[F_REFR][lnc] : 0.f;
+    const float tref = IF4 ? ldf(p.f[F_TREF], lnc) : 0.f;
+    const float g_l = LEAKY ? ldf(p.f[F_GL], lnc) : 1.f;
+    const float leak = LEAKY ? ldf(p.f[F_LEAK], lnc) : 0.f;
+    const float alpha = (ADAPT || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) ? ldf(p.f[F_ALPHA], lnc) : 0.f;
+    const float beta = ADAPT ? ldf(p.f[F_BETA], lnc) : 0.f;
+
+    // the single neurotransmitter type of the CHEMG == 1 fast path
+    const uint32_t ty0 = (CHEMG == 1) ? (uint32_t)(__ffs((int)p.nt_used) - 1) : 0u;
 
     int li = 0;
     bool post_trig = false;
     if (STDP) {
-        li = lat_index(p, lnc);
+        li = NET ? lat_index(p, lnc) : 0;
         post_trig = p.apply_pending && p.lat[li].do_plasticity && lft_me == (int)p.clock - 1;
     }
 
     // ---- gather over in-edges (ascending presynaptic index = canonical summation order) ----------
-    float acc_e = 0.f;
-    uint32_t n_in = 0;
-    float acc_t[kNT] = {0.f, 0.f, 0.f};
-    uint32_t cnt[kNT] = {0u, 0u, 0u};
+    EdgeAcc A;
+    A.acc_e = 0.f; A.n_in = 0;
+#pragma unroll
+    for (int ty = 0; ty < kNT; ++ty) { A.acc_t[ty] = 0.f; A.cnt[ty] = 0; }
     const bool do_e = p.electrical != 0;
-    const bool do_c = CHEM && p.chemical != 0;
-    {
-        // Edges are consumed in chunks of U: first all (coalesced) col/weight loads of the chunk, then all neighbour
-        // gathers, then the strictly ordered accumulation.  U independent requests per thread keep enough bytes in
-        // flight to cover HBM latency; the arithmetic order is unchanged.
-        constexpr int U = 8;
-        const uint32_t k0 = p.slice_off[warp_global], k1 = p.slice_off[warp_global + 1];
-        const bool pending = STDP && p.apply_pending;
-        for (uint32_t k = k0; k < k1; k += U) {
-            uint32_t c[U];
-            float w[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool in = valid && (k + u) < k1;
-                const size_t e = (size_t)(k + u) * 32u + lane;
-                c[u] = in ? __ldg(p.col + e) : kColPad;
-                w[u] = in ? p.wgt[e] : 0.f;
-            }
-            float vj[U];
-            int lj[U];
-            float tj[U][kNT];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                vj[u] = 0.f; lj[u] = -1;
-#pragma unroll
-                for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = 0.f;
-                if (c[u] == kColPad) continue;
-                const uint32_t j = c[u] & kColIdxMask;
-                if (do_e && !(c[u] & kColTrainBit)) vj[u] = p.v_in[j];
-                if (pending || (do_e && (c[u] & kColTrainBit))) lj[u] = p.lft_in[j];
-                if (do_c) {
-                    const uint32_t m = c[u] >> kColNtShift;
-#pragma unroll
-                    for (int ty = 0; ty < kNT; ++ty)
-                        if (m & (1u << ty)) tj[u][ty] = p.t_in[(size_t)ty * p.t_stride + j];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (c[u] == kColPad) continue;
-                const uint32_t j = c[u] & kColIdxMask;
-                float wu = w[u];
-                if (pending) {
-                    // lazy application of the previous step's STDP while the edge streams by: in-edge rule if the
-                    // post neuron spiked last step, out-edge rule if the pre neuron did (update_weights_from_neurons,
-                    // neuron/mod.rs:849-881, 2308-2417); both use the post lattice's rule.  No edge can get two
-                    // non-zero updates in one step.
-                    const int lft_pre = lj[u];
-                    bool pre_trig = !(c[u] & kColTrainBit) && lft_pre == (int)p.clock - 1;
-                    if (pre_trig) pre_trig = p.lat[p.n_lat > 1 ? lat_index(p, j - p.own0) : 0].do_plasticity != 0;
-                    if (post_trig | pre_trig) {
-                        const float d = stdp_delta(p.lat[li], lft_pre, lft_me);
-                        wu = wu + d;
-                        if (post_trig & pre_trig) wu = wu + d;
-                        p.wgt[(size_t)(k + u) * 32u + lane] = wu;
-                    }
-                }
-                if (do_e) {
-                    float final_input;
-                    if (!(c[u] & kColTrainBit)) {
-                        // gap_junction, neuron/mod.rs:54-60
-                        final_input = gap * (vj[u] - v);
-                    } else {
-                        // spike_train_gap_junction, neuron/mod.rs:119-137
-                        const uint32_t tjx = j - p.train0;
-                        const int lt = lj[u];
-                        const float v_rest = ldf(p.tf[TF_VREST], tjx);
-                        if (lt < 0) final_input = v_rest;
-                        else
-                            final_input = gap * refract_effect(p.refract, ldf(p.tf[TF_K], tjx), p.clock, (uint32_t)lt,
-                                                               ldf(p.tf[TF_VTH], tjx), v_rest, ldf(p.tf[TF_DT], tjx));
-                    }
-                    acc_e = acc_e + final_input * wu;
-                }
-                if (do_c) {
-                    const uint32_t m = c[u] >> kColNtShift;
-#pragma unroll
-                    for (int ty = 0; ty < kNT; ++ty)
-                        if (m & (1u << ty)) {
-                            // weight_neurotransmitter_concentration + aggregate, iterate_and_spike/mod.rs:2837-2866
-                            acc_t[ty] = acc_t[ty] + tj[u][ty] * wu;
-                            cnt[ty]++;
-                        }
-                }
-                n_in++;
-            }
-        }
-    }
+    const bool do_c = NTREL && p.chemical != 0;
+    gather_edges<CHEMG, STDP, NET>(p, warp_global, lane, i, v, gap, lft_me, post_trig, li, ty0, A);
     // neuron/mod.rs:722-729: divide by the number of incoming edges (1 if none)
-    const float input = do_e ? acc_e / (n_in == 0 ? 1.f : (float)n_in) : 0.f;
+    const float input = do_e ? A.acc_e / (A.n_in == 0 ? 1.f : (float)A.n_in) : 0.f;
 
     // ---- receptors (iterate_with_neurotransmitter_and_spike: kinetics then currents from pre-update V)
     float rc_total = 0.f;
-    const float c_m = (CHEM || MODEL == SNN_MODEL_HODGKIN_HUXLEY || MODEL == SNN_MODEL_IZHIKEVICH ||
-                       MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
-                       MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE)
-                          ? ldf(p.f[F_CM], lnc) : 1.f;
-    if (CHEM) {
+    if (NTREL) {
         const uint32_t rcm = flags >> 4;
         if (do_c) {
 #pragma unroll
@@ -292,8 +360,10 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
                 if (!(rcm & (1u << ty))) continue;
                 const size_t o = (size_t)ty * p.rc_stride + lnc;
                 float r = p.rc[RCF_R][o];
-                if (cnt[ty] > 0) {
-                    const float tin = acc_t[ty] / (float)cnt[ty];
+                const uint32_t cnt = (CHEMG == 1) ? (ty == (int)ty0 ? A.cnt[0] : 0u) : A.cnt[ty];
+                if (cnt > 0) {
+                    const float acc = (CHEMG == 1) ? A.acc_t[0] : A.acc_t[ty];
+                    const float tin = acc / (float)cnt;
                     float k1 = 0.f, k2 = 0.f;
                     if (p.rck != SNN_RC_APPROXIMATE) { k1 = ldf(p.rc[RCF_K1], o); k2 = ldf(p.rc[RCF_K2], o); }
                     r = rc_apply(p.rck, r, k1, k2, tin, dt);
@@ -314,53 +384,39 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     // ---- neuron update --------------------------------------------------------------------------
     bool spike = false;
     float v_release;  // membrane voltage seen by the neurotransmitter kinetics (post-update, pre-reset)
-    if constexpr (MODEL == SNN_MODEL_IZHIKEVICH || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH) {
-        float w = p.f[F_W][lnc];
-        const float a = ldf(p.f[F_A], lnc), b = ldf(p.f[F_B], lnc);
-        const float tau_m = ldf(p.f[F_TAUM], lnc);
+    if constexpr (IZH) {
         float dv;
         if constexpr (MODEL == SNN_MODEL_IZHIKEVICH)  // integrate_and_fire/mod.rs:1255-1260
-            dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - w) + input) * (dt / c_m);
+            dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - w_adapt) + input) * (dt / c_m);
         else                                            // :1342-1348
-            dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - (w * (v - ldf(p.f[F_EL], lnc)))) + input) * (dt / c_m);
-        const float dw = (a * (b * v - w)) * (dt / tau_m);  // :1225-1231
-        if (do_c) v += dv + (-rc_dv); else v += dv;       // :226, :246
-        w += dw;
+            dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - (w_adapt * (v - e_l))) + input) * (dt / c_m);
+        const float dw = (pa * (pb * v - w_adapt)) * (dt / tau_m);  // :1225-1231
+        if (do_c) v += dv + (-rc_dv); else v += dv;               // :226, :246
+        w_adapt += dw;
         v_release = v;
-        if (v >= ldf(p.f[F_VTH], lnc)) {                    // izhikevich_handle_spiking :1235-1247
+        if (v >= v_th) {                                            // izhikevich_handle_spiking :1235-1247
             spike = true;
-            v = ldf(p.f[F_C], lnc);
-            w += ldf(p.f[F_D], lnc);
+            v = pc;
+            w_adapt += pd;
         }
-        if (valid) p.f[F_W][lnc] = w;
-    } else if constexpr (MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE ||
-                         MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
-                         MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE) {
-        constexpr bool ADAPT = MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
-                               MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
-        const float tau_m = ldf(p.f[F_TAUM], lnc);
-        const float v_th = ldf(p.f[F_VTH], lnc), v_reset = ldf(p.f[F_VRESET], lnc);
-        const float integ = ldf(p.f[F_INTEG], lnc);
-        float refr = p.f[F_REFR][lnc];
-        float w = 0.f, dw = 0.f, dv;
+        if (valid) p.f[F_W][lnc] = w_adapt;
+    } else if constexpr (IF4) {
+        float dw = 0.f, dv;
         if constexpr (MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE) {  // :176-181
-            dv = ((ldf(p.f[F_LEAK], lnc) * (v - ldf(p.f[F_EL], lnc))) + (integ * (input / ldf(p.f[F_GL], lnc)))) * (dt / tau_m);
+            dv = ((leak * (v - e_l)) + (integ * (input / g_l))) * (dt / tau_m);
         } else if constexpr (MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) {  // :324-327
-            dv = (((ldf(p.f[F_ALPHA], lnc) * (v - v_reset)) * (v - ldf(p.f[F_VC], lnc))) + integ * input) * (dt / tau_m);
+            dv = (((alpha * (v - v_reset)) * (v - ldf(p.f[F_VC], lnc))) + integ * input) * (dt / tau_m);
         } else {
-            w = p.f[F_W][lnc];
-            const float e_l = ldf(p.f[F_EL], lnc), g_l = ldf(p.f[F_GL], lnc);
-            const float leak = ldf(p.f[F_LEAK], lnc);
             if constexpr (MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE)  // :1035-1041
-                dv = (((leak * (v - e_l)) + (integ * (input / g_l))) - (w / g_l)) * (dt / c_m);
+                dv = (((leak * (v - e_l)) + (integ * (input / g_l))) - (w_adapt / g_l)) * (dt / c_m);
             else {                                                                  // :1138-1145
                 const float sf = ldf(p.f[F_SLOPE], lnc);
-                dv = ((((leak * (v - e_l)) + (sf * expf((v - v_th) / sf))) + (integ * (input / g_l))) - (w / g_l)) * (dt / c_m);
+                dv = ((((leak * (v - e_l)) + (sf * expf((v - v_th) / sf))) + (integ * (input / g_l))) - (w_adapt / g_l)) * (dt / c_m);
             }
-            dw = (ldf(p.f[F_ALPHA], lnc) * (v - e_l) - w) * (dt / tau_m);  // :1002-1009
+            dw = (alpha * (v - e_l) - w_adapt) * (dt / tau_m);  // :1002-1009
         }
         if (do_c) v += dv + (-rc_dv); else v += dv;
-        if (ADAPT) w += dw;
+        if (ADAPT) w_adapt += dw;
         v_release = v;
         // impl_default_handle_spiking :87-102 / adaptive_handle_spiking :1013-1029
         if (refr > 0.f) {
@@ -369,18 +425,18 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
         } else if (v >= v_th) {
             spike = true;
             v = v_reset;
-            if (ADAPT) w += ldf(p.f[F_BETA], lnc);
-            refr = ldf(p.f[F_TREF], lnc) / dt;
+            if (ADAPT) w_adapt += beta;
+            refr = tref / dt;
         }
         if (valid) {
             p.f[F_REFR][lnc] = refr;
-            if (ADAPT) p.f[F_W][lnc] = w;
+            if (ADAPT) p.f[F_W][lnc] = w_adapt;
         }
     } else if constexpr (MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) {
         const float dv = (ldf(p.f[F_G], lnc) * (v - ldf(p.f[F_E], lnc)) + input) * dt;  // :1592-1594
         if (do_c) v += dv + (-rc_dv); else v += dv;
         v_release = v;
-        if (v >= ldf(p.f[F_VTH], lnc)) { spike = true; v = ldf(p.f[F_VRESET], lnc); }  // :1579-1590
+        if (v >= v_th) { spike = true; v = v_reset; }  // :1579-1590
     } else {  // Hodgkin-Huxley, hodgkin_huxley/mod.rs:156-241; ion_channels/mod.rs:40-44, 219-235, 268-281, 310-312
         const float last_voltage = v;
         float m = p.f[F_M][lnc], h = p.f[F_H][lnc], n = p.f[F_N][lnc];
@@ -402,7 +458,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
         const uint32_t wi_word = p.was_inc[warp_global];
         const bool was_increasing = (wi_word >> lane) & 1u;
         const bool increasing_right_now = last_voltage < v;
-        spike = (v > ldf(p.f[F_VTH], lnc)) && was_increasing && !increasing_right_now;
+        spike = (v > v_th) && was_increasing && !increasing_right_now;
         const uint32_t wi_new = __ballot_sync(0xffffffffu, increasing_right_now && valid);
         if (lane == 0) p.was_inc[warp_global] = wi_new;
         if (valid) { p.f[F_M][lnc] = m; p.f[F_H][lnc] = h; p.f[F_N][lnc] = n; }
@@ -410,7 +466,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
 
     // ---- neurotransmitter release: post-update voltage, previous step's spike flag
     //      (intermediate_delegate/mod.rs:18-24, integrate_and_fire/mod.rs:229)
-    if (CHEM) {
+    if (NTREL) {
         const uint32_t ntm = flags & 0xFu;
 #pragma unroll
         for (int ty = 0; ty < kNT; ++ty) {
@@ -460,7 +516,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     // ---- multi-GPU: publish "my boundary values of this step have landed" to each neighbour.
     // Every exporting warp fences its remote stores, then bumps a local counter; the last one raises
     // the neighbour's arrival flag to halo_epoch + 1.
-    if (p.halo[0].active | p.halo[1].active) {
+    if (!NET && (p.halo[0].active | p.halo[1].active)) {
         const uint32_t w0 = warp_global * 32u, w1 = min(w0 + 32u, p.n_neurons);
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
@@ -535,7 +591,8 @@ __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__
         const uint32_t c = __ldg(p.col + e);
         if (c == kColPad) continue;
         const uint32_t j = c & kColIdxMask;
-        const int lft_pre = p.lft_in[j];
+        // spike trains: last_firing_time from before their last iterate (see gather_edges); lft_out is that buffer here
+        const int lft_pre = (c & kColTrainBit) ? p.lft_out[j] : p.lft_in[j];
         bool pre_trig = !(c & kColTrainBit) && lft_pre == (int)p.clock - 1;
         if (pre_trig) pre_trig = p.lat[p.n_lat > 1 ? lat_index(p, j - p.own0) : 0].do_plasticity != 0;
         if (post_trig | pre_trig) {
@@ -769,27 +826,39 @@ __global__ void transpose_out_kernel(const float *src_tm, float *dst_nm, uint64_
 // ------------------------------------------------------------------------------------------------
 static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
 
-template <int MODEL>
-static cudaError_t launch_step_model(const StepParams &p, bool chem, bool stdp, cudaStream_t s) {
+template <int MODEL, int CHEMG, bool NTREL, bool NET>
+static cudaError_t launch_step_3(const StepParams &p, bool stdp, cudaStream_t s) {
     const unsigned grid = blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256);
-    if (chem && stdp) step_kernel<MODEL, true, true><<<grid, 256, 0, s>>>(p);
-    else if (chem) step_kernel<MODEL, true, false><<<grid, 256, 0, s>>>(p);
-    else if (stdp) step_kernel<MODEL, false, true><<<grid, 256, 0, s>>>(p);
-    else step_kernel<MODEL, false, false><<<grid, 256, 0, s>>>(p);
+    if (stdp) step_kernel<MODEL, CHEMG, NTREL, true, NET><<<grid, 256, 0, s>>>(p);
+    else step_kernel<MODEL, CHEMG, NTREL, false, NET><<<grid, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_step(const StepParams &p, int model, bool chem, bool stdp, cudaStream_t s) {
+template <int MODEL>
+static cudaError_t launch_step_model(const StepParams &p, int chemg, bool ntrel, bool stdp, bool net, cudaStream_t s) {
+    if (net) {
+        // several lattices and/or spike trains: general per-edge type masks
+        if (chemg) return launch_step_3<MODEL, 3, true, true>(p, stdp, s);
+        if (ntrel) return launch_step_3<MODEL, 0, true, true>(p, stdp, s);
+        return launch_step_3<MODEL, 0, false, true>(p, stdp, s);
+    }
+    if (chemg == 1) return launch_step_3<MODEL, 1, true, false>(p, stdp, s);
+    if (chemg == 3) return launch_step_3<MODEL, 3, true, false>(p, stdp, s);
+    if (ntrel) return launch_step_3<MODEL, 0, true, false>(p, stdp, s);
+    return launch_step_3<MODEL, 0, false, false>(p, stdp, s);
+}
+
+cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
     switch (model) {
-    case SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE>(p, chem, stdp, s);
-    case SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE>(p, chem, stdp, s);
-    case SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE>(p, chem, stdp, s);
-    case SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE>(p, chem, stdp, s);
-    case SNN_MODEL_IZHIKEVICH: return launch_step_model<SNN_MODEL_IZHIKEVICH>(p, chem, stdp, s);
-    case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_step_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, chem, stdp, s);
-    case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, chem, stdp, s);
-    case SNN_MODEL_HODGKIN_HUXLEY: return launch_step_model<SNN_MODEL_HODGKIN_HUXLEY>(p, chem, stdp, s);
+    case SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_IZHIKEVICH: return launch_step_model<SNN_MODEL_IZHIKEVICH>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_step_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_HODGKIN_HUXLEY: return launch_step_model<SNN_MODEL_HODGKIN_HUXLEY>(p, chemg, ntrel, stdp, net, s);
     }
     return cudaErrorInvalidValue;
 }

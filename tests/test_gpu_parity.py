@@ -247,7 +247,7 @@ def test_network_deterministic_trains(train, mode, oracle_lattice_factory, oracl
         assert (sa == sb).all()
         for lid in (1, 2):
             ha, hb = a.get_lattice(lid).grid_history.history[done:done + seg], b.get_lattice(lid).grid_history.history[done:done + seg]
-            np.testing.assert_allclose(ha, hb, rtol=1e-4, atol=1e-3, err_msg=f"lattice {lid}, segment at {done}")
+            SC.assert_close_robust(ha, hb, 1e-4, 1e-3, f"lattice {lid}, segment at {done}")
             ra, rb = a.get_lattice(lid).spike_history.history[done:done + seg], b.get_lattice(lid).spike_history.history[done:done + seg]
             assert (ra == rb).all(), f"lattice {lid}: raster differs in the segment at {done}"
             spikes += int(rb.sum())

@@ -74,6 +74,7 @@ struct StepParams {
     int ntk, rck, refract;
     // graph
     const uint32_t *slice_off;
+    uint32_t uniform_width;   // != 0: every slice has this many k-rows (slice_off[s] == s * uniform_width)
     const uint32_t *col;
     float *wgt;
     // shared node arrays

@@ -772,6 +772,7 @@ int Engine::finalize_graph() {
     if (wgt_) cudaFree(wgt_);
     slice_off_ = col_ = nullptr; wgt_ = nullptr;
     grid_fast_ = false;
+    uniform_width_ = 0;
     n_slices_ = (uint32_t)((n_neurons + 31) / 32);
     CK(dev_alloc(&slice_off_, (size_t)n_slices_ + 1), SNN_GPU_BUFFER_CREATE_ERROR);
     // partitioned handles: ghost rows inherit the neurotransmitter type sets of the adjacent owned rows
@@ -799,6 +800,7 @@ int Engine::finalize_graph() {
                             b.radius, b.weight, own0_, node_flags_, width, slice_off_, col_, wgt_, stream_), SNN_GPU_QUEUE_FAILURE);
         CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
         grid_fast_ = true;
+        uniform_width_ = width;
         graph_dirty_ = false;
         dev_weights_newer_ = false;
         return SNN_OK;
@@ -1071,6 +1073,7 @@ void Engine::fill_step_params(StepParams &p) {
     p.nt_used = nt_used(); p.rc_used = rc_used();
     p.ntk = ntk; p.rck = rck; p.refract = refract;
     p.slice_off = slice_off_; p.col = col_; p.wgt = wgt_;
+    p.uniform_width = uniform_width_;
     p.t_stride = node_cap_; p.node_flags = node_flags_;
     for (int s = 0; s < F_COUNT; ++s) p.f[s] = F_[s];
     p.was_inc = was_inc_;

@@ -206,36 +206,32 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, uint32_t warp_
                 for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? p.t_in[(size_t)ty * p.t_stride + j[u]] : 0.f;
             }
         }
-        // (1) lazy application of the previous step's STDP while the edges stream by: in-edge rule if the post neuron
-        // spiked last step, out-edge rule if the pre neuron did (update_weights_from_neurons, neuron/mod.rs:849-881,
-        // 2308-2417); both use the post lattice's rule.  No edge can get two non-zero updates in one step.
-        if (pending) {
-            const bool plast0 = NET ? false : (p.lat[0].do_plasticity != 0);
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool ok = c[u] != kColPad;
+        for (int u = 0; u < U; ++u) {
+            const bool ok = c[u] != kColPad;
+            float wu = w[u];
+            if (pending) {
+                // lazy application of the previous step's STDP while the edge streams by: in-edge rule if the post
+                // neuron spiked last step, out-edge rule if the pre neuron did (update_weights_from_neurons,
+                // neuron/mod.rs:849-881, 2308-2417); both use the post lattice's rule.  No edge can get two non-zero
+                // updates in one step.
                 bool pre_trig = ok && lj[u] == prev;
                 if (NET) {
                     if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
                 } else {
-                    pre_trig = pre_trig && plast0;
+                    pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
                 }
                 if ((post_trig && ok) || pre_trig) {
                     const float d = stdp_delta(p.lat[li], lj[u], lft_me);
-                    float wu = w[u] + d;
+                    wu = wu + d;
                     if (post_trig && pre_trig) wu = wu + d;
-                    w[u] = wu;
                     wp[u * 32] = wu;
                 }
             }
-        }
-        // (2) electrical input, strictly in ascending presynaptic order
-        if (do_e) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
+            if (do_e) {
                 float final_input = gap * (vj[u] - v);  // gap_junction, neuron/mod.rs:54-60
                 if (NET) {
-                    if (c[u] != kColPad && (c[u] & kColTrainBit)) {
+                    if (ok && (c[u] & kColTrainBit)) {
                         // spike_train_gap_junction, neuron/mod.rs:119-137
                         const uint32_t tjx = j[u] - p.train0;
                         const int lt = p.lft_in[j[u]];
@@ -246,33 +242,26 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, uint32_t warp_
                                                                ldf(p.tf[TF_VTH], tjx), v_rest, ldf(p.tf[TF_DT], tjx));
                     }
                 }
-                A.acc_e = A.acc_e + final_input * w[u];
+                A.acc_e = A.acc_e + final_input * wu;
             }
-        }
-        // (3) neurotransmitter input: weight_neurotransmitter_concentration + aggregate, iterate_and_spike/mod.rs:2837-2866
-        if (CHEMG == 1) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const bool has = c[u] != kColPad && ((c[u] >> (kColNtShift + ty0)) & 1u);
-                const float term = tj[u][0] * w[u];
+            if (CHEMG == 1) {
+                // weight_neurotransmitter_concentration + aggregate, iterate_and_spike/mod.rs:2837-2866
+                const bool has = ok && ((c[u] >> (kColNtShift + ty0)) & 1u);
+                const float term = tj[u][0] * wu;
                 A.acc_t[0] = A.acc_t[0] + (has ? term : 0.f);
                 A.cnt[0] += has ? 1u : 0u;
-            }
-        } else if (CHEMG == 3) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const uint32_t m = (c[u] != kColPad) ? (c[u] >> kColNtShift) : 0u;
+            } else if (CHEMG == 3) {
+                const uint32_t m = ok ? (c[u] >> kColNtShift) : 0u;
 #pragma unroll
                 for (int ty = 0; ty < kNT; ++ty) {
                     const bool has = (m >> ty) & 1u;
-                    const float term = tj[u][ty] * w[u];
+                    const float term = tj[u][ty] * wu;
                     A.acc_t[ty] = A.acc_t[ty] + (has ? term : 0.f);
                     A.cnt[ty] += has ? 1u : 0u;
                 }
             }
+            A.n_in += ok ? 1u : 0u;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) A.n_in += (c[u] != kColPad) ? 1u : 0u;
     }
 }
 

@@ -120,6 +120,32 @@ struct TrainParams {
     float *grid_hist; uint32_t *spike_hist;   // this step's record over all trains (nullptr = off)
 };
 
+// ---- TMA-staged step kernel (step_tma.cu) -----------------------------------------------------
+constexpr int kTmaTile = 256;            // neurons per tile
+constexpr int kTmaConsumerWarps = 8;
+constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;   // + one producer warp
+constexpr int kMaxTmaStreams = 56;
+
+struct TmaStream {           // one contiguous operand range per tile
+    const unsigned char *src;
+    uint32_t bytes_per_tile;  // multiple of 16
+    uint32_t smem_off;        // multiple of 128, inside a stage
+};
+
+struct TmaParams {
+    uint32_t n_tiles, n_streams, stage_bytes, stages, tx_bytes;
+    TmaStream st[kMaxTmaStreams];
+    // byte offsets inside a stage of each logical operand
+    uint32_t o_v, o_lft, o_flags, o_col, o_wgt;
+    uint32_t o_t[kNT];
+    uint32_t o_f[F_COUNT];
+    uint32_t o_nt[NTF_COUNT][kNT];
+    uint32_t o_rc[RCF_COUNT][kNT];
+};
+
+cudaError_t launch_step_tma(const StepParams &p, const TmaParams &tp, int model, int chemg, bool ntrel, bool stdp, unsigned grid,
+                            cudaStream_t s);
+
 // ---- kernel launchers (kernels.cu) ------------------------------------------------------------
 // chemg: 0 no chemical gather, 1 one neurotransmitter type in the whole node array, 3 general; ntrel: neurotransmitter /
 // receptor state is present and must be stepped; net: several lattices and/or spike trains share the node array

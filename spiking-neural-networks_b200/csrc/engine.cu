@@ -108,8 +108,9 @@ void Engine::compute_layout() {
     train0_ = (uint32_t)round_up(own0_ + n_neurons, 32);
     ghost_hi0_ = train0_;
     n_nodes_ = (part_world > 1) ? ghost_hi0_ + halo_hi : train0_ + (uint32_t)n_trains;
-    node_cap_ = round_up(std::max<uint64_t>(n_nodes_, 1), 32) + 32;
-    neuron_cap_ = round_up(std::max<uint64_t>(n_neurons, 1), 32);
+    // capacities cover whole 256-neuron tiles so that the TMA-staged kernel may copy full tiles past the last neuron
+    node_cap_ = round_up(std::max<uint64_t>(n_nodes_, 1), 32) + kTmaTile + 32;
+    neuron_cap_ = round_up(std::max<uint64_t>(n_neurons, 1), kTmaTile);
     train_cap_ = round_up(std::max<uint64_t>(n_trains, 1), 32);
 }
 
@@ -793,8 +794,11 @@ int Engine::finalize_graph() {
         const Block &b = blocks_.begin()->second;
         const uint32_t width = (2 * b.radius + 1) * (2 * b.radius + 1) - 1;
         sell_krows_ = (uint64_t)n_slices_ * width;
-        CK(dev_alloc(&col_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
-        CK(dev_alloc(&wgt_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+        const uint64_t alloc_krows = round_up(n_slices_, kTmaConsumerWarps) * width;  // whole tiles for the TMA kernel
+        CK(dev_alloc(&col_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(dev_alloc(&wgt_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(cudaMemsetAsync(col_, 0xFF, alloc_krows * 32 * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(cudaMemsetAsync(wgt_, 0, alloc_krows * 32 * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
         if (n_neurons == 0) CK(cudaMemset(slice_off_, 0, 4), SNN_GPU_BUFFER_WRITE_ERROR);
         CK(launch_sell_grid(only->rows, only->cols, part_world > 1 ? row0_global : 0, part_world > 1 ? rows_global : only->rows,
                             b.radius, b.weight, own0_, node_flags_, width, slice_off_, col_, wgt_, stream_), SNN_GPU_QUEUE_FAILURE);
@@ -1091,6 +1095,85 @@ void Engine::fill_step_params(StepParams &p) {
     p.halo_done = halo_done_;
 }
 
+// Operand streams of the TMA-staged kernel for the current configuration; false = not eligible (use the general kernel).
+bool Engine::build_tma_params(TmaParams &tp, bool ntrel, bool stdp, bool lft_pp, unsigned *grid) {
+    memset(&tp, 0xFF, sizeof tp);
+    if (!grid_fast_ || !uniform_width_ || n_neurons == 0) return false;
+    int mode = use_tma;
+    if (mode < 0) {
+        const char *e = getenv("SNN_B200_TMA");
+        mode = e ? atoi(e) : 1;
+    }
+    if (mode == 0) return false;
+    // tiny lattices are launch-latency bound: the persistent kernel only pays off with at least a few tiles per SM
+    if (mode < 2 && n_neurons < 64 * 1024) return false;
+    uint32_t off = 0, n = 0;
+    auto add = [&](const void *src, uint32_t bytes_per_tile) -> uint32_t {
+        if (n >= (uint32_t)kMaxTmaStreams) return 0xFFFFFFFFu;
+        tp.st[n].src = (const unsigned char *)src;
+        tp.st[n].bytes_per_tile = bytes_per_tile;
+        tp.st[n].smem_off = off;
+        const uint32_t o = off;
+        off += (uint32_t)round_up(bytes_per_tile, 128);
+        ++n;
+        return o;
+    };
+    const uint32_t fb = kTmaTile * 4;
+    tp.o_v = add(V_[0] + own0_, fb);            // src patched per step (ping-pong)
+    tp.o_lft = (stdp || lft_pp) ? add(LFT_[0] + own0_, fb) : 0u;
+    tp.o_flags = ntrel ? add(node_flags_ + own0_, kTmaTile) : 0u;
+    const uint32_t eb = kTmaConsumerWarps * uniform_width_ * 32u * 4u;
+    tp.o_col = add(col_, eb);
+    tp.o_wgt = add(wgt_, eb);
+    for (int i = 0; i < kNumNeuronFields; ++i) {
+        const FieldDef &fd = kNeuronFields[i];
+        if (fd.kind != FK_NEURON_DEV || !(fd.models & SNN_M(model)) || fd.slot >= F_NA_CUR) continue;
+        tp.o_f[fd.slot] = add(F_[fd.slot], fb);
+    }
+    if (ntrel) {
+        const uint32_t ntu = nt_used(), rcu = rc_used();
+        for (int ty = 0; ty < kNT; ++ty) {
+            if (ntu & (1u << ty)) {
+                tp.o_t[ty] = add(T_[0] + (size_t)ty * node_cap_ + own0_, fb);   // src patched per step
+                tp.o_nt[NTF_TMAX][ty] = add(NT_[NTF_TMAX] + (size_t)ty * node_cap_ + own0_, fb);
+                if (ntk != SNN_NT_DISCRETE_SPIKE) tp.o_nt[NTF_P1][ty] = add(NT_[NTF_P1] + (size_t)ty * node_cap_ + own0_, fb);
+                if (ntk == SNN_NT_DESTEXHE) tp.o_nt[NTF_P2][ty] = add(NT_[NTF_P2] + (size_t)ty * node_cap_ + own0_, fb);
+            }
+            if (rcu & (1u << ty)) {
+                tp.o_rc[RCF_R][ty] = add(RC_[RCF_R] + (size_t)ty * neuron_cap_, fb);
+                tp.o_rc[RCF_G][ty] = add(RC_[RCF_G] + (size_t)ty * neuron_cap_, fb);
+                tp.o_rc[RCF_E][ty] = add(RC_[RCF_E] + (size_t)ty * neuron_cap_, fb);
+                if (rck != SNN_RC_APPROXIMATE) {
+                    tp.o_rc[RCF_K1][ty] = add(RC_[RCF_K1] + (size_t)ty * neuron_cap_, fb);
+                    tp.o_rc[RCF_K2][ty] = add(RC_[RCF_K2] + (size_t)ty * neuron_cap_, fb);
+                }
+                if (ty == SNN_NT_NMDA) tp.o_rc[RCF_MG][ty] = add(RC_[RCF_MG] + (size_t)ty * neuron_cap_, fb);
+            }
+        }
+    }
+    if (n >= (uint32_t)kMaxTmaStreams) return false;
+    tp.n_streams = n;
+    tp.stage_bytes = off;
+    tp.tx_bytes = 0;
+    for (uint32_t k = 0; k < n; ++k) tp.tx_bytes += tp.st[k].bytes_per_tile;
+    tp.n_tiles = (uint32_t)((n_neurons + kTmaTile - 1) / kTmaTile);
+    // shared-memory budget: prefer two resident CTAs per SM with 2-4 stages each
+    const uint32_t budget = 220 * 1024;
+    uint32_t ctas = 2, stages = (budget / ctas) / off;
+    const char *es = getenv("SNN_B200_TMA_STAGES"), *ec = getenv("SNN_B200_TMA_CTAS");
+    if (ec) { ctas = (uint32_t)std::max(1, atoi(ec)); stages = (budget / ctas) / off; }
+    if (stages < 2) { ctas = 1; stages = budget / off; }
+    if (stages < 2) return false;
+    stages = std::min<uint32_t>(stages, 4);
+    if (es) stages = (uint32_t)std::max(2, atoi(es));
+    if ((uint64_t)stages * off + 64 > 227 * 1024) return false;
+    tp.stages = stages;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    *grid = (unsigned)std::min<uint64_t>(tp.n_tiles, (uint64_t)sms * ctas);
+    return true;
+}
+
 int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     if (elapsed_ms) *elapsed_ms = 0.f;
     if (launches) *launches = 0;
@@ -1128,6 +1211,18 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     StepParams sp;
     fill_step_params(sp);
     sp.lft_pp = lft_pp;
+    TmaParams tma;
+    unsigned tma_grid = 0;
+    const bool tma_ok = !net && build_tma_params(tma, ntrel, stdp, lft_pp, &tma_grid);
+    // indices of the ping-ponged streams, patched every step
+    int tma_iv = -1, tma_il = -1, tma_it[kNT] = {-1, -1, -1};
+    if (tma_ok) {
+        for (uint32_t k = 0; k < tma.n_streams; ++k) {
+            if (tma.st[k].smem_off == tma.o_v) tma_iv = (int)k;
+            if ((stdp || lft_pp) && tma.st[k].smem_off == tma.o_lft) tma_il = (int)k;
+            for (int ty = 0; ty < kNT; ++ty) if (tma.o_t[ty] != 0xFFFFFFFFu && tma.st[k].smem_off == tma.o_t[ty]) tma_it[ty] = (int)k;
+        }
+    }
     TrainParams tp;
     memset(&tp, 0, sizeof tp);
     if (n_trains) {
@@ -1194,7 +1289,15 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             sp.spike_hist = want_spk ? d_spk + s * n_words : nullptr;
             sp.out_par = (uint32_t)out;
             sp.halo_epoch = halo_epoch_;
-            if (n_neurons) {
+            if (n_neurons && tma_ok) {
+                tma.st[tma_iv].src = (const unsigned char *)(sp.v_in + own0_);
+                if (tma_il >= 0) tma.st[tma_il].src = (const unsigned char *)(sp.lft_in + own0_);
+                for (int ty = 0; ty < kNT; ++ty)
+                    if (tma_it[ty] >= 0) tma.st[tma_it[ty]].src = (const unsigned char *)(sp.t_in + (size_t)ty * node_cap_ + own0_);
+                cudaError_t e = launch_step_tma(sp, tma, model, chemg, ntrel, stdp, tma_grid, stream_);
+                if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_tma"); break; }
+                n_launch++;
+            } else if (n_neurons) {
                 cudaError_t e = launch_step(sp, model, chemg, ntrel, stdp, net, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step"); break; }
                 n_launch++;
@@ -1230,6 +1333,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             fp.clock = (uint32_t)internal_clock;
             fp.lft_in = LFT_[lft_loc_];
             fp.lft_out = LFT_[lft_loc_ ^ 1];  // spike trains: last_firing_time from before their last iterate
+            fp.halo_epoch = halo_epoch_;
             cudaError_t e = launch_flush_stdp(fp, stream_);
             if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "flush_stdp"); break; }
             n_launch++;

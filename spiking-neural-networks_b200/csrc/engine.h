@@ -104,6 +104,7 @@ public:
     uint64_t internal_clock = 0;
     uint64_t seed = 0x5EED5EEDull;
     uint32_t steps_per_graph = 0;
+    int use_tma = -1;   // -1 auto (env SNN_B200_TMA), 0 never, 1 whenever eligible
     std::string last_error;
 
     int model, ntk, rck, train_kind, refract, device;
@@ -179,6 +180,7 @@ private:
     mutable uint32_t nt_used_ = 0, rc_used_ = 0;
     void fill_step_params(StepParams &p);
     int upload_lat_table();
+    bool build_tma_params(TmaParams &tp, bool ntrel, bool stdp, bool lft_pp, unsigned *grid);
 };
 
 }  // namespace snn

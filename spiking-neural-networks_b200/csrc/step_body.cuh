@@ -1,0 +1,552 @@
+// step_body.cuh — the per-neuron step shared by the two step kernels.
+//
+// `neuron_step` is the whole timestep of one postsynaptic neuron: in-edge gather, receptors, model update,
+// neurotransmitter release, spike ballot, stores and halo export.  It is parameterised on a *source policy* that says
+// where the once-per-neuron streamed operands (own state, parameters, the slice's col/weight rows) come from:
+//   GlobalSrc — straight from HBM with per-thread loads            (step_kernel, kernels.cu: general graphs, networks)
+//   SmemSrc   — from a shared-memory stage filled by TMA bulk copies (step_tma_kernel, step_tma.cu: stencil lattices)
+// Neighbour gathers (V, last_firing_time, t) always go through L1/L2, results are always stored to HBM directly.
+#pragma once
+#include "common.h"
+
+namespace snn {
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lat_index(const StepParams &p, uint32_t ln) {
+    if (p.n_lat <= 1) return 0;
+    int l = 0;
+#pragma unroll 1
+    for (int k = 1; k < p.n_lat; ++k)
+        if (ln >= p.lat[k].base) l = k;
+    return l;
+}
+
+// STDP::update_weight, plasticity/mod.rs:46-65
+__device__ __forceinline__ float stdp_delta(const LatInfo &L, int t_pre_i, int t_post_i) {
+    float delta_w = 0.f;
+    if (t_pre_i >= 0 && t_post_i >= 0) {
+        const float t_pre = (float)t_pre_i, t_post = (float)t_post_i;
+        if (t_pre < t_post) {
+            delta_w = L.a_plus * expf((-1.f * fabsf((t_pre - t_post) * L.dt)) / L.tau_plus);
+        } else if (t_pre > t_post) {
+            delta_w = (-1.f * L.a_minus) * expf((-1.f * fabsf((t_post - t_pre) * L.dt)) / L.tau_minus);
+        }
+    }
+    return delta_w;
+}
+
+// NeurotransmitterKinetics::apply_t_change, iterate_and_spike/mod.rs:147-150, 192-196, 301-304, 352-357
+__device__ __forceinline__ float nt_apply(int kind, float t, float t_max, float p1, float p2, float voltage,
+                                          bool is_spiking, float dt) {
+    const float flag = is_spiking ? 1.f : 0.f;
+    switch (kind) {
+    case SNN_NT_APPROXIMATE: {
+        const float a = dt * -p1;
+        const float b = a * t;
+        const float c = flag * t_max;
+        t = t + (b + c);
+        return fminf(t_max, fmaxf(t, 0.f));
+    }
+    case SNN_NT_DESTEXHE:
+        return t_max / (1.f + expf(-(voltage - p1) / p2));
+    case SNN_NT_DISCRETE_SPIKE:
+        return t_max * flag;
+    default: {  // SNN_NT_EXPONENTIAL_DECAY
+        const float t_change = -t * expf(dt / -p1);
+        t = t + (t_change + flag * t_max);
+        return fminf(t_max, fmaxf(t, 0.f));
+    }
+    }
+}
+
+// ReceptorKinetics::apply_r_change, iterate_and_spike/mod.rs:403-406, 434-437, 510-514
+__device__ __forceinline__ float rc_apply(int kind, float r, float k1, float k2, float t, float dt) {
+    switch (kind) {
+    case SNN_RC_APPROXIMATE:
+        return t;
+    case SNN_RC_DESTEXHE: {
+        const float a = k1 * t;
+        const float b = a * (1.f - r);
+        const float c = k2 * r;
+        return r + (b - c) * dt;
+    }
+    default: {  // SNN_RC_EXPONENTIAL_DECAY: k1 = r_max, k2 = decay_constant
+        const float dec = -r * expf(dt / -k2);
+        r = r + (dec + t);
+        return fminf(k1, fmaxf(r, 0.f));
+    }
+    }
+}
+
+// AMPA / NMDA / GABA ::iterate, iterate_and_spike/mod.rs:1101-1103, 1132-1137, 1164-1166
+__device__ __forceinline__ float receptor_current(int type, float g, float e, float mg, float r, float v) {
+    if (type == SNN_NT_NMDA) {
+        const float ex = expf(-0.062f * v);
+        const float den = 1.0f + ((ex * mg) / 3.75f);
+        return (((1.0f / den) * g) * r) * (v - e);
+    }
+    return (g * r) * (v - e);
+}
+
+// NeuralRefractoriness::get_effect, spike_train/mod.rs:68-73, 84-86, 174-176
+__device__ __forceinline__ float refract_effect(int kind, float k, uint32_t timestep, uint32_t last, float v_max,
+                                                float v_resting, float dt) {
+    const float a = v_max - v_resting;
+    const float td = (float)(timestep - last);
+    if (kind == SNN_REFRACT_DELTA_DIRAC) return a * expf((-1.f / (k / dt)) * (td * td)) + v_resting;
+    return a * expf((-1.f / (k / dt)) * td) + v_resting;
+}
+
+__device__ __forceinline__ float ldf(const float *p, size_t i) { return __ldg(p + i); }
+
+// ------------------------------------------------------------------------------------------------
+// halo synchronisation over NVLink peer memory (multi-GPU row strips)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Spin until the neighbour's arrival counter reaches `epoch`.  Bounded (~4e9 SM cycles, about two seconds): a
+// neighbour that died must not hang this GPU; the host turns the error flag into SNN_GPU_WAIT_ERROR.
+__device__ __forceinline__ void halo_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *err) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < epoch) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// source policies
+// ------------------------------------------------------------------------------------------------
+struct GlobalSrc {
+    const StepParams &p;
+    uint32_t lnc;   // clamped local neuron number
+    uint32_t i;     // node index
+    uint32_t lane;
+    uint32_t k0, k1;  // k-rows of this warp's slice
+    __device__ __forceinline__ float f(int slot) const { return __ldg(p.f[slot] + lnc); }
+    __device__ __forceinline__ float state(int slot) const { return p.f[slot][lnc]; }
+    __device__ __forceinline__ float v() const { return p.v_in[i]; }
+    __device__ __forceinline__ int lft() const { return p.lft_in[i]; }
+    __device__ __forceinline__ uint32_t flags() const { return p.node_flags[i]; }
+    __device__ __forceinline__ float t_own(int ty) const { return p.t_in[(size_t)ty * p.t_stride + i]; }
+    __device__ __forceinline__ float nt(int slot, int ty) const { return __ldg(p.nt[slot] + (size_t)ty * p.nt_stride + i); }
+    __device__ __forceinline__ float rc(int slot, int ty) const { return __ldg(p.rc[slot] + (size_t)ty * p.rc_stride + lnc); }
+    __device__ __forceinline__ float rc_state(int slot, int ty) const { return p.rc[slot][(size_t)ty * p.rc_stride + lnc]; }
+    __device__ __forceinline__ uint32_t width() const { return k1 - k0; }
+    __device__ __forceinline__ uint32_t col(uint32_t kk) const { return __ldg(p.col + (size_t)(k0 + kk) * 32u + lane); }
+    __device__ __forceinline__ float wgt(uint32_t kk) const { return p.wgt[(size_t)(k0 + kk) * 32u + lane]; }
+    __device__ __forceinline__ float *wgt_ptr(uint32_t kk) const { return p.wgt + (size_t)(k0 + kk) * 32u + lane; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// in-edge gather
+// ------------------------------------------------------------------------------------------------
+struct EdgeAcc {
+    float acc_e;
+    uint32_t n_in;
+    float acc_t[kNT];
+    uint32_t cnt[kNT];
+};
+
+// CHEMG: 0 = no chemical gather, 1 = exactly one neurotransmitter type in the whole node array (type index ty0),
+//        3 = general per-edge type masks.  NET: the node array holds several lattices and/or spike trains.
+//
+// Edges are consumed in chunks of 8 (slice widths are padded to a multiple of 4): first all coalesced col/weight
+// loads of the chunk, then all neighbour gathers, then the strictly ordered accumulation.  Eight independent
+// requests per thread keep enough bytes in flight to cover HBM latency; the arithmetic order is the canonical one
+// (ascending presynaptic index).  Padding slots carry weight 0 and gather the neuron itself, so they add an exact
+// +0 and need no branch.
+template <int CHEMG, bool STDP, bool NET, class SRC>
+__device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
+                                             bool post_trig, int li, uint32_t ty0, EdgeAcc &A) {
+    constexpr int U = 8;
+    const uint32_t width = src.width();
+    const bool pending = STDP && p.apply_pending;
+    const bool do_e = p.electrical != 0;
+    const int prev = (int)p.clock - 1;
+    const float *t0 = (CHEMG == 1) ? p.t_in + (size_t)ty0 * p.t_stride : nullptr;
+    for (uint32_t kk = 0; kk < width; kk += U) {
+        const bool full = kk + U <= width;
+        uint32_t c[U];
+        float w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (u < 4 || full) { c[u] = src.col(kk + u); w[u] = src.wgt(kk + u); }
+            else { c[u] = kColPad; w[u] = 0.f; }
+        }
+        uint32_t j[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = (c[u] == kColPad) ? i : (c[u] & kColIdxMask);
+        float vj[U];
+        if (do_e) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) vj[u] = p.v_in[j[u]];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) vj[u] = v;
+        }
+        int lj[U];
+        if (pending) {
+            // a spike train steps AFTER the neurons and their STDP (neuron/mod.rs:2573-2591): the rule of step s must
+            // see the train's last_firing_time from before its step-s iterate, which still sits in the other
+            // ping-pong buffer (the train kernel of this step has not run yet)
+#pragma unroll
+            for (int u = 0; u < U; ++u) lj[u] = (NET && (c[u] & kColTrainBit) && c[u] != kColPad) ? p.lft_out[j[u]] : p.lft_in[j[u]];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) lj[u] = -1;
+        }
+        float tj[U][CHEMG == 3 ? kNT : 1];
+        if (CHEMG == 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) tj[u][0] = t0[j[u]];
+        } else if (CHEMG == 3) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const uint32_t m = (c[u] == kColPad) ? 0u : (c[u] >> kColNtShift);
+#pragma unroll
+                for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? p.t_in[(size_t)ty * p.t_stride + j[u]] : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = c[u] != kColPad;
+            float wu = w[u];
+            if (pending) {
+                // lazy application of the previous step's STDP while the edge streams by: in-edge rule if the post
+                // neuron spiked last step, out-edge rule if the pre neuron did (update_weights_from_neurons,
+                // neuron/mod.rs:849-881, 2308-2417); both use the post lattice's rule.  No edge can get two non-zero
+                // updates in one step.
+                bool pre_trig = ok && lj[u] == prev;
+                if (NET) {
+                    if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
+                } else {
+                    pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
+                }
+                if ((post_trig && ok) || pre_trig) {
+                    const float d = stdp_delta(p.lat[li], lj[u], lft_me);
+                    wu = wu + d;
+                    if (post_trig && pre_trig) wu = wu + d;
+                    *src.wgt_ptr(kk + u) = wu;
+                }
+            }
+            if (do_e) {
+                float final_input = gap * (vj[u] - v);  // gap_junction, neuron/mod.rs:54-60
+                if (NET) {
+                    if (ok && (c[u] & kColTrainBit)) {
+                        // spike_train_gap_junction, neuron/mod.rs:119-137
+                        const uint32_t tjx = j[u] - p.train0;
+                        const int lt = p.lft_in[j[u]];
+                        const float v_rest = ldf(p.tf[TF_VREST], tjx);
+                        if (lt < 0) final_input = v_rest;
+                        else
+                            final_input = gap * refract_effect(p.refract, ldf(p.tf[TF_K], tjx), p.clock, (uint32_t)lt,
+                                                               ldf(p.tf[TF_VTH], tjx), v_rest, ldf(p.tf[TF_DT], tjx));
+                    }
+                }
+                A.acc_e = A.acc_e + final_input * wu;
+            }
+            if (CHEMG == 1) {
+                // weight_neurotransmitter_concentration + aggregate, iterate_and_spike/mod.rs:2837-2866
+                const bool has = ok && ((c[u] >> (kColNtShift + ty0)) & 1u);
+                const float term = tj[u][0] * wu;
+                A.acc_t[0] = A.acc_t[0] + (has ? term : 0.f);
+                A.cnt[0] += has ? 1u : 0u;
+            } else if (CHEMG == 3) {
+                const uint32_t m = ok ? (c[u] >> kColNtShift) : 0u;
+#pragma unroll
+                for (int ty = 0; ty < kNT; ++ty) {
+                    const bool has = (m >> ty) & 1u;
+                    const float term = tj[u][ty] * wu;
+                    A.acc_t[ty] = A.acc_t[ty] + (has ? term : 0.f);
+                    A.cnt[ty] += has ? 1u : 0u;
+                }
+            }
+            A.n_in += ok ? 1u : 0u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// one neuron, one timestep
+// ------------------------------------------------------------------------------------------------
+// warp_global: slice index (neuron-local word index of the spike bitmask); ln: local neuron number; lnc: clamped copy
+// used for addressing by invalid lanes of the last warp.
+template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET, class SRC>
+__device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src, uint32_t warp_global, uint32_t lane,
+                                            uint32_t ln, uint32_t lnc, bool valid, bool export_lo, bool export_hi) {
+    const uint32_t i = p.own0 + lnc;
+    // ---- own state and parameters ------------------------------------------------------------------
+    float v = src.v();
+    const float gap = src.f(F_GAP);
+    const float dt = src.f(F_DT);
+    const float v_th = src.f(F_VTH);
+    constexpr bool NEEDS_CM = NTREL || MODEL == SNN_MODEL_HODGKIN_HUXLEY || MODEL == SNN_MODEL_IZHIKEVICH ||
+                              MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
+                              MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    const float c_m = NEEDS_CM ? src.f(F_CM) : 1.f;
+    const int lft_me = (STDP || p.lft_pp) ? src.lft() : 0;
+    const uint32_t spk_word_in = __ldg(p.spk_in + (p.own0 >> 5) + warp_global);
+    const bool spiking_prev = (spk_word_in >> lane) & 1u;
+    const uint32_t flags = NTREL ? src.flags() : 0u;
+    constexpr bool IZH = MODEL == SNN_MODEL_IZHIKEVICH || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH;
+    constexpr bool IF4 = MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE ||
+                         MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    constexpr bool ADAPT = MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    constexpr bool LEAKY = MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || ADAPT;
+    // model parameters (only the ones this model reads are loaded; the rest fold away)
+    float w_adapt = (IZH || ADAPT) ? src.state(F_W) : 0.f;
+    const float pa = IZH ? src.f(F_A) : 0.f, pb = IZH ? src.f(F_B) : 0.f;
+    const float pc = IZH ? src.f(F_C) : 0.f, pd = IZH ? src.f(F_D) : 0.f;
+    const float tau_m = (IZH || IF4) ? src.f(F_TAUM) : 1.f;
+    const float e_l = (LEAKY || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH) ? src.f(F_EL) : 0.f;
+    const float v_reset = (IF4 || MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) ? src.f(F_VRESET) : 0.f;
+    const float integ = IF4 ? src.f(F_INTEG) : 0.f;
+    float refr = IF4 ? src.state(F_REFR) : 0.f;
+    const float tref = IF4 ? src.f(F_TREF) : 0.f;
+    const float g_l = LEAKY ? src.f(F_GL) : 1.f;
+    const float leak = LEAKY ? src.f(F_LEAK) : 0.f;
+    const float alpha = (ADAPT || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) ? src.f(F_ALPHA) : 0.f;
+    const float beta = ADAPT ? src.f(F_BETA) : 0.f;
+
+    // the single neurotransmitter type of the CHEMG == 1 fast path
+    const uint32_t ty0 = (CHEMG == 1) ? (uint32_t)(__ffs((int)p.nt_used) - 1) : 0u;
+
+    int li = 0;
+    bool post_trig = false;
+    if (STDP) {
+        li = NET ? lat_index(p, lnc) : 0;
+        post_trig = p.apply_pending && p.lat[li].do_plasticity && lft_me == (int)p.clock - 1;
+    }
+
+    // ---- gather over in-edges (ascending presynaptic index = canonical summation order) ----------
+    EdgeAcc A;
+    A.acc_e = 0.f; A.n_in = 0;
+#pragma unroll
+    for (int ty = 0; ty < kNT; ++ty) { A.acc_t[ty] = 0.f; A.cnt[ty] = 0; }
+    const bool do_e = p.electrical != 0;
+    const bool do_c = NTREL && p.chemical != 0;
+    gather_edges<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
+    // neuron/mod.rs:722-729: divide by the number of incoming edges (1 if none)
+    const float input = do_e ? A.acc_e / (A.n_in == 0 ? 1.f : (float)A.n_in) : 0.f;
+
+    // ---- receptors (iterate_with_neurotransmitter_and_spike: kinetics then currents from pre-update V)
+    float rc_total = 0.f;
+    if (NTREL) {
+        const uint32_t rcm = flags >> 4;
+        if (do_c) {
+#pragma unroll
+            for (int ty = 0; ty < kNT; ++ty) {
+                if (!(p.rc_used & (1u << ty))) continue;
+                if (!(rcm & (1u << ty))) continue;
+                float r = src.rc_state(RCF_R, ty);
+                const uint32_t cnt = (CHEMG == 1) ? (ty == (int)ty0 ? A.cnt[0] : 0u) : A.cnt[ty];
+                if (cnt > 0) {
+                    const float acc = (CHEMG == 1) ? A.acc_t[0] : A.acc_t[ty];
+                    const float tin = acc / (float)cnt;
+                    float k1 = 0.f, k2 = 0.f;
+                    if (p.rck != SNN_RC_APPROXIMATE) { k1 = src.rc(RCF_K1, ty); k2 = src.rc(RCF_K2, ty); }
+                    r = rc_apply(p.rck, r, k1, k2, tin, dt);
+                    if (valid) p.rc[RCF_R][(size_t)ty * p.rc_stride + lnc] = r;
+                }
+                const float mg = (ty == SNN_NT_NMDA) ? src.rc(RCF_MG, ty) : 0.f;
+                rc_total += receptor_current(ty, src.rc(RCF_G, ty), src.rc(RCF_E, ty), mg, r, v);
+            }
+        } else if (MODEL == SNN_MODEL_HODGKIN_HUXLEY) {
+            // hodgkin_huxley/mod.rs:161-164: the electrical-only path still subtracts the stored ligand currents
+#pragma unroll
+            for (int ty = 0; ty < kNT; ++ty)
+                if ((p.rc_used & (1u << ty)) && (rcm & (1u << ty))) rc_total += p.rc[RCF_CUR][(size_t)ty * p.rc_stride + lnc];
+        }
+    }
+    const float rc_dv = rc_total * (dt / c_m);  // Ionotropic::get_receptor_currents, iterate_and_spike/mod.rs:1286-1304
+
+    // ---- neuron update --------------------------------------------------------------------------
+    bool spike = false;
+    float v_release;  // membrane voltage seen by the neurotransmitter kinetics (post-update, pre-reset)
+    if constexpr (IZH) {
+        float dv;
+        if constexpr (MODEL == SNN_MODEL_IZHIKEVICH)  // integrate_and_fire/mod.rs:1255-1260
+            dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - w_adapt) + input) * (dt / c_m);
+        else                                            // :1342-1348
+            dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - (w_adapt * (v - e_l))) + input) * (dt / c_m);
+        const float dw = (pa * (pb * v - w_adapt)) * (dt / tau_m);  // :1225-1231
+        if (do_c) v += dv + (-rc_dv); else v += dv;               // :226, :246
+        w_adapt += dw;
+        v_release = v;
+        if (v >= v_th) {                                            // izhikevich_handle_spiking :1235-1247
+            spike = true;
+            v = pc;
+            w_adapt += pd;
+        }
+        if (valid) p.f[F_W][lnc] = w_adapt;
+    } else if constexpr (IF4) {
+        float dw = 0.f, dv;
+        if constexpr (MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE) {  // :176-181
+            dv = ((leak * (v - e_l)) + (integ * (input / g_l))) * (dt / tau_m);
+        } else if constexpr (MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) {  // :324-327
+            dv = (((alpha * (v - v_reset)) * (v - src.f(F_VC))) + integ * input) * (dt / tau_m);
+        } else {
+            if constexpr (MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE)  // :1035-1041
+                dv = (((leak * (v - e_l)) + (integ * (input / g_l))) - (w_adapt / g_l)) * (dt / c_m);
+            else {                                                                  // :1138-1145
+                const float sf = src.f(F_SLOPE);
+                dv = ((((leak * (v - e_l)) + (sf * expf((v - v_th) / sf))) + (integ * (input / g_l))) - (w_adapt / g_l)) * (dt / c_m);
+            }
+            dw = (alpha * (v - e_l) - w_adapt) * (dt / tau_m);  // :1002-1009
+        }
+        if (do_c) v += dv + (-rc_dv); else v += dv;
+        if (ADAPT) w_adapt += dw;
+        v_release = v;
+        // impl_default_handle_spiking :87-102 / adaptive_handle_spiking :1013-1029
+        if (refr > 0.f) {
+            v = v_reset;
+            refr -= 1.f;
+        } else if (v >= v_th) {
+            spike = true;
+            v = v_reset;
+            if (ADAPT) w_adapt += beta;
+            refr = tref / dt;
+        }
+        if (valid) {
+            p.f[F_REFR][lnc] = refr;
+            if (ADAPT) p.f[F_W][lnc] = w_adapt;
+        }
+    } else if constexpr (MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) {
+        const float dv = (src.f(F_G) * (v - src.f(F_E)) + input) * dt;  // :1592-1594
+        if (do_c) v += dv + (-rc_dv); else v += dv;
+        v_release = v;
+        if (v >= v_th) { spike = true; v = v_reset; }  // :1579-1590
+    } else {  // Hodgkin-Huxley, hodgkin_huxley/mod.rs:156-241; ion_channels/mod.rs:40-44, 219-235, 268-281, 310-312
+        const float last_voltage = v;
+        float m = src.state(F_M), h = src.state(F_H), n = src.state(F_N);
+        const float m_alpha = 0.1f * ((v + 40.f) / (1.f - expf(-(v + 40.f) / 10.f)));
+        const float m_beta = 4.f * expf(-(v + 65.f) / 18.f);
+        const float h_alpha = 0.07f * expf(-(v + 65.f) / 20.f);
+        const float h_beta = 1.f / (expf(-(v + 35.f) / 10.f) + 1.f);
+        m += dt * (m_alpha * (1.f - m) - m_beta * m);
+        h += dt * (h_alpha * (1.f - h) - h_beta * h);
+        const float i_na = ((powf(m, 3.f) * h) * src.f(F_GNA)) * (v - src.f(F_ENA));
+        const float n_alpha = (0.01f * (v + 55.f)) / (1.f - expf(-(v + 55.f) / 10.f));
+        const float n_beta = 0.125f * expf(-(v + 65.f) / 80.f);
+        n += dt * (n_alpha * (1.f - n) - n_beta * n);
+        const float i_k = (powf(n, 4.f) * src.f(F_GK)) * (v - src.f(F_EK));
+        const float i_kl = src.f(F_GKL) * (v - src.f(F_EKL));
+        const float i_sum = input - ((i_na + i_k) + i_kl);
+        v += (dt * i_sum) / c_m - rc_dv;
+        v_release = v;
+        const uint32_t wi_word = p.was_inc[warp_global];
+        const bool was_increasing = (wi_word >> lane) & 1u;
+        const bool increasing_right_now = last_voltage < v;
+        spike = (v > v_th) && was_increasing && !increasing_right_now;
+        const uint32_t wi_new = __ballot_sync(0xffffffffu, increasing_right_now && valid);
+        if (lane == 0) p.was_inc[warp_global] = wi_new;
+        if (valid) { p.f[F_M][lnc] = m; p.f[F_H][lnc] = h; p.f[F_N][lnc] = n; }
+    }
+
+    // ---- neurotransmitter release: post-update voltage, previous step's spike flag
+    //      (intermediate_delegate/mod.rs:18-24, integrate_and_fire/mod.rs:229)
+    if (NTREL) {
+        const uint32_t ntm = flags & 0xFu;
+#pragma unroll
+        for (int ty = 0; ty < kNT; ++ty) {
+            if (!(p.nt_used & (1u << ty))) continue;
+            if (!(ntm & (1u << ty))) continue;
+            const float t_old = src.t_own(ty);
+            float p1 = 0.f, p2 = 0.f;
+            if (p.ntk != SNN_NT_DISCRETE_SPIKE) p1 = src.nt(NTF_P1, ty);
+            if (p.ntk == SNN_NT_DESTEXHE) p2 = src.nt(NTF_P2, ty);
+            const float t_new = nt_apply(p.ntk, t_old, src.nt(NTF_TMAX, ty), p1, p2, v_release, spiking_prev, dt);
+            if (valid) {
+                p.t_out[(size_t)ty * p.t_stride + i] = t_new;
+                if (export_lo) p.halo[0].peer_t[p.out_par][(size_t)ty * p.halo[0].peer_t_stride + p.halo[0].peer_node0 + (ln - p.halo[0].first)] = t_new;
+                if (export_hi) p.halo[1].peer_t[p.out_par][(size_t)ty * p.halo[1].peer_t_stride + p.halo[1].peer_node0 + (ln - p.halo[1].first)] = t_new;
+            }
+        }
+    }
+
+    // ---- spike compaction: one bit per neuron, one word per warp --------------------------------
+    const uint32_t spk_word = __ballot_sync(0xffffffffu, spike && valid);
+    if (lane == 0) {
+        p.spk_out[(p.own0 >> 5) + warp_global] = spk_word;
+        if (p.spike_hist) p.spike_hist[warp_global] = spk_word;
+    }
+    if (valid) {
+        p.v_out[i] = v;
+        // set_last_firing_time(Some(internal_clock)), neuron/mod.rs:964-966
+        int lft_new = lft_me;
+        if (p.lft_pp) { lft_new = spike ? (int)p.clock : lft_me; p.lft_out[i] = lft_new; }
+        else if (spike) { lft_new = (int)p.clock; p.lft_out[i] = lft_new; }
+        if (p.grid_hist) p.grid_hist[ln] = v;  // GridVoltageHistory::update, neuron/mod.rs:293-296
+        if (export_lo) {
+            const HaloDir &H = p.halo[0];
+            const uint32_t dst = H.peer_node0 + (ln - H.first);
+            H.peer_v[p.out_par][dst] = v;
+            if (p.lft_pp) H.peer_lft[p.out_par][dst] = lft_new;
+        }
+        if (export_hi) {
+            const HaloDir &H = p.halo[1];
+            const uint32_t dst = H.peer_node0 + (ln - H.first);
+            H.peer_v[p.out_par][dst] = v;
+            if (p.lft_pp) H.peer_lft[p.out_par][dst] = lft_new;
+        }
+    }
+}
+
+// ---- multi-GPU: does this warp's slice touch a halo?  If so wait for the neighbour's previous step first.
+__device__ __forceinline__ void halo_import(const StepParams &p, uint32_t warp_global, uint32_t lane, uint32_t ln, bool valid,
+                                            bool &export_lo, bool &export_hi) {
+    export_lo = export_hi = false;
+    if (!(p.halo[0].active | p.halo[1].active)) return;
+    const uint32_t w0 = warp_global * 32u, w1 = min(w0 + 32u, p.n_neurons);
+    const bool near_lo = p.halo[0].active && w0 < p.halo[0].first + p.halo[0].count;
+    const bool near_hi = p.halo[1].active && w1 > p.halo[1].first;
+    if (near_lo) {
+        if (lane == 0) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2);
+        __syncwarp();
+    }
+    if (near_hi) {
+        if (lane == 0) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
+        __syncwarp();
+    }
+    export_lo = near_lo && valid && ln >= p.halo[0].first && ln < p.halo[0].first + p.halo[0].count;
+    export_hi = near_hi && valid && ln >= p.halo[1].first && ln < p.halo[1].first + p.halo[1].count;
+}
+
+// ---- multi-GPU: publish "my boundary values of this step have landed" to each neighbour.  Every exporting warp
+// fences its remote stores, then bumps a local counter; the last one raises the neighbour's arrival flag.
+__device__ __forceinline__ void halo_publish(const StepParams &p, uint32_t warp_global, uint32_t lane) {
+    if (!(p.halo[0].active | p.halo[1].active)) return;
+    const uint32_t w0 = warp_global * 32u, w1 = min(w0 + 32u, p.n_neurons);
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const HaloDir &H = p.halo[d];
+        if (!H.active) continue;
+        const bool mine = w0 < H.first + H.count && w1 > H.first;
+        if (!mine) continue;
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_system();
+            const uint32_t first_w = H.first >> 5, last_w = (H.first + H.count - 1) >> 5;
+            const uint32_t n_warps = last_w - first_w + 1;
+            const unsigned int done = atomicAdd(&p.halo_done[d], 1u) + 1u;
+            if (done == n_warps) {
+                p.halo_done[d] = 0u;
+                __threadfence_system();
+                st_release_sys(H.peer_flag, p.halo_epoch + 1ull);
+            }
+        }
+    }
+}
+
+}  // namespace snn

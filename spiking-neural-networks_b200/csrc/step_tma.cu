@@ -1,0 +1,173 @@
+// step_tma.cu — the step kernel for stencil lattices: persistent CTAs, TMA-staged operands.
+//
+// The general step_kernel (kernels.cu) issues ~60 dependent per-thread loads per neuron and is latency-bound
+// (ncu: 42 % issue slots, 33 % DRAM, profiles/).  Every operand that is read exactly once per neuron per step —
+// own state, the per-neuron parameters, the slice's col/weight rows — is a contiguous byte range per tile of 256
+// neurons, so here one producer lane moves them with TMA bulk copies (cp.async.bulk.shared::cluster.global with
+// mbarrier complete_tx) into a multi-stage shared-memory ring, a whole tile (or more) ahead of the 8 consumer warps.
+// Consumers read their operands from shared memory (conflict-free: one float per lane), do the neighbour gathers
+// through L1/L2, and store results straight to HBM.  The arithmetic is the shared neuron_step (step_body.cuh), so
+// results are bit-identical to the general kernel.
+//
+// Grid = resident CTAs (SM count x CTAs/SM), tiles are taken round-robin; 288 threads = 8 consumer warps + 1 producer.
+#include "step_body.cuh"
+
+namespace snn {
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct SmemSrc {
+    const StepParams &p;
+    const TmaParams &tp;
+    const unsigned char *st;  // this stage
+    uint32_t tid;             // neuron within the tile
+    uint32_t lane, warp;
+    uint32_t w;               // uniform slice width
+    uint32_t k0g;             // first k-row of this warp's slice in the global edge arrays
+    __device__ __forceinline__ float ld(uint32_t off) const { return *reinterpret_cast<const float *>(st + off + tid * 4u); }
+    __device__ __forceinline__ float f(int slot) const { return ld(tp.o_f[slot]); }
+    __device__ __forceinline__ float state(int slot) const { return ld(tp.o_f[slot]); }
+    __device__ __forceinline__ float v() const { return ld(tp.o_v); }
+    __device__ __forceinline__ int lft() const { return *reinterpret_cast<const int *>(st + tp.o_lft + tid * 4u); }
+    __device__ __forceinline__ uint32_t flags() const { return st[tp.o_flags + tid]; }
+    __device__ __forceinline__ float t_own(int ty) const { return ld(tp.o_t[ty]); }
+    __device__ __forceinline__ float nt(int slot, int ty) const { return ld(tp.o_nt[slot][ty]); }
+    __device__ __forceinline__ float rc(int slot, int ty) const { return ld(tp.o_rc[slot][ty]); }
+    __device__ __forceinline__ float rc_state(int slot, int ty) const { return ld(tp.o_rc[slot][ty]); }
+    __device__ __forceinline__ uint32_t width() const { return w; }
+    __device__ __forceinline__ uint32_t col(uint32_t kk) const {
+        return *reinterpret_cast<const uint32_t *>(st + tp.o_col + ((warp * w + kk) * 32u + lane) * 4u);
+    }
+    __device__ __forceinline__ float wgt(uint32_t kk) const {
+        return *reinterpret_cast<const float *>(st + tp.o_wgt + ((warp * w + kk) * 32u + lane) * 4u);
+    }
+    __device__ __forceinline__ float *wgt_ptr(uint32_t kk) const { return p.wgt + (size_t)(k0g + kk) * 32u + lane; }
+};
+
+template <int MODEL, int CHEMG, bool NTREL, bool STDP>
+__global__ void __launch_bounds__(kTmaThreads) step_tma_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TmaParams tp) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)tp.stages * tp.stage_bytes);
+    uint64_t *empty = full + tp.stages;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < tp.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTmaConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == kTmaConsumerWarps) {
+        // ---- producer: one lane streams whole tiles ahead of the consumers ---------------------------
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t s = it % tp.stages, ph = (it / tp.stages) & 1u;
+                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_arrive_expect_tx(&full[s], tp.tx_bytes);
+                unsigned char *dst = smem + (size_t)s * tp.stage_bytes;
+                for (uint32_t k = 0; k < tp.n_streams; ++k)
+                    tma_bulk_g2s(dst + tp.st[k].smem_off, tp.st[k].src + (size_t)tile * tp.st[k].bytes_per_tile,
+                                 tp.st[k].bytes_per_tile, &full[s]);
+            }
+        }
+        return;
+    }
+    // ---- consumers: 8 warps x 32 neurons per tile --------------------------------------------------
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x, ++it) {
+        const uint32_t s = it % tp.stages, ph = (it / tp.stages) & 1u;
+        const uint32_t warp_global = tile * kTmaConsumerWarps + warp;
+        const uint32_t ln = warp_global * 32u + lane;
+        const bool active = warp_global * 32u < p.n_neurons;
+        const bool valid = ln < p.n_neurons;
+        const uint32_t lnc = valid ? ln : p.n_neurons - 1;
+        bool export_lo = false, export_hi = false;
+        if (active) halo_import(p, warp_global, lane, ln, valid, export_lo, export_hi);
+        mbar_wait(&full[s], ph);
+        if (active) {
+            const SmemSrc src{p, tp, smem + (size_t)s * tp.stage_bytes, threadIdx.x, lane, warp, p.uniform_width,
+                              warp_global * p.uniform_width};
+            neuron_step<MODEL, CHEMG, NTREL, STDP, false>(p, src, warp_global, lane, ln, lnc, valid, export_lo, export_hi);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (active) halo_publish(p, warp_global, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launcher
+// ------------------------------------------------------------------------------------------------
+template <int MODEL, int CHEMG, bool NTREL>
+static cudaError_t launch_tma_3(const StepParams &p, const TmaParams &tp, bool stdp, unsigned grid, size_t smem, cudaStream_t s) {
+    if (stdp) {
+        auto k = step_tma_kernel<MODEL, CHEMG, NTREL, true>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, kTmaThreads, smem, s>>>(p, tp);
+    } else {
+        auto k = step_tma_kernel<MODEL, CHEMG, NTREL, false>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, kTmaThreads, smem, s>>>(p, tp);
+    }
+    return cudaGetLastError();
+}
+
+template <int MODEL>
+static cudaError_t launch_tma_model(const StepParams &p, const TmaParams &tp, int chemg, bool ntrel, bool stdp, unsigned grid,
+                                    size_t smem, cudaStream_t s) {
+    if (chemg == 1) return launch_tma_3<MODEL, 1, true>(p, tp, stdp, grid, smem, s);
+    if (chemg == 3) return launch_tma_3<MODEL, 3, true>(p, tp, stdp, grid, smem, s);
+    if (ntrel) return launch_tma_3<MODEL, 0, true>(p, tp, stdp, grid, smem, s);
+    return launch_tma_3<MODEL, 0, false>(p, tp, stdp, grid, smem, s);
+}
+
+cudaError_t launch_step_tma(const StepParams &p, const TmaParams &tp, int model, int chemg, bool ntrel, bool stdp, unsigned grid,
+                            cudaStream_t s) {
+    if (p.n_neurons == 0) return cudaSuccess;
+    const size_t smem = (size_t)tp.stages * tp.stage_bytes + 2 * tp.stages * sizeof(uint64_t);
+    switch (model) {
+    case SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE: return launch_tma_model<SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE: return launch_tma_model<SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE: return launch_tma_model<SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE: return launch_tma_model<SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_IZHIKEVICH: return launch_tma_model<SNN_MODEL_IZHIKEVICH>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_tma_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_tma_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_HODGKIN_HUXLEY: return launch_tma_model<SNN_MODEL_HODGKIN_HUXLEY>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace snn

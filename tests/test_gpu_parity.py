@@ -15,6 +15,14 @@ pytestmark = pytest.mark.gpu
 f32 = np.float32
 
 
+@pytest.fixture(autouse=True, params=["auto", "tma"])
+def kernel_path(request, monkeypatch):
+    """Every parity test runs twice: with the automatic kernel choice (general step_kernel for small lattices) and with
+    the TMA-staged persistent kernel forced wherever it is eligible (stencil graphs), so both are held to the same bar."""
+    monkeypatch.setenv("SNN_B200_TMA", "2" if request.param == "tma" else "1")
+    return request.param
+
+
 def pair(oracle_factory, **kw):
     return SC.build_lattice(None, **kw), SC.build_lattice(oracle_factory, **kw)
 

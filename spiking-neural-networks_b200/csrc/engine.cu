@@ -1152,6 +1152,7 @@ bool Engine::build_tma_params(TmaParams &tp, bool ntrel, bool stdp, bool lft_pp,
         }
     }
     if (n >= (uint32_t)kMaxTmaStreams) return false;
+    if (const char *ek = getenv("SNN_B200_TMA_EXPERIMENT_KEEP")) n = std::min<uint32_t>(n, (uint32_t)atoi(ek));  // timing experiment only: results are wrong
     tp.n_streams = n;
     tp.stage_bytes = off;
     tp.tx_bytes = 0;

@@ -24,7 +24,7 @@ __device__ __forceinline__ int lat_index(const StepParams &p, uint32_t ln) {
 }
 
 // STDP::update_weight, plasticity/mod.rs:46-65
-__device__ __forceinline__ float stdp_delta(const LatInfo &L, int t_pre_i, int t_post_i) {
+static __device__ __noinline__ float stdp_delta(const LatInfo &L, int t_pre_i, int t_post_i) {
     float delta_w = 0.f;
     if (t_pre_i >= 0 && t_post_i >= 0) {
         const float t_pre = (float)t_pre_i, t_post = (float)t_post_i;
@@ -91,7 +91,7 @@ __device__ __forceinline__ float receptor_current(int type, float g, float e, fl
 }
 
 // NeuralRefractoriness::get_effect, spike_train/mod.rs:68-73, 84-86, 174-176
-__device__ __forceinline__ float refract_effect(int kind, float k, uint32_t timestep, uint32_t last, float v_max,
+static __device__ __noinline__ float refract_effect(int kind, float k, uint32_t timestep, uint32_t last, float v_max,
                                                 float v_resting, float dt) {
     const float a = v_max - v_resting;
     const float td = (float)(timestep - last);
@@ -128,6 +128,9 @@ __device__ __forceinline__ void halo_wait(const unsigned long long *flag, unsign
 // source policies
 // ------------------------------------------------------------------------------------------------
 struct GlobalSrc {
+    // per-thread HBM loads: issue every parameter load before the edge loop so that the latencies overlap
+    static constexpr bool kEarlyLoads = true;
+    static constexpr bool kCheapEdges = false;
     const StepParams &p;
     uint32_t lnc;   // clamped local neuron number
     uint32_t i;     // node index
@@ -181,7 +184,7 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
         float w[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (u < 4 || full) { c[u] = src.col(kk + u); w[u] = src.wgt(kk + u); }
+            if (u < 4 || full) { c[u] = src.col(kk + u); w[u] = SRC::kCheapEdges ? 0.f : src.wgt(kk + u); }
             else { c[u] = kColPad; w[u] = 0.f; }
         }
         uint32_t j[U];
@@ -218,28 +221,44 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
                 for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? p.t_in[(size_t)ty * p.t_stride + j[u]] : 0.f;
             }
         }
+        // lazy application of the previous step's STDP while the edges stream by: in-edge rule if the post neuron spiked
+        // last step, out-edge rule if the pre neuron did (update_weights_from_neurons, neuron/mod.rs:849-881, 2308-2417);
+        // both use the post lattice's rule.  No edge can get two non-zero updates in one step.  Spikes are rare: one
+        // test per chunk decides whether the slow path runs at all.
+        if (SRC::kCheapEdges) {
+            // operands in shared memory: re-read instead of holding 16 registers across the gather latency
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (u < 4 || full) { c[u] = src.col(kk + u); w[u] = src.wgt(kk + u); }
+        }
+        if (pending) {
+            bool any = post_trig;
+#pragma unroll
+            for (int u = 0; u < U; ++u) any |= (lj[u] == prev);
+            if (any) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool ok = c[u] != kColPad;
+                    bool pre_trig = ok && lj[u] == prev;
+                    if (NET) {
+                        if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
+                    } else {
+                        pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
+                    }
+                    if ((post_trig && ok) || pre_trig) {
+                        const float d = stdp_delta(p.lat[li], lj[u], lft_me);
+                        float wu = w[u] + d;
+                        if (post_trig && pre_trig) wu = wu + d;
+                        w[u] = wu;
+                        *src.wgt_ptr(kk + u) = wu;
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool ok = c[u] != kColPad;
-            float wu = w[u];
-            if (pending) {
-                // lazy application of the previous step's STDP while the edge streams by: in-edge rule if the post
-                // neuron spiked last step, out-edge rule if the pre neuron did (update_weights_from_neurons,
-                // neuron/mod.rs:849-881, 2308-2417); both use the post lattice's rule.  No edge can get two non-zero
-                // updates in one step.
-                bool pre_trig = ok && lj[u] == prev;
-                if (NET) {
-                    if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
-                } else {
-                    pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
-                }
-                if ((post_trig && ok) || pre_trig) {
-                    const float d = stdp_delta(p.lat[li], lj[u], lft_me);
-                    wu = wu + d;
-                    if (post_trig && pre_trig) wu = wu + d;
-                    *src.wgt_ptr(kk + u) = wu;
-                }
-            }
+            const float wu = w[u];
             if (do_e) {
                 float final_input = gap * (vj[u] - v);  // gap_junction, neuron/mod.rs:54-60
                 if (NET) {
@@ -290,11 +309,11 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     float v = src.v();
     const float gap = src.f(F_GAP);
     const float dt = src.f(F_DT);
-    const float v_th = src.f(F_VTH);
     constexpr bool NEEDS_CM = NTREL || MODEL == SNN_MODEL_HODGKIN_HUXLEY || MODEL == SNN_MODEL_IZHIKEVICH ||
                               MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
                               MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
-    const float c_m = NEEDS_CM ? src.f(F_CM) : 1.f;
+    float c_m = 1.f, v_th = 0.f;
+    if (SRC::kEarlyLoads) { if (NEEDS_CM) c_m = src.f(F_CM); v_th = src.f(F_VTH); }
     const int lft_me = (STDP || p.lft_pp) ? src.lft() : 0;
     const uint32_t spk_word_in = __ldg(p.spk_in + (p.own0 >> 5) + warp_global);
     const bool spiking_prev = (spk_word_in >> lane) & 1u;
@@ -304,20 +323,23 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
                          MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
     constexpr bool ADAPT = MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
     constexpr bool LEAKY = MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || ADAPT;
-    // model parameters (only the ones this model reads are loaded; the rest fold away)
-    float w_adapt = (IZH || ADAPT) ? src.state(F_W) : 0.f;
-    const float pa = IZH ? src.f(F_A) : 0.f, pb = IZH ? src.f(F_B) : 0.f;
-    const float pc = IZH ? src.f(F_C) : 0.f, pd = IZH ? src.f(F_D) : 0.f;
-    const float tau_m = (IZH || IF4) ? src.f(F_TAUM) : 1.f;
-    const float e_l = (LEAKY || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH) ? src.f(F_EL) : 0.f;
-    const float v_reset = (IF4 || MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) ? src.f(F_VRESET) : 0.f;
-    const float integ = IF4 ? src.f(F_INTEG) : 0.f;
-    float refr = IF4 ? src.state(F_REFR) : 0.f;
-    const float tref = IF4 ? src.f(F_TREF) : 0.f;
-    const float g_l = LEAKY ? src.f(F_GL) : 1.f;
-    const float leak = LEAKY ? src.f(F_LEAK) : 0.f;
-    const float alpha = (ADAPT || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) ? src.f(F_ALPHA) : 0.f;
-    const float beta = ADAPT ? src.f(F_BETA) : 0.f;
+    // model parameters (only the ones this model reads are loaded; the rest fold away).  With HBM-sourced operands the
+    // loads are issued before the edge loop (latency overlap); with shared-memory operands they are deferred until
+    // after it (they are cheap, and not holding them across the loop saves ~15 registers = one more resident CTA).
+    float w_adapt = 0.f, pa = 0.f, pb = 0.f, pc = 0.f, pd = 0.f, tau_m = 1.f, e_l = 0.f, v_reset = 0.f, integ = 0.f, refr = 0.f,
+          tref = 0.f, g_l = 1.f, leak = 0.f, alpha = 0.f, beta = 0.f;
+    auto load_model_params = [&]() {
+        if (IZH || ADAPT) w_adapt = src.state(F_W);
+        if (IZH) { pa = src.f(F_A); pb = src.f(F_B); pc = src.f(F_C); pd = src.f(F_D); }
+        if (IZH || IF4) tau_m = src.f(F_TAUM);
+        if (LEAKY || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH) e_l = src.f(F_EL);
+        if (IF4 || MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) v_reset = src.f(F_VRESET);
+        if (IF4) { integ = src.f(F_INTEG); refr = src.state(F_REFR); tref = src.f(F_TREF); }
+        if (LEAKY) { g_l = src.f(F_GL); leak = src.f(F_LEAK); }
+        if (ADAPT || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) alpha = src.f(F_ALPHA);
+        if (ADAPT) beta = src.f(F_BETA);
+    };
+    if (SRC::kEarlyLoads) load_model_params();
 
     // the single neurotransmitter type of the CHEMG == 1 fast path
     const uint32_t ty0 = (CHEMG == 1) ? (uint32_t)(__ffs((int)p.nt_used) - 1) : 0u;
@@ -337,6 +359,7 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     const bool do_e = p.electrical != 0;
     const bool do_c = NTREL && p.chemical != 0;
     gather_edges<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
+    if (!SRC::kEarlyLoads) { load_model_params(); if (NEEDS_CM) c_m = src.f(F_CM); v_th = src.f(F_VTH); }
     // neuron/mod.rs:722-729: divide by the number of incoming edges (1 if none)
     const float input = do_e ? A.acc_e / (A.n_in == 0 ? 1.f : (float)A.n_in) : 0.f;
 

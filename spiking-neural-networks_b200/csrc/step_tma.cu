@@ -36,6 +36,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// producer-side wait: back off between probes so that the spinning lane does not eat issue slots of the consumers
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(256);
+    }
+}
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
@@ -44,6 +58,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 }
 
 struct SmemSrc {
+    static constexpr bool kEarlyLoads = false;  // operands sit in shared memory: read them where they are used
+    static constexpr bool kCheapEdges = true;
     const StepParams &p;
     const TmaParams &tp;
     const unsigned char *st;  // this stage
@@ -71,8 +87,11 @@ struct SmemSrc {
     __device__ __forceinline__ float *wgt_ptr(uint32_t kk) const { return p.wgt + (size_t)(k0g + kk) * 32u + lane; }
 };
 
+#ifndef SNN_TMA_MIN_CTAS
+#define SNN_TMA_MIN_CTAS 2
+#endif
 template <int MODEL, int CHEMG, bool NTREL, bool STDP>
-__global__ void __launch_bounds__(kTmaThreads) step_tma_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TmaParams tp) {
+__global__ void __launch_bounds__(kTmaThreads, SNN_TMA_MIN_CTAS) step_tma_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TmaParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)tp.stages * tp.stage_bytes);
     uint64_t *empty = full + tp.stages;
@@ -92,7 +111,7 @@ __global__ void __launch_bounds__(kTmaThreads) step_tma_kernel(const __grid_cons
             uint32_t it = 0;
             for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t s = it % tp.stages, ph = (it / tp.stages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
+                mbar_wait_backoff(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full[s], tp.tx_bytes);
                 unsigned char *dst = smem + (size_t)s * tp.stage_bytes;
                 for (uint32_t k = 0; k < tp.n_streams; ++k)

@@ -1158,9 +1158,11 @@ bool Engine::build_tma_params(TmaParams &tp, bool ntrel, bool stdp, bool lft_pp,
     tp.tx_bytes = 0;
     for (uint32_t k = 0; k < n; ++k) tp.tx_bytes += tp.st[k].bytes_per_tile;
     tp.n_tiles = (uint32_t)((n_neurons + kTmaTile - 1) / kTmaTile);
-    // shared-memory budget: prefer two resident CTAs per SM with 2-4 stages each
+    // shared-memory budget: as many resident CTAs per SM as the kernel's register budget allows (3, or 2 for
+    // Hodgkin-Huxley / general neurotransmitter masks: tma_min_ctas in step_tma.cu) with at least two stages each
     const uint32_t budget = 220 * 1024;
-    uint32_t ctas = 2, stages = (budget / ctas) / off;
+    uint32_t ctas = 3, stages = (budget / ctas) / off;
+    if (stages < 2) { ctas = 2; stages = (budget / ctas) / off; }
     const char *es = getenv("SNN_B200_TMA_STAGES"), *ec = getenv("SNN_B200_TMA_CTAS");
     if (ec) { ctas = (uint32_t)std::max(1, atoi(ec)); stages = (budget / ctas) / off; }
     if (stages < 2) { ctas = 1; stages = budget / off; }

@@ -178,6 +178,7 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
     const bool do_e = p.electrical != 0;
     const int prev = (int)p.clock - 1;
     const float *t0 = (CHEMG == 1) ? p.t_in + (size_t)ty0 * p.t_stride : nullptr;
+    asm volatile("" : "+l"(t0));  // keep the row pointer materialised: one IMAD.WIDE per gather instead of re-deriving ty0 * stride
     for (uint32_t kk = 0; kk < width; kk += U) {
         const bool full = kk + U <= width;
         uint32_t c[U];

@@ -87,11 +87,14 @@ struct SmemSrc {
     __device__ __forceinline__ float *wgt_ptr(uint32_t kk) const { return p.wgt + (size_t)(k0g + kk) * 32u + lane; }
 };
 
-#ifndef SNN_TMA_MIN_CTAS
-#define SNN_TMA_MIN_CTAS 2
-#endif
+// Register budget: three resident CTAs per SM (<= 75 registers) for the light configurations, two for the ones whose
+// live state does not fit (Hodgkin-Huxley, general per-edge neurotransmitter masks) — measured: 3 CTAs/SM is worth
+// +15 % on the Izhikevich + AMPA + STDP workload, but costs 150 B of spills on HH with three receptor types.
+template <int MODEL, int CHEMG>
+constexpr int tma_min_ctas() { return (MODEL == SNN_MODEL_HODGKIN_HUXLEY || CHEMG == 3) ? 2 : 3; }
+
 template <int MODEL, int CHEMG, bool NTREL, bool STDP>
-__global__ void __launch_bounds__(kTmaThreads, SNN_TMA_MIN_CTAS) step_tma_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TmaParams tp) {
+__global__ void __launch_bounds__(kTmaThreads, tma_min_ctas<MODEL, CHEMG>()) step_tma_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TmaParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)tp.stages * tp.stage_bytes);
     uint64_t *empty = full + tp.stages;
@@ -108,23 +111,22 @@ __global__ void __launch_bounds__(kTmaThreads, SNN_TMA_MIN_CTAS) step_tma_kernel
     if (warp == kTmaConsumerWarps) {
         // ---- producer: one lane streams whole tiles ahead of the consumers ---------------------------
         if (lane == 0) {
-            uint32_t it = 0;
-            for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x, ++it) {
-                const uint32_t s = it % tp.stages, ph = (it / tp.stages) & 1u;
+            uint32_t s = 0, ph = 0;
+            for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
                 mbar_wait_backoff(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full[s], tp.tx_bytes);
                 unsigned char *dst = smem + (size_t)s * tp.stage_bytes;
                 for (uint32_t k = 0; k < tp.n_streams; ++k)
                     tma_bulk_g2s(dst + tp.st[k].smem_off, tp.st[k].src + (size_t)tile * tp.st[k].bytes_per_tile,
                                  tp.st[k].bytes_per_tile, &full[s]);
+                if (++s == tp.stages) { s = 0; ph ^= 1u; }
             }
         }
         return;
     }
     // ---- consumers: 8 warps x 32 neurons per tile --------------------------------------------------
-    uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x, ++it) {
-        const uint32_t s = it % tp.stages, ph = (it / tp.stages) & 1u;
+    uint32_t s = 0, ph = 0;
+    for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
         const uint32_t warp_global = tile * kTmaConsumerWarps + warp;
         const uint32_t ln = warp_global * 32u + lane;
         const bool active = warp_global * 32u < p.n_neurons;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(kTmaThreads, SNN_TMA_MIN_CTAS) step_tma_kernel
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (active) halo_publish(p, warp_global, lane);
+        if (++s == tp.stages) { s = 0; ph ^= 1u; }
     }
 }
 

@@ -267,15 +267,22 @@ def main():
     e2e = None
     if not args.no_e2e:
         pinned = {k: torch.from_numpy(v).pin_memory().numpy() for k, v in fields.items()}
-        outs = {}
+        outs = {name: torch.from_numpy(np.empty_like(fields[name])).pin_memory().numpy() for name in STATE_FIELDS}
         h2d = sum(v.nbytes for v in pinned.values())
         barrier()
         t1 = time.perf_counter()
         for _ in range(args.e2e_steps):
+            ta = time.perf_counter()
             configure(be, pinned)
+            tb = time.perf_counter()
             be.run(iters)
+            tc = time.perf_counter()
             for name in STATE_FIELDS:
-                outs[name] = be.get_field(0, name)
+                be.get_field(0, name, out=outs[name])
+            td = time.perf_counter()
+            if os.environ.get("SNN_BENCH_VERBOSE"):
+                print(f"[e2e rank {rank}] upload {1e3 * (tb - ta):.1f} ms, run {1e3 * (tc - tb):.1f} ms, download {1e3 * (td - tc):.1f} ms",
+                      file=sys.stderr, flush=True)
         barrier()
         e2e_wall = time.perf_counter() - t1
         tt = torch.tensor([e2e_wall], dtype=torch.float64, device="cuda")

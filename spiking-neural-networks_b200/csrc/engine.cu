@@ -768,14 +768,26 @@ uint32_t Engine::rc_used() const { refresh_flag_cache(); return rc_used_; }
 int Engine::finalize_graph() {
     if (!graph_dirty_) return SNN_OK;
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
-    if (slice_off_) cudaFree(slice_off_);
-    if (col_) cudaFree(col_);
-    if (wgt_) cudaFree(wgt_);
-    slice_off_ = col_ = nullptr; wgt_ = nullptr;
+    // the stencil fast path re-generates the table in place when its size is unchanged (set_graph_grid called again,
+    // e.g. once per run by a caller that mirrors LatticeGPU's upload-everything-per-run behaviour)
+    const uint32_t new_slices = (uint32_t)((n_neurons + 31) / 32);
+    bool reuse = false;
+    if (blocks_.size() == 1 && blocks_.begin()->second.kind == Block::GRID && col_ && wgt_ && slice_off_ && n_slices_ == new_slices) {
+        const Block &b0 = blocks_.begin()->second;
+        const uint32_t width0 = (2 * b0.radius + 1) * (2 * b0.radius + 1) - 1;
+        reuse = sell_alloc_krows_ == round_up(new_slices, kTmaConsumerWarps) * width0;
+    }
+    if (!reuse) {
+        if (slice_off_) cudaFree(slice_off_);
+        if (col_) cudaFree(col_);
+        if (wgt_) cudaFree(wgt_);
+        slice_off_ = col_ = nullptr; wgt_ = nullptr;
+        sell_alloc_krows_ = 0;
+    }
     grid_fast_ = false;
     uniform_width_ = 0;
-    n_slices_ = (uint32_t)((n_neurons + 31) / 32);
-    CK(dev_alloc(&slice_off_, (size_t)n_slices_ + 1), SNN_GPU_BUFFER_CREATE_ERROR);
+    n_slices_ = new_slices;
+    if (!reuse) CK(dev_alloc(&slice_off_, (size_t)n_slices_ + 1), SNN_GPU_BUFFER_CREATE_ERROR);
     // partitioned handles: ghost rows inherit the neurotransmitter type sets of the adjacent owned rows
     if (part_world > 1 && n_neurons) {
         for (uint32_t g = 0; g < halo_; ++g) {
@@ -795,10 +807,17 @@ int Engine::finalize_graph() {
         const uint32_t width = (2 * b.radius + 1) * (2 * b.radius + 1) - 1;
         sell_krows_ = (uint64_t)n_slices_ * width;
         const uint64_t alloc_krows = round_up(n_slices_, kTmaConsumerWarps) * width;  // whole tiles for the TMA kernel
-        CK(dev_alloc(&col_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
-        CK(dev_alloc(&wgt_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
-        CK(cudaMemsetAsync(col_, 0xFF, alloc_krows * 32 * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
-        CK(cudaMemsetAsync(wgt_, 0, alloc_krows * 32 * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+        if (!reuse) {
+            CK(dev_alloc(&col_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+            CK(dev_alloc(&wgt_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+            sell_alloc_krows_ = alloc_krows;
+            // only the slices beyond the last neuron are not written by the generator
+            const uint64_t tail0 = sell_krows_ * 32, tail_n = (alloc_krows - sell_krows_) * 32;
+            if (tail_n) {
+                CK(cudaMemsetAsync(col_ + tail0, 0xFF, tail_n * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+                CK(cudaMemsetAsync(wgt_ + tail0, 0, tail_n * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+            }
+        }
         if (n_neurons == 0) CK(cudaMemset(slice_off_, 0, 4), SNN_GPU_BUFFER_WRITE_ERROR);
         CK(launch_sell_grid(only->rows, only->cols, part_world > 1 ? row0_global : 0, part_world > 1 ? rows_global : only->rows,
                             b.radius, b.weight, own0_, node_flags_, width, slice_off_, col_, wgt_, stream_), SNN_GPU_QUEUE_FAILURE);

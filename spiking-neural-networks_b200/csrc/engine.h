@@ -148,7 +148,7 @@ private:
     bool dev_weights_newer_ = false;
     bool grid_fast_ = false;
     uint32_t *slice_off_ = nullptr, *col_ = nullptr; float *wgt_ = nullptr;
-    uint64_t sell_krows_ = 0; uint32_t n_slices_ = 0, uniform_width_ = 0;
+    uint64_t sell_krows_ = 0, sell_alloc_krows_ = 0; uint32_t n_slices_ = 0, uniform_width_ = 0;
     // halo
     unsigned long long *flags_ = nullptr;  // [0] arrivals from rank-1, [1] arrivals from rank+1
     unsigned int *halo_done_ = nullptr;

@@ -70,9 +70,13 @@ class _CudaBase:
         a = _as(np.asarray(arr).reshape(-1), _NP[dt])
         self._ck(self._set_field(id, name.encode(), _ptr(a), a.size, dt))
 
-    def get_field(self, id, name):
+    def get_field(self, id, name, out=None):
+        """Read one named field.  `out` may be a preallocated (e.g. pinned) array of the right dtype and size."""
         dt, per = self.field_meta(id, name)
-        out = np.empty(self.size(id) * per, dtype=_NP[dt])
+        if out is None:
+            out = np.empty(self.size(id) * per, dtype=_NP[dt])
+        elif out.dtype != _NP[dt] or out.size != self.size(id) * per or not out.flags.c_contiguous:
+            raise ValueError(f"out buffer for {name} must be contiguous {_NP[dt].__name__}[{self.size(id) * per}]")
         self._ck(self._get_field(id, name.encode(), _ptr(out), out.size, dt))
         return out
 

@@ -106,7 +106,9 @@ void Engine::compute_layout() {
     const uint32_t halo_hi = (part_world > 1 && part_rank < part_world - 1) ? halo_ : 0;
     own0_ = (uint32_t)round_up(halo_lo, 32);
     train0_ = (uint32_t)round_up(own0_ + n_neurons, 32);
-    ghost_hi0_ = train0_;
+    // upper ghosts follow the owned neurons without a gap: the stencil generator addresses the row below the strip as
+    // own0 + rows_local * cols + c
+    ghost_hi0_ = (part_world > 1) ? own0_ + (uint32_t)n_neurons : train0_;
     n_nodes_ = (part_world > 1) ? ghost_hi0_ + halo_hi : train0_ + (uint32_t)n_trains;
     // capacities cover whole 256-neuron tiles so that the TMA-staged kernel may copy full tiles past the last neuron
     node_cap_ = round_up(std::max<uint64_t>(n_nodes_, 1), 32) + kTmaTile + 32;

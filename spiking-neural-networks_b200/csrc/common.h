@@ -146,6 +146,91 @@ struct TmaParams {
 cudaError_t launch_step_tma(const StepParams &p, const TmaParams &tp, int model, int chemg, bool ntrel, bool stdp, unsigned grid,
                             cudaStream_t s);
 
+// ---- window-staged step kernel (step_win.cu): radius-1 stencil lattices ----------------------
+// One persistent CTA per SM; every operand of a 256-neuron tile, INCLUDING the three neighbour row windows of the node
+// arrays (V, last_firing_time, t), is moved into a shared-memory stage by TMA bulk copies.  The stage layout of
+// everything but the per-type chemical parameters is a compile-time function of the kernel's template arguments, so
+// operand addresses are immediates.
+constexpr uint32_t kWinTile = 256;                      // neurons per tile (8 consumer warps)
+constexpr uint32_t kWinRowElems = kWinTile + 8;         // a window row: tile + 1 neighbour each side + 16-byte alignment slack
+constexpr uint32_t kWinRowBytes = kWinRowElems * 4;     // 1056
+constexpr uint32_t kWinWidth = 8;                       // k-rows per slice of a radius-1 stencil
+constexpr uint32_t kWinEdgeBytes = 8 * kWinWidth * 32 * 4;  // col (or weight) bytes per tile
+
+struct WinLayout {
+    uint32_t lrows, trows, tslots;   // window rows kept for last_firing_time / t, neurotransmitter type slots
+    uint32_t o_vwin, o_lwin, o_twin, o_spk, o_flags, o_col, o_wgt;
+    uint32_t o_f[F_NA_CUR];          // 0xFFFFFFFF = not read by this model
+    uint32_t fixed_end;              // first byte after the compile-time part (multiple of 128)
+};
+
+// fields the step of `model` reads (must mirror neuron_step, step_body.cuh)
+__host__ __device__ constexpr bool win_field_read(int model, bool ntrel, int slot) {
+    const bool izh = model == SNN_MODEL_IZHIKEVICH || model == SNN_MODEL_LEAKY_IZHIKEVICH;
+    const bool adapt = model == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || model == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    const bool if4 = model == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || model == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE || adapt;
+    const bool leaky = model == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || adapt;
+    const bool qif = model == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE;
+    const bool simple = model == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE;
+    const bool hh = model == SNN_MODEL_HODGKIN_HUXLEY;
+    switch (slot) {
+    case F_GAP: case F_DT: case F_VTH: return true;
+    case F_CM: return ntrel || hh || izh || adapt;
+    case F_W: return izh || adapt;
+    case F_A: case F_B: case F_C: case F_D: return izh;
+    case F_TAUM: return izh || if4;
+    case F_EL: return leaky || model == SNN_MODEL_LEAKY_IZHIKEVICH;
+    case F_VRESET: return if4 || simple;
+    case F_INTEG: case F_REFR: case F_TREF: return if4;
+    case F_GL: case F_LEAK: return leaky;
+    case F_ALPHA: return adapt || qif;
+    case F_BETA: return adapt;
+    case F_VC: return qif;
+    case F_SLOPE: return model == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
+    case F_G: case F_E: return simple;
+    case F_GNA: case F_ENA: case F_M: case F_H: case F_GK: case F_EK: case F_N: case F_GKL: case F_EKL: return hh;
+    default: return false;
+    }
+}
+
+__host__ __device__ constexpr WinLayout win_layout(int model, int chemg, bool ntrel, bool stdp) {
+    WinLayout L{};
+    uint32_t off = 0;
+    L.lrows = stdp ? 3u : 1u;
+    L.trows = chemg ? 3u : 1u;
+    L.tslots = !ntrel ? 0u : (chemg == 1 ? 1u : (uint32_t)kNT);
+    L.o_vwin = off; off += 3u * kWinRowBytes;
+    L.o_lwin = off; off += L.lrows * kWinRowBytes;
+    L.o_twin = off; off += L.tslots * L.trows * kWinRowBytes;
+    off = (off + 127u) & ~127u;
+    L.o_spk = off; off += 128u;
+    L.o_flags = off; off += kWinTile;
+    L.o_col = off; off += kWinEdgeBytes;
+    L.o_wgt = off; off += kWinEdgeBytes;
+    for (int s = 0; s < F_NA_CUR; ++s) {
+        if (win_field_read(model, ntrel, s)) { L.o_f[s] = off; off += kWinTile * 4u; }
+        else L.o_f[s] = 0xFFFFFFFFu;
+    }
+    L.fixed_end = off;
+    return L;
+}
+
+struct WinParams {
+    uint32_t n_tiles, n_streams, stage_bytes, stages, fixed_tx_bytes;
+    uint32_t node_cap;            // elements allocated per node array (window copies are clamped to [0, node_cap))
+    uint32_t cols;
+    uint32_t lft_copy;            // copy last_firing_time windows at all (STDP or ping-ponged lft)
+    TmaStream st[kMaxTmaStreams]; // per-tile contiguous operands (src + tile * bytes_per_tile)
+    uint32_t o_nt[NTF_COUNT][kNT];   // run-time part of the stage layout: per-type chemical parameters
+    uint32_t o_rc[RCF_COUNT][kNT];
+};
+
+// groups of 8 consumer warps per CTA (register budget: 65536 / ((groups * 8 + 1) * 32))
+__host__ __device__ constexpr int win_groups(int model, int chemg) { return (model == SNN_MODEL_HODGKIN_HUXLEY || chemg == 3) ? 2 : 3; }
+
+cudaError_t launch_step_win(const StepParams &p, const WinParams &wp, int model, int chemg, bool ntrel, bool stdp, unsigned grid,
+                            cudaStream_t s);
+
 // ---- kernel launchers (kernels.cu) ------------------------------------------------------------
 // chemg: 0 no chemical gather, 1 one neurotransmitter type in the whole node array, 3 general; ntrel: neurotransmitter /
 // receptor state is present and must be stepped; net: several lattices and/or spike trains share the node array

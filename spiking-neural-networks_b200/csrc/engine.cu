@@ -1198,6 +1198,88 @@ bool Engine::build_tma_params(TmaParams &tp, bool ntrel, bool stdp, bool lft_pp,
     return true;
 }
 
+// Operand streams of the window-staged kernel (step_win.cu): radius-1 stencil lattices.  false = not eligible.
+bool Engine::build_win_params(WinParams &wp, int chemg, bool ntrel, bool stdp, bool lft_pp, unsigned *grid) {
+    memset(&wp, 0xFF, sizeof wp);
+    if (!grid_fast_ || uniform_width_ != kWinWidth || n_neurons == 0) return false;
+    int mode = use_tma;
+    if (mode < 0) {
+        const char *e = getenv("SNN_B200_TMA");
+        mode = e ? atoi(e) : 1;
+    }
+    if (mode == 0) return false;
+    if (const char *e = getenv("SNN_B200_WIN")) if (atoi(e) == 0) return false;
+    // tiny lattices are launch-latency bound: the persistent kernel only pays off with at least a few tiles per SM
+    if (mode < 2 && n_neurons < 64 * 1024) return false;
+    uint32_t cols = 0;
+    for (auto &L : lats_) if (!L.is_train) cols = L.cols;
+    if (cols == 0) return false;
+    const WinLayout L = win_layout(model, chemg, ntrel, stdp);
+    uint32_t off = L.fixed_end, n = 0, tx = 0;
+    auto add_at = [&](const void *src, uint32_t bytes_per_tile, uint32_t smem_off) {
+        if (n >= (uint32_t)kMaxTmaStreams) { n = kMaxTmaStreams + 1; return; }
+        wp.st[n].src = (const unsigned char *)src;
+        wp.st[n].bytes_per_tile = bytes_per_tile;
+        wp.st[n].smem_off = smem_off;
+        tx += bytes_per_tile;
+        ++n;
+    };
+    auto add = [&](const void *src, uint32_t bytes_per_tile) -> uint32_t {
+        const uint32_t o = off;
+        add_at(src, bytes_per_tile, o);
+        off += (uint32_t)round_up(bytes_per_tile, 128);
+        return o;
+    };
+    const uint32_t fb = kWinTile * 4;
+    if (ntrel) add_at(node_flags_ + own0_, kWinTile, L.o_flags);
+    add_at(col_, kWinEdgeBytes, L.o_col);
+    add_at(wgt_, kWinEdgeBytes, L.o_wgt);
+    for (int sl = 0; sl < F_NA_CUR; ++sl)
+        if (L.o_f[sl] != 0xFFFFFFFFu) {
+            if (!F_[sl]) return false;
+            add_at(F_[sl], fb, L.o_f[sl]);
+        }
+    if (ntrel) {
+        const uint32_t ntu = nt_used(), rcu = rc_used();
+        for (int ty = 0; ty < kNT; ++ty) {
+            if (ntu & (1u << ty)) {
+                wp.o_nt[NTF_TMAX][ty] = add(NT_[NTF_TMAX] + (size_t)ty * node_cap_ + own0_, fb);
+                if (ntk != SNN_NT_DISCRETE_SPIKE) wp.o_nt[NTF_P1][ty] = add(NT_[NTF_P1] + (size_t)ty * node_cap_ + own0_, fb);
+                if (ntk == SNN_NT_DESTEXHE) wp.o_nt[NTF_P2][ty] = add(NT_[NTF_P2] + (size_t)ty * node_cap_ + own0_, fb);
+            }
+            if (rcu & (1u << ty)) {
+                wp.o_rc[RCF_R][ty] = add(RC_[RCF_R] + (size_t)ty * neuron_cap_, fb);
+                wp.o_rc[RCF_G][ty] = add(RC_[RCF_G] + (size_t)ty * neuron_cap_, fb);
+                wp.o_rc[RCF_E][ty] = add(RC_[RCF_E] + (size_t)ty * neuron_cap_, fb);
+                if (rck != SNN_RC_APPROXIMATE) {
+                    wp.o_rc[RCF_K1][ty] = add(RC_[RCF_K1] + (size_t)ty * neuron_cap_, fb);
+                    wp.o_rc[RCF_K2][ty] = add(RC_[RCF_K2] + (size_t)ty * neuron_cap_, fb);
+                }
+                if (ty == SNN_NT_NMDA) wp.o_rc[RCF_MG][ty] = add(RC_[RCF_MG] + (size_t)ty * neuron_cap_, fb);
+            }
+        }
+    }
+    if (n > (uint32_t)kMaxTmaStreams) return false;
+    wp.n_streams = n;
+    wp.stage_bytes = off;
+    wp.fixed_tx_bytes = tx;
+    wp.n_tiles = (uint32_t)((n_neurons + kWinTile - 1) / kWinTile);
+    wp.node_cap = (uint32_t)node_cap_;
+    wp.cols = cols;
+    wp.lft_copy = (stdp || lft_pp) ? 1u : 0u;
+    const uint32_t G = (uint32_t)win_groups(model, chemg);
+    uint32_t stages = (224u * 1024u) / (off + 16u);
+    if (const char *es = getenv("SNN_B200_WIN_STAGES")) stages = std::min<uint32_t>(stages, (uint32_t)std::max(1, atoi(es)));
+    stages = std::min<uint32_t>(stages, 8);
+    if (stages < G) return false;   // the consumer groups need a stage each
+    wp.stages = stages;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    *grid = (unsigned)std::min<uint64_t>((wp.n_tiles + G - 1) / G, (uint64_t)sms);
+    if (*grid == 0) *grid = 1;
+    return true;
+}
+
 int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     if (elapsed_ms) *elapsed_ms = 0.f;
     if (launches) *launches = 0;
@@ -1237,7 +1319,10 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     sp.lft_pp = lft_pp;
     TmaParams tma;
     unsigned tma_grid = 0;
-    const bool tma_ok = !net && build_tma_params(tma, ntrel, stdp, lft_pp, &tma_grid);
+    WinParams win;
+    unsigned win_grid = 0;
+    const bool win_ok = !net && build_win_params(win, chemg, ntrel, stdp, lft_pp, &win_grid);
+    const bool tma_ok = !win_ok && !net && build_tma_params(tma, ntrel, stdp, lft_pp, &tma_grid);
     // indices of the ping-ponged streams, patched every step
     int tma_iv = -1, tma_il = -1, tma_it[kNT] = {-1, -1, -1};
     if (tma_ok) {
@@ -1313,7 +1398,11 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             sp.spike_hist = want_spk ? d_spk + s * n_words : nullptr;
             sp.out_par = (uint32_t)out;
             sp.halo_epoch = halo_epoch_;
-            if (n_neurons && tma_ok) {
+            if (n_neurons && win_ok) {
+                cudaError_t e = launch_step_win(sp, win, model, chemg, ntrel, stdp, win_grid, stream_);
+                if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_win"); break; }
+                n_launch++;
+            } else if (n_neurons && tma_ok) {
                 tma.st[tma_iv].src = (const unsigned char *)(sp.v_in + own0_);
                 if (tma_il >= 0) tma.st[tma_il].src = (const unsigned char *)(sp.lft_in + own0_);
                 for (int ty = 0; ty < kNT; ++ty)

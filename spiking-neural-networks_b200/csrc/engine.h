@@ -181,6 +181,7 @@ private:
     void fill_step_params(StepParams &p);
     int upload_lat_table();
     bool build_tma_params(TmaParams &tp, bool ntrel, bool stdp, bool lft_pp, unsigned *grid);
+    bool build_win_params(WinParams &wp, int chemg, bool ntrel, bool stdp, bool lft_pp, unsigned *grid);
 };
 
 }  // namespace snn

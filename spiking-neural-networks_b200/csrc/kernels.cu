@@ -37,7 +37,9 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     // uniform slice width (stencil graphs): no dependent load for the slice bounds
     const uint32_t k0 = p.uniform_width ? warp_global * p.uniform_width : __ldg(p.slice_off + warp_global);
     const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + warp_global + 1);
-    const GlobalSrc src{p, lnc, p.own0 + lnc, lane, k0, k1};
+    const float *t0 = nullptr;
+    if (CHEMG == 1) t0 = p.t_in + (size_t)(__ffs((int)p.nt_used) - 1) * p.t_stride;
+    const GlobalSrc src{p, lnc, p.own0 + lnc, lane, k0, k1, t0};
     neuron_step<MODEL, CHEMG, NTREL, STDP, NET>(p, src, warp_global, lane, ln, lnc, valid, export_lo, export_hi);
     if (!NET) halo_publish(p, warp_global, lane);
 }

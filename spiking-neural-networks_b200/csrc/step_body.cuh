@@ -131,16 +131,19 @@ struct GlobalSrc {
     // per-thread HBM loads: issue every parameter load before the edge loop so that the latencies overlap
     static constexpr bool kEarlyLoads = true;
     static constexpr bool kCheapEdges = false;
+    static constexpr uint32_t kWidth = 0;   // slice width known at run time only
     const StepParams &p;
     uint32_t lnc;   // clamped local neuron number
     uint32_t i;     // node index
     uint32_t lane;
     uint32_t k0, k1;  // k-rows of this warp's slice
-    __device__ __forceinline__ float f(int slot) const { return __ldg(p.f[slot] + lnc); }
-    __device__ __forceinline__ float state(int slot) const { return p.f[slot][lnc]; }
+    const float *t0;  // CHEMG == 1: row of the single neurotransmitter type in t_in
+    template <int SLOT> __device__ __forceinline__ float f() const { return __ldg(p.f[SLOT] + lnc); }
+    template <int SLOT> __device__ __forceinline__ float state() const { return p.f[SLOT][lnc]; }
     __device__ __forceinline__ float v() const { return p.v_in[i]; }
     __device__ __forceinline__ int lft() const { return p.lft_in[i]; }
     __device__ __forceinline__ uint32_t flags() const { return p.node_flags[i]; }
+    __device__ __forceinline__ uint32_t spk_prev_word(uint32_t warp_global) const { return __ldg(p.spk_in + (p.own0 >> 5) + warp_global); }
     __device__ __forceinline__ float t_own(int ty) const { return p.t_in[(size_t)ty * p.t_stride + i]; }
     __device__ __forceinline__ float nt(int slot, int ty) const { return __ldg(p.nt[slot] + (size_t)ty * p.nt_stride + i); }
     __device__ __forceinline__ float rc(int slot, int ty) const { return __ldg(p.rc[slot] + (size_t)ty * p.rc_stride + lnc); }
@@ -149,6 +152,13 @@ struct GlobalSrc {
     __device__ __forceinline__ uint32_t col(uint32_t kk) const { return __ldg(p.col + (size_t)(k0 + kk) * 32u + lane); }
     __device__ __forceinline__ float wgt(uint32_t kk) const { return p.wgt[(size_t)(k0 + kk) * 32u + lane]; }
     __device__ __forceinline__ float *wgt_ptr(uint32_t kk) const { return p.wgt + (size_t)(k0 + kk) * 32u + lane; }
+    // neighbour gathers: a handle is whatever addresses presynaptic node j (here: j itself, through L1/L2)
+    typedef uint32_t Handle;
+    __device__ __forceinline__ Handle gh(uint32_t j) const { return j; }
+    __device__ __forceinline__ float gv(Handle h) const { return p.v_in[h]; }
+    __device__ __forceinline__ int glft(Handle h) const { return p.lft_in[h]; }
+    __device__ __forceinline__ float gt0(Handle h) const { return t0[h]; }
+    __device__ __forceinline__ float gt(Handle h, int ty) const { return p.t_in[(size_t)ty * p.t_stride + h]; }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -159,7 +169,127 @@ struct EdgeAcc {
     uint32_t n_in;
     float acc_t[kNT];
     uint32_t cnt[kNT];
+    bool fast8;   // warp-uniform: every lane had exactly 8 in-edges (and, CHEMG == 1, all of them release the type):
+                  // the averaging divisions are by 8 = exact multiplications by 0.125
 };
+
+// The lazily applied STDP of the previous step for one chunk of U edges (see gather_edges); shared by both gathers.
+template <int U, bool NET, class SRC>
+__device__ __forceinline__ void stdp_chunk(const StepParams &p, const SRC &src, uint32_t kk, const uint32_t (&c)[U], const uint32_t (&j)[U],
+                                           const int (&lj)[U], float (&w)[U], bool post_trig, int lft_me, int li, int prev) {
+    bool any = post_trig;
+#pragma unroll
+    for (int u = 0; u < U; ++u) any |= (lj[u] == prev);
+    if (!any) return;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool ok = c[u] != kColPad;
+        bool pre_trig = ok && lj[u] == prev;
+        if (NET) {
+            if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
+        } else {
+            pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
+        }
+        if ((post_trig && ok) || pre_trig) {
+            const float d = stdp_delta(p.lat[li], lj[u], lft_me);
+            float wu = w[u] + d;
+            if (post_trig && pre_trig) wu = wu + d;
+            w[u] = wu;
+            *src.wgt_ptr(kk + u) = wu;
+        }
+    }
+}
+
+// Gather for sources whose slices are exactly 8 k-rows wide (radius-1 stencil tables, step_win.cu): one chunk, no loop.
+// FULL (warp-uniform): no lane of the warp has a padding slot and, with a single neurotransmitter type, every
+// presynaptic neuron releases it — the per-edge validity / type tests and the in-edge counters fold away.  The
+// accumulation order and every rounding are those of gather_edges (a skipped `+ 0` term of a padding slot is exact).
+template <int CHEMG, bool STDP, bool FULL, class SRC>
+__device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
+                                                   bool post_trig, int li, uint32_t ty0, const uint32_t (&c)[8], float (&w)[8], EdgeAcc &A) {
+    constexpr int U = 8;
+    const bool pending = STDP && p.apply_pending;
+    const bool do_e = p.electrical != 0;
+    const int prev = (int)p.clock - 1;
+    uint32_t j[U];
+    typename SRC::Handle h[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        j[u] = (FULL || c[u] != kColPad) ? (c[u] & kColIdxMask) : i;
+        h[u] = src.gh(j[u]);
+    }
+    float vj[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) vj[u] = do_e ? src.gv(h[u]) : v;
+    int lj[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) lj[u] = pending ? src.glft(h[u]) : -1;
+    float tj[U][CHEMG == 3 ? kNT : 1];
+    if (CHEMG == 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) tj[u][0] = src.gt0(h[u]);
+    } else if (CHEMG == 3) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t m = (FULL || c[u] != kColPad) ? (c[u] >> kColNtShift) : 0u;
+#pragma unroll
+            for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? src.gt(h[u], ty) : 0.f;
+        }
+    }
+    if (pending) stdp_chunk<U, false>(p, src, 0, c, j, lj, w, post_trig, lft_me, li, prev);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool ok = FULL || c[u] != kColPad;
+        const float wu = w[u];
+        if (do_e) {
+            const float final_input = gap * (vj[u] - v);  // gap_junction, neuron/mod.rs:54-60
+            A.acc_e = A.acc_e + final_input * wu;
+        }
+        if (CHEMG == 1) {
+            const float term = tj[u][0] * wu;
+            if (FULL) {
+                A.acc_t[0] = A.acc_t[0] + term;
+            } else {
+                const bool has = ok && ((c[u] >> (kColNtShift + ty0)) & 1u);
+                A.acc_t[0] = A.acc_t[0] + (has ? term : 0.f);
+                A.cnt[0] += has ? 1u : 0u;
+            }
+        } else if (CHEMG == 3) {
+            const uint32_t m = ok ? (c[u] >> kColNtShift) : 0u;
+#pragma unroll
+            for (int ty = 0; ty < kNT; ++ty) {
+                const bool has = (m >> ty) & 1u;
+                const float term = tj[u][ty] * wu;
+                A.acc_t[ty] = A.acc_t[ty] + (has ? term : 0.f);
+                A.cnt[ty] += has ? 1u : 0u;
+            }
+        }
+        if (!FULL) A.n_in += ok ? 1u : 0u;
+    }
+    if (FULL) {
+        A.n_in = 8u;
+        if (CHEMG == 1) A.cnt[0] = 8u;
+    }
+}
+
+template <int CHEMG, bool STDP, class SRC>
+__device__ __forceinline__ void gather_edges8(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
+                                              bool post_trig, int li, uint32_t ty0, EdgeAcc &A) {
+    uint32_t c[8];
+    float w[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { c[u] = src.col(u); w[u] = src.wgt(u); }
+    // sliced-ELL rows keep their valid entries first (sell_grid_kernel / sell_from_csr_kernel pad at the end), so a valid
+    // last slot means a full row
+    bool lane_full = c[7] != kColPad;
+    if (CHEMG == 1) {
+        const uint32_t all = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
+        lane_full = lane_full && ((all >> (kColNtShift + ty0)) & 1u);
+    }
+    A.fast8 = __all_sync(0xffffffffu, lane_full);
+    if (A.fast8) gather_edges8_body<CHEMG, STDP, true>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, w, A);
+    else gather_edges8_body<CHEMG, STDP, false>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, w, A);
+}
 
 // CHEMG: 0 = no chemical gather, 1 = exactly one neurotransmitter type in the whole node array (type index ty0),
 //        3 = general per-edge type masks.  NET: the node array holds several lattices and/or spike trains.
@@ -173,12 +303,10 @@ template <int CHEMG, bool STDP, bool NET, class SRC>
 __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
                                              bool post_trig, int li, uint32_t ty0, EdgeAcc &A) {
     constexpr int U = 8;
-    const uint32_t width = src.width();
+    const uint32_t width = SRC::kWidth ? SRC::kWidth : src.width();
     const bool pending = STDP && p.apply_pending;
     const bool do_e = p.electrical != 0;
     const int prev = (int)p.clock - 1;
-    const float *t0 = (CHEMG == 1) ? p.t_in + (size_t)ty0 * p.t_stride : nullptr;
-    asm volatile("" : "+l"(t0));  // keep the row pointer materialised: one IMAD.WIDE per gather instead of re-deriving ty0 * stride
     for (uint32_t kk = 0; kk < width; kk += U) {
         const bool full = kk + U <= width;
         uint32_t c[U];
@@ -189,12 +317,13 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
             else { c[u] = kColPad; w[u] = 0.f; }
         }
         uint32_t j[U];
+        typename SRC::Handle h[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) j[u] = (c[u] == kColPad) ? i : (c[u] & kColIdxMask);
+        for (int u = 0; u < U; ++u) { j[u] = (c[u] == kColPad) ? i : (c[u] & kColIdxMask); h[u] = src.gh(j[u]); }
         float vj[U];
         if (do_e) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) vj[u] = p.v_in[j[u]];
+            for (int u = 0; u < U; ++u) vj[u] = src.gv(h[u]);
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) vj[u] = v;
@@ -205,7 +334,7 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
             // see the train's last_firing_time from before its step-s iterate, which still sits in the other
             // ping-pong buffer (the train kernel of this step has not run yet)
 #pragma unroll
-            for (int u = 0; u < U; ++u) lj[u] = (NET && (c[u] & kColTrainBit) && c[u] != kColPad) ? p.lft_out[j[u]] : p.lft_in[j[u]];
+            for (int u = 0; u < U; ++u) lj[u] = (NET && (c[u] & kColTrainBit) && c[u] != kColPad) ? p.lft_out[j[u]] : src.glft(h[u]);
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) lj[u] = -1;
@@ -213,13 +342,13 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
         float tj[U][CHEMG == 3 ? kNT : 1];
         if (CHEMG == 1) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) tj[u][0] = t0[j[u]];
+            for (int u = 0; u < U; ++u) tj[u][0] = src.gt0(h[u]);
         } else if (CHEMG == 3) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const uint32_t m = (c[u] == kColPad) ? 0u : (c[u] >> kColNtShift);
 #pragma unroll
-                for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? p.t_in[(size_t)ty * p.t_stride + j[u]] : 0.f;
+                for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? src.gt(h[u], ty) : 0.f;
             }
         }
         // lazy application of the previous step's STDP while the edges stream by: in-edge rule if the post neuron spiked
@@ -232,30 +361,7 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
             for (int u = 0; u < U; ++u)
                 if (u < 4 || full) { c[u] = src.col(kk + u); w[u] = src.wgt(kk + u); }
         }
-        if (pending) {
-            bool any = post_trig;
-#pragma unroll
-            for (int u = 0; u < U; ++u) any |= (lj[u] == prev);
-            if (any) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool ok = c[u] != kColPad;
-                    bool pre_trig = ok && lj[u] == prev;
-                    if (NET) {
-                        if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
-                    } else {
-                        pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
-                    }
-                    if ((post_trig && ok) || pre_trig) {
-                        const float d = stdp_delta(p.lat[li], lj[u], lft_me);
-                        float wu = w[u] + d;
-                        if (post_trig && pre_trig) wu = wu + d;
-                        w[u] = wu;
-                        *src.wgt_ptr(kk + u) = wu;
-                    }
-                }
-            }
-        }
+        if (pending) stdp_chunk<U, NET>(p, src, kk, c, j, lj, w, post_trig, lft_me, li, prev);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const bool ok = c[u] != kColPad;
@@ -308,15 +414,15 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     const uint32_t i = p.own0 + lnc;
     // ---- own state and parameters ------------------------------------------------------------------
     float v = src.v();
-    const float gap = src.f(F_GAP);
-    const float dt = src.f(F_DT);
+    const float gap = src.template f<F_GAP>();
+    const float dt = src.template f<F_DT>();
     constexpr bool NEEDS_CM = NTREL || MODEL == SNN_MODEL_HODGKIN_HUXLEY || MODEL == SNN_MODEL_IZHIKEVICH ||
                               MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
                               MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
     float c_m = 1.f, v_th = 0.f;
-    if (SRC::kEarlyLoads) { if (NEEDS_CM) c_m = src.f(F_CM); v_th = src.f(F_VTH); }
+    if (SRC::kEarlyLoads) { if constexpr (NEEDS_CM) c_m = src.template f<F_CM>(); v_th = src.template f<F_VTH>(); }
     const int lft_me = (STDP || p.lft_pp) ? src.lft() : 0;
-    const uint32_t spk_word_in = __ldg(p.spk_in + (p.own0 >> 5) + warp_global);
+    const uint32_t spk_word_in = NTREL ? src.spk_prev_word(warp_global) : 0u;
     const bool spiking_prev = (spk_word_in >> lane) & 1u;
     const uint32_t flags = NTREL ? src.flags() : 0u;
     constexpr bool IZH = MODEL == SNN_MODEL_IZHIKEVICH || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH;
@@ -330,15 +436,15 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     float w_adapt = 0.f, pa = 0.f, pb = 0.f, pc = 0.f, pd = 0.f, tau_m = 1.f, e_l = 0.f, v_reset = 0.f, integ = 0.f, refr = 0.f,
           tref = 0.f, g_l = 1.f, leak = 0.f, alpha = 0.f, beta = 0.f;
     auto load_model_params = [&]() {
-        if (IZH || ADAPT) w_adapt = src.state(F_W);
-        if (IZH) { pa = src.f(F_A); pb = src.f(F_B); pc = src.f(F_C); pd = src.f(F_D); }
-        if (IZH || IF4) tau_m = src.f(F_TAUM);
-        if (LEAKY || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH) e_l = src.f(F_EL);
-        if (IF4 || MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) v_reset = src.f(F_VRESET);
-        if (IF4) { integ = src.f(F_INTEG); refr = src.state(F_REFR); tref = src.f(F_TREF); }
-        if (LEAKY) { g_l = src.f(F_GL); leak = src.f(F_LEAK); }
-        if (ADAPT || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) alpha = src.f(F_ALPHA);
-        if (ADAPT) beta = src.f(F_BETA);
+        if constexpr (IZH || ADAPT) w_adapt = src.template state<F_W>();
+        if constexpr (IZH) { pa = src.template f<F_A>(); pb = src.template f<F_B>(); pc = src.template f<F_C>(); pd = src.template f<F_D>(); }
+        if constexpr (IZH || IF4) tau_m = src.template f<F_TAUM>();
+        if constexpr (LEAKY || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH) e_l = src.template f<F_EL>();
+        if constexpr (IF4 || MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) v_reset = src.template f<F_VRESET>();
+        if constexpr (IF4) { integ = src.template f<F_INTEG>(); refr = src.template state<F_REFR>(); tref = src.template f<F_TREF>(); }
+        if constexpr (LEAKY) { g_l = src.template f<F_GL>(); leak = src.template f<F_LEAK>(); }
+        if constexpr (ADAPT || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) alpha = src.template f<F_ALPHA>();
+        if constexpr (ADAPT) beta = src.template f<F_BETA>();
     };
     if (SRC::kEarlyLoads) load_model_params();
 
@@ -359,10 +465,14 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     for (int ty = 0; ty < kNT; ++ty) { A.acc_t[ty] = 0.f; A.cnt[ty] = 0; }
     const bool do_e = p.electrical != 0;
     const bool do_c = NTREL && p.chemical != 0;
-    gather_edges<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
-    if (!SRC::kEarlyLoads) { load_model_params(); if (NEEDS_CM) c_m = src.f(F_CM); v_th = src.f(F_VTH); }
+    A.fast8 = false;
+    if constexpr (SRC::kWidth == 8 && !NET) gather_edges8<CHEMG, STDP>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
+    else gather_edges<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
+    if (!SRC::kEarlyLoads) { load_model_params(); if constexpr (NEEDS_CM) c_m = src.template f<F_CM>(); v_th = src.template f<F_VTH>(); }
     // neuron/mod.rs:722-729: divide by the number of incoming edges (1 if none)
-    const float input = do_e ? A.acc_e / (A.n_in == 0 ? 1.f : (float)A.n_in) : 0.f;
+    // (x / 8 == x * 0.125 exactly, subnormals included: both round the same real number)
+    float input = 0.f;
+    if (do_e) input = A.fast8 ? A.acc_e * 0.125f : A.acc_e / (A.n_in == 0 ? 1.f : (float)A.n_in);
 
     // ---- receptors (iterate_with_neurotransmitter_and_spike: kinetics then currents from pre-update V)
     float rc_total = 0.f;
@@ -377,7 +487,7 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
                 const uint32_t cnt = (CHEMG == 1) ? (ty == (int)ty0 ? A.cnt[0] : 0u) : A.cnt[ty];
                 if (cnt > 0) {
                     const float acc = (CHEMG == 1) ? A.acc_t[0] : A.acc_t[ty];
-                    const float tin = acc / (float)cnt;
+                    const float tin = (CHEMG == 1 && A.fast8) ? acc * 0.125f : acc / (float)cnt;
                     float k1 = 0.f, k2 = 0.f;
                     if (p.rck != SNN_RC_APPROXIMATE) { k1 = src.rc(RCF_K1, ty); k2 = src.rc(RCF_K2, ty); }
                     r = rc_apply(p.rck, r, k1, k2, tin, dt);
@@ -419,12 +529,12 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
         if constexpr (MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE) {  // :176-181
             dv = ((leak * (v - e_l)) + (integ * (input / g_l))) * (dt / tau_m);
         } else if constexpr (MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) {  // :324-327
-            dv = (((alpha * (v - v_reset)) * (v - src.f(F_VC))) + integ * input) * (dt / tau_m);
+            dv = (((alpha * (v - v_reset)) * (v - src.template f<F_VC>())) + integ * input) * (dt / tau_m);
         } else {
             if constexpr (MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE)  // :1035-1041
                 dv = (((leak * (v - e_l)) + (integ * (input / g_l))) - (w_adapt / g_l)) * (dt / c_m);
             else {                                                                  // :1138-1145
-                const float sf = src.f(F_SLOPE);
+                const float sf = src.template f<F_SLOPE>();
                 dv = ((((leak * (v - e_l)) + (sf * expf((v - v_th) / sf))) + (integ * (input / g_l))) - (w_adapt / g_l)) * (dt / c_m);
             }
             dw = (alpha * (v - e_l) - w_adapt) * (dt / tau_m);  // :1002-1009
@@ -447,25 +557,25 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
             if (ADAPT) p.f[F_W][lnc] = w_adapt;
         }
     } else if constexpr (MODEL == SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE) {
-        const float dv = (src.f(F_G) * (v - src.f(F_E)) + input) * dt;  // :1592-1594
+        const float dv = (src.template f<F_G>() * (v - src.template f<F_E>()) + input) * dt;  // :1592-1594
         if (do_c) v += dv + (-rc_dv); else v += dv;
         v_release = v;
         if (v >= v_th) { spike = true; v = v_reset; }  // :1579-1590
     } else {  // Hodgkin-Huxley, hodgkin_huxley/mod.rs:156-241; ion_channels/mod.rs:40-44, 219-235, 268-281, 310-312
         const float last_voltage = v;
-        float m = src.state(F_M), h = src.state(F_H), n = src.state(F_N);
+        float m = src.template state<F_M>(), h = src.template state<F_H>(), n = src.template state<F_N>();
         const float m_alpha = 0.1f * ((v + 40.f) / (1.f - expf(-(v + 40.f) / 10.f)));
         const float m_beta = 4.f * expf(-(v + 65.f) / 18.f);
         const float h_alpha = 0.07f * expf(-(v + 65.f) / 20.f);
         const float h_beta = 1.f / (expf(-(v + 35.f) / 10.f) + 1.f);
         m += dt * (m_alpha * (1.f - m) - m_beta * m);
         h += dt * (h_alpha * (1.f - h) - h_beta * h);
-        const float i_na = ((powf(m, 3.f) * h) * src.f(F_GNA)) * (v - src.f(F_ENA));
+        const float i_na = ((powf(m, 3.f) * h) * src.template f<F_GNA>()) * (v - src.template f<F_ENA>());
         const float n_alpha = (0.01f * (v + 55.f)) / (1.f - expf(-(v + 55.f) / 10.f));
         const float n_beta = 0.125f * expf(-(v + 65.f) / 80.f);
         n += dt * (n_alpha * (1.f - n) - n_beta * n);
-        const float i_k = (powf(n, 4.f) * src.f(F_GK)) * (v - src.f(F_EK));
-        const float i_kl = src.f(F_GKL) * (v - src.f(F_EKL));
+        const float i_k = (powf(n, 4.f) * src.template f<F_GK>()) * (v - src.template f<F_EK>());
+        const float i_kl = src.template f<F_GKL>() * (v - src.template f<F_EKL>());
         const float i_sum = input - ((i_na + i_k) + i_kl);
         v += (dt * i_sum) / c_m - rc_dv;
         v_release = v;
@@ -545,6 +655,15 @@ __device__ __forceinline__ void halo_import(const StepParams &p, uint32_t warp_g
     }
     export_lo = near_lo && valid && ln >= p.halo[0].first && ln < p.halo[0].first + p.halo[0].count;
     export_hi = near_hi && valid && ln >= p.halo[1].first && ln < p.halo[1].first + p.halo[1].count;
+}
+
+// ---- multi-GPU, window kernel: ghosts arrive through the producer's TMA copies (it does the waiting), consumers only
+// need to know which of their neurons are exported
+__device__ __forceinline__ void halo_export_flags(const StepParams &p, uint32_t ln, bool valid, bool &export_lo, bool &export_hi) {
+    export_lo = export_hi = false;
+    if (!(p.halo[0].active | p.halo[1].active)) return;
+    export_lo = p.halo[0].active && valid && ln >= p.halo[0].first && ln < p.halo[0].first + p.halo[0].count;
+    export_hi = p.halo[1].active && valid && ln >= p.halo[1].first && ln < p.halo[1].first + p.halo[1].count;
 }
 
 // ---- multi-GPU: publish "my boundary values of this step have landed" to each neighbour.  Every exporting warp

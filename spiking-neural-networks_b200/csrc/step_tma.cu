@@ -11,51 +11,9 @@
 //
 // Grid = resident CTAs (SM count x CTAs/SM), tiles are taken round-robin; 288 threads = 8 consumer warps + 1 producer.
 #include "step_body.cuh"
+#include "tma_util.cuh"
 
 namespace snn {
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// producer-side wait: back off between probes so that the spinning lane does not eat issue slots of the consumers
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (true) {
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-        if (done) break;
-        __nanosleep(256);
-    }
-}
-// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 struct SmemSrc {
     static constexpr bool kEarlyLoads = false;  // operands sit in shared memory: read them where they are used
@@ -68,8 +26,17 @@ struct SmemSrc {
     uint32_t w;               // uniform slice width
     uint32_t k0g;             // first k-row of this warp's slice in the global edge arrays
     __device__ __forceinline__ float ld(uint32_t off) const { return *reinterpret_cast<const float *>(st + off + tid * 4u); }
-    __device__ __forceinline__ float f(int slot) const { return ld(tp.o_f[slot]); }
-    __device__ __forceinline__ float state(int slot) const { return ld(tp.o_f[slot]); }
+    static constexpr uint32_t kWidth = 0;
+    const float *t0;          // CHEMG == 1: row of the single neurotransmitter type in t_in
+    template <int SLOT> __device__ __forceinline__ float f() const { return ld(tp.o_f[SLOT]); }
+    template <int SLOT> __device__ __forceinline__ float state() const { return ld(tp.o_f[SLOT]); }
+    __device__ __forceinline__ uint32_t spk_prev_word(uint32_t warp_global) const { return __ldg(p.spk_in + (p.own0 >> 5) + warp_global); }
+    typedef uint32_t Handle;
+    __device__ __forceinline__ Handle gh(uint32_t j) const { return j; }
+    __device__ __forceinline__ float gv(Handle h) const { return p.v_in[h]; }
+    __device__ __forceinline__ int glft(Handle h) const { return p.lft_in[h]; }
+    __device__ __forceinline__ float gt0(Handle h) const { return t0[h]; }
+    __device__ __forceinline__ float gt(Handle h, int ty) const { return p.t_in[(size_t)ty * p.t_stride + h]; }
     __device__ __forceinline__ float v() const { return ld(tp.o_v); }
     __device__ __forceinline__ int lft() const { return *reinterpret_cast<const int *>(st + tp.o_lft + tid * 4u); }
     __device__ __forceinline__ uint32_t flags() const { return st[tp.o_flags + tid]; }
@@ -136,8 +103,10 @@ __global__ void __launch_bounds__(kTmaThreads, tma_min_ctas<MODEL, CHEMG>()) ste
         if (active) halo_import(p, warp_global, lane, ln, valid, export_lo, export_hi);
         mbar_wait(&full[s], ph);
         if (active) {
+            const float *t0 = nullptr;
+            if (CHEMG == 1) t0 = p.t_in + (size_t)(__ffs((int)p.nt_used) - 1) * p.t_stride;
             const SmemSrc src{p, tp, smem + (size_t)s * tp.stage_bytes, threadIdx.x, lane, warp, p.uniform_width,
-                              warp_global * p.uniform_width};
+                              warp_global * p.uniform_width, t0};
             neuron_step<MODEL, CHEMG, NTREL, STDP, false>(p, src, warp_global, lane, ln, lnc, valid, export_lo, export_hi);
         }
         __syncwarp();

@@ -15,11 +15,14 @@ pytestmark = pytest.mark.gpu
 f32 = np.float32
 
 
-@pytest.fixture(autouse=True, params=["auto", "tma"])
+@pytest.fixture(autouse=True, params=["auto", "tma", "tma_l1"])
 def kernel_path(request, monkeypatch):
-    """Every parity test runs twice: with the automatic kernel choice (general step_kernel for small lattices) and with
-    the TMA-staged persistent kernel forced wherever it is eligible (stencil graphs), so both are held to the same bar."""
-    monkeypatch.setenv("SNN_B200_TMA", "2" if request.param == "tma" else "1")
+    """Every parity test runs three times: with the automatic kernel choice (general step_kernel for small lattices), with
+    the TMA-staged persistent kernels forced wherever they are eligible (stencil graphs: the window-staged step_win_kernel
+    for radius 1, the L1-gather step_tma_kernel for larger radii), and with the window kernel disabled so that
+    step_tma_kernel also serves radius 1 — all three are held to the same bar."""
+    monkeypatch.setenv("SNN_B200_TMA", "1" if request.param == "auto" else "2")
+    monkeypatch.setenv("SNN_B200_WIN", "0" if request.param == "tma_l1" else "1")
     return request.param
 
 

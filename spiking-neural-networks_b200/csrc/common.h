@@ -102,6 +102,7 @@ struct StepParams {
     unsigned long long halo_epoch;   // value the arrival counters must reach before ghosts are read
     uint32_t out_par;                // parity of the *_out ping-pong buffers (same on every rank)
     unsigned int *halo_done;         // [2] per-direction CTA completion counters
+    unsigned long long *dbg;         // SNN_DEBUG_TIMING: {clock64, globaltimer} at the start and end of CTA 0 (else null)
 };
 
 struct TrainParams {

@@ -1,5 +1,6 @@
 // engine.cu — host runtime: device memory layout, named-field I/O, graph ingestion, the step loop.
 #include "engine.h"
+#include <chrono>
 
 #include <algorithm>
 #include <cstdio>
@@ -1385,9 +1386,16 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     while (done < iterations && status == SNN_OK) {
         const uint64_t steps = std::min(chunk, iterations - done);
         cudaEventRecord(ev0_, stream_);
+        const auto host_t0 = std::chrono::steady_clock::now();
+        static const bool dbg_timing = getenv("SNN_DEBUG_TIMING") != nullptr;
+        std::vector<cudaEvent_t> dbg_ev;
+        unsigned long long *dbg_clk = nullptr;
+        if (dbg_timing && steps <= 32) { cudaMalloc(&dbg_clk, 32 * 4 * sizeof(unsigned long long)); cudaMemset(dbg_clk, 0, 32 * 4 * sizeof(unsigned long long)); }
         for (uint64_t s = 0; s < steps; ++s) {
+            if (dbg_timing && steps <= 32) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, stream_); dbg_ev.push_back(ev); }
             const int in = cur_, out = cur_ ^ 1;
             sp.clock = (uint32_t)internal_clock;
+            sp.dbg = dbg_clk ? dbg_clk + 4 * s : nullptr;
             sp.apply_pending = (stdp && !first_step) ? 1u : 0u;
             sp.v_in = V_[in]; sp.v_out = V_[out];
             sp.spk_in = SPK_[in]; sp.spk_out = SPK_[out];
@@ -1452,8 +1460,35 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             n_launch++;
         }
         cudaEventRecord(ev1_, stream_);
+        const auto host_t1 = std::chrono::steady_clock::now();
         cudaError_t e = cudaStreamSynchronize(stream_);
         if (e != cudaSuccess) { bail(e, SNN_GPU_WAIT_ERROR, "cudaStreamSynchronize(step loop)"); break; }
+        if (dbg_timing && !dbg_ev.empty()) {
+            fprintf(stderr, "[snn] per-step device us:");
+            for (size_t k = 0; k < dbg_ev.size(); ++k) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, dbg_ev[k], k + 1 < dbg_ev.size() ? dbg_ev[k + 1] : ev1_);
+                fprintf(stderr, " %.0f", ms * 1e3f);
+                cudaEventDestroy(dbg_ev[k]);
+            }
+            fprintf(stderr, "\n");
+            if (dbg_clk) {
+                unsigned long long h[32 * 4];
+                cudaMemcpy(h, dbg_clk, sizeof h, cudaMemcpyDeviceToHost);
+                fprintf(stderr, "[snn] effective SM MHz of CTA 0 per step:");
+                for (uint64_t k = 0; k < steps; ++k)
+                    if (h[4 * k + 3] > h[4 * k + 1]) fprintf(stderr, " %.0f", (double)(h[4 * k + 2] - h[4 * k]) * 1e3 / (double)(h[4 * k + 3] - h[4 * k + 1]));
+                fprintf(stderr, "\n");
+                cudaFree(dbg_clk);
+            }
+        }
+        sp.dbg = nullptr;
+        if (dbg_timing) {
+            const auto host_t2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "[snn] %llu steps: enqueue %.1f us/step on the host, then waited %.1f us/step\n", (unsigned long long)steps,
+                    std::chrono::duration<double, std::micro>(host_t1 - host_t0).count() / steps,
+                    std::chrono::duration<double, std::micro>(host_t2 - host_t1).count() / steps);
+        }
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev0_, ev1_);
         total_ms += ms;

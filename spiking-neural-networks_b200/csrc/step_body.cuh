@@ -174,30 +174,112 @@ struct EdgeAcc {
 };
 
 // The lazily applied STDP of the previous step for one chunk of U edges (see gather_edges); shared by both gathers.
+//
+// Spikes are rare (~0.2 % of the neurons per step in the bench workload) but a warp that meets one used to walk its
+// U edges serially through a divergent call of stdp_delta (ncu, profiles/r1_step_win_active_full.txt: +20 % kernel
+// time at that spike rate because the slow warp holds its shared-memory stage).  The work is spread over the warp
+// instead, with the same stdp_delta evaluations on the same operands (bit-identical weights):
+//   * out-edge rule (the presynaptic neuron spiked): delta(prev, last_firing_time of this lane) does not depend on the
+//     edge, so every lane evaluates it once, without divergence;
+//   * in-edge rule (this lane's neuron spiked): its U deltas delta(lj[u], prev) are evaluated by lanes 0..U-1 in
+//     parallel and shuffled back.
 template <int U, bool NET, class SRC>
 __device__ __forceinline__ void stdp_chunk(const StepParams &p, const SRC &src, uint32_t kk, const uint32_t (&c)[U], const uint32_t (&j)[U],
                                            const int (&lj)[U], float (&w)[U], bool post_trig, int lft_me, int li, int prev) {
-    bool any = post_trig;
+    constexpr uint32_t kAll = 0xffffffffu;
+    {   // one cheap test per chunk decides whether the warp has anything to do
+        bool any = post_trig;
 #pragma unroll
-    for (int u = 0; u < U; ++u) any |= (lj[u] == prev);
-    if (!any) return;
+        for (int u = 0; u < U; ++u) any |= (lj[u] == prev);
+        if (!__any_sync(kAll, any)) return;
+    }
+    uint32_t pre_mask = 0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const bool ok = c[u] != kColPad;
-        bool pre_trig = ok && lj[u] == prev;
+        bool pre_trig = c[u] != kColPad && lj[u] == prev;
         if (NET) {
             if (pre_trig) pre_trig = !(c[u] & kColTrainBit) && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
         } else {
             pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
         }
-        if ((post_trig && ok) || pre_trig) {
-            const float d = stdp_delta(p.lat[li], lj[u], lft_me);
-            float wu = w[u] + d;
-            if (post_trig && pre_trig) wu = wu + d;
+        pre_mask |= (pre_trig ? 1u : 0u) << u;
+    }
+    const uint32_t post_lanes = __ballot_sync(kAll, post_trig);
+    const bool any_pre = __any_sync(kAll, pre_mask != 0u);
+    if (post_lanes == 0u && !any_pre) return;   // warp-uniform
+    const int lane = (int)(threadIdx.x & 31u);
+    float d_pre = 0.f;
+    if (any_pre) d_pre = stdp_delta(p.lat[li], prev, lft_me);
+    for (uint32_t rem = post_lanes; rem != 0u; rem &= rem - 1u) {
+        const int src_lane = __ffs((int)rem) - 1;
+        int t_pre = -1;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int x = __shfl_sync(kAll, lj[u], src_lane);
+            if (lane == u) t_pre = x;
+        }
+        const int li_src = NET ? __shfl_sync(kAll, li, src_lane) : 0;
+        const float d = (lane < U) ? stdp_delta(p.lat[li_src], t_pre, prev) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float x = __shfl_sync(kAll, d, u);
+            if (lane == src_lane && c[u] != kColPad) w[u] = w[u] + x;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool in_rule = post_trig && c[u] != kColPad, out_rule = (pre_mask >> u) & 1u;
+        if (in_rule || out_rule) {
+            float wu = w[u];                 // the in-edge delta was added above
+            if (out_rule) wu = wu + d_pre;   // both rules on one edge: t_pre == t_post, both deltas are 0
             w[u] = wu;
             *src.wgt_ptr(kk + u) = wu;
         }
     }
+}
+
+// The same lazy STDP for sources whose weight rows sit in a shared-memory stage (step_win.cu).  It runs BEFORE the
+// gather loads the weights and updates them in place (stage and HBM), so the common path carries no register state of
+// the rare path: the weight registers are loaded afterwards, and a warp without a trigger leaves after one vote.
+template <class SRC>
+__device__ __forceinline__ void stdp_chunk8_staged(const StepParams &p, const SRC &src, const uint32_t (&c)[8], const int (&lj)[8],
+                                                   bool post_trig, int lft_me, int li, int prev) {
+    constexpr uint32_t kAll = 0xffffffffu;
+    {
+        bool any = post_trig;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) any |= (lj[u] == prev);
+        if (!__any_sync(kAll, any)) return;
+    }
+    const bool plastic = p.lat[0].do_plasticity != 0;
+    uint32_t pre_mask = 0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) pre_mask |= ((plastic && c[u] != kColPad && lj[u] == prev) ? 1u : 0u) << u;
+    const int lane = (int)(threadIdx.x & 31u);
+    // in-edge rule: the 8 deltas of a neuron that spiked are evaluated by lanes 0..7 in parallel
+    for (uint32_t rem = __ballot_sync(kAll, post_trig); rem != 0u; rem &= rem - 1u) {
+        const int src_lane = __ffs((int)rem) - 1;
+        int t_pre = -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int x = __shfl_sync(kAll, lj[u], src_lane);
+            if (lane == u) t_pre = x;
+        }
+        const float d = (lane < 8) ? stdp_delta(p.lat[li], t_pre, prev) : 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float x = __shfl_sync(kAll, d, u);
+            if (lane == src_lane && c[u] != kColPad) src.wgt_update(u, src.wgt(u) + x);
+        }
+    }
+    // out-edge rule: delta(prev, own last_firing_time) is the same for every edge of a lane
+    if (__any_sync(kAll, pre_mask != 0u)) {
+        const float d_pre = stdp_delta(p.lat[li], prev, lft_me);
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if ((pre_mask >> u) & 1u) src.wgt_update(u, src.wgt(u) + d_pre);   // both rules on one edge: both deltas are 0
+    }
+    src.wgt_updates_done();
 }
 
 // Gather for sources whose slices are exactly 8 k-rows wide (radius-1 stencil tables, step_win.cu): one chunk, no loop.
@@ -206,7 +288,7 @@ __device__ __forceinline__ void stdp_chunk(const StepParams &p, const SRC &src, 
 // accumulation order and every rounding are those of gather_edges (a skipped `+ 0` term of a padding slot is exact).
 template <int CHEMG, bool STDP, bool FULL, class SRC>
 __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
-                                                   bool post_trig, int li, uint32_t ty0, const uint32_t (&c)[8], float (&w)[8], EdgeAcc &A) {
+                                                   bool post_trig, int li, uint32_t ty0, const uint32_t (&c)[8], EdgeAcc &A) {
     constexpr int U = 8;
     const bool pending = STDP && p.apply_pending;
     const bool do_e = p.electrical != 0;
@@ -218,12 +300,18 @@ __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SR
         j[u] = (FULL || c[u] != kColPad) ? (c[u] & kColIdxMask) : i;
         h[u] = src.gh(j[u]);
     }
+    if (pending) {
+        int lj[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) lj[u] = src.glft(h[u]);
+        stdp_chunk8_staged(p, src, c, lj, post_trig, lft_me, li, prev);
+    }
+    float w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) w[u] = src.wgt(u);
     float vj[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) vj[u] = do_e ? src.gv(h[u]) : v;
-    int lj[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) lj[u] = pending ? src.glft(h[u]) : -1;
     float tj[U][CHEMG == 3 ? kNT : 1];
     if (CHEMG == 1) {
 #pragma unroll
@@ -236,7 +324,6 @@ __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SR
             for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? src.gt(h[u], ty) : 0.f;
         }
     }
-    if (pending) stdp_chunk<U, false>(p, src, 0, c, j, lj, w, post_trig, lft_me, li, prev);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const bool ok = FULL || c[u] != kColPad;
@@ -276,9 +363,8 @@ template <int CHEMG, bool STDP, class SRC>
 __device__ __forceinline__ void gather_edges8(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
                                               bool post_trig, int li, uint32_t ty0, EdgeAcc &A) {
     uint32_t c[8];
-    float w[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) { c[u] = src.col(u); w[u] = src.wgt(u); }
+    for (int u = 0; u < 8; ++u) c[u] = src.col(u);
     // sliced-ELL rows keep their valid entries first (sell_grid_kernel / sell_from_csr_kernel pad at the end), so a valid
     // last slot means a full row
     bool lane_full = c[7] != kColPad;
@@ -287,8 +373,8 @@ __device__ __forceinline__ void gather_edges8(const StepParams &p, const SRC &sr
         lane_full = lane_full && ((all >> (kColNtShift + ty0)) & 1u);
     }
     A.fast8 = __all_sync(0xffffffffu, lane_full);
-    if (A.fast8) gather_edges8_body<CHEMG, STDP, true>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, w, A);
-    else gather_edges8_body<CHEMG, STDP, false>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, w, A);
+    if (A.fast8) gather_edges8_body<CHEMG, STDP, true>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, A);
+    else gather_edges8_body<CHEMG, STDP, false>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, A);
 }
 
 // CHEMG: 0 = no chemical gather, 1 = exactly one neurotransmitter type in the whole node array (type index ty0),

@@ -86,6 +86,13 @@ struct WinSrc {
     __device__ __forceinline__ uint32_t col(uint32_t kk) const { return lds_u32<lay().o_col>(edge + kk * 128u); }
     __device__ __forceinline__ float wgt(uint32_t kk) const { return lds_f32<lay().o_wgt>(edge + kk * 128u); }
     __device__ __forceinline__ float *wgt_ptr(uint32_t kk) const { return p.wgt + (size_t)(k0g + kk) * 32u + lane; }
+    // STDP: the new weight goes to the stage (this step's gather reads it from there) and to HBM
+    __device__ __forceinline__ void wgt_update(uint32_t kk, float x) const {
+        asm volatile("st.shared.f32 [%0+%1], %2;" ::"r"(edge + kk * 128u), "n"(lay().o_wgt), "f"(x) : "memory");
+        *wgt_ptr(kk) = x;
+    }
+    // generic-proxy stores into a stage that TMA (async proxy) overwrites after the empty barrier
+    __device__ __forceinline__ void wgt_updates_done() const { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
     // neighbour gathers: the handle is the shared address of V[j] inside whichever window holds node j
     typedef uint32_t Handle;
@@ -116,6 +123,11 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * wp.stage_bytes);
     uint64_t *empty = full + S;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.dbg[0] = (unsigned long long)clock64(); p.dbg[1] = gt;
+    }
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
@@ -240,6 +252,11 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
         if (active) halo_publish(p, warp_global, lane);
         s += G;
         if (s >= S) { s -= S; ph ^= 1u; }
+    }
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.dbg[2] = (unsigned long long)clock64(); p.dbg[3] = gt;
     }
 }
 

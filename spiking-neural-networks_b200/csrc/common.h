@@ -102,6 +102,8 @@ struct StepParams {
     unsigned long long halo_epoch;   // value the arrival counters must reach before ghosts are read
     uint32_t out_par;                // parity of the *_out ping-pong buffers (same on every rank)
     unsigned int *halo_done;         // [2] per-direction CTA completion counters
+    uint32_t reverse;                // window kernel: sweep the tiles back to front (alternates per step: the tail of the
+                                     // arrays that the previous step left in L2 is what this step reads first)
     unsigned long long *dbg;         // SNN_DEBUG_TIMING: {clock64, globaltimer} at the start and end of CTA 0 (else null)
 };
 

@@ -1381,6 +1381,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
         n_launch++;
     }
 
+    static const bool win_reverse = !(getenv("SNN_B200_WIN_REVERSE") && atoi(getenv("SNN_B200_WIN_REVERSE")) == 0);
     uint64_t done = 0;
     bool first_step = true;
     while (done < iterations && status == SNN_OK) {
@@ -1396,6 +1397,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             const int in = cur_, out = cur_ ^ 1;
             sp.clock = (uint32_t)internal_clock;
             sp.dbg = dbg_clk ? dbg_clk + 4 * s : nullptr;
+            sp.reverse = (win_reverse && (internal_clock & 1ull)) ? 1u : 0u;
             sp.apply_pending = (stdp && !first_step) ? 1u : 0u;
             sp.v_in = V_[in]; sp.v_out = V_[out];
             sp.spk_in = SPK_[in]; sp.spk_out = SPK_[out];

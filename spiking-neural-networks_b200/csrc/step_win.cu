@@ -11,7 +11,7 @@
 // only: no global load is left on their critical path, operand offsets are compile-time immediates (WinLayout,
 // common.h), and HBM latency is hidden by the depth of the stage ring instead of by warp occupancy.
 //
-// CTA = G groups of 8 consumer warps + 1 producer warp; tile n of the CTA goes to group n % G and stage n % S.
+// CTA = G groups of 8 consumer warps + kWinProducers producer warps; tile n of the CTA goes to group n % G and stage n % S.
 // The col words are still read and used (the window is selected by comparing the presynaptic index against the
 // tile's bounds), so any per-edge weight / type content of the sliced-ELL table keeps working; only the index
 // pattern must be the radius-1 stencil that set_graph_grid generates.
@@ -111,7 +111,10 @@ struct WinSrc {
     __device__ __forceinline__ float gt(Handle h, int ty) const { return lds_f32_rt(h + lay().o_twin + (uint32_t)ty * 3u * kWinRowBytes); }
 };
 
-constexpr int kWinProducers = 2;   // producer warps per CTA; warp q issues the copies of the CTA's tiles q, q + 2, ...
+#ifndef SNN_WIN_PRODUCERS
+#define SNN_WIN_PRODUCERS 4
+#endif
+constexpr int kWinProducers = SNN_WIN_PRODUCERS;   // producer warps per CTA; together they issue the copies of every tile
 template <int G> constexpr int win_threads() { return (G * 8 + kWinProducers) * 32; }
 
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, int G>
@@ -130,7 +133,7 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
     }
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], kWinProducers);   // every producer warp announces its share of the bytes
             mbar_init(&empty[s], 8);   // the eight warps of the group that consumed the stage
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -138,13 +141,14 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
     __syncthreads();
 
     if (warp >= G * 8) {
-        // ---- producers: every lane of the warp prepares one copy (address arithmetic in parallel), then the copies are
-        // issued back to back.  A single lane walking the ~35 operand streams of a tile was the bottleneck of the first
-        // version of this kernel (ncu: consumers stalled on the full barrier, 41 % of DRAM peak).
+        // ---- producers: kWinProducers warps fill every stage TOGETHER.  A cp.async.bulk costs its warp ~32 ns of issue
+        // time whatever its size or the number of active lanes (tools/tma_bench.cu: 1 warp sustains 4.3 TB/s chip-wide with
+        // 1 KB copies, 2 warps 7.0 TB/s), and a tile needs ~45 of them: one warp per tile put 1.4 us of serial issue in
+        // front of every stage.  Copy k of a tile is issued by warp k % P, lane k / P; each warp announces its own bytes
+        // on the stage's full barrier (initialised to P arrivals).
         const uint32_t q = warp - G * 8;
         bool waited_lo = !p.halo[0].active, waited_hi = !p.halo[1].active;
         const uint32_t ty0 = (CHEMG == 1) ? (uint32_t)(__ffs((int)p.nt_used) - 1) : 0u;
-        // window copies of a tile, one per lane: lane -> (array, row)
         const bool lft_on = wp.lft_copy != 0;
         uint32_t n_t = 0, t_types[kNT] = {0, 0, 0};
         if constexpr (NTREL) {
@@ -153,8 +157,19 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
                 if (p.nt_used & (1u << ty)) t_types[n_t++] = k;
             }
         }
-        uint32_t s = q % S, ph = (q / S) & 1u;
-        for (uint32_t tile = blockIdx.x + q * gridDim.x; tile < wp.n_tiles; tile += kWinProducers * gridDim.x) {
+        // this lane's copy: a per-tile contiguous operand stream, or window row r of node array arr (0: V, 1:
+        // last_firing_time, 2..: t slots)
+        const uint32_t idx = q + kWinProducers * lane;
+        const bool is_stream = idx < wp.n_streams;
+        const uint32_t wv = idx - wp.n_streams, arr = wv / 3u, r = wv - arr * 3u;
+        bool is_win = !is_stream && arr < 2u + n_t;
+        if (is_win && arr == 1u) is_win = lft_on && (L.lrows == 3 || r == 1u);
+        if (is_win && arr >= 2u) is_win = (L.trows == 3 || r == 1u);
+        TmaStream my{nullptr, 0u, 0u};
+        if (is_stream) my = wp.st[idx];
+        uint32_t s = 0, ph = 0;
+        for (uint32_t tile_seq = blockIdx.x; tile_seq < wp.n_tiles; tile_seq += gridDim.x) {
+            const uint32_t tile = p.reverse ? wp.n_tiles - 1u - tile_seq : tile_seq;
             if (lane == 0) mbar_wait_backoff(&empty[s], ph ^ 1u);
             const uint32_t ts = tile * kWinTile;   // first local neuron of the tile
             // multi-GPU: ghost rows are written by the neighbouring GPU over NVLink; they must have landed before TMA reads
@@ -169,52 +184,43 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
                 if (lane == 0) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
                 waited_hi = ghosts = true;
             }
-            // the three windows: node indices [a4, a4 + kWinRowElems) with a4 = floor4(own0 + ts + dr * cols - 1), clamped
-            // to the allocation
-            int32_t lo[3], cnt[3];
-            int64_t g0[3];
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int64_t a = (int64_t)p.own0 + ts + (int64_t)(r - 1) * wp.cols - 1;
+            unsigned char *dst = smem + (size_t)s * wp.stage_bytes;
+            const void *src = nullptr;
+            uint32_t bytes = 0;
+            if (is_stream) {
+                src = my.src + (size_t)tile * my.bytes_per_tile;
+                dst += my.smem_off;
+                bytes = my.bytes_per_tile;
+            } else if (is_win) {
+                // window row r: node indices [a4, a4 + kWinRowElems) with a4 = floor4(own0 + ts + (r - 1) * cols - 1), clamped
+                // to the allocation
+                const int64_t a = (int64_t)p.own0 + ts + ((int64_t)r - 1) * wp.cols - 1;
                 const int64_t a4 = a & ~(int64_t)3;
                 const int64_t b = a4 < 0 ? 0 : a4;
                 const int64_t e = (a4 + kWinRowElems) > (int64_t)wp.node_cap ? (int64_t)wp.node_cap : (a4 + kWinRowElems);
-                lo[r] = (int32_t)(b - a4);                 // elements skipped at the front of the window row
-                cnt[r] = e > b ? (int32_t)(e - b) : 0;
-                g0[r] = b;                                  // first node index copied
-            }
-            const uint32_t win_elems = (uint32_t)(cnt[0] + cnt[1] + cnt[2]);
-            uint32_t tx = wp.fixed_tx_bytes + win_elems * 4u;
-            if (lft_on) tx += (L.lrows == 3 ? win_elems : (uint32_t)cnt[1]) * 4u;
-            tx += n_t * (L.trows == 3 ? win_elems : (uint32_t)cnt[1]) * 4u;
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], tx);
-            __syncwarp();
-            if (ghosts) fence_proxy_async();   // lane 0's acquire of the arrival flag, then every lane's TMA reads of the ghosts
-            unsigned char *dst = smem + (size_t)s * wp.stage_bytes;
-            // per-tile contiguous operands: stream k -> lane k % 32
-            for (uint32_t k = lane; k < wp.n_streams; k += 32u)
-                tma_bulk_g2s(dst + wp.st[k].smem_off, wp.st[k].src + (size_t)tile * wp.st[k].bytes_per_tile,
-                             wp.st[k].bytes_per_tile, &full[s]);
-            // windows: copy w = array * 3 + row -> lane 31 - w (the low lanes carry the streams)
-            {
-                const uint32_t w = 31u - lane, arr = w / 3u, r = w - arr * 3u;   // arr 0: V, 1: last_firing_time, 2..: t slots
-                if (arr < 2u + n_t && cnt[r] != 0) {
-                    const uint32_t so = (uint32_t)lo[r] * 4u, nb = (uint32_t)cnt[r] * 4u;
-                    if (arr == 0) {
-                        tma_bulk_g2s(dst + L.o_vwin + r * kWinRowBytes + so, p.v_in + g0[r], nb, &full[s]);
-                    } else if (arr == 1) {
-                        if (lft_on && (L.lrows == 3 || r == 1))
-                            tma_bulk_g2s(dst + L.o_lwin + (L.lrows == 3 ? r : 0) * kWinRowBytes + so, p.lft_in + g0[r], nb, &full[s]);
-                    } else if (L.trows == 3 || r == 1) {
+                if (e > b) {
+                    bytes = (uint32_t)(e - b) * 4u;
+                    const uint32_t so = (uint32_t)(b - a4) * 4u;   // bytes skipped at the front of the window row
+                    if (arr == 0u) {
+                        dst += L.o_vwin + r * kWinRowBytes + so;
+                        src = p.v_in + b;
+                    } else if (arr == 1u) {
+                        dst += L.o_lwin + (L.lrows == 3 ? r : 0u) * kWinRowBytes + so;
+                        src = p.lft_in + b;
+                    } else {
                         const uint32_t k = t_types[arr - 2u];
                         const uint32_t ty = (CHEMG == 1) ? ty0 : k;
-                        tma_bulk_g2s(dst + L.o_twin + (k * L.trows + (L.trows == 3 ? r : 0)) * kWinRowBytes + so,
-                                     p.t_in + (size_t)ty * p.t_stride + g0[r], nb, &full[s]);
+                        dst += L.o_twin + (k * L.trows + (L.trows == 3 ? r : 0u)) * kWinRowBytes + so;
+                        src = p.t_in + (size_t)ty * p.t_stride + b;
                     }
                 }
             }
-            s += kWinProducers;
-            if (s >= S) { s -= S; ph ^= 1u; }
+            const uint32_t tx = __reduce_add_sync(0xffffffffu, bytes);
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], tx);
+            __syncwarp();
+            if (ghosts) fence_proxy_async();   // lane 0's acquire of the arrival flag, then every lane's TMA reads of the ghosts
+            if (bytes) tma_bulk_g2s(dst, src, bytes, &full[s]);
+            if (++s == S) { s = 0; ph ^= 1u; }
         }
         return;
     }
@@ -223,7 +229,8 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
     const uint32_t g = warp >> 3, wg = warp & 7u, tid = threadIdx.x & 255u;
     const uint32_t smem_s = smem_u32(smem);
     uint32_t s = g % S, ph = (g / S) & 1u;
-    for (uint32_t tile = blockIdx.x + g * gridDim.x; tile < wp.n_tiles; tile += G * gridDim.x) {
+    for (uint32_t tile_seq = blockIdx.x + g * gridDim.x; tile_seq < wp.n_tiles; tile_seq += G * gridDim.x) {
+        const uint32_t tile = p.reverse ? wp.n_tiles - 1u - tile_seq : tile_seq;
         const uint32_t warp_global = tile * 8u + wg;
         const uint32_t ln = warp_global * 32u + lane;
         const bool active = warp_global * 32u < p.n_neurons;
@@ -231,6 +238,11 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
         const uint32_t lnc = valid ? ln : p.n_neurons - 1;
         bool export_lo = false, export_hi = false;
         halo_export_flags(p, ln, valid, export_lo, export_hi);
+        // A group returns to a stage only every lcm(S, G) / S rounds, and a parity wait cannot tell "round k landed" from
+        // "round k - 1 is still landing" (two phases apart).  Bulk copies of different stages complete out of order, so
+        // first make sure that round k - 1 of this stage has been consumed (the empty barrier; a producer that issued this
+        // warp's previous tile has already seen round k - 2 consumed, so this wait is unambiguous), then wait for the data.
+        if (S % G != 0u) mbar_wait(&empty[s], ph ^ 1u);
         mbar_wait(&full[s], ph);
         if (active) {
             const uint32_t ts_node = p.own0 + tile * kWinTile;

@@ -2,6 +2,13 @@
 #pragma once
 #include <cstdint>
 
+#ifndef SNN_WIN_PROD_SLEEP
+#define SNN_WIN_PROD_SLEEP 256   // ns between probes of a producer waiting for a free stage
+#endif
+#ifndef SNN_WIN_CONS_HINT
+#define SNN_WIN_CONS_HINT 0      // ns a consumer's try_wait may stay suspended (0 = no hint)
+#endif
+
 namespace snn {
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -16,6 +23,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if SNN_WIN_CONS_HINT
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SNN_WIN_CONS_HINT) : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
@@ -25,6 +43,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra WAIT_LOOP;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 // producer-side wait: back off between probes so that the spinning lane does not eat issue slots of the consumers
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
@@ -37,7 +56,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity
             "selp.u32 %0, 1, 0, P1;\n"
             "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(256);
+        if (SNN_WIN_PROD_SLEEP) __nanosleep(SNN_WIN_PROD_SLEEP);
     }
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)

@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libsnn_b200.so")
+# SNN_B200_LIB: load a tuning variant of the library (make BUILD=... OUT=... EXTRA=...) instead of the default build
+LIB_PATH = os.environ.get("SNN_B200_LIB") or os.path.join(os.path.dirname(_HERE), "libsnn_b200.so")
 
 # ---- enums (include/snn_b200.h) ---------------------------------------------------------------
 SNN_OK = 0

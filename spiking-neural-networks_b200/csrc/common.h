@@ -229,7 +229,10 @@ struct WinParams {
 };
 
 // groups of 8 consumer warps per CTA (register budget: 65536 / ((groups * 8 + 1) * 32))
-__host__ __device__ constexpr int win_groups(int model, int chemg) { return (model == SNN_MODEL_HODGKIN_HUXLEY || chemg == 3) ? 2 : 3; }
+#ifndef SNN_WIN_GROUPS
+#define SNN_WIN_GROUPS 3
+#endif
+__host__ __device__ constexpr int win_groups(int model, int chemg) { return (model == SNN_MODEL_HODGKIN_HUXLEY || chemg == 3) ? 2 : SNN_WIN_GROUPS; }
 
 cudaError_t launch_step_win(const StepParams &p, const WinParams &wp, int model, int chemg, bool ntrel, bool stdp, unsigned grid,
                             cudaStream_t s);

@@ -298,7 +298,9 @@ __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SR
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         j[u] = (FULL || c[u] != kColPad) ? (c[u] & kColIdxMask) : i;
-        h[u] = src.gh(j[u]);
+        // a full row of a generated radius-1 stencil lists its presynaptic neurons in ascending order: three in the row
+        // above, the two side neighbours, three in the row below
+        h[u] = FULL ? src.gh_row(u < 3 ? 0 : (u < 5 ? 1 : 2), j[u]) : src.gh(j[u]);   // u folds after unrolling
     }
     if (pending) {
         int lj[U];
@@ -498,6 +500,7 @@ template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET, class SRC>
 __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src, uint32_t warp_global, uint32_t lane,
                                             uint32_t ln, uint32_t lnc, bool valid, bool export_lo, bool export_hi) {
     const uint32_t i = p.own0 + lnc;
+    const bool part = (p.halo[0].active | p.halo[1].active) != 0;   // partitioned handle (uniform)
     // ---- own state and parameters ------------------------------------------------------------------
     float v = src.v();
     const float gap = src.template f<F_GAP>();
@@ -689,8 +692,10 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
             const float t_new = nt_apply(p.ntk, t_old, src.nt(NTF_TMAX, ty), p1, p2, v_release, spiking_prev, dt);
             if (valid) {
                 p.t_out[(size_t)ty * p.t_stride + i] = t_new;
-                if (export_lo) p.halo[0].peer_t[p.out_par][(size_t)ty * p.halo[0].peer_t_stride + p.halo[0].peer_node0 + (ln - p.halo[0].first)] = t_new;
-                if (export_hi) p.halo[1].peer_t[p.out_par][(size_t)ty * p.halo[1].peer_t_stride + p.halo[1].peer_node0 + (ln - p.halo[1].first)] = t_new;
+                if (part) {   // uniform: one branch instead of two predicated address computations on single-GPU handles
+                    if (export_lo) p.halo[0].peer_t[p.out_par][(size_t)ty * p.halo[0].peer_t_stride + p.halo[0].peer_node0 + (ln - p.halo[0].first)] = t_new;
+                    if (export_hi) p.halo[1].peer_t[p.out_par][(size_t)ty * p.halo[1].peer_t_stride + p.halo[1].peer_node0 + (ln - p.halo[1].first)] = t_new;
+                }
             }
         }
     }
@@ -708,13 +713,13 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
         if (p.lft_pp) { lft_new = spike ? (int)p.clock : lft_me; p.lft_out[i] = lft_new; }
         else if (spike) { lft_new = (int)p.clock; p.lft_out[i] = lft_new; }
         if (p.grid_hist) p.grid_hist[ln] = v;  // GridVoltageHistory::update, neuron/mod.rs:293-296
-        if (export_lo) {
+        if (part && export_lo) {
             const HaloDir &H = p.halo[0];
             const uint32_t dst = H.peer_node0 + (ln - H.first);
             H.peer_v[p.out_par][dst] = v;
             if (p.lft_pp) H.peer_lft[p.out_par][dst] = lft_new;
         }
-        if (export_hi) {
+        if (part && export_hi) {
             const HaloDir &H = p.halo[1];
             const uint32_t dst = H.peer_node0 + (ln - H.first);
             H.peer_v[p.out_par][dst] = v;

@@ -102,6 +102,7 @@ struct WinSrc {
         if (j > hi_thr) d = d2;
         return d + j * 4u;
     }
+    __device__ __forceinline__ Handle gh_row(int row, uint32_t j) const { return (row == 0 ? d0 : (row == 1 ? d1 : d2)) + j * 4u; }
     __device__ __forceinline__ float gv(Handle h) const { return lds_f32<lay().o_vwin>(h); }
     __device__ __forceinline__ int glft(Handle h) const {
         static_assert(!STDP || lay().lrows == 3, "gathered last_firing_time needs all three window rows");

@@ -8,6 +8,9 @@
 #ifndef SNN_WIN_CONS_HINT
 #define SNN_WIN_CONS_HINT 0      // ns a consumer's try_wait may stay suspended (0 = no hint)
 #endif
+#ifndef SNN_WIN_PROD_HINT
+#define SNN_WIN_PROD_HINT 0      // ns a producer's try_wait may stay suspended (0 = no hint: probe + nanosleep)
+#endif
 
 namespace snn {
 
@@ -47,6 +50,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 }
 // producer-side wait: back off between probes so that the spinning lane does not eat issue slots of the consumers
 __device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity) {
+#if SNN_WIN_PROD_HINT
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)SNN_WIN_PROD_HINT) : "memory");
+    return;
+#endif
     uint32_t done = 0;
     while (true) {
         asm volatile(

@@ -92,7 +92,8 @@ typedef enum snn_model {
     SNN_MODEL_LEAKY_IZHIKEVICH = 5,               /* :1270-1356 */
     SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE = 6,/* :1522-1630 */
     SNN_MODEL_HODGKIN_HUXLEY = 7,                 /* hodgkin_huxley/mod.rs:48-242 */
-    SNN_MODEL_COUNT = 8
+    SNN_MODEL_BCM_IZHIKEVICH = 8,                 /* :1358-1520 (Izhikevich + BCMActivity bookkeeping) */
+    SNN_MODEL_COUNT = 9
 } snn_model_t;
 
 /* NeurotransmitterKinetics impls, iterate_and_spike/mod.rs:122-366 */

@@ -16,7 +16,7 @@ from __future__ import annotations
 import numpy as np
 
 f32 = np.float32
-LIF, QIF, ADLIF, ADEX, IZH, LEAKY_IZH, SIMPLE_LIF, HH = range(8)
+LIF, QIF, ADLIF, ADEX, IZH, LEAKY_IZH, SIMPLE_LIF, HH, BCM_IZH = range(9)
 
 
 def _f(x):
@@ -128,9 +128,24 @@ class DenseLattice:
             rc_dv = total * (dt / c_m)
         spiking_prev = self.is_spiking.copy()
         spike = np.zeros(n, bool)
-        if m in (IZH, LEAKY_IZH):
+        if m == BCM_IZH:
+            # BCMIzhikevichNeuron bookkeeping (integrate_and_fire/mod.rs:1458-1467, 1485-1494): before the update, with the
+            # previous step's spike flag; the chemical variant divides by the window only
+            F["num_spikes"] = F["num_spikes"] + spiking_prev.astype(F["num_spikes"].dtype)
+            clk = F["firing_rate_clock"] + dt
+            roll = clk >= F["firing_rate_window"]
+            nsp = F["num_spikes"].astype(f32)
+            cur = nsp / F["firing_rate_window"] if self.chemical else nsp / (F["firing_rate_window"] * dt)
+            per = F["period"].astype(f32)
+            avg = F["average_activity"]
+            avg2 = avg - avg / per
+            avg2 = avg2 + cur / per
+            F["current_activity"] = np.where(roll, cur, F["current_activity"]).astype(f32)
+            F["average_activity"] = np.where(roll, avg2, avg).astype(f32)
+            F["firing_rate_clock"] = np.where(roll, f32(0), clk).astype(f32)
+        if m in (IZH, LEAKY_IZH, BCM_IZH):
             w = F["w_value"]
-            if m == IZH:
+            if m != LEAKY_IZH:
                 dv = (((((f32(0.04) * (v * v)) + (f32(5) * v)) + f32(140)) - w) + I) * (dt / c_m)
             else:
                 dv = (((((f32(0.04) * (v * v)) + (f32(5) * v)) + f32(140)) - (w * (v - F["e_l"]))) + I) * (dt / c_m)

@@ -109,7 +109,7 @@ def _as(a, dt):
 
 
 # field dtypes by name (everything else is f32)
-_U32_FIELDS = {"is_spiking", "was_increasing", "counter", "neurotransmitters$flags", "receptors$flags"}
+_U32_FIELDS = {"is_spiking", "was_increasing", "counter", "neurotransmitters$flags", "receptors$flags", "period", "num_spikes"}
 _I32_FIELDS = {"last_firing_time"}
 _PER3_PREFIX = "neurotransmitters$"
 

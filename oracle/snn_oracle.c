@@ -52,6 +52,9 @@ typedef struct {
     float g_k, e_k, k_current;
     o_gate n;
     float g_k_leak, e_k_leak, k_leak_current;
+    /* BCMIzhikevichNeuron integrate_and_fire/mod.rs:1393-1404 */
+    float average_activity, current_activity, firing_rate_clock, firing_rate_window;
+    uint32_t period, num_spikes;
     uint32_t was_increasing;
     uint32_t is_spiking;
     int32_t last_firing_time; /* Option<usize>, -1 = None */
@@ -158,6 +161,11 @@ static void neuron_default(o_neuron *c, int model) {
         c->current_voltage = -65.f; c->gap_conductance = 7.f; c->w_value = 30.f; c->a = 0.02f; c->b = 0.2f;
         c->c = -55.0f; c->d = 8.0f; c->v_th = 30.f; c->tau_m = 1.f; c->c_m = 100.f; c->v_init = -65.f;
         c->w_init = 30.f; c->dt = 0.1f; break;
+    case ORC_BCM_IZH: /* :1411-1438 */
+        c->current_voltage = -65.f; c->gap_conductance = 7.f; c->w_value = 30.f; c->a = 0.02f; c->b = 0.2f;
+        c->c = -55.0f; c->d = 8.0f; c->v_th = 30.f; c->tau_m = 1.f; c->c_m = 100.f; c->v_init = -65.f;
+        c->w_init = 30.f; c->dt = 0.1f; c->average_activity = 0.f; c->current_activity = 0.f; c->period = 3;
+        c->num_spikes = 0; c->firing_rate_clock = 0.f; c->firing_rate_window = 500.f; break;
     case ORC_LEAKY_IZH: /* :1313-1336 */
         c->current_voltage = -65.f; c->gap_conductance = 7.f; c->w_value = 30.f; c->a = 0.02f; c->b = 0.2f;
         c->c = -55.0f; c->d = 8.0f; c->v_th = 30.f; c->tau_m = 10.f; c->c_m = 100.f; c->v_init = -65.f;
@@ -185,7 +193,7 @@ static void train_default(o_train *s) {
 
 typedef struct { const char *name; int dtype; size_t off; int models; } o_fielddef;
 #define M(x) (1 << (x))
-#define ALLM 0xFF
+#define ALLM 0x1FF
 #define OFF(f) offsetof(o_neuron, f)
 static const o_fielddef neuron_fields[] = {
     {"current_voltage", ORC_F32, OFF(current_voltage), ALLM},
@@ -207,13 +215,19 @@ static const o_fielddef neuron_fields[] = {
     {"alpha", ORC_F32, OFF(alpha), M(ORC_QIF) | M(ORC_ADLIF) | M(ORC_ADEX)},
     {"beta", ORC_F32, OFF(beta), M(ORC_ADLIF) | M(ORC_ADEX)},
     {"slope_factor", ORC_F32, OFF(slope_factor), M(ORC_ADEX)},
-    {"w_value", ORC_F32, OFF(w_value), M(ORC_ADLIF) | M(ORC_ADEX) | M(ORC_IZH) | M(ORC_LEAKY_IZH)},
-    {"w_init", ORC_F32, OFF(w_init), M(ORC_ADLIF) | M(ORC_ADEX) | M(ORC_IZH) | M(ORC_LEAKY_IZH)},
+    {"w_value", ORC_F32, OFF(w_value), M(ORC_ADLIF) | M(ORC_ADEX) | M(ORC_IZH) | M(ORC_LEAKY_IZH) | M(ORC_BCM_IZH)},
+    {"w_init", ORC_F32, OFF(w_init), M(ORC_ADLIF) | M(ORC_ADEX) | M(ORC_IZH) | M(ORC_LEAKY_IZH) | M(ORC_BCM_IZH)},
     {"v_c", ORC_F32, OFF(v_c), M(ORC_QIF)},
-    {"a", ORC_F32, OFF(a), M(ORC_IZH) | M(ORC_LEAKY_IZH)},
-    {"b", ORC_F32, OFF(b), M(ORC_IZH) | M(ORC_LEAKY_IZH)},
-    {"c", ORC_F32, OFF(c), M(ORC_IZH) | M(ORC_LEAKY_IZH)},
-    {"d", ORC_F32, OFF(d), M(ORC_IZH) | M(ORC_LEAKY_IZH)},
+    {"average_activity", ORC_F32, OFF(average_activity), M(ORC_BCM_IZH)},
+    {"current_activity", ORC_F32, OFF(current_activity), M(ORC_BCM_IZH)},
+    {"period", ORC_U32, OFF(period), M(ORC_BCM_IZH)},
+    {"num_spikes", ORC_U32, OFF(num_spikes), M(ORC_BCM_IZH)},
+    {"firing_rate_clock", ORC_F32, OFF(firing_rate_clock), M(ORC_BCM_IZH)},
+    {"firing_rate_window", ORC_F32, OFF(firing_rate_window), M(ORC_BCM_IZH)},
+    {"a", ORC_F32, OFF(a), M(ORC_IZH) | M(ORC_LEAKY_IZH) | M(ORC_BCM_IZH)},
+    {"b", ORC_F32, OFF(b), M(ORC_IZH) | M(ORC_LEAKY_IZH) | M(ORC_BCM_IZH)},
+    {"c", ORC_F32, OFF(c), M(ORC_IZH) | M(ORC_LEAKY_IZH) | M(ORC_BCM_IZH)},
+    {"d", ORC_F32, OFF(d), M(ORC_IZH) | M(ORC_LEAKY_IZH) | M(ORC_BCM_IZH)},
     {"g", ORC_F32, OFF(g), M(ORC_SIMPLE_LIF)},
     {"e", ORC_F32, OFF(e), M(ORC_SIMPLE_LIF)},
     {"na_channel$g_na", ORC_F32, OFF(g_na), M(ORC_HH)},
@@ -867,7 +881,7 @@ static float get_dv(const o_neuron *c, int model, float i) {
     case ORC_ADEX: /* exp_adaptive_get_dv_change :1138-1145 */
         return ((((c->leak_constant * (v - c->e_l)) + (c->slope_factor * expf((v - c->v_th) / c->slope_factor))) +
                  (c->integration_constant * (i / c->g_l))) - (c->w_value / c->g_l)) * (c->dt / c->c_m);
-    case ORC_IZH: /* izhikevich_get_dv_change :1255-1260 (powf(2.0) == v*v) */
+    case ORC_IZH: case ORC_BCM_IZH: /* izhikevich_get_dv_change :1255-1260, :1446-1451 (powf(2.0) == v*v) */
         return (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - c->w_value) + i) * (c->dt / c->c_m);
     case ORC_LEAKY_IZH: /* izhikevich_leaky_get_dv_change :1342-1348 */
         return (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - (c->w_value * (v - c->e_l))) + i) * (c->dt / c->c_m);
@@ -881,7 +895,7 @@ static float get_dw(const o_neuron *c, int model) {
     switch (model) {
     case ORC_ADLIF: case ORC_ADEX: /* adaptive_get_dw_change :1002-1009 */
         return (c->alpha * (c->current_voltage - c->e_l) - c->w_value) * (c->dt / c->tau_m);
-    case ORC_IZH: case ORC_LEAKY_IZH: /* izhikevich_get_dw_change :1225-1231 */
+    case ORC_IZH: case ORC_LEAKY_IZH: case ORC_BCM_IZH: /* izhikevich_get_dw_change :1225-1231 */
         return (c->a * (c->b * c->current_voltage - c->w_value)) * (c->dt / c->tau_m);
     }
     return 0.f;
@@ -891,7 +905,7 @@ static int handle_spiking(o_neuron *c, int model) {
     switch (model) {
     case ORC_LIF: case ORC_QIF: return default_handle_spiking(c);
     case ORC_ADLIF: case ORC_ADEX: return adaptive_handle_spiking(c);
-    case ORC_IZH: case ORC_LEAKY_IZH: return izhikevich_handle_spiking(c);
+    case ORC_IZH: case ORC_LEAKY_IZH: case ORC_BCM_IZH: return izhikevich_handle_spiking(c);
     case ORC_SIMPLE_LIF: return simple_handle_spiking(c);
     }
     return 0;
@@ -951,7 +965,18 @@ static int neuron_iterate(o_neuron *c, int model, int ntk, int rck, float input,
     }
     /* integrate_and_fire/mod.rs:189-214 (LIF), :222-252 (macro: AdLIF, AdEx, Izh, LeakyIzh), :339-364 (QIF),
      * :1604-1629 (SimpleLIF) */
-    int adaptive = model == ORC_ADLIF || model == ORC_ADEX || model == ORC_IZH || model == ORC_LEAKY_IZH;
+    int adaptive = model == ORC_ADLIF || model == ORC_ADEX || model == ORC_IZH || model == ORC_LEAKY_IZH || model == ORC_BCM_IZH;
+    if (model == ORC_BCM_IZH) { /* BCMIzhikevichNeuron :1458-1467 (iterate_and_spike), :1485-1494 (with neurotransmitter) */
+        if (c->is_spiking) c->num_spikes += 1;
+        c->firing_rate_clock += c->dt;
+        if (c->firing_rate_clock >= c->firing_rate_window) {
+            c->firing_rate_clock = 0.f;
+            if (chem) c->current_activity = (float)c->num_spikes / c->firing_rate_window;
+            else c->current_activity = (float)c->num_spikes / (c->firing_rate_window * c->dt);
+            c->average_activity -= c->average_activity / (float)c->period;
+            c->average_activity += c->current_activity / (float)c->period;
+        }
+    }
     if (chem) {
         receptors_update_kinetics(c, rck, t, has, c->dt);
         receptors_set_currents(c, c->current_voltage);

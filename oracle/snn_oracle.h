@@ -36,7 +36,7 @@ extern "C" {
 
 #define ORC_NT 3 /* AMPA, NMDA, GABA : iterate_and_spike/mod.rs:1068-1073, 1322-1330 */
 
-enum { ORC_LIF = 0, ORC_QIF = 1, ORC_ADLIF = 2, ORC_ADEX = 3, ORC_IZH = 4, ORC_LEAKY_IZH = 5, ORC_SIMPLE_LIF = 6, ORC_HH = 7 };
+enum { ORC_LIF = 0, ORC_QIF = 1, ORC_ADLIF = 2, ORC_ADEX = 3, ORC_IZH = 4, ORC_LEAKY_IZH = 5, ORC_SIMPLE_LIF = 6, ORC_HH = 7, ORC_BCM_IZH = 8 };
 enum { ORC_NTK_APPROX = 0, ORC_NTK_DESTEXHE = 1, ORC_NTK_DISCRETE = 2, ORC_NTK_EXPDECAY = 3 };
 enum { ORC_RCK_APPROX = 0, ORC_RCK_DESTEXHE = 1, ORC_RCK_EXPDECAY = 2 };
 enum { ORC_TRAIN_POISSON = 0, ORC_TRAIN_RATE = 1, ORC_TRAIN_PRESET = 2 };

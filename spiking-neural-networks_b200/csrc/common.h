@@ -24,6 +24,8 @@ enum NeuronSlot : int {
     F_GAP = 0, F_DT, F_CM, F_VTH, F_VRESET, F_REFR, F_TREF, F_LEAK, F_INTEG, F_EL, F_GL, F_TAUM,
     F_ALPHA, F_BETA, F_SLOPE, F_W, F_VC, F_A, F_B, F_C, F_D, F_G, F_E,
     F_GNA, F_ENA, F_M, F_H, F_GK, F_EK, F_N, F_GKL, F_EKL,
+    // BCMIzhikevichNeuron activity bookkeeping (period and num_spikes hold u32 bit patterns)
+    F_AVG_ACT, F_CUR_ACT, F_PERIOD, F_NSPK, F_FRCLK, F_FRWIN,
     // derived (written by the finalize kernel only, never inside the step loop)
     F_NA_CUR, F_M_ALPHA, F_M_BETA, F_H_ALPHA, F_H_BETA, F_K_CUR, F_N_ALPHA, F_N_BETA, F_KL_CUR,
     F_COUNT
@@ -169,7 +171,8 @@ struct WinLayout {
 
 // fields the step of `model` reads (must mirror neuron_step, step_body.cuh)
 __host__ __device__ constexpr bool win_field_read(int model, bool ntrel, int slot) {
-    const bool izh = model == SNN_MODEL_IZHIKEVICH || model == SNN_MODEL_LEAKY_IZHIKEVICH;
+    const bool bcm = model == SNN_MODEL_BCM_IZHIKEVICH;
+    const bool izh = model == SNN_MODEL_IZHIKEVICH || model == SNN_MODEL_LEAKY_IZHIKEVICH || bcm;
     const bool adapt = model == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || model == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
     const bool if4 = model == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || model == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE || adapt;
     const bool leaky = model == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || adapt;
@@ -192,6 +195,7 @@ __host__ __device__ constexpr bool win_field_read(int model, bool ntrel, int slo
     case F_SLOPE: return model == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
     case F_G: case F_E: return simple;
     case F_GNA: case F_ENA: case F_M: case F_H: case F_GK: case F_EK: case F_N: case F_GKL: case F_EKL: return hh;
+    case F_AVG_ACT: case F_CUR_ACT: case F_PERIOD: case F_NSPK: case F_FRCLK: case F_FRWIN: return bcm;
     default: return false;
     }
 }

@@ -6,6 +6,8 @@
 // 1212-1240).  Models the reference never gave a GPU map (Izhikevich, HH, ...) use the Rust struct
 // field names, nested members joined with '$' as the reference does for its own nested structs.
 #pragma once
+#include <cstring>
+
 #include "common.h"
 
 namespace snn {
@@ -37,13 +39,14 @@ struct FieldDef {
 };
 
 #define SNN_M(x) (1u << (x))
-constexpr uint32_t kAllModels = 0xFFu;
+constexpr uint32_t kAllModels = 0x1FFu;
 constexpr uint32_t kIF4 = SNN_M(SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE) | SNN_M(SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) |
                           SNN_M(SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE) | SNN_M(SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE);
 constexpr uint32_t kLeaky3 = SNN_M(SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE) | SNN_M(SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE) |
                              SNN_M(SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE);
 constexpr uint32_t kAdapt2 = SNN_M(SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE) | SNN_M(SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE);
-constexpr uint32_t kIzh2 = SNN_M(SNN_MODEL_IZHIKEVICH) | SNN_M(SNN_MODEL_LEAKY_IZHIKEVICH);
+constexpr uint32_t kBcm = SNN_M(SNN_MODEL_BCM_IZHIKEVICH);
+constexpr uint32_t kIzh2 = SNN_M(SNN_MODEL_IZHIKEVICH) | SNN_M(SNN_MODEL_LEAKY_IZHIKEVICH) | kBcm;   // every Izhikevich variant
 constexpr uint32_t kHH = SNN_M(SNN_MODEL_HODGKIN_HUXLEY);
 constexpr uint32_t kSimple = SNN_M(SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE);
 
@@ -74,6 +77,13 @@ static const FieldDef kNeuronFields[] = {
     {"b", SNN_F32, 1, FK_NEURON_DEV, F_B, 0, kIzh2},
     {"c", SNN_F32, 1, FK_NEURON_DEV, F_C, 0, kIzh2},
     {"d", SNN_F32, 1, FK_NEURON_DEV, F_D, 0, kIzh2},
+    // BCMIzhikevichNeuron (integrate_and_fire/mod.rs:1393-1404); usize fields travel as u32 like the reference's bools
+    {"average_activity", SNN_F32, 1, FK_NEURON_DEV, F_AVG_ACT, 0, kBcm},
+    {"current_activity", SNN_F32, 1, FK_NEURON_DEV, F_CUR_ACT, 0, kBcm},
+    {"period", SNN_U32, 1, FK_NEURON_DEV, F_PERIOD, 0, kBcm},
+    {"num_spikes", SNN_U32, 1, FK_NEURON_DEV, F_NSPK, 0, kBcm},
+    {"firing_rate_clock", SNN_F32, 1, FK_NEURON_DEV, F_FRCLK, 0, kBcm},
+    {"firing_rate_window", SNN_F32, 1, FK_NEURON_DEV, F_FRWIN, 0, kBcm},
     {"g", SNN_F32, 1, FK_NEURON_DEV, F_G, 0, kSimple},
     {"e", SNN_F32, 1, FK_NEURON_DEV, F_E, 0, kSimple},
     {"na_channel$g_na", SNN_F32, 1, FK_NEURON_DEV, F_GNA, 0, kHH},
@@ -150,7 +160,7 @@ constexpr int kNumTrainFields = sizeof(kTrainFields) / sizeof(kTrainFields[0]);
 // 1106-1134, 1198-1220, 1313-1336, 1552-1570; hodgkin_huxley/mod.rs:80-99; ion_channels/mod.rs:205-215,
 // 255-264, 299-307)
 inline float neuron_default(int model, int kind, int slot) {
-    const bool izh = model == SNN_MODEL_IZHIKEVICH || model == SNN_MODEL_LEAKY_IZHIKEVICH;
+    const bool izh = model == SNN_MODEL_IZHIKEVICH || model == SNN_MODEL_LEAKY_IZHIKEVICH || model == SNN_MODEL_BCM_IZHIKEVICH;
     const bool hh = model == SNN_MODEL_HODGKIN_HUXLEY;
     if (kind == FK_V) return (izh || hh) ? -65.f : -75.f;
     if (kind == FK_NEURON_COLD) {
@@ -171,7 +181,7 @@ inline float neuron_default(int model, int kind, int slot) {
     case F_GL: return 10.f;
     case F_TAUM:
         if (model == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE) return 100.f;
-        if (model == SNN_MODEL_IZHIKEVICH) return 1.f;
+        if (model == SNN_MODEL_IZHIKEVICH || model == SNN_MODEL_BCM_IZHIKEVICH) return 1.f;
         return 10.f;
     case F_ALPHA: return model == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE ? 1.f : 6.f;
     case F_BETA: return 10.f;
@@ -190,6 +200,8 @@ inline float neuron_default(int model, int kind, int slot) {
     case F_EK: return -77.f;
     case F_GKL: return 0.3f;
     case F_EKL: return -55.f;
+    case F_PERIOD: { const uint32_t three = 3u; float bits; memcpy(&bits, &three, 4); return bits; }   // period: usize = 3
+    case F_FRWIN: return 500.f;
     default: return 0.f;  // gate states, currents, rates
     }
 }

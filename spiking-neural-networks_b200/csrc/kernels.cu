@@ -371,6 +371,7 @@ cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, b
     case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_step_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, chemg, ntrel, stdp, net, s);
     case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_step_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, s);
     case SNN_MODEL_HODGKIN_HUXLEY: return launch_step_model<SNN_MODEL_HODGKIN_HUXLEY>(p, chemg, ntrel, stdp, net, s);
+    case SNN_MODEL_BCM_IZHIKEVICH: return launch_step_model<SNN_MODEL_BCM_IZHIKEVICH>(p, chemg, ntrel, stdp, net, s);
     }
     return cudaErrorInvalidValue;
 }

@@ -505,16 +505,17 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     float v = src.v();
     const float gap = src.template f<F_GAP>();
     const float dt = src.template f<F_DT>();
-    constexpr bool NEEDS_CM = NTREL || MODEL == SNN_MODEL_HODGKIN_HUXLEY || MODEL == SNN_MODEL_IZHIKEVICH ||
+    constexpr bool BCM = MODEL == SNN_MODEL_BCM_IZHIKEVICH;
+    constexpr bool NEEDS_CM = NTREL || BCM || MODEL == SNN_MODEL_HODGKIN_HUXLEY || MODEL == SNN_MODEL_IZHIKEVICH ||
                               MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE ||
                               MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
     float c_m = 1.f, v_th = 0.f;
     if (SRC::kEarlyLoads) { if constexpr (NEEDS_CM) c_m = src.template f<F_CM>(); v_th = src.template f<F_VTH>(); }
     const int lft_me = (STDP || p.lft_pp) ? src.lft() : 0;
-    const uint32_t spk_word_in = NTREL ? src.spk_prev_word(warp_global) : 0u;
+    const uint32_t spk_word_in = (NTREL || BCM) ? src.spk_prev_word(warp_global) : 0u;
     const bool spiking_prev = (spk_word_in >> lane) & 1u;
     const uint32_t flags = NTREL ? src.flags() : 0u;
-    constexpr bool IZH = MODEL == SNN_MODEL_IZHIKEVICH || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH;
+    constexpr bool IZH = MODEL == SNN_MODEL_IZHIKEVICH || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || BCM;
     constexpr bool IF4 = MODEL == SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE ||
                          MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
     constexpr bool ADAPT = MODEL == SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE || MODEL == SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE;
@@ -597,9 +598,28 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     // ---- neuron update --------------------------------------------------------------------------
     bool spike = false;
     float v_release;  // membrane voltage seen by the neurotransmitter kinetics (post-update, pre-reset)
+    if constexpr (BCM) {
+        // BCMIzhikevichNeuron activity bookkeeping, integrate_and_fire/mod.rs:1458-1467 / :1485-1494: runs before the
+        // Izhikevich update and sees the spike flag of the previous step.  The two iterate variants of the reference
+        // normalise current_activity differently (window * dt vs window); both are restated literally.
+        uint32_t num_spikes = __float_as_uint(src.template state<F_NSPK>());
+        if (spiking_prev) num_spikes += 1u;
+        float fr_clock = src.template state<F_FRCLK>() + dt;
+        const float fr_window = src.template f<F_FRWIN>();
+        if (fr_clock >= fr_window) {
+            fr_clock = 0.f;
+            const float current_activity = p.chemical ? (float)num_spikes / fr_window : (float)num_spikes / (fr_window * dt);
+            const float period = (float)__float_as_uint(src.template f<F_PERIOD>());
+            float average_activity = src.template state<F_AVG_ACT>();
+            average_activity = average_activity - average_activity / period;
+            average_activity = average_activity + current_activity / period;
+            if (valid) { p.f[F_CUR_ACT][lnc] = current_activity; p.f[F_AVG_ACT][lnc] = average_activity; }
+        }
+        if (valid) { p.f[F_NSPK][lnc] = __uint_as_float(num_spikes); p.f[F_FRCLK][lnc] = fr_clock; }
+    }
     if constexpr (IZH) {
         float dv;
-        if constexpr (MODEL == SNN_MODEL_IZHIKEVICH)  // integrate_and_fire/mod.rs:1255-1260
+        if constexpr (MODEL != SNN_MODEL_LEAKY_IZHIKEVICH)  // integrate_and_fire/mod.rs:1255-1260 (also :1446-1451, BCM)
             dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - w_adapt) + input) * (dt / c_m);
         else                                            // :1342-1348
             dv = (((((0.04f * (v * v)) + (5.f * v)) + 140.f) - (w_adapt * (v - e_l))) + input) * (dt / c_m);

@@ -157,6 +157,7 @@ cudaError_t launch_step_tma(const StepParams &p, const TmaParams &tp, int model,
     case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_tma_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, tp, chemg, ntrel, stdp, grid, smem, s);
     case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_tma_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, tp, chemg, ntrel, stdp, grid, smem, s);
     case SNN_MODEL_HODGKIN_HUXLEY: return launch_tma_model<SNN_MODEL_HODGKIN_HUXLEY>(p, tp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_BCM_IZHIKEVICH: return launch_tma_model<SNN_MODEL_BCM_IZHIKEVICH>(p, tp, chemg, ntrel, stdp, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }

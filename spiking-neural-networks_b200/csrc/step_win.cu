@@ -315,6 +315,7 @@ cudaError_t launch_step_win(const StepParams &p, const WinParams &wp, int model,
     case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_win_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, wp, chemg, ntrel, stdp, grid, smem, s);
     case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_win_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, wp, chemg, ntrel, stdp, grid, smem, s);
     case SNN_MODEL_HODGKIN_HUXLEY: return launch_win_model<SNN_MODEL_HODGKIN_HUXLEY>(p, wp, chemg, ntrel, stdp, grid, smem, s);
+    case SNN_MODEL_BCM_IZHIKEVICH: return launch_win_model<SNN_MODEL_BCM_IZHIKEVICH>(p, wp, chemg, ntrel, stdp, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }

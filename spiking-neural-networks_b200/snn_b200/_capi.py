@@ -31,7 +31,7 @@ SNN_DTYPE_MISMATCH = 66
 SNN_SIZE_MISMATCH = 67
 SNN_UNSUPPORTED = 68
 
-MODEL_LIF, MODEL_QIF, MODEL_ADLIF, MODEL_ADEX, MODEL_IZH, MODEL_LEAKY_IZH, MODEL_SIMPLE_LIF, MODEL_HH = range(8)
+MODEL_LIF, MODEL_QIF, MODEL_ADLIF, MODEL_ADEX, MODEL_IZH, MODEL_LEAKY_IZH, MODEL_SIMPLE_LIF, MODEL_HH, MODEL_BCM_IZH = range(9)
 NT_APPROXIMATE, NT_DESTEXHE, NT_DISCRETE_SPIKE, NT_EXPONENTIAL_DECAY = range(4)
 RC_APPROXIMATE, RC_DESTEXHE, RC_EXPONENTIAL_DECAY = range(3)
 TRAIN_POISSON, TRAIN_RATE, TRAIN_PRESET = range(3)

@@ -255,6 +255,8 @@ class Lattice(_CellLattice):
                     v = bool(v)
                 elif name == "last_firing_time":
                     v = None if v < 0 else int(v)
+                elif a.dtype.kind in "ui":   # usize fields (BCM period, num_spikes)
+                    v = int(v)
                 else:
                     v = float(v)
                 c.scalar_fields()[name] = v

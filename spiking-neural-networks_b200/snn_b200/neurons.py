@@ -136,6 +136,10 @@ _MODEL_DEFAULTS = {
     # :1552-1570
     K.MODEL_SIMPLE_LIF: dict(current_voltage=-75.0, gap_conductance=10.0, v_th=-55.0, v_reset=-75.0, c_m=100.0, g=-0.1,
                              v_init=-75.0, e=0.0, dt=0.1),
+    # :1411-1438 (BCMIzhikevichNeuron: Izhikevich + BCMActivity bookkeeping)
+    K.MODEL_BCM_IZH: dict(current_voltage=-65.0, gap_conductance=7.0, w_value=30.0, a=0.02, b=0.2, c=-55.0, d=8.0, v_th=30.0,
+                          tau_m=1.0, c_m=100.0, v_init=-65.0, w_init=30.0, dt=0.1, average_activity=0.0, current_activity=0.0,
+                          period=3, num_spikes=0, firing_rate_clock=0.0, firing_rate_window=500.0),
     # hodgkin_huxley/mod.rs:80-99; ion_channels/mod.rs:23-31, 205-215, 255-264, 299-307
     K.MODEL_HH: {"current_voltage": -65.0, "gap_conductance": 7.0, "dt": 0.01, "c_m": 1.0, "v_th": 0.0,
                  "na_channel$g_na": 120.0, "na_channel$e_na": 50.0, "na_channel$current": 0.0,
@@ -236,6 +240,17 @@ class LeakyIzhikevichNeuron(Neuron):
     model = K.MODEL_LEAKY_IZH
 
 
+class BCMIzhikevichNeuron(Neuron):
+    """integrate_and_fire/mod.rs:1358-1520; get_activity / get_averaged_activity mirror BCMActivity (:1510-1519)."""
+    model = K.MODEL_BCM_IZH
+
+    def get_activity(self):
+        return self.current_activity
+
+    def get_averaged_activity(self):
+        return self.average_activity
+
+
 class SimpleLeakyIntegrateAndFire(Neuron):
     model = K.MODEL_SIMPLE_LIF
 
@@ -250,7 +265,7 @@ class HodgkinHuxleyNeuron(Neuron):
 NEURON_CLASSES = {c.model: c for c in (LeakyIntegrateAndFireNeuron, QuadraticIntegrateAndFireNeuron,
                                        AdaptiveLeakyIntegrateAndFireNeuron, AdaptiveExpLeakyIntegrateAndFireNeuron,
                                        IzhikevichNeuron, LeakyIzhikevichNeuron, SimpleLeakyIntegrateAndFire,
-                                       HodgkinHuxleyNeuron)}
+                                       HodgkinHuxleyNeuron, BCMIzhikevichNeuron)}
 
 
 # ---- spike trains (spike_train/mod.rs) ----------------------------------------------------------

@@ -31,6 +31,9 @@ DEFAULTS = {
                 dt=0.1),
     R.LEAKY_IZH: dict(current_voltage=-65, gap_conductance=7, w_value=30, a=0.02, b=0.2, c=-55, d=8, v_th=30, tau_m=10,
                       c_m=100, e_l=-65, dt=0.1),
+    R.BCM_IZH: dict(current_voltage=-65, gap_conductance=7, w_value=30, a=0.02, b=0.2, c=-55, d=8, v_th=30, tau_m=1, c_m=100,
+                    dt=0.1, average_activity=0, current_activity=0, period=3, num_spikes=0, firing_rate_clock=0,
+                    firing_rate_window=500),
     R.SIMPLE_LIF: dict(current_voltage=-75, gap_conductance=10, v_th=-55, v_reset=-75, c_m=100, g=-0.1, e=0, dt=0.1),
     R.HH: dict(current_voltage=-65, gap_conductance=7, dt=0.01, c_m=1, v_th=0, g_na=120, e_na=50, g_k=36, e_k=-77,
                g_k_leak=0.3, e_k_leak=-55, m=0, h=0, n=0),
@@ -62,14 +65,18 @@ def make(name, model, rows, cols, steps, seed, graph="moore", chem=None, stdp=Fa
     n = rows * cols
     conn = moore(rows, cols) if graph == "moore" else random_conn(n, seed + 7)
     w = np.where(conn, rng.uniform(0.5, 1.5, (n, n)), 0).astype(f32)
-    fields = {k: np.full(n, v, f32) for k, v in DEFAULTS[model].items()}
-    lo, hi = (-65, 30) if model in (R.IZH, R.LEAKY_IZH) else ((-65, -50) if model == R.HH else (-75, -55))
+    fields = {k: np.full(n, v, np.uint32 if k in ("period", "num_spikes") else f32) for k, v in DEFAULTS[model].items()}
+    lo, hi = (-65, 30) if model in (R.IZH, R.LEAKY_IZH, R.BCM_IZH) else ((-65, -50) if model == R.HH else (-75, -55))
     fields["current_voltage"] = rng.uniform(lo, hi, n).astype(f32)
     fields["gap_conductance"] = (gap * rng.uniform(0.5, 1.5, n)).astype(f32)
     # make the lattices fire tonically without an external current (the reference drives lattices only
     # through synapses): Izhikevich b > 0.27 removes the fixed point; leak reversal above threshold; QIF reset
     # above the critical voltage
-    if model in (R.IZH, R.LEAKY_IZH):
+    if model == R.BCM_IZH:
+        # short, per-neuron firing-rate windows so that the activity averages roll over many times in the fixture
+        fields["firing_rate_window"] = rng.choice([1.5, 2.0, 3.25], n).astype(f32)
+        fields["period"] = rng.choice([2, 3, 5], n).astype(np.uint32)
+    if model in (R.IZH, R.LEAKY_IZH, R.BCM_IZH):
         fields["b"] = rng.uniform(0.25, 0.36, n).astype(f32)
         fields["a"] = rng.uniform(0.015, 0.03, n).astype(f32)
         fields["c_m"] = np.full(n, 2, f32)
@@ -124,5 +131,7 @@ if __name__ == "__main__":
     make("simple_lif_random", R.SIMPLE_LIF, 4, 4, 600, 8, graph="random", gap=5.0)
     make("izh_chem_ampa", R.IZH, 4, 5, 600, 9, chem="ampa")
     make("izh_chem_all_stdp", R.IZH, 4, 4, 600, 10, chem="all", stdp=True, c_m=12, stdp_a=0.05)
+    make("bcm_izh_moore", R.BCM_IZH, 4, 5, 600, 13)
+    make("bcm_izh_chem_ampa", R.BCM_IZH, 4, 4, 600, 14, chem="ampa")
     make("hh_moore", R.HH, 3, 4, 3000, 11, gap=2.0)
     make("hh_chem_destexhe", R.HH, 3, 3, 3000, 12, chem="destexhe", gap=2.0)

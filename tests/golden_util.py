@@ -12,7 +12,9 @@ HH_MAP = {"m": "na_channel$m$state", "h": "na_channel$h$state", "n": "k_channel$
           "e_na": "na_channel$e_na", "g_k": "k_channel$g_k", "e_k": "k_channel$e_k", "g_k_leak": "k_leak_channel$g_k_leak",
           "e_k_leak": "k_leak_channel$e_k_leak"}
 # fixtures whose step has no transcendental function: every value must match bit for bit
-EXACT = {"izh_moore", "qif_random", "adlif_moore", "leaky_izh_moore", "simple_lif_random", "izh_chem_ampa"}
+EXACT = {"izh_moore", "qif_random", "adlif_moore", "leaky_izh_moore", "simple_lif_random", "izh_chem_ampa", "bcm_izh_moore",
+         "bcm_izh_chem_ampa"}
+BCM_FIELDS = ("average_activity", "current_activity", "num_spikes", "firing_rate_clock", "w_value")
 
 
 def load(name):
@@ -76,6 +78,10 @@ def check(name, be, g):
         if chem:
             fl = g["nt_flags"].astype(bool)
             assert (be.get_field(0, "neurotransmitters$t").reshape(n, 3)[fl] == g["t_final"][fl]).all()
+        if name.startswith("bcm_"):   # BCMActivity bookkeeping (integrate_and_fire/mod.rs:1458-1467, 1485-1494)
+            assert g["o_average_activity"].max() > 0, "fixture must roll the firing-rate window over"
+            for fname in BCM_FIELDS:
+                assert (be.get_field(0, fname) == g["o_" + fname]).all(), f"{name}: {fname} differs"
         return
     np.testing.assert_allclose(v[:50], g["v_hist"][:50], rtol=1e-5, atol=1e-4)
     bound = 5.0 if chem else 2.0

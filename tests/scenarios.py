@@ -17,9 +17,10 @@ MODELS = {
     "leaky_izh": S.LeakyIzhikevichNeuron,
     "simple_lif": S.SimpleLeakyIntegrateAndFire,
     "hh": S.HodgkinHuxleyNeuron,
+    "bcm_izh": S.BCMIzhikevichNeuron,
 }
 # models whose step uses only + - * / and comparisons: rasters and voltages must match the oracle bit for bit
-EXACT_MODELS = ["lif", "qif", "adlif", "izh", "leaky_izh", "simple_lif"]
+EXACT_MODELS = ["lif", "qif", "adlif", "izh", "leaky_izh", "simple_lif", "bcm_izh"]
 
 
 def random_graph(rows, cols, seed, radius=2.0, p=0.8, weights="ones"):
@@ -80,14 +81,17 @@ def build_lattice(factory, model="izh", rows=6, cols=7, seed=1, graph="grid", ch
     n = rows * cols
     rng = np.random.default_rng(seed)
     if n:
-        lo = -65.0 if model in ("izh", "leaky_izh", "hh") else -75.0
-        hi = {"izh": 30.0, "leaky_izh": 30.0, "hh": -50.0}.get(model, -55.0)
+        lo = -65.0 if model in ("izh", "leaky_izh", "hh", "bcm_izh") else -75.0
+        hi = {"izh": 30.0, "leaky_izh": 30.0, "hh": -50.0, "bcm_izh": 30.0}.get(model, -55.0)
         lat.set_field("current_voltage", rng.uniform(lo, hi, n).astype(f32))
         if hetero:
             lat.set_field("gap_conductance", (gap * rng.uniform(0.5, 1.5, n)).astype(f32))
             # tonic firing without an external current: Izhikevich b > 0.27 removes the fixed point; leak reversal
             # above threshold; QIF reset above the critical voltage (same recipe as tests/golden/make_golden.py)
-            if model in ("izh", "leaky_izh"):
+            if model == "bcm_izh":
+                lat.set_field("firing_rate_window", rng.choice([1.5, 2.0, 3.25], n).astype(f32))
+                lat.set_field("period", rng.choice([2, 3, 5], n).astype(np.uint32))
+            if model in ("izh", "leaky_izh", "bcm_izh"):
                 lat.set_field("a", rng.uniform(0.015, 0.03, n).astype(f32))
                 lat.set_field("b", rng.uniform(0.25, 0.36, n).astype(f32))
                 lat.set_field("d", rng.uniform(6.0, 9.0, n).astype(f32))

@@ -144,7 +144,8 @@ typedef enum snn_option {
     SNN_OPT_PARALLEL = 6,             /* accepted for API parity; the device path is always parallel */
     SNN_OPT_RNG_SEED = 7,             /* Philox key for Poisson spike trains (reference: unseeded thread_rng) */
     SNN_OPT_UPDATE_AVERAGE_HISTORY = 8, /* AverageVoltageHistory, neuron/mod.rs:303-322 */
-    SNN_OPT_STEPS_PER_GRAPH = 9       /* runtime knob: timesteps captured per CUDA graph replay (0 = plain launches) */
+    SNN_OPT_STEPS_PER_GRAPH = 9,      /* runtime knob: timesteps captured per CUDA graph replay (0 = plain launches) */
+    SNN_OPT_UPDATE_EEG_HISTORY = 10   /* default 0 (per lattice): EEGHistory, neuron/mod.rs:231-284 */
 } snn_option_t;
 
 /* STDP, backend/src/neuron/plasticity/mod.rs:14-39 (defaults 2, 2, 4.5, 4.5, 0.1) */
@@ -259,6 +260,10 @@ SNN_API int32_t snn_lattice_history_len(const snn_lattice_t *h, uint64_t *steps)
 SNN_API int32_t snn_lattice_get_grid_history(snn_lattice_t *h, float *out, uint64_t capacity_floats);
 SNN_API int32_t snn_lattice_get_spike_history(snn_lattice_t *h, uint8_t *out, uint64_t capacity_bytes);
 SNN_API int32_t snn_lattice_get_average_history(snn_lattice_t *h, float *out, uint64_t capacity_floats);
+/* EEGHistory (neuron/mod.rs:231-284): one value per step, (1 / (4 pi conductivity distance)) * sum(V - reference_voltage).
+ * Defaults 0.007 mV, 0.8 mm, 251 S/mm (EEGHistory::default, :243-252). */
+SNN_API int32_t snn_lattice_set_eeg_parameters(snn_lattice_t *h, float reference_voltage, float distance, float conductivity);
+SNN_API int32_t snn_lattice_get_eeg_history(snn_lattice_t *h, float *out, uint64_t capacity_floats);
 SNN_API int32_t snn_lattice_reset_history(snn_lattice_t *h);
 
 /* ---- multi-GPU row strips (one process per GPU; plumbing by the caller, e.g. torch.distributed) */
@@ -339,6 +344,9 @@ SNN_API int32_t snn_network_run_timed(snn_network_t *h, uint64_t iterations, flo
 SNN_API int32_t snn_network_history_len(const snn_network_t *h, uint64_t id, uint64_t *steps);
 SNN_API int32_t snn_network_get_grid_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats);
 SNN_API int32_t snn_network_get_spike_history(snn_network_t *h, uint64_t id, uint8_t *out, uint64_t capacity_bytes);
+SNN_API int32_t snn_network_get_average_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats);
+SNN_API int32_t snn_network_set_eeg_parameters(snn_network_t *h, uint64_t id, float reference_voltage, float distance, float conductivity);
+SNN_API int32_t snn_network_get_eeg_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats);
 SNN_API int32_t snn_network_reset_history(snn_network_t *h);
 
 #ifdef __cplusplus

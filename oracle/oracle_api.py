@@ -71,6 +71,8 @@ def lib():
         "orc_seed": ([P, u64], None),
         "orc_run": ([P, u64], i32),
         "orc_history_len": ([P, u64], u64),
+        "orc_set_reduced_history": ([P, u64, i32, i32, f, f, f], i32),
+        "orc_get_reduced_history": ([P, u64, i32, P, u64], i32),
         "orc_get_grid_history": ([P, u64, P, u64], i32),
         "orc_get_spike_history": ([P, u64, P, u64], i32),
         "orc_reset_history": ([P], None),
@@ -127,6 +129,7 @@ class OracleBackend:
         self.L = lib()
         self.h = self.L.orc_network_create(model, ntk, rck, train_kind, refract)
         self._flags = {}
+        self._red = {}
         if rows is not None:
             self.add_lattice(0, rows, cols)
 
@@ -232,6 +235,11 @@ class OracleBackend:
             self.L.orc_set_parallel(self.h, value)
         elif option == 7:
             self.L.orc_seed(self.h, value)
+        elif option in (8, 10):
+            lid = 0 if id is None else id
+            r = self._red.setdefault(lid, [0, 0, 0.007, 0.8, 251.0])
+            r[0 if option == 8 else 1] = value
+            self._ck(self.L.orc_set_reduced_history(self.h, lid, *r))
         elif option == 9:
             pass
         else:
@@ -269,6 +277,23 @@ class OracleBackend:
         out = np.zeros(steps * n, np.uint8)
         self._ck(self.L.orc_get_spike_history(self.h, id, _ptr(out), out.size))
         return out.reshape(steps, n)
+
+    def set_eeg_parameters(self, id, reference_voltage, distance, conductivity):
+        lid = 0 if id is None else id
+        r = self._red.setdefault(lid, [0, 0, 0.007, 0.8, 251.0])
+        r[2:] = [float(reference_voltage), float(distance), float(conductivity)]
+        self._ck(self.L.orc_set_reduced_history(self.h, lid, *r))
+
+    def _reduced(self, id, eeg):
+        out = np.zeros(self.history_len(id), np.float32)
+        self._ck(self.L.orc_get_reduced_history(self.h, id, eeg, _ptr(out), out.size))
+        return out
+
+    def average_history(self, id=0):
+        return self._reduced(id, 0)
+
+    def eeg_history(self, id=0):
+        return self._reduced(id, 1)
 
     def reset_history(self):
         self.L.orc_reset_history(self.h)

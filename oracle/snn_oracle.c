@@ -93,6 +93,11 @@ typedef struct {
     orc_stdp plasticity;
     uint64_t internal_clock;
     float *grid_history;
+    /* AverageVoltageHistory / EEGHistory neuron/mod.rs:231-322 */
+    int update_average_history, update_eeg_history;
+    float eeg_reference_voltage, eeg_distance, eeg_conductivity;
+    float *average_history, *eeg_history;
+    uint64_t red_cap;
     uint8_t *spike_history;
     uint64_t hist_len, hist_cap;
 } o_lattice;
@@ -325,7 +330,7 @@ void orc_network_destroy(orc_network *net) {
     for (int i = 0; i < net->n_lat; i++) {
         o_lattice *L = net->lat[i];
         if (L->trains) for (uint64_t j = 0; j < L->n; j++) free(L->trains[j].firing_times);
-        free(L->cells); free(L->trains); free(L->grid_history); free(L->spike_history); free(L);
+        free(L->cells); free(L->trains); free(L->grid_history); free(L->spike_history); free(L->average_history); free(L->eeg_history); free(L);
     }
     free(net->lat); free(net);
 }
@@ -688,6 +693,24 @@ int orc_set_lattice_flags(orc_network *net, uint64_t id, int do_plasticity, int 
     if (!L) return 35;
     L->do_plasticity = do_plasticity; L->update_grid_history = update_grid_history;
     L->update_spike_history = update_spike_history;
+    return 0;
+}
+
+int orc_set_reduced_history(orc_network *net, uint64_t id, int average, int eeg, float reference_voltage, float distance,
+                            float conductivity) {
+    o_lattice *L = find_lat(net, id);
+    if (!L) return 35;
+    L->update_average_history = average; L->update_eeg_history = eeg;
+    L->eeg_reference_voltage = reference_voltage; L->eeg_distance = distance; L->eeg_conductivity = conductivity;
+    return 0;
+}
+
+int orc_get_reduced_history(orc_network *net, uint64_t id, int eeg, float *out, uint64_t capacity) {
+    o_lattice *L = find_lat(net, id);
+    if (!L) return 35;
+    if (capacity < L->hist_len) return 67;
+    const float *h = eeg ? L->eeg_history : L->average_history;
+    if (h) memcpy(out, h, sizeof(float) * L->hist_len);
     return 0;
 }
 
@@ -1197,6 +1220,23 @@ static void update_weights_from_neuron(orc_network *net, o_lattice *L, uint64_t 
 }
 
 static void history_push(o_lattice *L) {
+    if (!L->is_train && (L->update_average_history || L->update_eeg_history)) {
+        if (L->hist_len >= L->red_cap) {
+            L->red_cap = L->red_cap ? L->red_cap * 2 : 64;
+            while (L->red_cap <= L->hist_len) L->red_cap *= 2;
+            L->average_history = realloc(L->average_history, sizeof(float) * L->red_cap);
+            L->eeg_history = realloc(L->eeg_history, sizeof(float) * L->red_cap);
+        }
+        /* AverageVoltageHistory::update :310-316: voltages.into_iter().sum::<f32>() / length (sequential f32 sum) */
+        float sum = 0.f, total_current = 0.f;
+        for (uint64_t j = 0; j < L->n; j++) {
+            sum += L->cells[j].current_voltage;
+            total_current += L->cells[j].current_voltage - L->eeg_reference_voltage; /* EEGHistory::update :266-279 */
+        }
+        L->average_history[L->hist_len] = sum / (float)L->n;
+        L->eeg_history[L->hist_len] = (1.f / (4.f * 3.14159274101257324f * L->eeg_conductivity * L->eeg_distance)) * total_current;
+        if (!L->update_grid_history && !L->update_spike_history) { L->hist_len++; return; }
+    }
     if (!L->update_grid_history && !L->update_spike_history) return;
     if (L->hist_len == L->hist_cap) {
         L->hist_cap = L->hist_cap ? L->hist_cap * 2 : 64;

@@ -92,6 +92,10 @@ void orc_seed(orc_network *net, uint64_t seed); /* oracle-local xorshift for Poi
 /* RunNetwork::run_lattices / RunLattice::run_lattice */
 int orc_run(orc_network *net, uint64_t iterations);
 
+/* AverageVoltageHistory / EEGHistory (neuron/mod.rs:231-322): one f32 per step, sequential f32 sums like the reference */
+int orc_set_reduced_history(orc_network *net, uint64_t id, int average, int eeg, float reference_voltage, float distance,
+                            float conductivity);
+int orc_get_reduced_history(orc_network *net, uint64_t id, int eeg, float *out, uint64_t capacity);
 uint64_t orc_history_len(orc_network *net, uint64_t id);
 int orc_get_grid_history(orc_network *net, uint64_t id, float *out, uint64_t capacity);
 int orc_get_spike_history(orc_network *net, uint64_t id, uint8_t *out, uint64_t capacity);

@@ -225,7 +225,8 @@ static int32_t engine_set_option(Engine *e, bool have_id, uint64_t id, int32_t o
     case SNN_OPT_DO_PLASTICITY: if (!L) break; L->do_plasticity = value != 0; return SNN_OK;
     case SNN_OPT_UPDATE_GRID_HISTORY: if (!L) break; L->grid_hist = value != 0; return SNN_OK;
     case SNN_OPT_UPDATE_SPIKE_HISTORY: if (!L) break; L->spike_hist = value != 0; return SNN_OK;
-    case SNN_OPT_UPDATE_AVERAGE_HISTORY: return e->fail(SNN_UNSUPPORTED, "AverageVoltageHistory is not implemented yet");
+    case SNN_OPT_UPDATE_AVERAGE_HISTORY: if (!L || L->is_train) break; L->avg_hist = value != 0; return SNN_OK;
+    case SNN_OPT_UPDATE_EEG_HISTORY: if (!L || L->is_train) break; L->eeg_hist = value != 0; return SNN_OK;
     }
     return e->fail(SNN_INVALID_ARGUMENT, "unknown option or missing lattice id");
 }
@@ -243,7 +244,8 @@ static int32_t engine_get_option(const Engine *e, bool have_id, uint64_t id, int
     case SNN_OPT_DO_PLASTICITY: if (!L) break; *value = L->do_plasticity; return SNN_OK;
     case SNN_OPT_UPDATE_GRID_HISTORY: if (!L) break; *value = L->grid_hist; return SNN_OK;
     case SNN_OPT_UPDATE_SPIKE_HISTORY: if (!L) break; *value = L->spike_hist; return SNN_OK;
-    case SNN_OPT_UPDATE_AVERAGE_HISTORY: *value = 0; return SNN_OK;
+    case SNN_OPT_UPDATE_AVERAGE_HISTORY: if (!L) break; *value = L->avg_hist; return SNN_OK;
+    case SNN_OPT_UPDATE_EEG_HISTORY: if (!L) break; *value = L->eeg_hist; return SNN_OK;
     }
     return SNN_INVALID_ARGUMENT;
 }
@@ -294,9 +296,17 @@ int32_t snn_lattice_get_spike_history(snn_lattice_t *h, uint8_t *out, uint64_t c
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->get_spike_history(kLatticeId, out, capacity_bytes); SNN_CATCH(h)
 }
-int32_t snn_lattice_get_average_history(snn_lattice_t *h, float *, uint64_t) {
+int32_t snn_lattice_get_average_history(snn_lattice_t *h, float *out, uint64_t capacity_floats) {
     if (!h) return SNN_INVALID_ARGUMENT;
-    return h->e->fail(SNN_UNSUPPORTED, "AverageVoltageHistory is not implemented yet");
+    SNN_TRY return h->e->get_reduced_history(kLatticeId, false, out, capacity_floats); SNN_CATCH(h)
+}
+int32_t snn_lattice_set_eeg_parameters(snn_lattice_t *h, float reference_voltage, float distance, float conductivity) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    return h->e->set_eeg_parameters(kLatticeId, reference_voltage, distance, conductivity);
+}
+int32_t snn_lattice_get_eeg_history(snn_lattice_t *h, float *out, uint64_t capacity_floats) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_reduced_history(kLatticeId, true, out, capacity_floats); SNN_CATCH(h)
 }
 int32_t snn_lattice_reset_history(snn_lattice_t *h) {
     if (!h) return SNN_INVALID_ARGUMENT;
@@ -450,6 +460,18 @@ int32_t snn_network_history_len(const snn_network_t *h, uint64_t id, uint64_t *s
 int32_t snn_network_get_grid_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats) {
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->get_grid_history(id, out, capacity_floats); SNN_CATCH(h)
+}
+int32_t snn_network_get_average_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_reduced_history(id, false, out, capacity_floats); SNN_CATCH(h)
+}
+int32_t snn_network_set_eeg_parameters(snn_network_t *h, uint64_t id, float reference_voltage, float distance, float conductivity) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    return h->e->set_eeg_parameters(id, reference_voltage, distance, conductivity);
+}
+int32_t snn_network_get_eeg_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_reduced_history(id, true, out, capacity_floats); SNN_CATCH(h)
 }
 int32_t snn_network_get_spike_history(snn_network_t *h, uint64_t id, uint8_t *out, uint64_t capacity_bytes) {
     if (!h) return SNN_INVALID_ARGUMENT;

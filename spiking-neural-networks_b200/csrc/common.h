@@ -255,6 +255,9 @@ cudaError_t launch_sell_grid(uint32_t rows_local, uint32_t cols, uint32_t row0_g
                              uint32_t radius, float weight, uint32_t own0, const uint8_t *node_flags, uint32_t width,
                              uint32_t *slice_off, uint32_t *col, float *wgt, cudaStream_t s);
 cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s);
+// per (step, lattice): sum of V and sum of (V - ref) over the lattice's neurons, f64, fixed reduction order
+cudaError_t launch_history_reduce(const float *grid, uint64_t n_neurons, uint32_t steps, const uint32_t *lat_base, const uint32_t *lat_n,
+                                  const float *lat_ref, int n_lat, double *out, cudaStream_t s);
 cudaError_t launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t s);
 cudaError_t launch_bits_from_u32(const uint32_t *src, uint32_t *words, uint64_t n, uint64_t bit0, cudaStream_t s);
 cudaError_t launch_u32_from_bits(const uint32_t *words, uint32_t *dst, uint64_t n, uint64_t bit0, cudaStream_t s);

@@ -1044,7 +1044,7 @@ int Engine::reset_timing() {
 }
 
 int Engine::reset_history() {
-    for (auto &L : lats_) { L.grid_history.clear(); L.spike_history.clear(); L.hist_len = 0; }
+    for (auto &L : lats_) { L.grid_history.clear(); L.spike_history.clear(); L.average_history.clear(); L.eeg_history.clear(); L.hist_len = 0; }
     return SNN_OK;
 }
 
@@ -1060,6 +1060,22 @@ int Engine::get_grid_history(uint64_t id, float *out, uint64_t capacity) {
     if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
     if (capacity < L->grid_history.size()) return fail(SNN_SIZE_MISMATCH, "history buffer too small");
     if (!L->grid_history.empty()) memcpy(out, L->grid_history.data(), L->grid_history.size() * 4);
+    return SNN_OK;
+}
+
+int Engine::get_reduced_history(uint64_t id, bool eeg, float *out, uint64_t capacity) {
+    Lat *L = find(id);
+    if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    const std::vector<float> &h = eeg ? L->eeg_history : L->average_history;
+    if (capacity < h.size()) return fail(SNN_SIZE_MISMATCH, "history buffer too small");
+    if (!h.empty()) memcpy(out, h.data(), h.size() * 4);
+    return SNN_OK;
+}
+
+int Engine::set_eeg_parameters(uint64_t id, float reference_voltage, float distance, float conductivity) {
+    Lat *L = find(id);
+    if (!L || L->is_train) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    L->eeg_ref = reference_voltage; L->eeg_dist = distance; L->eeg_cond = conductivity;
     return SNN_OK;
 }
 
@@ -1299,9 +1315,9 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     r = upload_lat_table();
     if (r) return r;
 
-    bool stdp = false, want_grid = false, want_spk = false, want_tgrid = false, want_tspk = false;
+    bool stdp = false, want_grid = false, want_spk = false, want_tgrid = false, want_tspk = false, want_red = false;
     for (auto &L : lats_) {
-        if (!L.is_train) { stdp |= L.do_plasticity; want_grid |= L.grid_hist; want_spk |= L.spike_hist; }
+        if (!L.is_train) { stdp |= L.do_plasticity; want_grid |= L.grid_hist; want_spk |= L.spike_hist; want_red |= L.avg_hist || L.eeg_hist; }
         else { want_tgrid |= L.grid_hist; want_tspk |= L.spike_hist; }
     }
     // kernel specialisation: ntrel = neurotransmitter / receptor state must be stepped; chemg = how the chemical gather
@@ -1348,6 +1364,9 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     // history staging: chunks of steps recorded on the device, drained to the host between chunks
     const uint64_t n_words = (n_neurons + 31) / 32, t_words = (n_trains + 31) / 32;
     uint64_t per_step_bytes = 0;
+    // AverageVoltageHistory / EEGHistory are reductions of the staged grid record (it stays on the device for them)
+    const bool copy_grid = want_grid;
+    want_grid = want_grid || want_red;
     if (want_grid) per_step_bytes += n_neurons * 4;
     if (want_spk) per_step_bytes += n_words * 4;
     if (want_tgrid) per_step_bytes += n_trains * 4;
@@ -1359,7 +1378,22 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     if (want_spk) CK(dev_alloc(&d_spk, chunk * n_words), SNN_GPU_BUFFER_CREATE_ERROR);
     if (want_tgrid) CK(dev_alloc(&d_tgrid, chunk * n_trains), SNN_GPU_BUFFER_CREATE_ERROR);
     if (want_tspk) CK(dev_alloc(&d_tspk, chunk * t_words), SNN_GPU_BUFFER_CREATE_ERROR);
-    auto free_hist = [&]() { cudaFree(d_grid); cudaFree(d_spk); cudaFree(d_tgrid); cudaFree(d_tspk); };
+    double *d_red = nullptr; uint32_t *d_red_lat = nullptr;
+    std::vector<const Lat *> red_lats;
+    if (want_red) {
+        std::vector<uint32_t> meta;
+        for (auto &L : lats_) if (!L.is_train && (L.avg_hist || L.eeg_hist)) red_lats.push_back(&L);
+        const size_t nl = red_lats.size();
+        meta.resize(3 * nl);
+        for (size_t k = 0; k < nl; ++k) {
+            meta[k] = (uint32_t)red_lats[k]->off; meta[nl + k] = (uint32_t)red_lats[k]->n;
+            memcpy(&meta[2 * nl + k], &red_lats[k]->eeg_ref, 4);
+        }
+        CK(dev_alloc(&d_red, chunk * nl * 2), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(dev_alloc(&d_red_lat, 3 * nl), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(cudaMemcpy(d_red_lat, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    }
+    auto free_hist = [&]() { cudaFree(d_grid); cudaFree(d_spk); cudaFree(d_tgrid); cudaFree(d_tspk); cudaFree(d_red); cudaFree(d_red_lat); };
 
     uint64_t n_launch = 0;
     float total_ms = 0.f;
@@ -1497,7 +1531,26 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
         // drain histories
         if (per_step_bytes) {
             std::vector<float> hg, htg; std::vector<uint32_t> hs, hts;
-            if (want_grid) { hg.resize(steps * n_neurons); cudaMemcpy(hg.data(), d_grid, hg.size() * 4, cudaMemcpyDeviceToHost); }
+            if (copy_grid) { hg.resize(steps * n_neurons); cudaMemcpy(hg.data(), d_grid, hg.size() * 4, cudaMemcpyDeviceToHost); }
+            if (want_red) {
+                const size_t nl = red_lats.size();
+                cudaError_t re = launch_history_reduce(d_grid, n_neurons, (uint32_t)steps, d_red_lat, d_red_lat + nl,
+                                                       (const float *)(d_red_lat + 2 * nl), (int)nl, d_red, stream_);
+                std::vector<double> hr(steps * nl * 2);
+                if (re == cudaSuccess) re = cudaMemcpy(hr.data(), d_red, hr.size() * 8, cudaMemcpyDeviceToHost);
+                if (re != cudaSuccess) { bail(re, SNN_GPU_BUFFER_READ_ERROR, "history reduce"); break; }
+                for (size_t k = 0; k < nl; ++k) {
+                    Lat &L = const_cast<Lat &>(*red_lats[k]);
+                    for (uint64_t s = 0; s < steps; ++s) {
+                        const double sum_v = hr[(s * nl + k) * 2], sum_dv = hr[(s * nl + k) * 2 + 1];
+                        // AverageVoltageHistory::update, neuron/mod.rs:310-316: sum / len as f32
+                        if (L.avg_hist) L.average_history.push_back((float)sum_v / (float)L.n);
+                        // EEGHistory::update, neuron/mod.rs:266-279: (1 / (4 pi sigma d)) * total_current
+                        if (L.eeg_hist) L.eeg_history.push_back((1.f / (4.f * 3.14159274101257324f * L.eeg_cond * L.eeg_dist)) * (float)sum_dv);
+                    }
+                    if (!L.grid_hist && !L.spike_hist) L.hist_len += steps;
+                }
+            }
             if (want_spk) { hs.resize(steps * n_words); cudaMemcpy(hs.data(), d_spk, hs.size() * 4, cudaMemcpyDeviceToHost); }
             if (want_tgrid) { htg.resize(steps * n_trains); cudaMemcpy(htg.data(), d_tgrid, htg.size() * 4, cudaMemcpyDeviceToHost); }
             if (want_tspk) { hts.resize(steps * t_words); cudaMemcpy(hts.data(), d_tspk, hts.size() * 4, cudaMemcpyDeviceToHost); }

@@ -22,6 +22,9 @@ struct Lat {
     bool is_train = false;
     uint64_t off = 0;  // offset inside its domain (local neuron number / local train number)
     bool do_plasticity = false, grid_hist = false, spike_hist = false;
+    bool avg_hist = false, eeg_hist = false;        // AverageVoltageHistory / EEGHistory (neuron/mod.rs:231-322)
+    float eeg_ref = 0.007f, eeg_dist = 0.8f, eeg_cond = 251.f;   // EEGHistory::default, neuron/mod.rs:243-252
+    std::vector<float> average_history, eeg_history;
     snn_stdp_t stdp{2.f, 2.f, 4.5f, 4.5f, 0.1f};  // STDP::default, plasticity/mod.rs:29-39
     uint64_t clock = 0;                           // SpikeTrainLattice::internal_clock
     std::vector<float> cold[2];                   // v_init, w_init
@@ -94,6 +97,8 @@ public:
     int history_len(uint64_t id, uint64_t *steps) const;
     int get_grid_history(uint64_t id, float *out, uint64_t capacity);
     int get_spike_history(uint64_t id, uint8_t *out, uint64_t capacity);
+    int get_reduced_history(uint64_t id, bool eeg, float *out, uint64_t capacity);
+    int set_eeg_parameters(uint64_t id, float reference_voltage, float distance, float conductivity);
 
     // multi-GPU
     int ipc_export(IpcBlob *blob);

@@ -422,6 +422,37 @@ cudaError_t launch_sell_grid(uint32_t rows_local, uint32_t cols, uint32_t row0_g
     return cudaGetLastError();
 }
 
+// AverageVoltageHistory / EEGHistory (neuron/mod.rs:231-322): block (step, lattice) sums the staged grid record in f64 in a
+// fixed order (thread-strided partial sums, then a shared-memory tree), so repeated runs give identical values
+__global__ void history_reduce_kernel(const float *grid, uint64_t n_neurons, const uint32_t *lat_base, const uint32_t *lat_n,
+                                      const float *lat_ref, int n_lat, double *out) {
+    __shared__ double sh[2][256];
+    const uint32_t step = blockIdx.x, k = blockIdx.y;
+    const float *row = grid + (size_t)step * n_neurons + lat_base[k];
+    const uint32_t n = lat_n[k];
+    const float ref = lat_ref[k];
+    double a = 0.0, b = 0.0;
+    for (uint32_t i = threadIdx.x; i < n; i += 256u) {
+        const float v = row[i];
+        a += (double)v;
+        b += (double)(v - ref);   // value - self.reference_voltage in f32, neuron/mod.rs:272
+    }
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
+    __syncthreads();
+    for (uint32_t w = 128u; w > 0u; w >>= 1) {
+        if (threadIdx.x < w) { sh[0][threadIdx.x] += sh[0][threadIdx.x + w]; sh[1][threadIdx.x] += sh[1][threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[((size_t)step * n_lat + k) * 2] = sh[0][0]; out[((size_t)step * n_lat + k) * 2 + 1] = sh[1][0]; }
+}
+
+cudaError_t launch_history_reduce(const float *grid, uint64_t n_neurons, uint32_t steps, const uint32_t *lat_base, const uint32_t *lat_n,
+                                  const float *lat_ref, int n_lat, double *out, cudaStream_t s) {
+    if (steps == 0 || n_lat == 0) return cudaSuccess;
+    history_reduce_kernel<<<dim3(steps, (unsigned)n_lat), 256, 0, s>>>(grid, n_neurons, lat_base, lat_n, lat_ref, n_lat, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     fill_u32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, v, n);

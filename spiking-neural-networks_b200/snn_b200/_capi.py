@@ -38,7 +38,8 @@ TRAIN_POISSON, TRAIN_RATE, TRAIN_PRESET = range(3)
 REFRACT_DELTA_DIRAC, REFRACT_EXPONENTIAL_DECAY = range(2)
 F32, U32, I32 = range(3)
 (OPT_ELECTRICAL_SYNAPSE, OPT_CHEMICAL_SYNAPSE, OPT_DO_PLASTICITY, OPT_UPDATE_GRID_HISTORY, OPT_UPDATE_SPIKE_HISTORY,
- OPT_INTERNAL_CLOCK, OPT_PARALLEL, OPT_RNG_SEED, OPT_UPDATE_AVERAGE_HISTORY, OPT_STEPS_PER_GRAPH) = range(10)
+ OPT_INTERNAL_CLOCK, OPT_PARALLEL, OPT_RNG_SEED, OPT_UPDATE_AVERAGE_HISTORY, OPT_STEPS_PER_GRAPH,
+ OPT_UPDATE_EEG_HISTORY) = range(11)
 
 
 class StdpStruct(C.Structure):
@@ -107,6 +108,8 @@ SIGNATURES = {
     "snn_lattice_get_grid_history": ([_P, _P, _u64], _i32),
     "snn_lattice_get_spike_history": ([_P, _P, _u64], _i32),
     "snn_lattice_get_average_history": ([_P, _P, _u64], _i32),
+    "snn_lattice_set_eeg_parameters": ([_P, C.c_float, C.c_float, C.c_float], _i32),
+    "snn_lattice_get_eeg_history": ([_P, _P, _u64], _i32),
     "snn_lattice_reset_history": ([_P], _i32),
     "snn_partition_begin": ([_u32, _i32, _i32], _u32),
     "snn_lattice_ipc_blob_size": ([], _u32),
@@ -141,6 +144,9 @@ SIGNATURES = {
     "snn_network_history_len": ([_P, _u64, C.POINTER(_u64)], _i32),
     "snn_network_get_grid_history": ([_P, _u64, _P, _u64], _i32),
     "snn_network_get_spike_history": ([_P, _u64, _P, _u64], _i32),
+    "snn_network_get_average_history": ([_P, _u64, _P, _u64], _i32),
+    "snn_network_set_eeg_parameters": ([_P, _u64, C.c_float, C.c_float, C.c_float], _i32),
+    "snn_network_get_eeg_history": ([_P, _u64, _P, _u64], _i32),
     "snn_network_reset_history": ([_P], _i32),
 }
 

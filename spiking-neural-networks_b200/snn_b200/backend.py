@@ -202,6 +202,19 @@ class CudaLatticeBackend(_CudaBase):
         self._ck(self.lib.snn_lattice_get_spike_history(self.h, _ptr(out), out.size))
         return out.reshape(steps, n)
 
+    def set_eeg_parameters(self, id, reference_voltage, distance, conductivity):
+        self._ck(self.lib.snn_lattice_set_eeg_parameters(self.h, reference_voltage, distance, conductivity))
+
+    def average_history(self, id=0):
+        out = np.zeros(self.history_len(), np.float32)
+        self._ck(self.lib.snn_lattice_get_average_history(self.h, _ptr(out), out.size))
+        return out
+
+    def eeg_history(self, id=0):
+        out = np.zeros(self.history_len(), np.float32)
+        self._ck(self.lib.snn_lattice_get_eeg_history(self.h, _ptr(out), out.size))
+        return out
+
     def reset_history(self):
         self._ck(self.lib.snn_lattice_reset_history(self.h))
 
@@ -313,6 +326,19 @@ class CudaNetworkBackend(_CudaBase):
         out = np.zeros(steps * n, np.uint8)
         self._ck(self.lib.snn_network_get_spike_history(self.h, id, _ptr(out), out.size))
         return out.reshape(steps, n)
+
+    def set_eeg_parameters(self, id, reference_voltage, distance, conductivity):
+        self._ck(self.lib.snn_network_set_eeg_parameters(self.h, id, reference_voltage, distance, conductivity))
+
+    def average_history(self, id):
+        out = np.zeros(self.history_len(id), np.float32)
+        self._ck(self.lib.snn_network_get_average_history(self.h, id, _ptr(out), out.size))
+        return out
+
+    def eeg_history(self, id):
+        out = np.zeros(self.history_len(id), np.float32)
+        self._ck(self.lib.snn_network_get_eeg_history(self.h, id, _ptr(out), out.size))
+        return out
 
     def reset_history(self):
         self._ck(self.lib.snn_network_reset_history(self.h))

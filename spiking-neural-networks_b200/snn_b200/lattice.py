@@ -52,6 +52,7 @@ def _enc(v):
 
 class GridVoltageHistory:
     """neuron/mod.rs:286-301: `.history[step][row][col]`."""
+    option = K.OPT_UPDATE_GRID_HISTORY
 
     def __init__(self, owner):
         self._o = owner
@@ -75,6 +76,28 @@ class SpikeHistory(GridVoltageHistory):
 
     def aggregate(self):
         return self.history.sum(axis=0).astype(np.int64)
+
+
+class AverageVoltageHistory(GridVoltageHistory):
+    """neuron/mod.rs:303-322: `.history[step]` = mean membrane voltage of the lattice."""
+    option = K.OPT_UPDATE_AVERAGE_HISTORY
+
+    @property
+    def history(self):
+        return self._o._be.average_history(self._o._bid)
+
+
+class EEGHistory(GridVoltageHistory):
+    """neuron/mod.rs:231-284: `.history[step]` = (1 / (4 pi conductivity distance)) * sum(V - reference_voltage)."""
+    option = K.OPT_UPDATE_EEG_HISTORY
+
+    def __init__(self, owner, reference_voltage=0.007, distance=0.8, conductivity=251.0):
+        super().__init__(owner)
+        self.reference_voltage, self.distance, self.conductivity = reference_voltage, distance, conductivity
+
+    @property
+    def history(self):
+        return self._o._be.eeg_history(self._o._bid)
 
 
 class _CellLattice:
@@ -147,8 +170,11 @@ class _CellLattice:
 class Lattice(_CellLattice):
     """Lattice<T, U, V, W, N> (neuron/mod.rs:556-587) with T = `neuron_type`, W = STDP."""
 
-    def __init__(self, neuron_type=IzhikevichNeuron, id=0, backend_factory=None):
+    def __init__(self, neuron_type=IzhikevichNeuron, id=0, backend_factory=None, history_type=GridVoltageHistory):
+        """`history_type` mirrors the reference's LatticeHistory type parameter (GridVoltageHistory, AverageVoltageHistory
+        or EEGHistory); `update_grid_history` switches whichever was chosen on."""
         super().__init__()
+        self.grid_history = history_type(self)
         self.neuron_type = neuron_type
         self._id = id
         self._factory = backend_factory or _default_lattice_backend
@@ -378,7 +404,10 @@ class Lattice(_CellLattice):
             be.set_option(K.OPT_ELECTRICAL_SYNAPSE, self.electrical_synapse)
             be.set_option(K.OPT_CHEMICAL_SYNAPSE, self.chemical_synapse)
         be.set_option(K.OPT_DO_PLASTICITY, self.do_plasticity, i)
-        be.set_option(K.OPT_UPDATE_GRID_HISTORY, self.update_grid_history, i)
+        gh = self.grid_history
+        if isinstance(gh, EEGHistory):
+            be.set_eeg_parameters(i, gh.reference_voltage, gh.distance, gh.conductivity)
+        be.set_option(gh.option, self.update_grid_history, i)
         be.set_option(K.OPT_UPDATE_SPIKE_HISTORY, self.update_spike_history, i)
         p = self.plasticity
         be.set_plasticity(i, p.a_plus, p.a_minus, p.tau_plus, p.tau_minus, p.dt)

@@ -82,3 +82,24 @@ def test_network_assembly_and_errors(oracle_lattice_factory, oracle_network_fact
 def test_poisson_from_firing_rate_matches_reference_formula():
     p = S.PoissonNeuron.from_firing_rate(20.0, 0.1)
     assert p.chance_of_firing == float(f32(1.0) / ((f32(1000.0) / f32(0.1)) / f32(20.0)))
+
+
+def test_reduced_histories_on_the_oracle(oracle_lattice_factory):
+    """AverageVoltageHistory / EEGHistory restated literally (sequential f32 sums, neuron/mod.rs:266-279, 310-316)."""
+    kw = dict(model="izh", rows=5, cols=6, seed=2, graph="grid")
+    avg = SC.build_lattice(oracle_lattice_factory, history_type=S.AverageVoltageHistory, **kw)
+    eeg = SC.build_lattice(oracle_lattice_factory, history_type=S.EEGHistory, **kw)
+    grid = SC.build_lattice(oracle_lattice_factory, **kw)
+    for L in (avg, eeg, grid):
+        L.run_lattice(50)
+    v = grid.grid_history.history.reshape(50, -1)
+    want_avg, want_eeg = [], []
+    for row in v:
+        s, t = f32(0), f32(0)
+        for x in row:
+            s = f32(s + x)
+            t = f32(t + f32(x - f32(0.007)))
+        want_avg.append(f32(s / f32(30)))
+        want_eeg.append(f32(f32(1) / f32(f32(f32(f32(4) * f32(np.pi)) * f32(251.0)) * f32(0.8))) * t)
+    assert (avg.grid_history.history == np.array(want_avg, f32)).all()
+    assert (eeg.grid_history.history == np.array(want_eeg, f32)).all()

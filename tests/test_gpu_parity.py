@@ -74,6 +74,37 @@ def test_config1_izhikevich_100x100_first_steps(oracle_lattice_factory):
     SC.compare_lattices(a, b, exact=True, fields=state_fields("izh"))
 
 
+# ------------------------------------------------------------------ reduced histories
+@pytest.mark.parametrize("kind", ["average", "eeg"])
+@pytest.mark.parametrize("shape", [(7, 9), (40, 50)])
+def test_average_and_eeg_history(kind, shape, oracle_lattice_factory):
+    """AverageVoltageHistory / EEGHistory (neuron/mod.rs:231-322).  The reference sums sequentially in f32; the device
+    reduces the same voltages in f64 in a fixed order, so the bar is the rounding of a length-N f32 sum: rel 1e-5, and
+    1e-6 against the f64 mean of the (bit-exact) grid voltages."""
+    ht = S.AverageVoltageHistory if kind == "average" else S.EEGHistory
+    kw = dict(model="izh", rows=shape[0], cols=shape[1], seed=3, graph="grid")
+    a, b = SC.build_lattice(None, history_type=ht, **kw), SC.build_lattice(oracle_lattice_factory, history_type=ht, **kw)
+    g = SC.build_lattice(None, **kw)   # same lattice recording the full grid
+    if kind == "eeg":
+        for L in (a, b):
+            L.grid_history.reference_voltage, L.grid_history.distance, L.grid_history.conductivity = 0.5, 1.25, 100.0
+    for L in (a, b, g):
+        L.run_lattice(120)
+        L.run_lattice(80)   # histories append across run calls
+    ha, hb = a.grid_history.history, b.grid_history.history
+    assert ha.shape == hb.shape == (200,) and ha.dtype == np.float32
+    np.testing.assert_allclose(ha, hb, rtol=1e-5, atol=1e-5)
+    v = g.grid_history.history.reshape(200, -1)
+    if kind == "average":
+        np.testing.assert_allclose(ha, v.astype(np.float64).mean(axis=1), rtol=1e-6, atol=1e-6)
+    else:
+        tot = (v - f32(0.5)).astype(np.float64).sum(axis=1)
+        np.testing.assert_allclose(ha, tot / (4 * np.pi * 100.0 * 1.25), rtol=1e-6, atol=1e-6)
+    assert (a.spike_history.history == b.spike_history.history).all()
+    a.grid_history.reset()
+    assert a.grid_history.history.shape == (0,)
+
+
 # ------------------------------------------------------------------ transcendental models: tolerance
 @pytest.mark.parametrize("model,graph,steps", [("adex", "grid", 500), ("adex", "random", 500), ("hh", "grid", 2000),
                                                ("hh", "random", 2000)])

@@ -245,6 +245,9 @@ cudaError_t launch_step_win(const StepParams &p, const WinParams &wp, int model,
 // chemg: 0 no chemical gather, 1 one neurotransmitter type in the whole node array, 3 general; ntrel: neurotransmitter /
 // receptor state is present and must be stepped; net: several lattices and/or spike trains share the node array
 cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, cudaStream_t s);
+// same contract as launch_step, one CTA per slice (step_wide.cu): graphs with wide rows, single-GPU handles only
+constexpr uint32_t kWideMinWidth = 48;   // mean k-rows per slice from which the wide kernel is used
+cudaError_t launch_step_wide(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, cudaStream_t s);
 cudaError_t launch_trains(const TrainParams &p, cudaStream_t s);
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s);
 cudaError_t launch_finalize(const StepParams &p, int model, const float *v_prev, cudaStream_t s);

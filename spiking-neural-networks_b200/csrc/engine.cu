@@ -1340,6 +1340,9 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     unsigned win_grid = 0;
     const bool win_ok = !net && build_win_params(win, chemg, ntrel, stdp, lft_pp, &win_grid);
     const bool tma_ok = !win_ok && !net && build_tma_params(tma, ntrel, stdp, lft_pp, &tma_grid);
+    // wide rows (hundreds of in-edges per neuron, e.g. all-to-all spike-train input): one CTA per slice
+    bool wide = !win_ok && !tma_ok && part_world == 1 && n_slices_ > 0 && sell_krows_ / n_slices_ >= kWideMinWidth;
+    if (const char *e = getenv("SNN_B200_WIDE")) wide = wide && atoi(e) != 0;
     // indices of the ping-ponged streams, patched every step
     int tma_iv = -1, tma_il = -1, tma_it[kNT] = {-1, -1, -1};
     if (tma_ok) {
@@ -1455,7 +1458,8 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_tma"); break; }
                 n_launch++;
             } else if (n_neurons) {
-                cudaError_t e = launch_step(sp, model, chemg, ntrel, stdp, net, stream_);
+                cudaError_t e = wide ? launch_step_wide(sp, model, chemg, ntrel, stdp, net, stream_)
+                                     : launch_step(sp, model, chemg, ntrel, stdp, net, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step"); break; }
                 n_launch++;
             }

@@ -131,6 +131,7 @@ struct GlobalSrc {
     // per-thread HBM loads: issue every parameter load before the edge loop so that the latencies overlap
     static constexpr bool kEarlyLoads = true;
     static constexpr bool kCheapEdges = false;
+    static constexpr bool kWide = false;
     static constexpr uint32_t kWidth = 0;   // slice width known at run time only
     const StepParams &p;
     uint32_t lnc;   // clamped local neuron number
@@ -492,6 +493,144 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
 }
 
 // ------------------------------------------------------------------------------------------------
+// in-edge gather for wide rows (step_wide.cu): a whole CTA serves one 32-row slice
+// ------------------------------------------------------------------------------------------------
+// A LatticeNetwork like BASELINE.json configs[3] has few neurons with ~10^3 in-edges each (784 spike trains -> every
+// excitatory neuron): with one thread per row the general kernel walks those edges serially in 25 warps on the whole GPU
+// (1.6 ms per step).  Here the per-edge work (coalesced col/weight loads, neighbour gathers, spike-train refractoriness,
+// lazy STDP, the products) is spread over all warps of the CTA — warp w takes k-rows w, w + W, ... of a chunk, lane = row —
+// and parked in shared memory; the leader warp then adds the parked terms in ascending presynaptic order.  The terms and
+// the order of the additions are those of gather_edges, so the sums are bit-identical.
+constexpr uint32_t kWideChunk = 64;   // k-rows per chunk
+constexpr int kWideUnroll = 4;         // k-rows per thread and batch (kWideChunk = kWideUnroll * warps per CTA)
+
+struct WideSrc : GlobalSrc {
+    static constexpr bool kWide = true;
+    uint32_t warp, n_warps;
+    float *sm_e;          // [kWideChunk][32] electrical terms
+    float *sm_t;          // [kNT][kWideChunk][32] chemical terms
+    uint8_t *sm_f;        // [kWideChunk][32] bit 0: edge present, bits 1..3: presynaptic node releases type 0..2
+};
+
+template <int CHEMG, bool STDP, bool NET, class SRC>
+__device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
+                                                  bool post_trig, int li, uint32_t ty0, EdgeAcc &A) {
+    const uint32_t width = src.width();
+    const bool pending = STDP && p.apply_pending;
+    const bool do_e = p.electrical != 0;
+    const int prev = (int)p.clock - 1;
+    const uint32_t lane = src.lane;
+    for (uint32_t kk = 0; kk < width; kk += kWideChunk) {
+        const uint32_t kn = min(kWideChunk, width - kk);
+        // ---- phase A: every warp computes the terms of its k-rows, kWideUnroll at a time: all col/weight loads, then every
+        // gather they address (V, last_firing_time, t, the spike-train constants), then the arithmetic — two dependent
+        // memory round trips per batch instead of three per edge
+        for (uint32_t kb = src.warp; kb < kn; kb += kWideUnroll * src.n_warps) {
+            uint32_t c[kWideUnroll], j[kWideUnroll];
+            float w[kWideUnroll];
+            bool live[kWideUnroll], ok[kWideUnroll], train[kWideUnroll];
+#pragma unroll
+            for (int u = 0; u < kWideUnroll; ++u) {
+                const uint32_t k = kb + (uint32_t)u * src.n_warps;
+                live[u] = k < kn;
+                c[u] = live[u] ? src.col(kk + k) : kColPad;
+                w[u] = live[u] ? src.wgt(kk + k) : 0.f;
+            }
+            float vj[kWideUnroll], tj[kWideUnroll][CHEMG == 3 ? kNT : 1], tfv[kWideUnroll][4];
+            int lj[kWideUnroll], lt[kWideUnroll];
+#pragma unroll
+            for (int u = 0; u < kWideUnroll; ++u) {
+                ok[u] = c[u] != kColPad;
+                j[u] = ok[u] ? (c[u] & kColIdxMask) : i;
+                train[u] = NET && ok[u] && (c[u] & kColTrainBit);
+                vj[u] = do_e ? p.v_in[j[u]] : v;
+                // see gather_edges: a spike train's last_firing_time of before its step-s iterate sits in the other buffer
+                lj[u] = pending ? (train[u] ? p.lft_out[j[u]] : p.lft_in[j[u]]) : -1;
+                lt[u] = -1;
+                if (NET) {
+                    if (train[u] && do_e) {
+                        const uint32_t tjx = j[u] - p.train0;
+                        lt[u] = p.lft_in[j[u]];
+                        tfv[u][0] = ldf(p.tf[TF_VREST], tjx); tfv[u][1] = ldf(p.tf[TF_K], tjx);
+                        tfv[u][2] = ldf(p.tf[TF_VTH], tjx); tfv[u][3] = ldf(p.tf[TF_DT], tjx);
+                    }
+                }
+                if (CHEMG == 1) {
+                    tj[u][0] = src.gt0(j[u]);
+                } else if (CHEMG == 3) {
+                    const uint32_t m = ok[u] ? (c[u] >> kColNtShift) & 7u : 0u;
+#pragma unroll
+                    for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? src.gt(j[u], ty) : 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kWideUnroll; ++u) {
+                if (!live[u]) continue;
+                const uint32_t k = kb + (uint32_t)u * src.n_warps;
+                float wu = w[u];
+                if (pending) {
+                    bool pre_trig = ok[u] && lj[u] == prev;
+                    if (NET) {
+                        if (pre_trig) pre_trig = !train[u] && p.lat[lat_index(p, j[u] - p.own0)].do_plasticity != 0;
+                    } else {
+                        pre_trig = pre_trig && p.lat[0].do_plasticity != 0;
+                    }
+                    if ((post_trig && ok[u]) || pre_trig) {
+                        const float d = stdp_delta(p.lat[li], lj[u], lft_me);
+                        wu = wu + d;
+                        if (post_trig && pre_trig) wu = wu + d;
+                        *src.wgt_ptr(kk + k) = wu;
+                    }
+                }
+                float final_input = gap * (vj[u] - v);  // gap_junction, neuron/mod.rs:54-60
+                if (NET) {
+                    if (train[u] && do_e) {
+                        // spike_train_gap_junction, neuron/mod.rs:119-137
+                        if (lt[u] < 0) final_input = tfv[u][0];
+                        else final_input = gap * refract_effect(p.refract, tfv[u][1], p.clock, (uint32_t)lt[u], tfv[u][2], tfv[u][0], tfv[u][3]);
+                    }
+                }
+                src.sm_e[k * 32u + lane] = final_input * wu;
+                uint32_t f = ok[u] ? 1u : 0u;
+                if (CHEMG == 1) {
+                    const bool has = ok[u] && ((c[u] >> (kColNtShift + ty0)) & 1u);
+                    src.sm_t[k * 32u + lane] = tj[u][0] * wu;
+                    f |= has ? 2u : 0u;
+                } else if (CHEMG == 3) {
+                    const uint32_t m = ok[u] ? (c[u] >> kColNtShift) & 7u : 0u;
+#pragma unroll
+                    for (int ty = 0; ty < kNT; ++ty) src.sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] = tj[u][ty] * wu;
+                    f |= m << 1;
+                }
+                src.sm_f[k * 32u + lane] = (uint8_t)f;
+            }
+        }
+        __syncthreads();
+        // ---- phase B: the leader warp adds the parked terms in ascending presynaptic order -----------------------
+        if (src.warp == 0) {
+            for (uint32_t k = 0; k < kn; ++k) {
+                const uint32_t f = src.sm_f[k * 32u + lane];
+                if (do_e) A.acc_e = A.acc_e + src.sm_e[k * 32u + lane];
+                if (CHEMG == 1) {
+                    const bool has = (f >> 1) & 1u;
+                    A.acc_t[0] = A.acc_t[0] + (has ? src.sm_t[k * 32u + lane] : 0.f);
+                    A.cnt[0] += has ? 1u : 0u;
+                } else if (CHEMG == 3) {
+#pragma unroll
+                    for (int ty = 0; ty < kNT; ++ty) {
+                        const bool has = (f >> (1 + ty)) & 1u;
+                        A.acc_t[ty] = A.acc_t[ty] + (has ? src.sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] : 0.f);
+                        A.cnt[ty] += has ? 1u : 0u;
+                    }
+                }
+                A.n_in += f & 1u;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // one neuron, one timestep
 // ------------------------------------------------------------------------------------------------
 // warp_global: slice index (neuron-local word index of the spike bitmask); ln: local neuron number; lnc: clamped copy
@@ -557,7 +696,11 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     const bool do_c = NTREL && p.chemical != 0;
     A.fast8 = false;
     if constexpr (SRC::kWidth == 8 && !NET) gather_edges8<CHEMG, STDP>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
+    else if constexpr (SRC::kWide) gather_edges_wide<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
     else gather_edges<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
+    if constexpr (SRC::kWide) {
+        if (src.warp != 0) return;   // the helpers of a wide-row CTA are done; the leader warp steps the 32 neurons
+    }
     if (!SRC::kEarlyLoads) { load_model_params(); if constexpr (NEEDS_CM) c_m = src.template f<F_CM>(); v_th = src.template f<F_VTH>(); }
     // neuron/mod.rs:722-729: divide by the number of incoming edges (1 if none)
     // (x / 8 == x * 0.125 exactly, subnormals included: both round the same real number)

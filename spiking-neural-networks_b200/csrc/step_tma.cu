@@ -18,6 +18,7 @@ namespace snn {
 struct SmemSrc {
     static constexpr bool kEarlyLoads = false;  // operands sit in shared memory: read them where they are used
     static constexpr bool kCheapEdges = true;
+    static constexpr bool kWide = false;
     const StepParams &p;
     const TmaParams &tp;
     const unsigned char *st;  // this stage

@@ -47,6 +47,7 @@ template <int MODEL, int CHEMG, bool NTREL, bool STDP>
 struct WinSrc {
     static constexpr bool kEarlyLoads = false;   // operands sit in shared memory: read them where they are used
     static constexpr bool kCheapEdges = false;
+    static constexpr bool kWide = false;
     static constexpr uint32_t kWidth = kWinWidth;
     static __host__ __device__ constexpr WinLayout lay() { return win_layout(MODEL, CHEMG, NTREL, STDP); }
 

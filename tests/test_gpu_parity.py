@@ -219,7 +219,8 @@ def test_stdp_run_continuity(oracle_lattice_factory):
 
 
 # ------------------------------------------------------------------ networks
-def build_network(lattice_factory, network_factory, train="rate", stdp=True, chemical=True, electrical=True, seed=21):
+def build_network(lattice_factory, network_factory, train="rate", stdp=True, chemical=True, electrical=True, seed=21,
+                  st_shape=(3, 4)):
     """MNIST-shaped miniature of BASELINE.json configs[3]: spike trains -> excitatory <-> inhibitory."""
     rng = np.random.default_rng(seed)
     T = S.IonotropicNeurotransmitterType
@@ -248,13 +249,14 @@ def build_network(lattice_factory, network_factory, train="rate", stdp=True, che
         st_cls, base = S.PresetSpikeTrain, S.PresetSpikeTrain(firing_times=[1.0, 2.5, 0.7])
     base.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
     st = S.SpikeTrainLattice(st_cls, id=0, network_backend_factory=network_factory)
-    st.populate(base, 3, 4)
+    n_st = st_shape[0] * st_shape[1]
+    st.populate(base, *st_shape)
     if train == "rate":
-        st.set_field("rate", rng.choice([0.0, 1.5, 2.0, 3.0], 12).astype(f32))
+        st.set_field("rate", rng.choice([0.0, 1.5, 2.0, 3.0], n_st).astype(f32))
     st.update_spike_history = True
     net = S.LatticeNetwork.generate_network([exc, inh], [st], backend_factory=network_factory)
-    wmat = rng.uniform(0, 1, (12, 20)).astype(f32)
-    net.connect(0, 1, lambda x, y: True, lambda x, y: float(wmat[x[0] * 4 + x[1], y[0] * 5 + y[1]]))
+    wmat = rng.uniform(0, 1, (n_st, 20)).astype(f32)
+    net.connect(0, 1, lambda x, y: True, lambda x, y: float(wmat[x[0] * st_shape[1] + x[1], y[0] * 5 + y[1]]))
     net.connect(1, 2, lambda x, y: x == y, lambda x, y: 1.0)
     net.connect(2, 1, lambda x, y: x != y, lambda x, y: -1.0)
     net.electrical_synapse, net.chemical_synapse = electrical, chemical
@@ -273,13 +275,16 @@ def _sync_network(src, dst):
         dst._be.connect_dense(pre, post, c, w)
 
 
+@pytest.mark.parametrize("st_shape", [(3, 4), (8, 9)])
 @pytest.mark.parametrize("train", ["rate", "preset"])
 @pytest.mark.parametrize("mode", [(True, True), (True, False), (False, True)])
-def test_network_deterministic_trains(train, mode, oracle_lattice_factory, oracle_network_factory):
+def test_network_deterministic_trains(train, mode, st_shape, oracle_lattice_factory, oracle_network_factory):
     """Spike trains -> excitatory <-> inhibitory with STDP on every lattice, compared in lock-step segments (the
-    network is chaotic; see scenarios.lockstep_lattices)."""
-    a = build_network(None, None, train=train, electrical=mode[0], chemical=mode[1])
-    b = build_network(oracle_lattice_factory, oracle_network_factory, train=train, electrical=mode[0], chemical=mode[1])
+    network is chaotic; see scenarios.lockstep_lattices).  With 72 spike trains the mean slice width passes
+    kWideMinWidth and the wide-row kernel (step_wide.cu) steps the network."""
+    a = build_network(None, None, train=train, electrical=mode[0], chemical=mode[1], st_shape=st_shape)
+    b = build_network(oracle_lattice_factory, oracle_network_factory, train=train, electrical=mode[0], chemical=mode[1],
+                      st_shape=st_shape)
     total, seg, done, spikes = 400, 20, 0, 0
     while done < total:
         a.run_lattices(seg)
@@ -303,7 +308,8 @@ def test_network_deterministic_trains(train, mode, oracle_lattice_factory, oracl
         done += seg
     assert spikes > 20
     w_trains = b._be.get_connection_dense(0, 1)[1]
-    assert np.abs(w_trains - build_network(oracle_lattice_factory, oracle_network_factory, train=train)._be.get_connection_dense(0, 1)[1]).max() > 0
+    assert np.abs(w_trains - build_network(oracle_lattice_factory, oracle_network_factory, train=train,
+                                           st_shape=st_shape)._be.get_connection_dense(0, 1)[1]).max() > 0
 
 
 def test_network_electrical_rate_trains_bit_exact(oracle_lattice_factory, oracle_network_factory):

@@ -157,6 +157,20 @@ typedef struct snn_stdp {
     float dt;
 } snn_stdp_t;
 
+/* RewardModulatedSTDP, backend/src/neuron/plasticity/mod.rs:155-189 (defaults 0, 20, 0.0001, 2, 2, 4.5, 4.5, 0.1).  Its weights
+ * are TraceRSTDP values {counter, dw, weight, c} (:121-136): `weight` is the ordinary edge weight of the graph calls, the other
+ * three members are read with snn_lattice_get_connection_traces. */
+typedef struct snn_rstdp {
+    float dopamine;
+    float tau_d;
+    float tau_c;
+    float a_plus;
+    float a_minus;
+    float tau_plus;
+    float tau_minus;
+    float dt;
+} snn_rstdp_t;
+
 typedef struct snn_lattice_desc {
     uint32_t struct_size;       /* = sizeof(snn_lattice_desc_t) */
     int32_t model;              /* snn_model_t */
@@ -252,6 +266,22 @@ SNN_API int32_t snn_lattice_run(snn_lattice_t *h, uint64_t iterations);
  * engine's own stream, and the number of kernels launched inside it */
 SNN_API int32_t snn_lattice_run_timed(snn_lattice_t *h, uint64_t iterations, float *elapsed_ms,
                                       uint64_t *kernel_launches);
+
+/* RewardModulatedLattice (neuron/mod.rs:2717-3416).  set_reward_modulator(enable = 1) turns the handle into a reward-modulated
+ * lattice: the graph's weights become TraceRSTDP values and, while `do_modulation` is on, EVERY edge is updated twice per
+ * timestep by RewardModulatedSTDP::update_weight (once from each end, plasticity/mod.rs:197-233; do_update is always true).
+ * snn_lattice_run then is RunLattice::run_lattice (:3361-3374, no reward signal) and snn_lattice_run_with_rewards runs one
+ * timestep per entry of `rewards`, each preceded by RewardModulatedSTDP::update(reward) (run_lattice_with_reward, :3250-3257).
+ * Single-GPU, single-lattice handles only.  Traces are reset when the graph is rebuilt. */
+SNN_API int32_t snn_lattice_set_reward_modulator(snn_lattice_t *h, int32_t enable, int32_t do_modulation, const snn_rstdp_t *modulator);
+SNN_API int32_t snn_lattice_get_reward_modulator(const snn_lattice_t *h, snn_rstdp_t *modulator);
+SNN_API int32_t snn_lattice_run_with_rewards(snn_lattice_t *h, const float *rewards, uint64_t n_rewards);
+/* TraceRSTDP members of every edge in the order of snn_lattice_get_graph_csr (counter as u32); any pointer may be NULL */
+SNN_API int32_t snn_lattice_get_connection_traces(snn_lattice_t *h, uint32_t *counter, float *dw, float *c, uint64_t nnz);
+/* Graph::edit_weight with whole TraceRSTDP values on every existing edge (same order; NULL = leave that member alone):
+ * overwrites in place, the adjacency and the other members are kept */
+SNN_API int32_t snn_lattice_set_connection_traces(snn_lattice_t *h, const float *weight, const uint32_t *counter, const float *dw,
+                                                  const float *c, uint64_t nnz);
 
 /* histories recorded on the device during run when the matching option is on.
  * grid: steps x n f32 (GridVoltageHistory); spikes: steps x n u8 (SpikeHistory);

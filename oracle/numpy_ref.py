@@ -243,3 +243,53 @@ class DenseLattice:
             return
         for _ in range(iterations):
             self.step()
+
+
+class RewardDenseLattice(DenseLattice):
+    """RewardModulatedLattice<TraceRSTDP, ..., RewardModulatedSTDP> (mod.rs:2717-3416, plasticity/mod.rs:114-234), written
+    independently of the C oracle: dense per-edge TraceRSTDP members, the modulator applied literally inside the node loop in
+    ascending node order (in-edges, then out-edges of the node that was just stepped)."""
+
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        n = self.n
+        self.counter = np.zeros((n, n), np.int64)
+        self.dw = np.zeros((n, n), f32)
+        self.c = np.zeros((n, n), f32)
+        self.do_modulation = True
+        self.mod = dict(dopamine=f32(0), tau_d=f32(20), tau_c=f32(0.0001), a_plus=f32(2), a_minus=f32(2), tau_plus=f32(4.5),
+                        tau_minus=f32(4.5), dt=f32(0.1))
+
+    def _update_weight(self, a, b, t_pre, t_post):
+        m = self.mod
+        self.stdp = m  # same STDP curve, the modulator's own constants
+        self.dw[a, b] = self.dw[a, b] + self._stdp_dw(t_pre, t_post)
+        if self.counter[a, b] == 0:
+            self.counter[a, b] = 1
+        else:
+            self.c[a, b] = self.c[a, b] * np.exp(-m["dt"] / m["tau_c"]) + m["tau_c"] * self.dw[a, b]
+            self.counter[a, b] = 0
+            self.dw[a, b] = f32(0)
+        self.w[a, b] = self.w[a, b] + self.c[a, b] * m["dopamine"]
+
+    def step(self, reward=None):
+        if reward is not None:  # RewardModulatedSTDP::update, after the inputs and before iterate (mod.rs:3160-3172)
+            m = self.mod
+            m["dopamine"] = f32(m["dopamine"] * np.exp(-m["dt"] / m["tau_d"]) + m["tau_d"] * f32(reward))
+        old = self.lft.copy()
+        self.do_plasticity = False
+        super().step()   # neuron updates do not read weights, so stepping all of them first changes nothing
+        if not self.do_modulation:
+            return
+        new = self.lft
+        cur = old.copy()
+        for p in range(self.n):
+            cur[p] = new[p]
+            for i in np.nonzero(self.conn[:, p])[0]:
+                self._update_weight(i, p, cur[i], cur[p])
+            for j in np.nonzero(self.conn[p, :])[0]:
+                self._update_weight(p, j, cur[p], cur[j])
+
+    def run_with_rewards(self, rewards):
+        for r in rewards:
+            self.step(r)

@@ -19,6 +19,10 @@ F32, U32, I32 = 0, 1, 2
 _NP = {F32: np.float32, U32: np.uint32, I32: np.int32}
 
 
+class Rstdp(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("dopamine", "tau_d", "tau_c", "a_plus", "a_minus", "tau_plus", "tau_minus", "dt")]
+
+
 class Stdp(C.Structure):
     _fields_ = [("a_plus", C.c_float), ("a_minus", C.c_float), ("tau_plus", C.c_float), ("tau_minus", C.c_float),
                 ("dt", C.c_float)]
@@ -70,6 +74,10 @@ def lib():
         "orc_reset_timing": ([P], None),
         "orc_seed": ([P, u64], None),
         "orc_run": ([P, u64], i32),
+        "orc_set_reward_modulator": ([P, i32, i32, C.POINTER(Rstdp)], i32),
+        "orc_get_dopamine": ([P], f),
+        "orc_run_with_reward": ([P, f], i32),
+        "orc_get_connection_traces": ([P, u64, u64, P, P, P], i32),
         "orc_history_len": ([P, u64], u64),
         "orc_set_reduced_history": ([P, u64, i32, i32, f, f, f], i32),
         "orc_get_reduced_history": ([P, u64, i32, P, u64], i32),
@@ -253,6 +261,29 @@ class OracleBackend:
     def set_plasticity(self, id, a_plus, a_minus, tau_plus, tau_minus, dt):
         s = Stdp(a_plus, a_minus, tau_plus, tau_minus, dt)
         self._ck(self.L.orc_set_plasticity(self.h, id, C.byref(s)))
+
+    _RSTDP = ("dopamine", "tau_d", "tau_c", "a_plus", "a_minus", "tau_plus", "tau_minus", "dt")
+
+    def set_reward_modulator(self, enable, do_modulation, **m):
+        # the dopamine level lives on the back end between calls (the front end pushes its last read-back value)
+        s = Rstdp(*[float(m[k]) for k in self._RSTDP])
+        self._ck(self.L.orc_set_reward_modulator(self.h, int(enable), int(do_modulation), C.byref(s)))
+        self._rstdp = dict(m)
+
+    def get_reward_modulator(self):
+        d = dict(self._rstdp)
+        d["dopamine"] = self.L.orc_get_dopamine(self.h)
+        return d
+
+    def run_with_rewards(self, rewards):
+        for r in np.asarray(rewards, np.float32).reshape(-1):
+            self._ck(self.L.orc_run_with_reward(self.h, float(r)))
+
+    def connection_traces(self, pre_id=0, post_id=0):
+        nnz = self.connection_nnz(pre_id, post_id)
+        cnt, dw, c = np.zeros(max(nnz, 1), np.uint32), np.zeros(max(nnz, 1), np.float32), np.zeros(max(nnz, 1), np.float32)
+        self._ck(self.L.orc_get_connection_traces(self.h, pre_id, post_id, _ptr(cnt), _ptr(dw), _ptr(c)))
+        return cnt[:nnz], dw[:nnz], c[:nnz]
 
     def set_dt(self, dt):
         self.L.orc_set_dt(self.h, float(dt))

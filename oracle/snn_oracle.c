@@ -79,6 +79,9 @@ typedef struct {
 typedef struct {
     uint32_t pre; /* canonical global node index */
     float w;
+    /* TraceRSTDP plasticity/mod.rs:121-136 (w is its `weight`); all zero for plain f32 weights */
+    uint32_t counter;
+    float dw, c;
 } o_edge;
 
 typedef struct {
@@ -112,6 +115,9 @@ struct orc_network {
     o_edge **in;
     uint32_t *in_len, *in_cap;
     int electrical, chemical, parallel;
+    /* RewardModulatedLattice neuron/mod.rs:2719-2751: the lattice's plasticity is a RewardModulatedSTDP over TraceRSTDP weights */
+    int reward_mode, do_modulation;
+    orc_rstdp rstdp;
     uint64_t internal_clock;
     uint64_t rng;
     /* scratch */
@@ -542,7 +548,7 @@ static void edge_set(orc_network *net, uint64_t post, uint32_t pre, int has, flo
             e = net->in[post] = realloc(e, sizeof(o_edge) * net->in_cap[post]);
         }
         memmove(&e[lo + 1], &e[lo], sizeof(o_edge) * (len - lo));
-        e[lo].pre = pre; e[lo].w = w; net->in_len[post] = len + 1;
+        e[lo].pre = pre; e[lo].w = w; e[lo].counter = 0; e[lo].dw = 0.f; e[lo].c = 0.f; net->in_len[post] = len + 1;
     } else if (found) {
         memmove(&e[lo], &e[lo + 1], sizeof(o_edge) * (len - lo - 1));
         net->in_len[post] = len - 1;
@@ -1219,6 +1225,44 @@ static void update_weights_from_neuron(orc_network *net, o_lattice *L, uint64_t 
     }
 }
 
+/* RewardModulatedSTDP::update_weight plasticity/mod.rs:197-229 */
+static void rstdp_update_weight(const orc_rstdp *m, o_edge *e, int32_t t_pre_i, int32_t t_post_i) {
+    float delta_w = 0.f;
+    if (t_pre_i >= 0 && t_post_i >= 0) {
+        float t_pre = (float)t_pre_i, t_post = (float)t_post_i;
+        if (t_pre < t_post) {
+            delta_w = m->a_plus * expf((-1.f * fabsf((t_pre - t_post) * m->dt)) / m->tau_plus);
+        } else if (t_pre > t_post) {
+            delta_w = (-1.f * m->a_minus) * expf((-1.f * fabsf((t_post - t_pre) * m->dt)) / m->tau_minus);
+        }
+    }
+    e->dw += delta_w;
+    if (e->counter == 0) {
+        e->counter = 1;
+    } else {
+        e->c = e->c * expf(-m->dt / m->tau_c) + m->tau_c * e->dw; /* TraceRSTDP::update_trace :140-142 */
+        e->counter = 0;
+        e->dw = 0.f;
+    }
+    e->w += e->c * m->dopamine;
+}
+
+/* RewardModulatedLattice::update_weights_from_neurons neuron/mod.rs:3022-3054: every in-edge, then every out-edge of the
+ * neuron that was just stepped (do_update is always true, plasticity/mod.rs:231-233) */
+static void rstdp_update_from_neuron(orc_network *net, o_lattice *L, uint64_t q) {
+    uint64_t p = L->base + q;
+    for (uint32_t k = 0; k < net->in_len[p]; k++) {
+        o_edge *e = &net->in[p][k];
+        rstdp_update_weight(&net->rstdp, e, node_lft(net, e->pre), L->cells[q].last_firing_time);
+    }
+    for (uint64_t s = net->out_ptr[p]; s < net->out_ptr[p + 1]; s++) {
+        uint64_t post = net->out_post[s];
+        o_ref r = node_ref(net, post);
+        rstdp_update_weight(&net->rstdp, &net->in[post][net->out_pos[s]], L->cells[q].last_firing_time,
+                            r.L->cells[r.idx].last_firing_time);
+    }
+}
+
 static void history_push(o_lattice *L) {
     if (!L->is_train && (L->update_average_history || L->update_eeg_history)) {
         if (L->hist_len >= L->red_cap) {
@@ -1269,6 +1313,7 @@ static void step(orc_network *net) {
         }
     }
     /* phase 2: neuron update, ascending canonical order */
+    if (net->reward_mode && net->do_modulation && net->in) build_out_index(net);
     for (int li = 0; li < net->n_neuron_lat; li++) {
         o_lattice *B = net->lat[li];
         for (uint64_t q = 0; q < B->n; q++) {
@@ -1278,13 +1323,16 @@ static void step(orc_network *net) {
             int sp = neuron_iterate(c, net->model, net->ntk, net->rck, input, ch, &net->inp_t[post * ORC_NT],
                                     &net->inp_has[post * ORC_NT]);
             if (sp) c->last_firing_time = (int32_t)net->internal_clock; /* :964-966 */
+            /* RewardModulatedLattice::iterate neuron/mod.rs:3127-3156: the modulator runs inside the node loop, so an edge sees
+             * the new last_firing_time of its lower-indexed end and still the old one of the other (canonical order (1)) */
+            if (net->reward_mode && net->do_modulation && net->in) rstdp_update_from_neuron(net, B, q);
         }
         history_push(B); /* before this step's STDP (:2565-2576) */
     }
     /* phase 3: deferred STDP for spiking neurons of lattices with do_plasticity (:2559-2562, 2573-2576) */
     int any_plastic = 0;
     for (int li = 0; li < net->n_neuron_lat; li++) if (net->lat[li]->do_plasticity) any_plastic = 1;
-    if (any_plastic && net->in) {
+    if (any_plastic && net->in && !net->reward_mode) {
         build_out_index(net);
         for (int li = 0; li < net->n_neuron_lat; li++) {
             o_lattice *B = net->lat[li];
@@ -1318,6 +1366,43 @@ int orc_run(orc_network *net, uint64_t iterations) {
         net->inp_has = calloc(n * ORC_NT, 1);
     }
     for (uint64_t it = 0; it < iterations; it++) step(net);
+    return 0;
+}
+
+/* RewardModulatedLattice: switch the lattice's plasticity to RewardModulatedSTDP over TraceRSTDP weights */
+int orc_set_reward_modulator(orc_network *net, int enable, int do_modulation, const orc_rstdp *m) {
+    net->reward_mode = enable; net->do_modulation = do_modulation;
+    if (m) net->rstdp = *m;
+    return 0;
+}
+float orc_get_dopamine(orc_network *net) { return net->rstdp.dopamine; }
+
+/* RewardModulatedLattice::run_lattice_with_reward neuron/mod.rs:3250-3257 (one timestep): inputs, then
+ * RewardModulatedSTDP::update(reward) plasticity/mod.rs:193-195, then iterate */
+int orc_run_with_reward(orc_network *net, float reward) {
+    if (!net->electrical && !net->chemical) return 0;
+    net->rstdp.dopamine = net->rstdp.dopamine * expf(-net->rstdp.dt / net->rstdp.tau_d) + net->rstdp.tau_d * reward;
+    return orc_run(net, 1);
+}
+
+/* per-edge TraceRSTDP members in the order of orc_get_connection_csr */
+int orc_get_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw, float *c) {
+    o_lattice *A = find_lat(net, pre_id), *B = find_lat(net, post_id);
+    if (!A || !B || B->is_train) return 35;
+    ensure_graph(net);
+    uint64_t n = 0;
+    for (uint64_t q = 0; q < B->n; q++) {
+        uint64_t post = B->base + q;
+        for (uint32_t k = 0; k < net->in_len[post]; k++) {
+            const o_edge *e = &net->in[post][k];
+            if (e->pre >= A->base && e->pre < A->base + A->n) {
+                if (counter) counter[n] = e->counter;
+                if (dw) dw[n] = e->dw;
+                if (c) c[n] = e->c;
+                n++;
+            }
+        }
+    }
     return 0;
 }
 

@@ -46,6 +46,8 @@ enum { ORC_F32 = 0, ORC_U32 = 1, ORC_I32 = 2 };
 typedef struct orc_network orc_network;
 
 typedef struct orc_stdp { float a_plus, a_minus, tau_plus, tau_minus, dt; } orc_stdp;
+/* RewardModulatedSTDP plasticity/mod.rs:155-189 (defaults 0, 20, 0.0001, 2, 2, 4.5, 4.5, 0.1) */
+typedef struct orc_rstdp { float dopamine, tau_d, tau_c, a_plus, a_minus, tau_plus, tau_minus, dt; } orc_rstdp;
 
 orc_network *orc_network_create(int model, int nt_kinetics, int rc_kinetics, int train_kind, int refract_kind);
 void orc_network_destroy(orc_network *net);
@@ -96,6 +98,11 @@ int orc_run(orc_network *net, uint64_t iterations);
 int orc_set_reduced_history(orc_network *net, uint64_t id, int average, int eeg, float reference_voltage, float distance,
                             float conductivity);
 int orc_get_reduced_history(orc_network *net, uint64_t id, int eeg, float *out, uint64_t capacity);
+/* RewardModulatedLattice (neuron/mod.rs:2717-3416) with RewardModulatedSTDP over TraceRSTDP weights (plasticity/mod.rs:114-234) */
+int orc_set_reward_modulator(orc_network *net, int enable, int do_modulation, const orc_rstdp *m);
+float orc_get_dopamine(orc_network *net);
+int orc_run_with_reward(orc_network *net, float reward);
+int orc_get_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw, float *c);
 uint64_t orc_history_len(orc_network *net, uint64_t id);
 int orc_get_grid_history(orc_network *net, uint64_t id, float *out, uint64_t capacity);
 int orc_get_spike_history(orc_network *net, uint64_t id, uint8_t *out, uint64_t capacity);

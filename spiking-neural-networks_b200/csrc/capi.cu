@@ -276,6 +276,29 @@ int32_t snn_lattice_reset_timing(snn_lattice_t *h) {
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->reset_timing(); SNN_CATCH(h)
 }
+int32_t snn_lattice_set_reward_modulator(snn_lattice_t *h, int32_t enable, int32_t do_modulation, const snn_rstdp_t *modulator) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->set_reward_modulator(enable != 0, do_modulation != 0, modulator); SNN_CATCH(h)
+}
+int32_t snn_lattice_get_reward_modulator(const snn_lattice_t *h, snn_rstdp_t *modulator) {
+    if (!h || !modulator) return SNN_INVALID_ARGUMENT;
+    *modulator = h->e->rstdp;
+    return SNN_OK;
+}
+int32_t snn_lattice_run_with_rewards(snn_lattice_t *h, const float *rewards, uint64_t n_rewards) {
+    if (!h || (n_rewards && !rewards)) return SNN_INVALID_ARGUMENT;
+    if (!h->e->reward_mode) return h->e->fail(SNN_INVALID_ARGUMENT, "handle is not a reward-modulated lattice (snn_lattice_set_reward_modulator)");
+    SNN_TRY return h->e->run(n_rewards, nullptr, nullptr, rewards); SNN_CATCH(h)
+}
+int32_t snn_lattice_get_connection_traces(snn_lattice_t *h, uint32_t *counter, float *dw, float *c, uint64_t nnz) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_connection_traces(counter, dw, c, nnz); SNN_CATCH(h)
+}
+int32_t snn_lattice_set_connection_traces(snn_lattice_t *h, const float *weight, const uint32_t *counter, const float *dw, const float *c,
+                                          uint64_t nnz) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->set_connection_traces(weight, counter, dw, c, nnz); SNN_CATCH(h)
+}
 int32_t snn_lattice_run(snn_lattice_t *h, uint64_t iterations) {
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->run(iterations, nullptr, nullptr); SNN_CATCH(h)

@@ -1,6 +1,7 @@
 // engine.cu — host runtime: device memory layout, named-field I/O, graph ingestion, the step loop.
 #include "engine.h"
 #include <chrono>
+#include <cmath>
 
 #include <algorithm>
 #include <cstdio>
@@ -129,6 +130,7 @@ void Engine::free_device() {
     for (auto &p : TF_) fr(p);
     fr(ft_off_); fr(ft_); fr(d_lat_);
     fr(slice_off_); fr(col_); fr(wgt_);
+    free_reward_arrays();
     chem_alloc_ = false;
     graph_dirty_ = true;
     grid_fast_ = false;
@@ -770,6 +772,7 @@ uint32_t Engine::rc_used() const { refresh_flag_cache(); return rc_used_; }
 
 int Engine::finalize_graph() {
     if (!graph_dirty_) return SNN_OK;
+    free_reward_arrays();   // a rebuilt graph starts from TraceRSTDP::default traces
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     // the stencil fast path re-generates the table in place when its size is unchanged (set_graph_grid called again,
     // e.g. once per run by a caller that mirrors LatticeGPU's upload-everything-per-run behaviour)
@@ -899,6 +902,127 @@ int Engine::finalize_graph() {
     if (e != cudaSuccess) return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "sell_from_csr");
     graph_dirty_ = false;
     dev_weights_newer_ = false;
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// RewardModulatedLattice
+// ------------------------------------------------------------------------------------------------
+int Engine::set_reward_modulator(bool enable, bool modulate, const snn_rstdp_t *m) {
+    if (enable && part_world > 1) return fail(SNN_UNSUPPORTED, "reward-modulated lattices are not supported on partitioned handles");
+    int n_neuron_lat = 0;
+    for (auto &L : lats_) if (!L.is_train) n_neuron_lat++;
+    if (enable && (n_neuron_lat > 1 || n_trains > 0)) return fail(SNN_UNSUPPORTED, "reward-modulated lattice networks are not built yet");
+    reward_mode = enable; do_modulation = modulate;
+    if (m) rstdp = *m;
+    if (!enable) free_reward_arrays();
+    return SNN_OK;
+}
+
+void Engine::free_reward_arrays() {
+    if (rs_counter_) cudaFree(rs_counter_);
+    if (rs_dw_) cudaFree(rs_dw_);
+    if (rs_c_) cudaFree(rs_c_);
+    rs_counter_ = nullptr; rs_dw_ = rs_c_ = nullptr; rs_elems_ = 0;
+}
+
+int Engine::ensure_reward_arrays() {
+    const uint64_t elems = std::max<uint64_t>(std::max(sell_alloc_krows_, sell_krows_) * 32, 1);
+    if (rs_counter_ && rs_elems_ == elems) return SNN_OK;
+    free_reward_arrays();
+    CK(dev_alloc(&rs_counter_, elems), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&rs_dw_, elems), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&rs_c_, elems), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemsetAsync(rs_counter_, 0, elems, stream_), SNN_GPU_BUFFER_WRITE_ERROR);   // TraceRSTDP::default: counter 0, dw 0, c 0
+    CK(cudaMemsetAsync(rs_dw_, 0, elems * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(cudaMemsetAsync(rs_c_, 0, elems * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    rs_elems_ = elems;
+    return SNN_OK;
+}
+
+int Engine::get_connection_traces(uint32_t *counter, float *dw, float *c, uint64_t nnz) {
+    const Lat *only = nullptr;
+    for (auto &L : lats_) if (!L.is_train) only = &L;
+    if (!only || !reward_mode) return fail(SNN_INVALID_ARGUMENT, "handle is not a reward-modulated lattice");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    int r = finalize_graph();
+    if (r) return r;
+    r = ensure_reward_arrays();
+    if (r) return r;
+    auto it = blocks_.find({only->id, only->id});
+    Block tmp;
+    if (it != blocks_.end()) { tmp = it->second; if (tmp.kind == Block::GRID) materialize_grid(tmp, *only); }
+    else tmp.row_ptr.assign(only->n + 1, 0);
+    if (tmp.pre.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
+    if (nnz == 0) return SNN_OK;
+    std::vector<uint32_t> so((size_t)n_slices_ + 1);
+    std::vector<uint8_t> hc(rs_elems_);
+    std::vector<float> hd(rs_elems_), hcc(rs_elems_);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    CK(cudaMemcpy(so.data(), slice_off_, so.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hc.data(), rs_counter_, rs_elems_, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hd.data(), rs_dw_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hcc.data(), rs_c_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    for (uint64_t q = 0; q < only->n; ++q) {
+        const uint64_t row = only->off + q;
+        const uint32_t s = (uint32_t)(row / 32), lane = (uint32_t)(row % 32);
+        uint32_t k = so[s];
+        for (uint64_t e = tmp.row_ptr[q]; e < tmp.row_ptr[q + 1]; ++e, ++k) {
+            const size_t o = (size_t)k * 32 + lane;
+            if (counter) counter[e] = hc[o];
+            if (dw) dw[e] = hd[o];
+            if (c) c[e] = hcc[o];
+        }
+    }
+    return SNN_OK;
+}
+
+int Engine::set_connection_traces(const float *weight, const uint32_t *counter, const float *dw, const float *c, uint64_t nnz) {
+    Lat *only = nullptr;
+    for (auto &L : lats_) if (!L.is_train) only = &L;
+    if (!only || !reward_mode) return fail(SNN_INVALID_ARGUMENT, "handle is not a reward-modulated lattice");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    int r = finalize_graph();
+    if (r) return r;
+    r = ensure_reward_arrays();
+    if (r) return r;
+    r = sync_weights_to_host();   // the host copy of the weights must be current before parts of it are overwritten
+    if (r) return r;
+    auto it = blocks_.find({only->id, only->id});
+    if (it == blocks_.end()) return nnz ? fail(SNN_SIZE_MISMATCH, "nnz mismatch") : SNN_OK;
+    Block tmp;
+    Block *b = &it->second;
+    if (b->kind == Block::GRID) { tmp = *b; materialize_grid(tmp, *only); b = &tmp; }   // keep the device fast path
+    if (b->pre.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
+    if (nnz == 0) return SNN_OK;
+    std::vector<uint32_t> so((size_t)n_slices_ + 1);
+    std::vector<uint8_t> hc(rs_elems_);
+    std::vector<float> hd(rs_elems_), hcc(rs_elems_), hw(rs_elems_);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    CK(cudaMemcpy(so.data(), slice_off_, so.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hc.data(), rs_counter_, rs_elems_, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hd.data(), rs_dw_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hcc.data(), rs_c_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hw.data(), wgt_, std::min<uint64_t>(rs_elems_, std::max(sell_alloc_krows_, sell_krows_) * 32) * 4, cudaMemcpyDeviceToHost),
+       SNN_GPU_BUFFER_READ_ERROR);
+    for (uint64_t q = 0; q < only->n; ++q) {
+        const uint64_t row = only->off + q;
+        const uint32_t s = (uint32_t)(row / 32), lane = (uint32_t)(row % 32);
+        uint32_t k = so[s];
+        for (uint64_t e = b->row_ptr[q]; e < b->row_ptr[q + 1]; ++e, ++k) {
+            const size_t o = (size_t)k * 32 + lane;
+            if (weight) { hw[o] = weight[e]; if (it->second.kind == Block::CSR) it->second.w[e] = weight[e]; }
+            if (counter) hc[o] = (uint8_t)counter[e];
+            if (dw) hd[o] = dw[e];
+            if (c) hcc[o] = c[e];
+        }
+    }
+    const uint64_t wel = std::max(sell_alloc_krows_, sell_krows_) * 32;
+    if (weight) CK(cudaMemcpy(wgt_, hw.data(), wel * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (counter) CK(cudaMemcpy(rs_counter_, hc.data(), rs_elems_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (dw) CK(cudaMemcpy(rs_dw_, hd.data(), rs_elems_ * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (c) CK(cudaMemcpy(rs_c_, hcc.data(), rs_elems_ * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (weight && it->second.kind == Block::GRID) dev_weights_newer_ = true;   // a stencil block's weights live on the device
     return SNN_OK;
 }
 
@@ -1297,7 +1421,7 @@ bool Engine::build_win_params(WinParams &wp, int chemg, bool ntrel, bool stdp, b
     return true;
 }
 
-int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
+int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, const float *rewards) {
     if (elapsed_ms) *elapsed_ms = 0.f;
     if (launches) *launches = 0;
     // gpu_lattices/mod.rs:1089-1091: empty lattice or zero iterations -> Ok(()); neuron/mod.rs:1217: both flags off -> Ok(())
@@ -1329,7 +1453,13 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
     const bool net = n_neuron_lat > 1 || n_trains > 0;
     int chemg = 0;
     if (chemical && ntrel && nt_used() != 0) chemg = (!net && __builtin_popcount(nt_used()) == 1) ? 1 : 3;
-    const bool lft_pp = stdp || (n_trains && electrical) || part_world > 1;
+    // reward-modulated lattice: the modulator replaces the plasticity rule and needs last_firing_time before and after a step
+    const bool rmod = reward_mode && do_modulation && n_neurons > 0;
+    if (reward_mode) stdp = false;
+    if (rmod) { int rr = ensure_reward_arrays(); if (rr) return rr; }
+    RstdpParams rsp{rstdp.dopamine, rstdp.tau_c, rstdp.a_plus, rstdp.a_minus, rstdp.tau_plus, rstdp.tau_minus, rstdp.dt,
+                    rs_counter_, rs_dw_, rs_c_};
+    const bool lft_pp = stdp || rmod || (n_trains && electrical) || part_world > 1;
 
     StepParams sp;
     fill_step_params(sp);
@@ -1463,6 +1593,16 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step"); break; }
                 n_launch++;
             }
+            if (reward_mode && rewards) {
+                // RewardModulatedSTDP::update, plasticity/mod.rs:193-195 (run_lattice_with_reward, neuron/mod.rs:3160-3172)
+                rstdp.dopamine = rstdp.dopamine * expf(-rstdp.dt / rstdp.tau_d) + rstdp.tau_d * rewards[done + s];
+            }
+            if (rmod) {
+                rsp.dopamine = rstdp.dopamine;
+                cudaError_t e = launch_rstdp_edges(sp, rsp, stream_);
+                if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_rstdp_edges"); break; }
+                n_launch++;
+            }
             if (part_world > 1) halo_epoch_ += 1;
             // LatticeNetwork::iterate: clock += 1, then the spike trains step with their own clocks
             // (neuron/mod.rs:2582-2591)
@@ -1588,7 +1728,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches) {
             return fail(SNN_GPU_WAIT_ERROR, "timed out waiting for a neighbouring strip's halo (is every rank running the same number of steps?)");
         }
     }
-    if (stdp) dev_weights_newer_ = true;
+    if (stdp || rmod) dev_weights_newer_ = true;
     // derived fields (receptor currents, HH gate rates / channel currents) from the retained pre-update V
     if ((chemical && chem_alloc_) || model == SNN_MODEL_HODGKIN_HUXLEY) {
         StepParams fp = sp;

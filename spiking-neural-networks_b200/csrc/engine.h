@@ -91,7 +91,14 @@ public:
     int reset_history();
 
     // run
-    int run(uint64_t iterations, float *elapsed_ms, uint64_t *launches);
+    int run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, const float *rewards = nullptr);
+
+    // RewardModulatedLattice (neuron/mod.rs:2717-3416)
+    int set_reward_modulator(bool enable, bool modulate, const snn_rstdp_t *m);
+    int get_connection_traces(uint32_t *counter, float *dw, float *c, uint64_t nnz);
+    int set_connection_traces(const float *weight, const uint32_t *counter, const float *dw, const float *c, uint64_t nnz);
+    bool reward_mode = false, do_modulation = true;
+    snn_rstdp_t rstdp{0.f, 20.f, 0.0001f, 2.f, 2.f, 4.5f, 4.5f, 0.1f};   // RewardModulatedSTDP::default, plasticity/mod.rs:176-189
 
     // histories
     int history_len(uint64_t id, uint64_t *steps) const;
@@ -153,6 +160,10 @@ private:
     bool dev_weights_newer_ = false;
     bool grid_fast_ = false;
     uint32_t *slice_off_ = nullptr, *col_ = nullptr; float *wgt_ = nullptr;
+    // TraceRSTDP members next to wgt_ (same sliced-ELL positions), allocated on the first reward-modulated run
+    uint8_t *rs_counter_ = nullptr; float *rs_dw_ = nullptr, *rs_c_ = nullptr; uint64_t rs_elems_ = 0;
+    int ensure_reward_arrays();
+    void free_reward_arrays();
     uint64_t sell_krows_ = 0, sell_alloc_krows_ = 0; uint32_t n_slices_ = 0, uniform_width_ = 0;
     // halo
     unsigned long long *flags_ = nullptr;  // [0] arrivals from rank-1, [1] arrivals from rank+1

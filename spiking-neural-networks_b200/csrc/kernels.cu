@@ -118,6 +118,76 @@ __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// RewardModulatedLattice: RewardModulatedSTDP::update_weight on every edge (plasticity/mod.rs:197-233)
+// ------------------------------------------------------------------------------------------------
+// The reference calls the modulator inside the node loop (RewardModulatedLattice::iterate, neuron/mod.rs:3127-3156): when node
+// p has been stepped, every in-edge and every out-edge of p is updated, so each edge a -> b is updated twice per timestep —
+// first when the lower-indexed end is visited (that end already carries this step's last_firing_time, the other end still
+// the previous one), then when the other end is visited (both new).  Per edge this is a closed recurrence over
+// {counter, dw, weight, c} driven by four integers, so one thread per (row, k) applies both calls from the ping-ponged
+// last_firing_time buffers: no atomics, no ordering between edges.  An edge whose trace is at rest (dw = c = 0, counter = 0)
+// and whose ends produce no STDP term is an exact no-op and is not written back.
+__device__ __forceinline__ void rstdp_call(const RstdpParams &r, float delta_w, float decay_c, uint32_t &counter, float &dw, float &c, float &w) {
+    dw = dw + delta_w;
+    if (counter == 0u) {
+        counter = 1u;
+    } else {
+        c = c * decay_c + r.tau_c * dw;   // TraceRSTDP::update_trace, plasticity/mod.rs:140-142
+        counter = 0u;
+        dw = 0.f;
+    }
+    w = w + c * r.dopamine;
+}
+
+__global__ void __launch_bounds__(256) rstdp_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ln = warp_global * 32u + lane;
+    if (ln >= p.n_neurons) return;
+    const uint32_t i = p.own0 + ln;
+    const int old_post = p.lft_in[i], new_post = p.lft_out[i];
+    const uint32_t k0 = p.uniform_width ? warp_global * p.uniform_width : __ldg(p.slice_off + warp_global);
+    const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + warp_global + 1);
+    LatInfo L;
+    L.a_plus = r.a_plus; L.a_minus = r.a_minus; L.tau_plus = r.tau_plus; L.tau_minus = r.tau_minus; L.dt = r.dt;
+    const float decay_c = expf(-r.dt / r.tau_c);
+    constexpr int U = 4;   // slice widths are multiples of 4
+    for (uint32_t k = k0; k < k1; k += U) {
+        uint32_t cw[U], cnt[U];
+        float dw[U], cc[U], w[U];
+        int old_pre[U], new_pre[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t e = (size_t)(k + u) * 32u + lane;
+            cw[u] = __ldg(p.col + e);
+            cnt[u] = r.counter[e]; dw[u] = r.dw[e]; cc[u] = r.c[e]; w[u] = p.wgt[e];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t j = cw[u] == kColPad ? i : (cw[u] & kColIdxMask);
+            old_pre[u] = p.lft_in[j]; new_pre[u] = p.lft_out[j];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (cw[u] == kColPad) continue;
+            const uint32_t j = cw[u] & kColIdxMask;
+            // first call: the end with the lower node index has been stepped, the other has not (a self-loop sees both new)
+            const int t_pre1 = (j <= i) ? new_pre[u] : old_pre[u];
+            const int t_post1 = (i <= j) ? new_post : old_post;
+            const bool first_live = (t_pre1 >= 0 && t_post1 >= 0 && t_pre1 != t_post1);
+            const bool second_live = (new_pre[u] >= 0 && new_post >= 0 && new_pre[u] != new_post);
+            if (!first_live && !second_live && dw[u] == 0.f && cc[u] == 0.f && cnt[u] == 0u) continue;
+            const float d1 = first_live ? stdp_delta(L, t_pre1, t_post1) : 0.f;
+            const float d2 = second_live ? stdp_delta(L, new_pre[u], new_post) : 0.f;
+            rstdp_call(r, d1, decay_c, cnt[u], dw[u], cc[u], w[u]);
+            rstdp_call(r, d2, decay_c, cnt[u], dw[u], cc[u], w[u]);
+            const size_t e = (size_t)(k + u) * 32u + lane;
+            r.counter[e] = (uint8_t)cnt[u]; r.dw[e] = dw[u]; r.c[e] = cc[u]; p.wgt[e] = w[u];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // derived fields (currents, gate rates): recomputed once after a run from the retained pre-update V
 // ------------------------------------------------------------------------------------------------
 template <int MODEL>
@@ -386,6 +456,12 @@ cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s) {
     const uint32_t cnt = max(p.halo[0].active ? p.halo[0].count : 0u, p.halo[1].active ? p.halo[1].count : 0u);
     if (cnt == 0) return cudaSuccess;
     halo_push_kernel<<<blocks_for(cnt, 256), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaStream_t s) {
+    if (p.n_neurons == 0) return cudaSuccess;
+    rstdp_edge_kernel<<<blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256), 256, 0, s>>>(p, r);
     return cudaGetLastError();
 }
 

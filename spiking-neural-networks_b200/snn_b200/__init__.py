@@ -5,6 +5,6 @@ The CUDA library is the product; this package holds no compute and no CPU fallba
 from . import _capi
 from ._capi import SnnError, load_library
 from .backend import CudaLatticeBackend, CudaNetworkBackend
-from .lattice import (AverageVoltageHistory, EEGHistory, GridVoltageHistory, Lattice, LatticeNetwork, SpikeHistory,
-                      SpikeTrainLattice)
+from .lattice import (AverageVoltageHistory, EEGHistory, GridVoltageHistory, Lattice, LatticeNetwork,
+                      RewardModulatedLattice, SpikeHistory, SpikeTrainLattice)
 from .neurons import *  # noqa: F401,F403

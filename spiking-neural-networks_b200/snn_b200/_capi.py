@@ -47,6 +47,10 @@ class StdpStruct(C.Structure):
                 ("dt", C.c_float)]
 
 
+class RstdpStruct(C.Structure):
+    _fields_ = [(k, C.c_float) for k in ("dopamine", "tau_d", "tau_c", "a_plus", "a_minus", "tau_plus", "tau_minus", "dt")]
+
+
 class LatticeDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("model", C.c_int32), ("nt_kinetics", C.c_int32),
                 ("receptor_kinetics", C.c_int32), ("rows", C.c_uint32), ("cols", C.c_uint32), ("device", C.c_int32),
@@ -104,6 +108,11 @@ SIGNATURES = {
     "snn_lattice_reset_timing": ([_P], _i32),
     "snn_lattice_run": ([_P, _u64], _i32),
     "snn_lattice_run_timed": ([_P, _u64, C.POINTER(_f), C.POINTER(_u64)], _i32),
+    "snn_lattice_set_reward_modulator": ([_P, _i32, _i32, C.POINTER(RstdpStruct)], _i32),
+    "snn_lattice_get_reward_modulator": ([_P, C.POINTER(RstdpStruct)], _i32),
+    "snn_lattice_run_with_rewards": ([_P, _P, _u64], _i32),
+    "snn_lattice_get_connection_traces": ([_P, _P, _P, _P, _u64], _i32),
+    "snn_lattice_set_connection_traces": ([_P, _P, _P, _P, _P, _u64], _i32),
     "snn_lattice_history_len": ([_P, C.POINTER(_u64)], _i32),
     "snn_lattice_get_grid_history": ([_P, _P, _u64], _i32),
     "snn_lattice_get_spike_history": ([_P, _P, _u64], _i32),

@@ -174,6 +174,36 @@ class CudaLatticeBackend(_CudaBase):
         s = K.StdpStruct(a_plus, a_minus, tau_plus, tau_minus, dt)
         self._ck(self.lib.snn_lattice_set_plasticity(self.h, C.byref(s)))
 
+    _RSTDP = ("dopamine", "tau_d", "tau_c", "a_plus", "a_minus", "tau_plus", "tau_minus", "dt")
+
+    def set_reward_modulator(self, enable, do_modulation, **m):
+        """RewardModulatedLattice: the graph's weights become TraceRSTDP values updated by RewardModulatedSTDP."""
+        s = K.RstdpStruct(*[float(m[k]) for k in self._RSTDP])
+        self._ck(self.lib.snn_lattice_set_reward_modulator(self.h, int(enable), int(do_modulation), C.byref(s)))
+
+    def get_reward_modulator(self):
+        s = K.RstdpStruct()
+        self._ck(self.lib.snn_lattice_get_reward_modulator(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k in self._RSTDP}
+
+    def run_with_rewards(self, rewards):
+        r = np.ascontiguousarray(np.asarray(rewards, np.float32).reshape(-1))
+        self._ck(self.lib.snn_lattice_run_with_rewards(self.h, _ptr(r), r.size))
+
+    def connection_traces(self):
+        nnz = self.connection_nnz()
+        cnt, dw, c = np.zeros(max(nnz, 1), np.uint32), np.zeros(max(nnz, 1), np.float32), np.zeros(max(nnz, 1), np.float32)
+        self._ck(self.lib.snn_lattice_get_connection_traces(self.h, _ptr(cnt), _ptr(dw), _ptr(c), nnz))
+        return cnt[:nnz], dw[:nnz], c[:nnz]
+
+    def set_connection_traces(self, weight=None, counter=None, dw=None, c=None):
+        """Overwrite TraceRSTDP members of every edge in place (order of get_connection_csr; None = keep)."""
+        nnz = self.connection_nnz()
+        arrs = [None if x is None else _as(np.asarray(x).reshape(-1), t)
+                for x, t in ((weight, np.float32), (counter, np.uint32), (dw, np.float32), (c, np.float32))]
+        assert all(a is None or a.size == nnz for a in arrs)
+        self._ck(self.lib.snn_lattice_set_connection_traces(self.h, *[None if a is None else _ptr(a) for a in arrs], nnz))
+
     def get_plasticity(self, id=0):
         s = K.StdpStruct()
         self._ck(self.lib.snn_lattice_get_plasticity(self.h, C.byref(s)))

@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _capi as K
 from .neurons import (NEURON_CLASSES, NT_KINETICS, RC_KINETICS, RECEPTORS, STDP, IonotropicNeurotransmitterType,
-                      IzhikevichNeuron, Neuron, PoissonNeuron, SpikeTrain)
+                      IzhikevichNeuron, Neuron, PoissonNeuron, SpikeTrain, RewardModulatedSTDP)
 
 _NT_PARAM_FIELDS = {
     K.NT_APPROXIMATE: ["clearance_constant"],
@@ -420,6 +420,52 @@ class Lattice(_CellLattice):
             return  # never populated: empty lattice, Ok(()) (gpu_lattices/mod.rs:1089-1091)
         self._push_options()
         self._be.run(iterations)
+
+
+class RewardModulatedLattice(Lattice):
+    """RewardModulatedLattice<TraceRSTDP, T, ..., RewardModulatedSTDP, N> (neuron/mod.rs:2717-3416): same stepping as Lattice,
+    but the graph holds TraceRSTDP weights and, while `do_modulation` is on, the reward modulator updates every edge twice per
+    timestep (once from each end).  `run_lattice` steps without a reward signal (:3361-3374), `run_lattice_with_reward(r)` is
+    one timestep preceded by `reward_modulator.update(r)` (:3250-3257); `run_lattice_with_rewards` batches such steps."""
+
+    def __init__(self, neuron_type=IzhikevichNeuron, id=0, backend_factory=None, history_type=GridVoltageHistory):
+        super().__init__(neuron_type, id, backend_factory, history_type)
+        self.do_modulation = True                      # RewardModulatedLattice::default, neuron/mod.rs:2762-2777
+        self.reward_modulator = RewardModulatedSTDP()
+        self.update_graph_history = False
+
+    def _push_options(self):
+        self.do_plasticity = False
+        super()._push_options()
+        m = self.reward_modulator
+        self._be.set_reward_modulator(True, self.do_modulation, **{k: getattr(m, k) for k in m._defaults})
+
+    def _pull_modulator(self):
+        self.reward_modulator.dopamine = self._be.get_reward_modulator()["dopamine"]
+
+    def set_dt(self, dt):
+        super().set_dt(dt)
+        self.reward_modulator.dt = dt
+
+    def run_lattice_with_reward(self, reward: float):
+        self.run_lattice_with_rewards([reward])
+
+    def run_lattice_with_rewards(self, rewards):
+        if self._be is None:
+            return
+        self._push_options()
+        self._be.run_with_rewards(rewards)
+        self._pull_modulator()
+
+    def graph_traces(self):
+        """(counter, dw, c) of every edge, in the order of graph_csr()."""
+        self._push_options()
+        return self._be.connection_traces()
+
+    def set_graph_traces(self, weight=None, counter=None, dw=None, c=None):
+        """Graph::edit_weight with whole TraceRSTDP values on every existing edge (order of graph_csr(); None = keep)."""
+        self._push_options()
+        self._be.set_connection_traces(weight, counter, dw, c)
 
 
 class SpikeTrainLattice(_CellLattice):

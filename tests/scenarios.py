@@ -70,13 +70,14 @@ def add_chemistry(neuron, chem):
 
 
 def build_lattice(factory, model="izh", rows=6, cols=7, seed=1, graph="grid", chem=None, stdp=False,
-                  electrical=True, chemical=None, gap=10.0, hetero=True, history=True, c_m=None, history_type=None):
+                  electrical=True, chemical=None, gap=10.0, hetero=True, history=True, c_m=None, history_type=None, cls=None):
+    lattice_cls = cls
     cls = MODELS[model]
     base = cls(gap_conductance=gap)
     if c_m is not None:
         base.c_m = c_m
     add_chemistry(base, chem)
-    lat = S.Lattice(cls, backend_factory=factory, **({"history_type": history_type} if history_type else {}))
+    lat = (lattice_cls or S.Lattice)(cls, backend_factory=factory, **({"history_type": history_type} if history_type else {}))
     lat.populate(base, rows, cols)
     n = rows * cols
     rng = np.random.default_rng(seed)

@@ -103,3 +103,42 @@ def test_reduced_histories_on_the_oracle(oracle_lattice_factory):
         want_eeg.append(f32(f32(1) / f32(f32(f32(f32(4) * f32(np.pi)) * f32(251.0)) * f32(0.8))) * t)
     assert (avg.grid_history.history == np.array(want_avg, f32)).all()
     assert (eeg.grid_history.history == np.array(want_eeg, f32)).all()
+
+
+def _reward_pair(oracle_lattice_factory, rows, cols, seed):
+    """A C-oracle RewardModulatedLattice and the independent numpy restatement of the same lattice."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import numpy_ref as R
+    lat = SC.build_lattice(oracle_lattice_factory, model="izh", rows=rows, cols=cols, seed=seed, graph="random", cls=S.RewardModulatedLattice)
+    lat.reward_modulator = S.RewardModulatedSTDP(tau_c=0.05, a_plus=0.4, a_minus=0.3)
+    n = rows * cols
+    conn, w = lat.graph_dense()
+    fields = {k: lat.get_field(k) for k in ("current_voltage", "gap_conductance", "w_value", "a", "b", "c", "d", "v_th", "tau_m", "c_m", "dt")}
+    ref = R.RewardDenseLattice(R.IZH, n, conn, w, fields)
+    ref.mod.update(tau_c=f32(0.05), a_plus=f32(0.4), a_minus=f32(0.3))
+    return lat, ref
+
+
+def test_reward_modulated_oracle_matches_independent_restatement(oracle_lattice_factory):
+    """RewardModulatedLattice + RewardModulatedSTDP/TraceRSTDP (neuron/mod.rs:2717-3416, plasticity/mod.rs:114-234): the C oracle
+    against the separately written numpy restatement — rasters bit-exact, weights and traces to expf rounding."""
+    lat, ref = _reward_pair(oracle_lattice_factory, 3, 4, 5)
+    rng = np.random.default_rng(0)
+    rewards = rng.uniform(-1, 1, 120).astype(f32)
+    w0 = lat.graph_csr()[2].copy()
+    lat.run_lattice_with_rewards(rewards[:70])
+    lat.run_lattice(30)                      # no reward signal: dopamine stays, the modulator keeps running
+    lat.run_lattice_with_rewards(rewards[70:])
+    ref.run_with_rewards(rewards[:70]); ref.run(30); ref.run_with_rewards(rewards[70:])
+    assert np.array(ref.s_hist).sum() > 5
+    assert (lat.spike_history.history.reshape(150, -1) == np.array(ref.s_hist)).all()
+    rp, pre, w = lat.graph_csr()
+    cnt, dw, c = lat.graph_traces()
+    post = np.repeat(np.arange(12), np.diff(rp).astype(int))
+    np.testing.assert_allclose(w, ref.w[pre, post], rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(c, ref.c[pre, post], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(dw, ref.dw[pre, post], rtol=2e-5, atol=1e-7)
+    assert (cnt == ref.counter[pre, post]).all()
+    assert np.abs(w - w0).max() > 1e-3, "the modulator must have moved the weights"
+    assert lat.reward_modulator.dopamine == pytest.approx(float(ref.mod["dopamine"]), rel=1e-5)

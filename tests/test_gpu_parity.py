@@ -105,6 +105,52 @@ def test_average_and_eeg_history(kind, shape, oracle_lattice_factory):
     assert a.grid_history.history.shape == (0,)
 
 
+# ------------------------------------------------------------------ reward-modulated lattices
+@pytest.mark.parametrize("graph,shape", [("grid", (9, 11)), ("random", (6, 7)), ("grid", (300, 300))])
+def test_reward_modulated_lattice(graph, shape, oracle_lattice_factory):
+    """RewardModulatedLattice with RewardModulatedSTDP over TraceRSTDP weights (neuron/mod.rs:2717-3416, plasticity/mod.rs:114-234):
+    every edge is updated twice per step from the ping-ponged last_firing_time.  Lock-step segments against the oracle (the
+    weights feed back into a chaotic lattice): rasters bit-exact, voltages / weights / traces to expf rounding."""
+    big = shape[0] * shape[1] > 10000
+    kw = dict(model="izh", rows=shape[0], cols=shape[1], seed=9, graph=graph, cls=S.RewardModulatedLattice, history=not big)
+    a, b = SC.build_lattice(None, **kw), SC.build_lattice(oracle_lattice_factory, **kw)
+    for L in (a, b):
+        L.reward_modulator = S.RewardModulatedSTDP(tau_c=0.05, a_plus=0.1, a_minus=0.08)   # tame: the rule has no weight clamp
+    rng = np.random.default_rng(1)
+    w0 = b.graph_csr()[2].copy()
+    # the lattice is strongly chaotic (tools/debug_reward.py: an ulp-level weight difference grows to 0.4 mV within 40 steps)
+    total, seg, done = (40, 10, 0) if big else (150, 10, 0)
+    while done < total:
+        rewards = rng.uniform(-0.3, 0.3, seg).astype(f32)
+        for L in (a, b):
+            if (done // seg) % 3 == 2:
+                L.run_lattice(seg)                 # RunLattice::run_lattice: no reward signal, modulation still on
+            else:
+                L.run_lattice_with_rewards(rewards)
+        if not big:
+            ha, hb = a.grid_history.history[done:done + seg], b.grid_history.history[done:done + seg]
+            SC.assert_close_robust(ha, hb, 1e-4, 1e-3, f"segment at {done}")
+            assert (a.spike_history.history[done:done + seg] == b.spike_history.history[done:done + seg]).all()
+        assert (a.get_field("last_firing_time") == b.get_field("last_firing_time")).all()
+        (rpa, pa, wa), (rpb, pb, wb) = a.graph_csr(), b.graph_csr()
+        assert (rpa == rpb).all() and (pa == pb).all()
+        np.testing.assert_allclose(wa, wb, rtol=1e-4, atol=1e-5, err_msg=f"weights after step {done + seg}")
+        (ca, da, cca), (cb, db, ccb) = a.graph_traces(), b.graph_traces()
+        assert (ca == cb).all()
+        np.testing.assert_allclose(da, db, rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(cca, ccb, rtol=1e-4, atol=1e-6)
+        assert a.reward_modulator.dopamine == pytest.approx(b.reward_modulator.dopamine, rel=1e-5)
+        SC.copy_lattice_state(b, a, weights=False)   # re-synchronise the neurons (see scenarios.lockstep_lattices) ...
+        a.set_graph_traces(wb, cb, db, ccb)          # ... and the TraceRSTDP values, in place
+        done += seg
+    assert (b.get_field("last_firing_time") >= 0).sum() > 5
+    assert np.abs(b.graph_csr()[2] - w0).max() > 1e-3, "the modulator must have moved the weights"
+    a.do_modulation = b.do_modulation = False
+    wa0 = a.graph_csr()[2].copy()
+    a.run_lattice(10)
+    assert (a.graph_csr()[2] == wa0).all(), "do_modulation = false freezes the weights"
+
+
 # ------------------------------------------------------------------ transcendental models: tolerance
 @pytest.mark.parametrize("model,graph,steps", [("adex", "grid", 500), ("adex", "random", 500), ("hh", "grid", 2000),
                                                ("hh", "random", 2000)])

@@ -127,6 +127,13 @@ __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__
 // {counter, dw, weight, c} driven by four integers, so one thread per (row, k) applies both calls from the ping-ponged
 // last_firing_time buffers: no atomics, no ordering between edges.  An edge whose trace is at rest (dw = c = 0, counter = 0)
 // and whose ends produce no STDP term is an exact no-op and is not written back.
+// the STDP term of RewardModulatedSTDP::update_weight (plasticity/mod.rs:200-214): same expression as stdp_delta
+__device__ __forceinline__ float rstdp_delta(const RstdpParams &r, int t_pre_i, int t_post_i) {
+    const float t_pre = (float)t_pre_i, t_post = (float)t_post_i;
+    if (t_pre < t_post) return r.a_plus * expf((-1.f * fabsf((t_pre - t_post) * r.dt)) / r.tau_plus);
+    return (-1.f * r.a_minus) * expf((-1.f * fabsf((t_post - t_pre) * r.dt)) / r.tau_minus);   // callers exclude None and t_pre == t_post
+}
+
 __device__ __forceinline__ void rstdp_call(const RstdpParams &r, float delta_w, float decay_c, uint32_t &counter, float &dw, float &c, float &w) {
     dw = dw + delta_w;
     if (counter == 0u) {
@@ -139,50 +146,69 @@ __device__ __forceinline__ void rstdp_call(const RstdpParams &r, float delta_w, 
     w = w + c * r.dopamine;
 }
 
-__global__ void __launch_bounds__(256) rstdp_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
-    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t ln = warp_global * 32u + lane;
-    if (ln >= p.n_neurons) return;
-    const uint32_t i = p.own0 + ln;
-    const int old_post = p.lft_in[i], new_post = p.lft_out[i];
-    const uint32_t k0 = p.uniform_width ? warp_global * p.uniform_width : __ldg(p.slice_off + warp_global);
-    const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + warp_global + 1);
-    LatInfo L;
-    L.a_plus = r.a_plus; L.a_minus = r.a_minus; L.tau_plus = r.tau_plus; L.tau_minus = r.tau_minus; L.dt = r.dt;
+// One CTA per kRsSlices 32-row slices; its 8 warps stride over the k-rows of each slice (a radius-1 stencil: one k-row per
+// warp and slice) and every thread works on one edge of each of the kRsSlices slices at a time: all col / trace loads first,
+// then the last_firing_time gathers they address, then the arithmetic — kRsSlices independent chains per thread, ~1000
+// resident threads per SM, so that two dependent memory round trips per edge still keep HBM busy.
+constexpr int kRsSlices = 4;
+
+__global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
+    uint32_t k0[kRsSlices], k1[kRsSlices], node[kRsSlices];
+    int old_post[kRsSlices], new_post[kRsSlices];
+    uint32_t rounds = 0;
+#pragma unroll
+    for (int u = 0; u < kRsSlices; ++u) {
+        const uint32_t slice = blockIdx.x * kRsSlices + u;
+        const uint32_t ln = slice * 32u + lane;
+        const bool ok = slice < n_slices && ln < p.n_neurons;
+        node[u] = p.own0 + (ok ? ln : 0u);
+        k0[u] = k1[u] = 0u;
+        if (ok) {
+            k0[u] = p.uniform_width ? slice * p.uniform_width : __ldg(p.slice_off + slice);
+            k1[u] = p.uniform_width ? k0[u] + p.uniform_width : __ldg(p.slice_off + slice + 1);
+        }
+        old_post[u] = p.lft_in[node[u]]; new_post[u] = p.lft_out[node[u]];
+        rounds = max(rounds, (k1[u] - k0[u] + 7u) >> 3);
+    }
+    rounds = __reduce_max_sync(0xffffffffu, rounds);   // lanes of a warp share the slices; keep the loop warp-uniform
     const float decay_c = expf(-r.dt / r.tau_c);
-    constexpr int U = 4;   // slice widths are multiples of 4
-    for (uint32_t k = k0; k < k1; k += U) {
-        uint32_t cw[U], cnt[U];
-        float dw[U], cc[U], w[U];
-        int old_pre[U], new_pre[U];
+    for (uint32_t t = 0; t < rounds; ++t) {
+        size_t e[kRsSlices];
+        uint32_t cw[kRsSlices], cnt[kRsSlices];
+        float dw[kRsSlices], cc[kRsSlices], w[kRsSlices];
+        int old_pre[kRsSlices], new_pre[kRsSlices];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const size_t e = (size_t)(k + u) * 32u + lane;
-            cw[u] = __ldg(p.col + e);
-            cnt[u] = r.counter[e]; dw[u] = r.dw[e]; cc[u] = r.c[e]; w[u] = p.wgt[e];
+        for (int u = 0; u < kRsSlices; ++u) {
+            const uint32_t k = k0[u] + warp + 8u * t;
+            e[u] = (size_t)k * 32u + lane;
+            cw[u] = k < k1[u] ? __ldg(p.col + e[u]) : kColPad;
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const uint32_t j = cw[u] == kColPad ? i : (cw[u] & kColIdxMask);
-            old_pre[u] = p.lft_in[j]; new_pre[u] = p.lft_out[j];
+        for (int u = 0; u < kRsSlices; ++u) {
+            if (cw[u] != kColPad) {
+                cnt[u] = r.counter[e[u]]; dw[u] = r.dw[e[u]]; cc[u] = r.c[e[u]]; w[u] = p.wgt[e[u]];
+                const uint32_t j = cw[u] & kColIdxMask;
+                old_pre[u] = p.lft_in[j]; new_pre[u] = p.lft_out[j];
+            }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
+        for (int u = 0; u < kRsSlices; ++u) {
             if (cw[u] == kColPad) continue;
-            const uint32_t j = cw[u] & kColIdxMask;
+            const uint32_t j = cw[u] & kColIdxMask, i = node[u];
             // first call: the end with the lower node index has been stepped, the other has not (a self-loop sees both new)
             const int t_pre1 = (j <= i) ? new_pre[u] : old_pre[u];
-            const int t_post1 = (i <= j) ? new_post : old_post;
+            const int t_post1 = (i <= j) ? new_post[u] : old_post[u];
             const bool first_live = (t_pre1 >= 0 && t_post1 >= 0 && t_pre1 != t_post1);
-            const bool second_live = (new_pre[u] >= 0 && new_post >= 0 && new_pre[u] != new_post);
+            const bool second_live = (new_pre[u] >= 0 && new_post[u] >= 0 && new_pre[u] != new_post[u]);
             if (!first_live && !second_live && dw[u] == 0.f && cc[u] == 0.f && cnt[u] == 0u) continue;
-            const float d1 = first_live ? stdp_delta(L, t_pre1, t_post1) : 0.f;
-            const float d2 = second_live ? stdp_delta(L, new_pre[u], new_post) : 0.f;
+            const float d2 = second_live ? rstdp_delta(r, new_pre[u], new_post[u]) : 0.f;
+            // the two calls see the same pair of spike times unless an end of the edge spiked in this very step
+            const float d1 = (t_pre1 == new_pre[u] && t_post1 == new_post[u]) ? d2 : (first_live ? rstdp_delta(r, t_pre1, t_post1) : 0.f);
             rstdp_call(r, d1, decay_c, cnt[u], dw[u], cc[u], w[u]);
             rstdp_call(r, d2, decay_c, cnt[u], dw[u], cc[u], w[u]);
-            const size_t e = (size_t)(k + u) * 32u + lane;
-            r.counter[e] = (uint8_t)cnt[u]; r.dw[e] = dw[u]; r.c[e] = cc[u]; p.wgt[e] = w[u];
+            r.counter[e[u]] = (uint8_t)cnt[u]; r.dw[e[u]] = dw[u]; r.c[e[u]] = cc[u]; p.wgt[e[u]] = w[u];
         }
     }
 }
@@ -461,7 +487,8 @@ cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s) {
 
 cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
-    rstdp_edge_kernel<<<blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256), 256, 0, s>>>(p, r);
+    const unsigned n_slices = (p.n_neurons + 31u) / 32u;
+    rstdp_edge_kernel<<<(n_slices + kRsSlices - 1) / kRsSlices, 256, 0, s>>>(p, r);
     return cudaGetLastError();
 }
 

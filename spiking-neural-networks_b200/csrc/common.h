@@ -265,6 +265,8 @@ cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s);
 // per (step, lattice): sum of V and sum of (V - ref) over the lattice's neurons, f64, fixed reduction order
 cudaError_t launch_history_reduce(const float *grid, uint64_t n_neurons, uint32_t steps, const uint32_t *lat_base, const uint32_t *lat_n,
                                   const float *lat_ref, int n_lat, double *out, cudaStream_t s);
+// node_flags[i] <- (node_flags[i] & ~(0xF << shift)) | (mask of the non-zero words of src[i*3 .. i*3+2]) << shift; *changed |= any
+cudaError_t launch_pack_flags(const uint32_t *src, uint8_t *node_flags, uint64_t n, int shift, unsigned int *changed, cudaStream_t s);
 cudaError_t launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t s);
 cudaError_t launch_bits_from_u32(const uint32_t *src, uint32_t *words, uint64_t n, uint64_t bit0, cudaStream_t s);
 cudaError_t launch_u32_from_bits(const uint32_t *words, uint32_t *dst, uint64_t n, uint64_t bit0, cudaStream_t s);

@@ -468,18 +468,36 @@ int Engine::field_io(Lat &L, const FieldDef &fd, void *data, uint64_t count, boo
             int r = ensure_chem();
             if (r) return r;
             bool changed = false;
-            for (uint64_t i = 0; i < n; ++i) {
-                uint8_t m = 0;
-                for (int ty = 0; ty < kNT; ++ty) if (h[i * kNT + ty]) m |= (uint8_t)(1u << ty);
-                uint8_t &f = h_node_flags_[no + i];
-                const uint8_t nf = (uint8_t)((f & ~(0xFu << shift)) | (m << shift));
-                changed |= nf != f;
-                f = nf;
+            if (n >= (1u << 16)) {
+                // large lattices: pack on the device (a host loop over 3 n words costs more than the copy), then refresh
+                // the host mirror only if something changed
+                r = ensure_scratch(n * kNT * 4 + 16);
+                if (r) return r;
+                unsigned int *d_changed = (unsigned int *)((char *)scratch_ + n * kNT * 4);
+                CK(cudaMemsetAsync(d_changed, 0, 4, stream_), wr);
+                CK(cudaMemcpyAsync(scratch_, h, n * kNT * 4, cudaMemcpyHostToDevice, stream_), wr);
+                CK(launch_pack_flags((const uint32_t *)scratch_, node_flags_ + no, n, shift, d_changed, stream_), SNN_GPU_QUEUE_FAILURE);
+                unsigned int hc = 0;
+                CK(cudaMemcpyAsync(&hc, d_changed, 4, cudaMemcpyDeviceToHost, stream_), wr);
+                CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+                changed = hc != 0;
+                if (changed) CK(cudaMemcpy(h_node_flags_.data() + no, node_flags_ + no, n, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+            } else {
+                for (uint64_t i = 0; i < n; ++i) {
+                    uint8_t m = 0;
+                    for (int ty = 0; ty < kNT; ++ty) if (h[i * kNT + ty]) m |= (uint8_t)(1u << ty);
+                    uint8_t &f = h_node_flags_[no + i];
+                    const uint8_t nf = (uint8_t)((f & ~(0xFu << shift)) | (m << shift));
+                    changed |= nf != f;
+                    f = nf;
+                }
+                if (changed) {
+                    CK(cudaMemcpyAsync(node_flags_ + no, h_node_flags_.data() + no, n, cudaMemcpyHostToDevice, stream_), wr);
+                    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+                }
             }
             if (!changed) return SNN_OK;
             flags_cache_valid_ = false;
-            CK(cudaMemcpyAsync(node_flags_ + no, h_node_flags_.data() + no, n, cudaMemcpyHostToDevice, stream_), wr);
-            CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
             if (shift == 0) {
                 // the presynaptic type bits are baked into the edge words: re-encode at the next run
                 if (dev_weights_newer_) { r = sync_weights_to_host(); if (r) return r; }
@@ -1681,7 +1699,9 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                 cudaError_t re = launch_history_reduce(d_grid, n_neurons, (uint32_t)steps, d_red_lat, d_red_lat + nl,
                                                        (const float *)(d_red_lat + 2 * nl), (int)nl, d_red, stream_);
                 std::vector<double> hr(steps * nl * 2);
-                if (re == cudaSuccess) re = cudaMemcpy(hr.data(), d_red, hr.size() * 8, cudaMemcpyDeviceToHost);
+                // stream_ is non-blocking: a copy on the legacy stream would not wait for the reduction
+                if (re == cudaSuccess) re = cudaMemcpyAsync(hr.data(), d_red, hr.size() * 8, cudaMemcpyDeviceToHost, stream_);
+                if (re == cudaSuccess) re = cudaStreamSynchronize(stream_);
                 if (re != cudaSuccess) { bail(re, SNN_GPU_BUFFER_READ_ERROR, "history reduce"); break; }
                 for (size_t k = 0; k < nl; ++k) {
                     Lat &L = const_cast<Lat &>(*red_lats[k]);

@@ -556,6 +556,26 @@ cudaError_t launch_history_reduce(const float *grid, uint64_t n_neurons, uint32_
     return cudaGetLastError();
 }
 
+__global__ void pack_flags_kernel(const uint32_t *src, uint8_t *node_flags, uint64_t n, int shift, unsigned int *changed) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ch = false;
+    if (i < n) {
+        uint32_t m = 0;
+        for (int ty = 0; ty < kNT; ++ty) if (src[i * kNT + ty]) m |= 1u << ty;
+        const uint8_t f = node_flags[i];
+        const uint8_t nf = (uint8_t)((f & ~(0xFu << shift)) | (m << shift));
+        ch = nf != f;
+        if (ch) node_flags[i] = nf;
+    }
+    if (__any_sync(0xffffffffu, ch) && (threadIdx.x & 31u) == 0) atomicOr(changed, 1u);
+}
+
+cudaError_t launch_pack_flags(const uint32_t *src, uint8_t *node_flags, uint64_t n, int shift, unsigned int *changed, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    pack_flags_kernel<<<blocks_for(n, 256), 256, 0, s>>>(src, node_flags, n, shift, changed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     fill_u32_kernel<<<blocks_for(n, 256), 256, 0, s>>>(p, v, n);

@@ -78,6 +78,7 @@ def lib():
         "orc_get_dopamine": ([P], f),
         "orc_run_with_reward": ([P, f], i32),
         "orc_get_connection_traces": ([P, u64, u64, P, P, P], i32),
+        "orc_set_connection_traces": ([P, u64, u64, P, P, P, P], i32),
         "orc_history_len": ([P, u64], u64),
         "orc_set_reduced_history": ([P, u64, i32, i32, f, f, f], i32),
         "orc_get_reduced_history": ([P, u64, i32, P, u64], i32),
@@ -284,6 +285,11 @@ class OracleBackend:
         cnt, dw, c = np.zeros(max(nnz, 1), np.uint32), np.zeros(max(nnz, 1), np.float32), np.zeros(max(nnz, 1), np.float32)
         self._ck(self.L.orc_get_connection_traces(self.h, pre_id, post_id, _ptr(cnt), _ptr(dw), _ptr(c)))
         return cnt[:nnz], dw[:nnz], c[:nnz]
+
+    def set_connection_traces(self, weight=None, counter=None, dw=None, c=None):
+        arrs = [None if x is None else _as(np.asarray(x).reshape(-1), t)
+                for x, t in ((weight, np.float32), (counter, np.uint32), (dw, np.float32), (c, np.float32))]
+        self._ck(self.L.orc_set_connection_traces(self.h, 0, 0, *[None if a is None else _ptr(a) for a in arrs]))
 
     def set_dt(self, dt):
         self.L.orc_set_dt(self.h, float(dt))

@@ -1406,6 +1406,29 @@ int orc_get_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_i
     return 0;
 }
 
+/* Graph::edit_weight with whole TraceRSTDP values, order of orc_get_connection_csr; NULL = keep */
+int orc_set_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_id, const float *weight, const uint32_t *counter,
+                              const float *dw, const float *c) {
+    o_lattice *A = find_lat(net, pre_id), *B = find_lat(net, post_id);
+    if (!A || !B || B->is_train) return 35;
+    ensure_graph(net);
+    uint64_t n = 0;
+    for (uint64_t q = 0; q < B->n; q++) {
+        uint64_t post = B->base + q;
+        for (uint32_t k = 0; k < net->in_len[post]; k++) {
+            o_edge *e = &net->in[post][k];
+            if (e->pre >= A->base && e->pre < A->base + A->n) {
+                if (weight) e->w = weight[n];
+                if (counter) e->counter = counter[n];
+                if (dw) e->dw = dw[n];
+                if (c) e->c = c[n];
+                n++;
+            }
+        }
+    }
+    return 0;
+}
+
 uint64_t orc_history_len(orc_network *net, uint64_t id) { o_lattice *L = find_lat(net, id); return L ? L->hist_len : 0; }
 
 int orc_get_grid_history(orc_network *net, uint64_t id, float *out, uint64_t capacity) {

@@ -103,6 +103,8 @@ int orc_set_reward_modulator(orc_network *net, int enable, int do_modulation, co
 float orc_get_dopamine(orc_network *net);
 int orc_run_with_reward(orc_network *net, float reward);
 int orc_get_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw, float *c);
+int orc_set_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_id, const float *weight, const uint32_t *counter,
+                              const float *dw, const float *c);
 uint64_t orc_history_len(orc_network *net, uint64_t id);
 int orc_get_grid_history(orc_network *net, uint64_t id, float *out, uint64_t capacity);
 int orc_get_spike_history(orc_network *net, uint64_t id, uint8_t *out, uint64_t capacity);

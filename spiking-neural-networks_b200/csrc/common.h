@@ -252,7 +252,11 @@ cudaError_t launch_trains(const TrainParams &p, cudaStream_t s);
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s);
 // RewardModulatedSTDP::update_weight on every edge, both calls of the timestep (p.lft_in = last_firing_time before the step,
 // p.lft_out = after it)
-struct RstdpParams { float dopamine, tau_c, a_plus, a_minus, tau_plus, tau_minus, dt; uint8_t *counter; float *dw, *c; };
+struct RstdpParams {
+    float dopamine, tau_c, a_plus, a_minus, tau_plus, tau_minus, dt;
+    uint8_t *counter; float *dw, *c;
+    uint32_t canonical;   // every edge has counter == 0 and dw == 0 between timesteps (see rstdp_edge_kernel)
+};
 cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaStream_t s);
 cudaError_t launch_finalize(const StepParams &p, int model, const float *v_prev, cudaStream_t s);
 cudaError_t launch_sell_from_csr(const uint64_t *row_ptr, const uint32_t *pre, const float *w, const uint8_t *node_flags,

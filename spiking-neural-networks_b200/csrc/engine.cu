@@ -955,6 +955,7 @@ int Engine::ensure_reward_arrays() {
     CK(cudaMemsetAsync(rs_dw_, 0, elems * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     CK(cudaMemsetAsync(rs_c_, 0, elems * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     rs_elems_ = elems;
+    rs_canonical_ = true;
     return SNN_OK;
 }
 
@@ -1030,8 +1031,8 @@ int Engine::set_connection_traces(const float *weight, const uint32_t *counter, 
         for (uint64_t e = b->row_ptr[q]; e < b->row_ptr[q + 1]; ++e, ++k) {
             const size_t o = (size_t)k * 32 + lane;
             if (weight) { hw[o] = weight[e]; if (it->second.kind == Block::CSR) it->second.w[e] = weight[e]; }
-            if (counter) hc[o] = (uint8_t)counter[e];
-            if (dw) hd[o] = dw[e];
+            if (counter) { hc[o] = (uint8_t)counter[e]; if (counter[e] != 0u) rs_canonical_ = false; }
+            if (dw) { hd[o] = dw[e]; if (dw[e] != 0.f) rs_canonical_ = false; }
             if (c) hcc[o] = c[e];
         }
     }
@@ -1476,7 +1477,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     if (reward_mode) stdp = false;
     if (rmod) { int rr = ensure_reward_arrays(); if (rr) return rr; }
     RstdpParams rsp{rstdp.dopamine, rstdp.tau_c, rstdp.a_plus, rstdp.a_minus, rstdp.tau_plus, rstdp.tau_minus, rstdp.dt,
-                    rs_counter_, rs_dw_, rs_c_};
+                    rs_counter_, rs_dw_, rs_c_, rs_canonical_ ? 1u : 0u};
     const bool lft_pp = stdp || rmod || (n_trains && electrical) || part_world > 1;
 
     StepParams sp;

@@ -162,6 +162,7 @@ private:
     uint32_t *slice_off_ = nullptr, *col_ = nullptr; float *wgt_ = nullptr;
     // TraceRSTDP members next to wgt_ (same sliced-ELL positions), allocated on the first reward-modulated run
     uint8_t *rs_counter_ = nullptr; float *rs_dw_ = nullptr, *rs_c_ = nullptr; uint64_t rs_elems_ = 0;
+    bool rs_canonical_ = true;   // counter == 0 and dw == 0 on every edge (TraceRSTDP::default, kept by two calls per timestep)
     int ensure_reward_arrays();
     void free_reward_arrays();
     uint64_t sell_krows_ = 0, sell_alloc_krows_ = 0; uint32_t n_slices_ = 0, uniform_width_ = 0;

@@ -152,6 +152,11 @@ __device__ __forceinline__ void rstdp_call(const RstdpParams &r, float delta_w, 
 // resident threads per SM, so that two dependent memory round trips per edge still keep HBM busy.
 constexpr int kRsSlices = 4;
 
+// CANON: every edge enters the timestep with counter == 0 and dw == 0.  That is the state TraceRSTDP::default starts in and
+// the state two calls per timestep always return to, so until a caller stores other values through
+// snn_lattice_set_connection_traces the counter / dw arrays hold zeros and need neither be read nor written:
+// dw = 0 + d1, then (0 + d1) + d2 — the same additions in the same order.
+template <bool CANON>
 __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
@@ -175,20 +180,22 @@ __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constan
     rounds = __reduce_max_sync(0xffffffffu, rounds);   // lanes of a warp share the slices; keep the loop warp-uniform
     const float decay_c = expf(-r.dt / r.tau_c);
     for (uint32_t t = 0; t < rounds; ++t) {
-        size_t e[kRsSlices];
+        uint32_t e[kRsSlices];   // element index in the sliced-ELL arrays (< 2^32, finalize_graph)
         uint32_t cw[kRsSlices], cnt[kRsSlices];
         float dw[kRsSlices], cc[kRsSlices], w[kRsSlices];
         int old_pre[kRsSlices], new_pre[kRsSlices];
 #pragma unroll
         for (int u = 0; u < kRsSlices; ++u) {
             const uint32_t k = k0[u] + warp + 8u * t;
-            e[u] = (size_t)k * 32u + lane;
+            e[u] = k * 32u + lane;
             cw[u] = k < k1[u] ? __ldg(p.col + e[u]) : kColPad;
         }
 #pragma unroll
         for (int u = 0; u < kRsSlices; ++u) {
+            cnt[u] = 0u; dw[u] = 0.f;
             if (cw[u] != kColPad) {
-                cnt[u] = r.counter[e[u]]; dw[u] = r.dw[e[u]]; cc[u] = r.c[e[u]]; w[u] = p.wgt[e[u]];
+                if (!CANON) { cnt[u] = r.counter[e[u]]; dw[u] = r.dw[e[u]]; }
+                cc[u] = r.c[e[u]]; w[u] = p.wgt[e[u]];
                 const uint32_t j = cw[u] & kColIdxMask;
                 old_pre[u] = p.lft_in[j]; new_pre[u] = p.lft_out[j];
             }
@@ -208,7 +215,8 @@ __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constan
             const float d1 = (t_pre1 == new_pre[u] && t_post1 == new_post[u]) ? d2 : (first_live ? rstdp_delta(r, t_pre1, t_post1) : 0.f);
             rstdp_call(r, d1, decay_c, cnt[u], dw[u], cc[u], w[u]);
             rstdp_call(r, d2, decay_c, cnt[u], dw[u], cc[u], w[u]);
-            r.counter[e[u]] = (uint8_t)cnt[u]; r.dw[e[u]] = dw[u]; r.c[e[u]] = cc[u]; p.wgt[e[u]] = w[u];
+            if (!CANON) { r.counter[e[u]] = (uint8_t)cnt[u]; r.dw[e[u]] = dw[u]; }
+            r.c[e[u]] = cc[u]; p.wgt[e[u]] = w[u];
         }
     }
 }
@@ -488,7 +496,8 @@ cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s) {
 cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
     const unsigned n_slices = (p.n_neurons + 31u) / 32u;
-    rstdp_edge_kernel<<<(n_slices + kRsSlices - 1) / kRsSlices, 256, 0, s>>>(p, r);
+    if (r.canonical) rstdp_edge_kernel<true><<<(n_slices + kRsSlices - 1) / kRsSlices, 256, 0, s>>>(p, r);
+    else rstdp_edge_kernel<false><<<(n_slices + kRsSlices - 1) / kRsSlices, 256, 0, s>>>(p, r);
     return cudaGetLastError();
 }
 

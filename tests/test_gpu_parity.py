@@ -106,8 +106,9 @@ def test_average_and_eeg_history(kind, shape, oracle_lattice_factory):
 
 
 # ------------------------------------------------------------------ reward-modulated lattices
+@pytest.mark.parametrize("canonical", [True, False])
 @pytest.mark.parametrize("graph,shape", [("grid", (9, 11)), ("random", (6, 7)), ("grid", (300, 300))])
-def test_reward_modulated_lattice(graph, shape, oracle_lattice_factory):
+def test_reward_modulated_lattice(graph, shape, canonical, oracle_lattice_factory):
     """RewardModulatedLattice with RewardModulatedSTDP over TraceRSTDP weights (neuron/mod.rs:2717-3416, plasticity/mod.rs:114-234):
     every edge is updated twice per step from the ping-ponged last_firing_time.  Lock-step segments against the oracle (the
     weights feed back into a chaotic lattice): rasters bit-exact, voltages / weights / traces to expf rounding."""
@@ -118,6 +119,13 @@ def test_reward_modulated_lattice(graph, shape, oracle_lattice_factory):
         L.reward_modulator = S.RewardModulatedSTDP(tau_c=0.05, a_plus=0.1, a_minus=0.08)   # tame: the rule has no weight clamp
     rng = np.random.default_rng(1)
     w0 = b.graph_csr()[2].copy()
+    if not canonical:
+        # traces stored through edit_weight with an odd call phase: leaves the device kernel's counter == 0 / dw == 0 fast path
+        cnt0 = (rng.random(w0.size) < 0.5).astype(np.uint32)
+        dw0 = (rng.uniform(-0.01, 0.01, w0.size) * cnt0).astype(f32)
+        c0 = rng.uniform(-0.001, 0.001, w0.size).astype(f32)
+        for L in (a, b):
+            L.set_graph_traces(None, cnt0, dw0, c0)
     # the lattice is strongly chaotic (tools/debug_reward.py: an ulp-level weight difference grows to 0.4 mV within 40 steps)
     total, seg, done = (40, 10, 0) if big else (150, 10, 0)
     while done < total:

@@ -27,6 +27,8 @@ for _ in range(3):
 us = min(res)
 cnt, dw, c = (None, None, None)
 out = {"us_per_timestep": us, "neuron_steps_per_s": n / (us * 1e-6), "launches_per_step": nl / steps,
-       "algorithmic_bytes_per_neuron_step": 120 + 8 + 8 * 30,
-       "achieved_GBps": (120 + 8 + 8 * 30) * n / (us * 1e-6) / 1e9}
+       # full TraceRSTDP traffic (col 4, weight RW 8, counter RW 2, dw RW 8, c RW 8 per edge) and what is left of it while the
+       # traces are in the canonical state (counter == 0 and dw == 0 between timesteps: neither array is touched)
+       "algorithmic_bytes_per_neuron_step": {"general": 120 + 8 + 8 * 30, "canonical": 120 + 8 + 8 * 20},
+       "achieved_GBps_canonical": (120 + 8 + 8 * 20) * n / (us * 1e-6) / 1e9}
 print(json.dumps(out))

@@ -650,7 +650,7 @@ int Engine::connect_dense(uint64_t pre_id, uint64_t post_id, const uint32_t *con
     int r = check_connect(*this, pre_id, post_id, &A, &B);
     if (r) return r;
     if (n_pre != A->n || n_post != B->n) return fail(SNN_GRAPH_DIMENSIONS_DO_NOT_MATCH, "Dimensions do not match");
-    if ((n_pre * n_post) && (!connections || !weights)) return fail(SNN_INVALID_ARGUMENT, "null graph pointers");
+    if (n_pre != 0 && n_post != 0 && (!connections || !weights)) return fail(SNN_INVALID_ARGUMENT, "null graph pointers");
     if (part_world > 1) return fail(SNN_UNSUPPORTED, "dense graphs are not supported on partitioned handles");
     if (itp) {
         if (pre_id != post_id) return fail(SNN_INVALID_ARGUMENT, "index_to_position only applies to an internal graph");

@@ -126,7 +126,7 @@ def test_reward_modulated_lattice(graph, shape, canonical, oracle_lattice_factor
         c0 = rng.uniform(-0.001, 0.001, w0.size).astype(f32)
         for L in (a, b):
             L.set_graph_traces(None, cnt0, dw0, c0)
-    # the lattice is strongly chaotic (tools/debug_reward.py: an ulp-level weight difference grows to 0.4 mV within 40 steps)
+    # the lattice is strongly chaotic (measured: an ulp-level weight difference grows to 0.4 mV within 40 free-running steps)
     total, seg, done = (40, 10, 0) if big else (150, 10, 0)
     while done < total:
         rewards = rng.uniform(-0.3, 0.3, seg).astype(f32)

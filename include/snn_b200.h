@@ -157,6 +157,13 @@ typedef struct snn_stdp {
     float dt;
 } snn_stdp_t;
 
+/* BCM, backend/src/neuron/plasticity/mod.rs:80-97 (defaults 0.1, 0.1, 0.1) */
+typedef struct snn_bcm {
+    float decay;
+    float average_scalar;
+    float dt;
+} snn_bcm_t;
+
 /* RewardModulatedSTDP, backend/src/neuron/plasticity/mod.rs:155-189 (defaults 0, 20, 0.0001, 2, 2, 4.5, 4.5, 0.1).  Its weights
  * are TraceRSTDP values {counter, dw, weight, c} (:121-136): `weight` is the ordinary edge weight of the graph calls, the other
  * three members are read with snn_lattice_get_connection_traces. */
@@ -266,6 +273,11 @@ SNN_API int32_t snn_lattice_run(snn_lattice_t *h, uint64_t iterations);
  * engine's own stream, and the number of kernels launched inside it */
 SNN_API int32_t snn_lattice_run_timed(snn_lattice_t *h, uint64_t iterations, float *elapsed_ms,
                                       uint64_t *kernel_launches);
+
+/* Lattice<BCMIzhikevichNeuron, ..., BCM, ...>: the plasticity rule of the lattice becomes BCM (plasticity/mod.rs:99-111, triggered
+ * by spiking neurons like STDP: every in-edge and out-edge of a neuron that spiked, using the BCMActivity values of both
+ * ends).  SNN_OPT_DO_PLASTICITY keeps switching plasticity on and off.  SNN_MODEL_BCM_IZHIKEVICH, single-GPU `Lattice` handles. */
+SNN_API int32_t snn_lattice_set_bcm_plasticity(snn_lattice_t *h, int32_t enable, const snn_bcm_t *bcm);
 
 /* RewardModulatedLattice (neuron/mod.rs:2717-3416).  set_reward_modulator(enable = 1) turns the handle into a reward-modulated
  * lattice: the graph's weights become TraceRSTDP values and, while `do_modulation` is on, EVERY edge is updated twice per

@@ -34,6 +34,8 @@ class DenseLattice:
         self.f = {k: (_f(v).copy() if np.asarray(v).dtype.kind == "f" else np.asarray(v).copy()) for k, v in fields.items()}
         self.electrical, self.chemical = True, False
         self.do_plasticity = False
+        self.use_bcm = False   # plasticity rule BCM (plasticity/mod.rs:80-112) instead of STDP; BCM_IZH lattices only
+        self.bcm = dict(decay=f32(0.1), average_scalar=f32(0.1), dt=f32(0.1))
         self.stdp = dict(a_plus=f32(2), a_minus=f32(2), tau_plus=f32(4.5), tau_minus=f32(4.5), dt=f32(0.1))
         self.clock = 0
         self.ntk = 0  # 0 approximate, 1 destexhe
@@ -230,8 +232,21 @@ class DenseLattice:
             return (f32(-1) * s["a_minus"]) * np.exp((f32(-1) * np.abs((tq - tp) * s["dt"])) / s["tau_minus"])
         return f32(0)
 
+    def _bcm_w(self, w, pre, post):
+        b, F = self.bcm, self.f
+        sliding_threshold = F["average_activity"][post] / b["average_scalar"]
+        activity_term = F["current_activity"][post] * (F["current_activity"][post] - sliding_threshold)
+        return f32(w + (activity_term * F["current_activity"][pre] - b["decay"] * w) * b["dt"])
+
     def _stdp(self, spike):
         # deferred (LatticeNetwork::iterate, mod.rs:2573-2576): in-edges then out-edges of every spiking neuron
+        if self.use_bcm:
+            for p in np.nonzero(spike)[0]:
+                for i in np.nonzero(self.conn[:, p])[0]:
+                    self.w[i, p] = self._bcm_w(self.w[i, p], i, p)
+                for j in np.nonzero(self.conn[p, :])[0]:
+                    self.w[p, j] = self._bcm_w(self.w[p, j], p, j)
+            return
         for p in np.nonzero(spike)[0]:
             for i in np.nonzero(self.conn[:, p])[0]:
                 self.w[i, p] = self.w[i, p] + self._stdp_dw(self.lft[i], self.lft[p])

@@ -23,6 +23,10 @@ class Rstdp(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("dopamine", "tau_d", "tau_c", "a_plus", "a_minus", "tau_plus", "tau_minus", "dt")]
 
 
+class Bcm(C.Structure):
+    _fields_ = [("decay", C.c_float), ("average_scalar", C.c_float), ("dt", C.c_float)]
+
+
 class Stdp(C.Structure):
     _fields_ = [("a_plus", C.c_float), ("a_minus", C.c_float), ("tau_plus", C.c_float), ("tau_minus", C.c_float),
                 ("dt", C.c_float)]
@@ -74,6 +78,7 @@ def lib():
         "orc_reset_timing": ([P], None),
         "orc_seed": ([P, u64], None),
         "orc_run": ([P, u64], i32),
+        "orc_set_bcm_plasticity": ([P, u64, i32, C.POINTER(Bcm)], i32),
         "orc_set_reward_modulator": ([P, i32, i32, C.POINTER(Rstdp)], i32),
         "orc_get_dopamine": ([P], f),
         "orc_run_with_reward": ([P, f], i32),
@@ -285,6 +290,10 @@ class OracleBackend:
         cnt, dw, c = np.zeros(max(nnz, 1), np.uint32), np.zeros(max(nnz, 1), np.float32), np.zeros(max(nnz, 1), np.float32)
         self._ck(self.L.orc_get_connection_traces(self.h, pre_id, post_id, _ptr(cnt), _ptr(dw), _ptr(c)))
         return cnt[:nnz], dw[:nnz], c[:nnz]
+
+    def set_bcm_plasticity(self, id, enable, decay, average_scalar, dt):
+        s = Bcm(decay, average_scalar, dt)
+        self._ck(self.L.orc_set_bcm_plasticity(self.h, 0 if id is None else id, int(enable), C.byref(s)))
 
     def set_connection_traces(self, weight=None, counter=None, dw=None, c=None):
         arrs = [None if x is None else _as(np.asarray(x).reshape(-1), t)

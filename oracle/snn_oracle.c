@@ -94,6 +94,8 @@ typedef struct {
     o_train *trains;
     int do_plasticity, update_grid_history, update_spike_history;
     orc_stdp plasticity;
+    int use_bcm;          /* the lattice's Plasticity is BCM (plasticity/mod.rs:80-112) instead of STDP */
+    orc_bcm bcm;
     uint64_t internal_clock;
     float *grid_history;
     /* AverageVoltageHistory / EEGHistory neuron/mod.rs:231-322 */
@@ -720,6 +722,22 @@ int orc_get_reduced_history(orc_network *net, uint64_t id, int eeg, float *out, 
     return 0;
 }
 
+int orc_set_bcm_plasticity(orc_network *net, uint64_t id, int enable, const orc_bcm *bcm) {
+    o_lattice *L = find_lat(net, id);
+    if (!L) return 35;
+    L->use_bcm = enable;
+    if (bcm) L->bcm = *bcm;
+    return 0;
+}
+
+/* BCM::update_weight plasticity/mod.rs:101-106 (BCMActivity of BCMIzhikevichNeuron: current / average activity) */
+static float bcm_update(const orc_bcm *b, float weight, const o_neuron *pre, const o_neuron *post) {
+    float sliding_threshold = post->average_activity / b->average_scalar;
+    float activity_term = post->current_activity * (post->current_activity - sliding_threshold);
+    float weight_decay = b->decay * weight;
+    return weight + (activity_term * pre->current_activity - weight_decay) * b->dt;
+}
+
 int orc_set_plasticity(orc_network *net, uint64_t id, const orc_stdp *stdp) {
     o_lattice *L = find_lat(net, id);
     if (!L) return 35;
@@ -744,7 +762,7 @@ void orc_set_dt(orc_network *net, float dt) {
             }
         } else {
             for (uint64_t j = 0; j < L->n; j++) L->cells[j].dt = dt;
-            L->plasticity.dt = dt;
+            L->plasticity.dt = dt; L->bcm.dt = dt;
         }
     }
 }
@@ -1215,12 +1233,18 @@ static void update_weights_from_neuron(orc_network *net, o_lattice *L, uint64_t 
     int32_t lft_p = L->cells[q].last_firing_time;
     for (uint32_t k = 0; k < net->in_len[p]; k++) {
         o_edge *e = &net->in[p][k];
+        if (L->use_bcm) { /* single lattice of BCM neurons: the presynaptic node is a neuron of the same lattice */
+            o_ref rp = node_ref(net, e->pre);
+            e->w = bcm_update(&L->bcm, e->w, &rp.L->cells[rp.idx], &L->cells[q]);
+            continue;
+        }
         e->w = orc_stdp_update(&L->plasticity, e->w, node_lft(net, e->pre), lft_p);
     }
     for (uint64_t s = net->out_ptr[p]; s < net->out_ptr[p + 1]; s++) {
         uint64_t post = net->out_post[s];
         o_ref r = node_ref(net, post);
         o_edge *e = &net->in[post][net->out_pos[s]];
+        if (r.L->use_bcm) { e->w = bcm_update(&r.L->bcm, e->w, &L->cells[q], &r.L->cells[r.idx]); continue; }
         e->w = orc_stdp_update(&r.L->plasticity, e->w, lft_p, r.L->cells[r.idx].last_firing_time);
     }
 }

@@ -47,6 +47,8 @@ typedef struct orc_network orc_network;
 
 typedef struct orc_stdp { float a_plus, a_minus, tau_plus, tau_minus, dt; } orc_stdp;
 /* RewardModulatedSTDP plasticity/mod.rs:155-189 (defaults 0, 20, 0.0001, 2, 2, 4.5, 4.5, 0.1) */
+/* BCM plasticity/mod.rs:80-97 (defaults 0.1, 0.1, 0.1) */
+typedef struct orc_bcm { float decay, average_scalar, dt; } orc_bcm;
 typedef struct orc_rstdp { float dopamine, tau_d, tau_c, a_plus, a_minus, tau_plus, tau_minus, dt; } orc_rstdp;
 
 orc_network *orc_network_create(int model, int nt_kinetics, int rc_kinetics, int train_kind, int refract_kind);
@@ -99,6 +101,8 @@ int orc_set_reduced_history(orc_network *net, uint64_t id, int average, int eeg,
                             float conductivity);
 int orc_get_reduced_history(orc_network *net, uint64_t id, int eeg, float *out, uint64_t capacity);
 /* RewardModulatedLattice (neuron/mod.rs:2717-3416) with RewardModulatedSTDP over TraceRSTDP weights (plasticity/mod.rs:114-234) */
+/* the lattice's plasticity rule becomes BCM (needs the BCM Izhikevich model); do_plasticity keeps switching it */
+int orc_set_bcm_plasticity(orc_network *net, uint64_t id, int enable, const orc_bcm *bcm);
 int orc_set_reward_modulator(orc_network *net, int enable, int do_modulation, const orc_rstdp *m);
 float orc_get_dopamine(orc_network *net);
 int orc_run_with_reward(orc_network *net, float reward);

@@ -276,6 +276,10 @@ int32_t snn_lattice_reset_timing(snn_lattice_t *h) {
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->reset_timing(); SNN_CATCH(h)
 }
+int32_t snn_lattice_set_bcm_plasticity(snn_lattice_t *h, int32_t enable, const snn_bcm_t *bcm) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->set_bcm_plasticity(enable != 0, bcm); SNN_CATCH(h)
+}
 int32_t snn_lattice_set_reward_modulator(snn_lattice_t *h, int32_t enable, int32_t do_modulation, const snn_rstdp_t *modulator) {
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->set_reward_modulator(enable != 0, do_modulation != 0, modulator); SNN_CATCH(h)

@@ -252,6 +252,9 @@ cudaError_t launch_trains(const TrainParams &p, cudaStream_t s);
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s);
 // RewardModulatedSTDP::update_weight on every edge, both calls of the timestep (p.lft_in = last_firing_time before the step,
 // p.lft_out = after it)
+// BCM::update_weight on the edges of the neurons that spiked in the step just computed (p.spk_out)
+struct BcmParams { float decay, average_scalar, dt; };
+cudaError_t launch_bcm_edges(const StepParams &p, const BcmParams &b, cudaStream_t s);
 struct RstdpParams {
     float dopamine, tau_c, a_plus, a_minus, tau_plus, tau_minus, dt;
     uint8_t *counter; float *dw, *c;

@@ -926,6 +926,16 @@ int Engine::finalize_graph() {
 // ------------------------------------------------------------------------------------------------
 // RewardModulatedLattice
 // ------------------------------------------------------------------------------------------------
+int Engine::set_bcm_plasticity(bool enable, const snn_bcm_t *b) {
+    if (enable && model != SNN_MODEL_BCM_IZHIKEVICH) return fail(SNN_INVALID_ARGUMENT, "BCM plasticity needs neurons with BCMActivity (SNN_MODEL_BCM_IZHIKEVICH)");
+    int n_neuron_lat = 0;
+    for (auto &L : lats_) if (!L.is_train) n_neuron_lat++;
+    if (enable && (part_world > 1 || n_neuron_lat > 1 || n_trains > 0)) return fail(SNN_UNSUPPORTED, "BCM plasticity: single-GPU Lattice handles only");
+    bcm_mode = enable;
+    if (b) bcm = *b;
+    return SNN_OK;
+}
+
 int Engine::set_reward_modulator(bool enable, bool modulate, const snn_rstdp_t *m) {
     if (enable && part_world > 1) return fail(SNN_UNSUPPORTED, "reward-modulated lattices are not supported on partitioned handles");
     int n_neuron_lat = 0;
@@ -1474,7 +1484,9 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     if (chemical && ntrel && nt_used() != 0) chemg = (!net && __builtin_popcount(nt_used()) == 1) ? 1 : 3;
     // reward-modulated lattice: the modulator replaces the plasticity rule and needs last_firing_time before and after a step
     const bool rmod = reward_mode && do_modulation && n_neurons > 0;
-    if (reward_mode) stdp = false;
+    // BCM rule instead of STDP: applied by its own per-edge kernel right after each step (it reads the activities the step wrote)
+    const bool bcm_on = bcm_mode && stdp && !reward_mode && n_neurons > 0;
+    if (reward_mode || bcm_mode) stdp = false;
     if (rmod) { int rr = ensure_reward_arrays(); if (rr) return rr; }
     RstdpParams rsp{rstdp.dopamine, rstdp.tau_c, rstdp.a_plus, rstdp.a_minus, rstdp.tau_plus, rstdp.tau_minus, rstdp.dt,
                     rs_counter_, rs_dw_, rs_c_, rs_canonical_ ? 1u : 0u};
@@ -1616,6 +1628,11 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                 // RewardModulatedSTDP::update, plasticity/mod.rs:193-195 (run_lattice_with_reward, neuron/mod.rs:3160-3172)
                 rstdp.dopamine = rstdp.dopamine * expf(-rstdp.dt / rstdp.tau_d) + rstdp.tau_d * rewards[done + s];
             }
+            if (bcm_on) {
+                cudaError_t e = launch_bcm_edges(sp, BcmParams{bcm.decay, bcm.average_scalar, bcm.dt}, stream_);
+                if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_bcm_edges"); break; }
+                n_launch++;
+            }
             if (rmod) {
                 rsp.dopamine = rstdp.dopamine;
                 cudaError_t e = launch_rstdp_edges(sp, rsp, stream_);
@@ -1749,7 +1766,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             return fail(SNN_GPU_WAIT_ERROR, "timed out waiting for a neighbouring strip's halo (is every rank running the same number of steps?)");
         }
     }
-    if (stdp || rmod) dev_weights_newer_ = true;
+    if (stdp || rmod || bcm_on) dev_weights_newer_ = true;
     // derived fields (receptor currents, HH gate rates / channel currents) from the retained pre-update V
     if ((chemical && chem_alloc_) || model == SNN_MODEL_HODGKIN_HUXLEY) {
         StepParams fp = sp;

@@ -95,6 +95,9 @@ public:
 
     // RewardModulatedLattice (neuron/mod.rs:2717-3416)
     int set_reward_modulator(bool enable, bool modulate, const snn_rstdp_t *m);
+    int set_bcm_plasticity(bool enable, const snn_bcm_t *b);
+    bool bcm_mode = false;
+    snn_bcm_t bcm{0.1f, 0.1f, 0.1f};   // BCM::default, plasticity/mod.rs:91-97
     int get_connection_traces(uint32_t *counter, float *dw, float *c, uint64_t nnz);
     int set_connection_traces(const float *weight, const uint32_t *counter, const float *dw, const float *c, uint64_t nnz);
     bool reward_mode = false, do_modulation = true;

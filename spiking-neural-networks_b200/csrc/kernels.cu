@@ -118,6 +118,44 @@ __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------------
+// BCM plasticity (plasticity/mod.rs:99-111) for lattices of BCM Izhikevich neurons
+// ------------------------------------------------------------------------------------------------
+// Lattice::update_weights_from_neurons (neuron/mod.rs:849-881) with Plasticity = BCM: every in-edge and every out-edge of a neuron
+// that spiked is updated with the same function of (weight, presynaptic activity, postsynaptic activity / average), so an edge
+// whose two ends both spiked is simply updated twice.  Runs after the step kernel (deferred, canonicalisation (3)): the raster
+// word of the step tells who spiked, the activities are the ones the step just wrote.
+__global__ void __launch_bounds__(256) bcm_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ BcmParams b) {
+    const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ln = warp_global * 32u + lane;
+    if (warp_global * 32u >= p.n_neurons) return;
+    const uint32_t k0 = p.uniform_width ? warp_global * p.uniform_width : __ldg(p.slice_off + warp_global);
+    const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + warp_global + 1);
+    const uint32_t word0 = p.own0 >> 5;
+    const bool valid = ln < p.n_neurons;
+    const bool post_spk = valid && ((p.spk_out[word0 + warp_global] >> lane) & 1u);
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t e = k * 32u + lane;
+        const uint32_t c = valid ? __ldg(p.col + e) : kColPad;
+        if (c == kColPad) continue;
+        const uint32_t j = c & kColIdxMask;
+        const bool pre_spk = (p.spk_out[j >> 5] >> (j & 31u)) & 1u;
+        const int n_upd = (post_spk ? 1 : 0) + (pre_spk ? 1 : 0);
+        if (n_upd == 0) continue;
+        const uint32_t jl = j - p.own0;
+        const float act_post = p.f[F_CUR_ACT][ln], avg_post = p.f[F_AVG_ACT][ln], act_pre = p.f[F_CUR_ACT][jl];
+        const float sliding_threshold = avg_post / b.average_scalar;
+        const float activity_term = act_post * (act_post - sliding_threshold);
+        float w = p.wgt[e];
+        for (int r = 0; r < n_upd; ++r) {
+            const float weight_decay = b.decay * w;
+            w = w + (activity_term * act_pre - weight_decay) * b.dt;
+        }
+        p.wgt[e] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // RewardModulatedLattice: RewardModulatedSTDP::update_weight on every edge (plasticity/mod.rs:197-233)
 // ------------------------------------------------------------------------------------------------
 // The reference calls the modulator inside the node loop (RewardModulatedLattice::iterate, neuron/mod.rs:3127-3156): when node
@@ -490,6 +528,12 @@ cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s) {
     const uint32_t cnt = max(p.halo[0].active ? p.halo[0].count : 0u, p.halo[1].active ? p.halo[1].count : 0u);
     if (cnt == 0) return cudaSuccess;
     halo_push_kernel<<<blocks_for(cnt, 256), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bcm_edges(const StepParams &p, const BcmParams &b, cudaStream_t s) {
+    if (p.n_neurons == 0) return cudaSuccess;
+    bcm_edge_kernel<<<blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256), 256, 0, s>>>(p, b);
     return cudaGetLastError();
 }
 

@@ -47,6 +47,10 @@ class StdpStruct(C.Structure):
                 ("dt", C.c_float)]
 
 
+class BcmStruct(C.Structure):
+    _fields_ = [("decay", C.c_float), ("average_scalar", C.c_float), ("dt", C.c_float)]
+
+
 class RstdpStruct(C.Structure):
     _fields_ = [(k, C.c_float) for k in ("dopamine", "tau_d", "tau_c", "a_plus", "a_minus", "tau_plus", "tau_minus", "dt")]
 
@@ -108,6 +112,7 @@ SIGNATURES = {
     "snn_lattice_reset_timing": ([_P], _i32),
     "snn_lattice_run": ([_P, _u64], _i32),
     "snn_lattice_run_timed": ([_P, _u64, C.POINTER(_f), C.POINTER(_u64)], _i32),
+    "snn_lattice_set_bcm_plasticity": ([_P, _i32, C.POINTER(BcmStruct)], _i32),
     "snn_lattice_set_reward_modulator": ([_P, _i32, _i32, C.POINTER(RstdpStruct)], _i32),
     "snn_lattice_get_reward_modulator": ([_P, C.POINTER(RstdpStruct)], _i32),
     "snn_lattice_run_with_rewards": ([_P, _P, _u64], _i32),

@@ -196,6 +196,10 @@ class CudaLatticeBackend(_CudaBase):
         self._ck(self.lib.snn_lattice_get_connection_traces(self.h, _ptr(cnt), _ptr(dw), _ptr(c), nnz))
         return cnt[:nnz], dw[:nnz], c[:nnz]
 
+    def set_bcm_plasticity(self, id, enable, decay, average_scalar, dt):
+        s = K.BcmStruct(decay, average_scalar, dt)
+        self._ck(self.lib.snn_lattice_set_bcm_plasticity(self.h, int(enable), C.byref(s)))
+
     def set_connection_traces(self, weight=None, counter=None, dw=None, c=None):
         """Overwrite TraceRSTDP members of every edge in place (order of get_connection_csr; None = keep)."""
         nnz = self.connection_nnz()

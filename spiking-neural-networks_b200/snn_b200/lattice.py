@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _capi as K
 from .neurons import (NEURON_CLASSES, NT_KINETICS, RC_KINETICS, RECEPTORS, STDP, IonotropicNeurotransmitterType,
-                      IzhikevichNeuron, Neuron, PoissonNeuron, SpikeTrain, RewardModulatedSTDP)
+                      IzhikevichNeuron, Neuron, PoissonNeuron, SpikeTrain, RewardModulatedSTDP, BCM)
 
 _NT_PARAM_FIELDS = {
     K.NT_APPROXIMATE: ["clearance_constant"],
@@ -410,7 +410,12 @@ class Lattice(_CellLattice):
         be.set_option(gh.option, self.update_grid_history, i)
         be.set_option(K.OPT_UPDATE_SPIKE_HISTORY, self.update_spike_history, i)
         p = self.plasticity
-        be.set_plasticity(i, p.a_plus, p.a_minus, p.tau_plus, p.tau_minus, p.dt)
+        if isinstance(p, BCM):   # Lattice<BCMIzhikevichNeuron, ..., BCM, ...>
+            be.set_bcm_plasticity(i, True, p.decay, p.average_scalar, p.dt)
+        else:
+            if self.neuron_type.model == K.MODEL_BCM_IZH and self._in_network is None:
+                be.set_bcm_plasticity(i, False, 0.1, 0.1, 0.1)
+            be.set_plasticity(i, p.a_plus, p.a_minus, p.tau_plus, p.tau_minus, p.dt)
 
     def run_lattice(self, iterations: int):
         """RunLattice::run_lattice (neuron/mod.rs:1209-1219)."""

@@ -350,6 +350,11 @@ class STDP(_Params):
     _defaults = dict(a_plus=2.0, a_minus=2.0, tau_plus=4.5, tau_minus=4.5, dt=0.1)
 
 
+class BCM(_Params):
+    """plasticity/mod.rs:80-112: Bienenstock-Cooper-Munro rule over the BCMActivity of BCMIzhikevichNeuron lattices."""
+    _defaults = dict(decay=0.1, average_scalar=0.1, dt=0.1)
+
+
 class RewardModulatedSTDP(_Params):
     """plasticity/mod.rs:155-189; `update(reward)` (:193-195) runs on the back end in run_lattice_with_reward."""
     _defaults = dict(dopamine=0.0, tau_d=20.0, tau_c=0.0001, a_plus=2.0, a_minus=2.0, tau_plus=4.5, tau_minus=4.5, dt=0.1)

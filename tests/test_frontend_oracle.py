@@ -142,3 +142,25 @@ def test_reward_modulated_oracle_matches_independent_restatement(oracle_lattice_
     assert (cnt == ref.counter[pre, post]).all()
     assert np.abs(w - w0).max() > 1e-3, "the modulator must have moved the weights"
     assert lat.reward_modulator.dopamine == pytest.approx(float(ref.mod["dopamine"]), rel=1e-5)
+
+
+def test_bcm_plasticity_oracle_matches_independent_restatement(oracle_lattice_factory):
+    """BCM rule (plasticity/mod.rs:80-112) on a BCMIzhikevichNeuron lattice: C oracle vs the numpy restatement, bit for bit."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import numpy_ref as R
+    lat = SC.build_lattice(oracle_lattice_factory, model="bcm_izh", rows=4, cols=5, seed=6, graph="random", stdp=True)
+    lat.plasticity = S.BCM(decay=0.05, average_scalar=0.5, dt=1e-6)   # tame: activities grow with the never-reset num_spikes
+    conn, w = lat.graph_dense()
+    names = ("current_voltage", "gap_conductance", "w_value", "a", "b", "c", "d", "v_th", "tau_m", "c_m", "dt", "average_activity",
+             "current_activity", "period", "num_spikes", "firing_rate_clock", "firing_rate_window")
+    ref = R.DenseLattice(R.BCM_IZH, 20, conn, w, {k: lat.get_field(k) for k in names})
+    ref.do_plasticity, ref.use_bcm = True, True
+    ref.bcm = dict(decay=f32(0.05), average_scalar=f32(0.5), dt=f32(1e-6))
+    lat.run_lattice(400)
+    ref.run(400)
+    assert np.array(ref.s_hist).sum() > 20 and ref.f["average_activity"].max() > 0 and np.isfinite(np.array(ref.v_hist)).all()
+    assert (lat.spike_history.history.reshape(400, -1) == np.array(ref.s_hist)).all()
+    assert (lat.grid_history.history.reshape(400, -1) == np.array(ref.v_hist)).all()
+    c2, w2 = lat.graph_dense()
+    assert (w2 == ref.w).all() and np.abs(w2 - w).max() > 1e-5

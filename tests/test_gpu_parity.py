@@ -105,6 +105,29 @@ def test_average_and_eeg_history(kind, shape, oracle_lattice_factory):
     assert a.grid_history.history.shape == (0,)
 
 
+# ------------------------------------------------------------------ BCM plasticity
+@pytest.mark.parametrize("graph", ["grid", "random"])
+def test_bcm_plasticity_bit_exact(graph, oracle_lattice_factory):
+    """Lattice<BCMIzhikevichNeuron, ..., BCM, ...> (plasticity/mod.rs:80-112): no transcendental anywhere, so voltages, rasters,
+    activities and weights must match the oracle bit for bit."""
+    kw = dict(model="bcm_izh", rows=7, cols=9, seed=4, graph=graph, stdp=True)
+    a, b = SC.build_lattice(None, **kw), SC.build_lattice(oracle_lattice_factory, **kw)
+    for L in (a, b):
+        L.plasticity = S.BCM(decay=0.05, average_scalar=0.5, dt=1e-6)   # tame: activities grow with the never-reset num_spikes
+    w0 = b.graph_csr()[2].copy()
+    for L in (a, b):
+        L.run_lattice(250)
+        L.run_lattice(150)
+    assert b.spike_history.history.sum() > 20
+    SC.compare_lattices(a, b, exact=True, fields=state_fields("bcm_izh"))
+    (rpa, pa, wa), (rpb, pb, wb) = a.graph_csr(), b.graph_csr()
+    assert (pa == pb).all() and (wa == wb).all()
+    assert np.abs(wb - w0).max() > 1e-5 and np.isfinite(wb).all(), "the BCM rule must have moved the weights"
+    a.do_plasticity = b.do_plasticity = False
+    a.run_lattice(20)
+    assert (a.graph_csr()[2] == wa).all()
+
+
 # ------------------------------------------------------------------ reward-modulated lattices (SURVEY 8f rank 1)
 @pytest.mark.parametrize("canonical", [True, False])
 @pytest.mark.parametrize("graph,shape", [("grid", (9, 11)), ("random", (6, 7)), ("grid", (300, 300))])

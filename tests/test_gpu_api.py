@@ -229,3 +229,32 @@ def test_spike_train_lattice_alone_and_rate_kat():
     assert (st.get_field("last_firing_time") == 999).all() and st.internal_clock == 1001
     cells = st.spike_train_grid()
     assert cells[0][0].rate == 100.0 and cells[1][2].last_firing_time == 999
+
+
+def test_plasticity_variant_error_behaviour():
+    """BCM / reward-modulation entry points: argument checks and scope limits (no abort, status + last-error string)."""
+    import ctypes as C
+    izh = CudaLatticeBackend(K.MODEL_IZH, 0, 0, 4, 4)
+    b = K.BcmStruct(0.1, 0.1, 0.1)
+    assert izh.lib.snn_lattice_set_bcm_plasticity(izh.h, 1, C.byref(b)) == K.SNN_INVALID_ARGUMENT   # neurons without BCMActivity
+    assert b"BCMActivity" in izh.lib.snn_lattice_last_error(izh.h)
+    r = np.zeros(3, f32)
+    assert izh.lib.snn_lattice_run_with_rewards(izh.h, r.ctypes.data, 3) == K.SNN_INVALID_ARGUMENT   # not a reward-modulated lattice
+    assert izh.lib.snn_lattice_get_connection_traces(izh.h, None, None, None, 0) == K.SNN_INVALID_ARGUMENT
+    izh.connect_grid(0, 1, 1.0)
+    izh.set_reward_modulator(True, True, dopamine=0.0, tau_d=20.0, tau_c=1e-4, a_plus=2.0, a_minus=2.0, tau_plus=4.5, tau_minus=4.5, dt=0.1)
+    assert izh.lib.snn_lattice_get_connection_traces(izh.h, None, None, None, 5) == K.SNN_SIZE_MISMATCH
+    cnt, dw, c = izh.connection_traces()
+    assert cnt.size == izh.connection_nnz() == 84 and not cnt.any() and not dw.any() and not c.any()   # TraceRSTDP::default
+    izh.run_with_rewards([])                      # zero iterations: Ok(())
+    assert izh.get_option(K.OPT_INTERNAL_CLOCK) == 0
+    izh.run_with_rewards([0.5, -0.25])
+    assert izh.get_option(K.OPT_INTERNAL_CLOCK) == 2
+    d = izh.get_reward_modulator()["dopamine"]
+    want = f32(f32(f32(0) * np.exp(f32(-0.1) / f32(20))) + f32(20) * f32(0.5))
+    want = f32(f32(want * np.exp(f32(-0.1) / f32(20), dtype=f32)) + f32(20) * f32(-0.25))
+    assert d == pytest.approx(float(want), rel=1e-6)
+    # partitioned handles: out of scope this round
+    part = CudaLatticeBackend(K.MODEL_IZH, 0, 0, 64, 8, rank=0, world=2)
+    s = K.RstdpStruct(0, 20, 1e-4, 2, 2, 4.5, 4.5, 0.1)
+    assert part.lib.snn_lattice_set_reward_modulator(part.h, 1, 1, C.byref(s)) == K.SNN_UNSUPPORTED

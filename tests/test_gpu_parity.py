@@ -453,6 +453,94 @@ def test_reference_poisson_to_izhikevich_behaviour(synapses):
     assert after > 2, after
 
 
+# ------------------------------------------------------------------ BASELINE.json configs[1..3] at their full sizes
+def test_config2_lif_1000x1000_stdp(oracle_lattice_factory):
+    """BASELINE.json configs[1]: leaky integrate-and-fire 1000 x 1000 with STDP (first steps; the oracle needs 0.1 s per step).
+    The LIF step has no transcendental, so rasters and last_firing_time are exact; voltages and weights to STDP's expf rounding."""
+    a, b = pair(oracle_lattice_factory, model="lif", rows=1000, cols=1000, seed=12, graph="grid", stdp=True, history=False, gap=40.0)
+    b._be.set_option(K.OPT_PARALLEL, 1)   # parallel = true: the oracle gathers with OpenMP (80 ms per step)
+    a.run_lattice(50)
+    a.run_lattice(30)
+    b.run_lattice(80)
+    la, lb = a.get_field("last_firing_time"), b.get_field("last_firing_time")
+    assert (lb >= 0).sum() > 10000 and (la == lb).all()
+    assert (a.get_field("refractory_count") == b.get_field("refractory_count")).all()
+    np.testing.assert_allclose(a.get_field("current_voltage"), b.get_field("current_voltage"), rtol=1e-5, atol=1e-4)
+    (rpa, pa, wa), (rpb, pb, wb) = a.graph_csr(), b.graph_csr()
+    assert (rpa == rpb).all() and (pa == pb).all() and wa.size == 8 * 10**6 - 6 * 2000 + 4
+    np.testing.assert_allclose(wa, wb, rtol=1e-5, atol=1e-6)
+    assert np.abs(wb - 1.0).max() > 1e-3
+
+
+def test_config3_hodgkin_huxley_256x256_receptors(oracle_lattice_factory):
+    """BASELINE.json configs[2]: Hodgkin-Huxley 256 x 256 with AMPA / NMDA / GABA receptors, Destexhe neurotransmitter and
+    receptor kinetics, electrical + chemical synapses, dt = 0.01 (expf / powf everywhere: tolerance)."""
+    a, b = pair(oracle_lattice_factory, model="hh", rows=256, cols=256, seed=13, graph="grid", chem="destexhe_all", history=False,
+                gap=2.0)
+    for L in (a, b):
+        L.run_lattice(60)
+    for name, tol in (("current_voltage", 1e-3), ("na_channel$m$state", 1e-5), ("na_channel$h$state", 1e-5), ("k_channel$n$state", 1e-5),
+                      ("neurotransmitters$t", 1e-5), ("receptors$AMPA$r$kinetics$r", 1e-5), ("receptors$NMDA$r$kinetics$r", 1e-5),
+                      ("receptors$GABA$r$kinetics$r", 1e-5), ("receptors$NMDA_current", 1e-3)):
+        # the gate rates are singular at V = -40 / -55 mV (0/0 forms): an expf ulp is amplified for the handful of neurons that
+        # sit next to the singularity, hence the robust form of allclose (at most 0.1 % of the cells, bounded in size)
+        SC.assert_close_robust(a.get_field(name), b.get_field(name), 1e-4, tol, name, max_frac=0.001, max_abs=0.05)
+    assert (a.get_field("was_increasing") == b.get_field("was_increasing")).all()
+    assert (a.get_field("last_firing_time") == b.get_field("last_firing_time")).all()
+
+
+def test_config4_mnist_shaped_network_full_size(oracle_lattice_factory, oracle_network_factory):
+    """BASELINE.json configs[3] at its full size: 784 spike trains (28 x 28, all-to-all onto the excitatory lattice) -> 400
+    excitatory <-> 400 inhibitory Izhikevich neurons, AMPA / GABA, STDP on both lattices.  Rate trains instead of Poisson so that
+    the run is deterministic (Poisson parity is statistical, test_poisson_network_firing_statistics); wide-row kernel."""
+    def build(lfac, nfac):
+        rng = np.random.default_rng(1)
+        T = S.IonotropicNeurotransmitterType
+        exc_base = S.IzhikevichNeuron(gap_conductance=5.0, c_m=10.0)
+        exc_base.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
+        exc_base.receptors[T.AMPA] = S.AMPAReceptor()
+        exc_base.receptors[T.GABA] = S.GABAReceptor()
+        inh_base = exc_base.clone()
+        inh_base.synaptic_neurotransmitters = {T.GABA: S.ApproximateNeurotransmitter()}
+        exc = S.Lattice(S.IzhikevichNeuron, id=1, backend_factory=lfac)
+        exc.populate(exc_base, 20, 20)
+        inh = S.Lattice(S.IzhikevichNeuron, id=2, backend_factory=lfac)
+        inh.populate(inh_base, 20, 20)
+        for L in (exc, inh):
+            L.set_field("current_voltage", rng.uniform(-65, 20, 400).astype(f32))
+            L.set_field("b", rng.uniform(0.25, 0.33, 400).astype(f32))
+            L.do_plasticity = True
+            L.plasticity = S.STDP(a_plus=0.01, a_minus=0.01)
+            L.update_grid_history = L.update_spike_history = True
+        base = S.RateSpikeTrain(rate=2.0)
+        base.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
+        st = S.SpikeTrainLattice(S.RateSpikeTrain, id=0, network_backend_factory=nfac)
+        st.populate(base, 28, 28)
+        st.set_field("rate", rng.choice([0.0, 1.5, 2.0, 3.0, 5.0], 784).astype(f32))
+        net = S.LatticeNetwork.generate_network([exc, inh], [st], backend_factory=nfac)
+        w = rng.uniform(0, 1, (784, 400)).astype(f32)
+        net.connect(0, 1, lambda x, y: True, lambda x, y: float(w[x[0] * 28 + x[1], y[0] * 20 + y[1]]))
+        net.connect(1, 2, lambda x, y: x == y, lambda x, y: 1.0)
+        net.connect(2, 1, lambda x, y: x != y, lambda x, y: -1.0)
+        net.electrical_synapse, net.chemical_synapse = True, True
+        return net
+    a, b = build(None, None), build(oracle_lattice_factory, oracle_network_factory)
+    a.run_lattices(40)
+    b.run_lattices(40)
+    spikes = 0
+    for lid in (1, 2):
+        ha, hb = a.get_lattice(lid).grid_history.history, b.get_lattice(lid).grid_history.history
+        SC.assert_close_robust(ha, hb, 1e-4, 1e-3, f"lattice {lid}")
+        ra, rb = a.get_lattice(lid).spike_history.history, b.get_lattice(lid).spike_history.history
+        assert (ra == rb).all()
+        spikes += int(rb.sum())
+    assert spikes > 50
+    for pre, post in ((0, 1), (1, 2), (2, 1)):
+        (ca, wa), (cb, wb) = a._be.get_connection_dense(pre, post), b._be.get_connection_dense(pre, post)
+        assert (ca == cb).all() and int(cb.sum()) == {(0, 1): 313600, (1, 2): 400, (2, 1): 159600}[(pre, post)]
+        np.testing.assert_allclose(wa, wb, rtol=1e-5, atol=1e-6, err_msg=f"weights {pre}->{post}")
+
+
 # ------------------------------------------------------------------ full size (BASELINE.json configs[4] shape)
 def _window_check(big, rows, cols, r0, c0, h, w, k, oracle_lattice_factory, init, extra_fields=()):
     """The state of a neuron after k steps depends only on cells within Chebyshev distance k (radius-1 stencil), so a

@@ -315,6 +315,7 @@ def main():
             "spiked_fraction": spikes / n_local,
             "clocks": clocks, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_of_nominal_8000": achieved / 8000.0,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "snn::step_win_kernel<IZHIKEVICH, CHEMG=1, NTREL, STDP, G=3> (csrc/step_win.cu)",
                          "bytes_per_neuron_step": BYTES_PER_NEURON_STEP,
                          "avg_launch_us": dev_ms_max * 1e3 / max(1, launches)},

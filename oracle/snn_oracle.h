@@ -22,7 +22,10 @@
  *  (3) STDP is applied after all neurons of the step have been updated (LatticeNetwork::iterate,
  *      neuron/mod.rs:2573-2576).  Lattice::iterate (neuron/mod.rs:954-982) applies it inside the
  *      node loop, which differs only when two connected neurons spike in the same step — a case
- *      in which the reference's own result depends on hash order.
+ *      in which the reference's own result depends on hash order;
+ *  (4) RewardModulatedLattice::iterate (neuron/mod.rs:3127-3156) runs the reward modulator inside the node loop and
+ *      do_update is always true, so the order matters for every edge in every step: kept inside the loop, in the
+ *      ascending node order of (1) (an edge first sees the new last_firing_time of its lower-indexed end only).
  */
 #ifndef SNN_ORACLE_H
 #define SNN_ORACLE_H

@@ -132,6 +132,11 @@ class _CellLattice:
         return self._id
 
     # ---- neurotransmitters of one cell <-> per-type arrays --------------------------------------
+    def _rep(self, a):
+        """Broadcast per-cell rows built for ONE base cell to the whole lattice (populate clones the base neuron)."""
+        reps = getattr(self, "_uniform_reps", 1)
+        return a if reps == 1 else np.tile(a, (reps,) + (1,) * (a.ndim - 1))
+
     def _upload_neurotransmitters(self, cells, ntk):
         n = len(cells)
         if not any(c.synaptic_neurotransmitters for c in cells):
@@ -148,9 +153,9 @@ class _CellLattice:
                 flags[i, int(ty)] = 1
                 for f in cols:
                     cols[f][i, int(ty)] = getattr(nt, f)
-        self.set_field("neurotransmitters$flags", flags)
+        self.set_field("neurotransmitters$flags", self._rep(flags))
         for f, a in cols.items():
-            self.set_field(f"neurotransmitters${f}", a)
+            self.set_field(f"neurotransmitters${f}", self._rep(a))
 
     def _download_neurotransmitters(self, cells, ntk):
         if not getattr(self, "_chem_touched", False):
@@ -235,7 +240,13 @@ class Lattice(_CellLattice):
         for name, v in base_neuron.scalar_fields().items():
             self.fill_field(name, v)
         if base_neuron.synaptic_neurotransmitters or base_neuron.receptors:
-            self._upload_chem([base_neuron] * self.size)
+            # every cell is a clone of the base neuron: build the per-cell rows once and tile them (a Python loop over 10^8 cells
+            # took minutes)
+            self._uniform_reps = self.size
+            try:
+                self._upload_chem([base_neuron])
+            finally:
+                self._uniform_reps = 1
 
     def _upload_chem(self, cells):
         n = len(cells)
@@ -263,9 +274,9 @@ class Lattice(_CellLattice):
                         arrs[(ty, "_" + f)][i] = getattr(rc, f)
                     for f in _RC_KIN_FIELDS[self._rck]:
                         arrs[(ty, "$r$kinetics$" + f)][i] = getattr(rc.r, f)
-            self.set_field("receptors$flags", flags)
+            self.set_field("receptors$flags", self._rep(flags))
             for (ty, suffix), a in arrs.items():
-                self.set_field(f"receptors${_TYPE_NAMES[ty]}{suffix}", a)
+                self.set_field(f"receptors${_TYPE_NAMES[ty]}{suffix}", self._rep(a))
 
     def cell_grid(self):
         """neuron/mod.rs:655-657 — materialised from the device fields."""

@@ -144,7 +144,8 @@ typedef enum snn_option {
     SNN_OPT_PARALLEL = 6,             /* accepted for API parity; the device path is always parallel */
     SNN_OPT_RNG_SEED = 7,             /* Philox key for Poisson spike trains (reference: unseeded thread_rng) */
     SNN_OPT_UPDATE_AVERAGE_HISTORY = 8, /* AverageVoltageHistory, neuron/mod.rs:303-322 */
-    SNN_OPT_STEPS_PER_GRAPH = 9,      /* runtime knob: timesteps captured per CUDA graph replay (0 = plain launches) */
+    SNN_OPT_STEPS_PER_GRAPH = 9,      /* reserved (stored, not acted on): a 10^4-neuron step is 4 us, at the floor of one
+                                         grid-wide synchronisation per timestep, so graph replay has nothing left to remove */
     SNN_OPT_UPDATE_EEG_HISTORY = 10   /* default 0 (per lattice): EEGHistory, neuron/mod.rs:231-284 */
 } snn_option_t;
 

@@ -257,20 +257,31 @@ __device__ __forceinline__ void stdp_chunk8_staged(const StepParams &p, const SR
 #pragma unroll
     for (int u = 0; u < 8; ++u) pre_mask |= ((plastic && c[u] != kColPad && lj[u] == prev) ? 1u : 0u) << u;
     const int lane = (int)(threadIdx.x & 31u);
-    // in-edge rule: the 8 deltas of a neuron that spiked are evaluated by lanes 0..7 in parallel
-    for (uint32_t rem = __ballot_sync(kAll, post_trig); rem != 0u; rem &= rem - 1u) {
-        const int src_lane = __ffs((int)rem) - 1;
+    // in-edge rule: the 8 deltas of a neuron that spiked are evaluated by 8 lanes in parallel, four spiking neurons per round
+    // (lane group g = lane / 8 serves the g-th spiking lane of the round), so that a synchronous burst costs a quarter of the
+    // rounds
+    for (uint32_t rem = __ballot_sync(kAll, post_trig); rem != 0u;) {
+        int psrc[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            psrc[g] = rem ? __ffs((int)rem) - 1 : -1;
+            rem &= rem - 1u;   // 0 stays 0
+        }
+        const int g_me = lane >> 3, u_me = lane & 7;
+        const int my_src = g_me == 0 ? psrc[0] : (g_me == 1 ? psrc[1] : (g_me == 2 ? psrc[2] : psrc[3]));
         int t_pre = -1;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int x = __shfl_sync(kAll, lj[u], src_lane);
-            if (lane == u) t_pre = x;
+            const int x = __shfl_sync(kAll, lj[u], my_src < 0 ? 0 : my_src);
+            if (u_me == u) t_pre = x;
         }
-        const float d = (lane < 8) ? stdp_delta(p.lat[li], t_pre, prev) : 0.f;
+        const float d = (my_src >= 0) ? stdp_delta(p.lat[li], t_pre, prev) : 0.f;
+        // which group serves this lane (if it is one of the round's spiking lanes)
+        const int g_of_me = lane == psrc[0] ? 0 : (lane == psrc[1] ? 1 : (lane == psrc[2] ? 2 : (lane == psrc[3] ? 3 : -1)));
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const float x = __shfl_sync(kAll, d, u);
-            if (lane == src_lane && c[u] != kColPad) src.wgt_update(u, src.wgt(u) + x);
+            const float x = __shfl_sync(kAll, d, (g_of_me < 0 ? 0 : g_of_me) * 8 + u);
+            if (g_of_me >= 0 && c[u] != kColPad) src.wgt_update(u, src.wgt(u) + x);
         }
     }
     // out-edge rule: delta(prev, own last_firing_time) is the same for every edge of a lane

@@ -41,6 +41,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the step rates of the other BASELINE.json configurations")
     ap.add_argument("--cpu-rows", type=int, default=512, help="side of the bounded CPU sample lattice")
     return ap.parse_args()
 
@@ -335,6 +336,16 @@ def main():
                 "sample": f"{r}x{r} lattice, same model/synapses/STDP, {it} timesteps x 2 (gather phase on {cores} OpenMP threads, "
                           f"update+STDP serial, mirroring parallel=true); oracle port = upper bound on the Rust path",
             }
+        if world == 1 and not args.no_configs:
+            # BASELINE.json configs[0..3] are parity-test cases, not bench lines; their device step rates ride along for the
+            # record (C1 / C4 are latency-bound, report us per step).  Never allowed to cost the headline line.
+            try:
+                be.close()
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_configs
+                line["other_configs"] = bench_configs.measure(cpu=False)
+            except Exception as exc:  # noqa: BLE001
+                line["other_configs"] = {"error": repr(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -25,7 +25,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef SNN_WIN_CONS_SLEEP
+#define SNN_WIN_CONS_SLEEP 0     // ns a consumer sleeps between probes of a barrier that is not ready (0 = spin)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#if SNN_WIN_CONS_SLEEP
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(SNN_WIN_CONS_SLEEP);
+    }
+    return;
+#endif
 #if SNN_WIN_CONS_HINT
     asm volatile(
         "{\n"

@@ -53,8 +53,7 @@ def network(lfac, nfac):
     return net
 
 
-def main():
-    cpu = "--cpu" in sys.argv
+def measure(cpu=False):
     out = {}
     for cfg, steps in (("C1", 1000), ("C2", 1000), ("C3", 1000)):
         lat = lattice(None, cfg)
@@ -79,7 +78,11 @@ def main():
         onet = network(lambda m, nt, rc, rows, cols: OracleBackend(m, nt, rc, rows=rows, cols=cols), lambda *a: OracleBackend(*a))
         t0 = time.perf_counter(); onet.run_lattices(50); dt = time.perf_counter() - t0
         out["C4"]["cpu_oracle_us_per_step"] = 1e6 * dt / 50
-    print(json.dumps(out, indent=1))
+    return out
+
+
+def main():
+    print(json.dumps(measure(cpu="--cpu" in sys.argv), indent=1))
 
 
 if __name__ == "__main__":

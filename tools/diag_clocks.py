@@ -13,10 +13,11 @@ be.run_timed(50)
 p = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active,utilization.memory",
                       "--format=csv,noheader", "-lms", "100"], stdout=subprocess.PIPE, text=True)
 time.sleep(0.5)
-for _ in range(6):
+be.run_timed(3000)
+for _ in range(3):
     ms, nl = be.run_timed(2000)
     print(f"2000 steps: {ms / 2000 * 1e3:.1f} us/step", flush=True)
 time.sleep(0.3)
 p.terminate()
 out = p.stdout.read().splitlines()
-print("\n".join(out[::4]))
+print("\n".join(out[-8::3]))

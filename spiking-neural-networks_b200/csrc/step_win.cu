@@ -172,7 +172,7 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
         uint32_t s = 0, ph = 0;
         for (uint32_t tile_seq = blockIdx.x; tile_seq < wp.n_tiles; tile_seq += gridDim.x) {
             const uint32_t tile = p.reverse ? wp.n_tiles - 1u - tile_seq : tile_seq;
-            if (lane == 0) mbar_wait_backoff(&empty[s], ph ^ 1u);
+            mbar_wait_backoff(&empty[s], ph ^ 1u);   // the whole warp probes: no divergent lane-0 loop with 31 lanes parked at a reconvergence barrier
             const uint32_t ts = tile * kWinTile;   // first local neuron of the tile
             // multi-GPU: ghost rows are written by the neighbouring GPU over NVLink; they must have landed before TMA reads
             // them.  Tiles whose upper window reaches below own0 read lower ghosts, tiles whose lower window reaches past the

@@ -236,7 +236,10 @@ struct WinParams {
 #ifndef SNN_WIN_GROUPS
 #define SNN_WIN_GROUPS 3
 #endif
-__host__ __device__ constexpr int win_groups(int model, int chemg) { return (model == SNN_MODEL_HODGKIN_HUXLEY || chemg == 3) ? 2 : SNN_WIN_GROUPS; }
+#ifndef SNN_WIN_GROUPS_WIDE
+#define SNN_WIN_GROUPS_WIDE 2   // models with wide operand sets (Hodgkin-Huxley, three neurotransmitter types): fewer, fatter stages
+#endif
+__host__ __device__ constexpr int win_groups(int model, int chemg) { return (model == SNN_MODEL_HODGKIN_HUXLEY || chemg == 3) ? SNN_WIN_GROUPS_WIDE : SNN_WIN_GROUPS; }
 
 cudaError_t launch_step_win(const StepParams &p, const WinParams &wp, int model, int chemg, bool ntrel, bool stdp, unsigned grid,
                             cudaStream_t s);

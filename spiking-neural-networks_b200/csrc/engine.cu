@@ -1543,10 +1543,10 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     if (want_tgrid) CK(dev_alloc(&d_tgrid, chunk * n_trains), SNN_GPU_BUFFER_CREATE_ERROR);
     if (want_tspk) CK(dev_alloc(&d_tspk, chunk * t_words), SNN_GPU_BUFFER_CREATE_ERROR);
     double *d_red = nullptr; uint32_t *d_red_lat = nullptr;
-    std::vector<const Lat *> red_lats;
+    std::vector<Lat *> red_lats;
     if (want_red) {
         std::vector<uint32_t> meta;
-        for (auto &L : lats_) if (!L.is_train && (L.avg_hist || L.eeg_hist)) red_lats.push_back(&L);
+        for (auto &L : lats_) if (!L.is_train && (L.avg_hist || L.eeg_hist)) red_lats.push_back(&L);   // lats_ is not resized inside run()
         const size_t nl = red_lats.size();
         meta.resize(3 * nl);
         for (size_t k = 0; k < nl; ++k) {
@@ -1722,7 +1722,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                 if (re == cudaSuccess) re = cudaStreamSynchronize(stream_);
                 if (re != cudaSuccess) { bail(re, SNN_GPU_BUFFER_READ_ERROR, "history reduce"); break; }
                 for (size_t k = 0; k < nl; ++k) {
-                    Lat &L = const_cast<Lat &>(*red_lats[k]);
+                    Lat &L = *red_lats[k];
                     for (uint64_t s = 0; s < steps; ++s) {
                         const double sum_v = hr[(s * nl + k) * 2], sum_dv = hr[(s * nl + k) * 2 + 1];
                         // AverageVoltageHistory::update, neuron/mod.rs:310-316: sum / len as f32

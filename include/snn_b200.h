@@ -285,7 +285,7 @@ SNN_API int32_t snn_lattice_set_bcm_plasticity(snn_lattice_t *h, int32_t enable,
  * timestep by RewardModulatedSTDP::update_weight (once from each end, plasticity/mod.rs:197-233; do_update is always true).
  * snn_lattice_run then is RunLattice::run_lattice (:3361-3374, no reward signal) and snn_lattice_run_with_rewards runs one
  * timestep per entry of `rewards`, each preceded by RewardModulatedSTDP::update(reward) (run_lattice_with_reward, :3250-3257).
- * Single-GPU, single-lattice handles only.  Traces are reset when the graph is rebuilt. */
+ * Single-lattice handles (whole or row-strip partitioned).  Traces are reset when the graph is rebuilt. */
 SNN_API int32_t snn_lattice_set_reward_modulator(snn_lattice_t *h, int32_t enable, int32_t do_modulation, const snn_rstdp_t *modulator);
 SNN_API int32_t snn_lattice_get_reward_modulator(const snn_lattice_t *h, snn_rstdp_t *modulator);
 SNN_API int32_t snn_lattice_run_with_rewards(snn_lattice_t *h, const float *rewards, uint64_t n_rewards);

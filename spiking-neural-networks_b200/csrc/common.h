@@ -61,6 +61,10 @@ struct HaloDir {
     uint64_t peer_t_stride;
     unsigned long long *peer_flag;   // peer-side arrival counter for data coming from me
     unsigned long long *my_flag;     // my arrival counter for data coming from this peer
+    // second pair, reward-modulated strips: "the per-edge kernel of step s has finished reading its old ghosts" — the step
+    // kernel of s + 1 waits for it instead of my_flag, because it overwrites those ghost slots in the neighbour's slab
+    unsigned long long *peer_flag2;
+    unsigned long long *my_flag2;
     uint32_t active;
 };
 

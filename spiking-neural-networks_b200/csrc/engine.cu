@@ -65,8 +65,8 @@ int Engine::init() {
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), SNN_GPU_QUEUE_FAILURE);
     CK(cudaEventCreate(&ev0_), SNN_GPU_QUEUE_FAILURE);
     CK(cudaEventCreate(&ev1_), SNN_GPU_QUEUE_FAILURE);
-    CK(dev_alloc(&flags_, 2), SNN_GPU_BUFFER_CREATE_ERROR);
-    CK(cudaMemset(flags_, 0, 2 * sizeof(unsigned long long)), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(dev_alloc(&flags_, 4), SNN_GPU_BUFFER_CREATE_ERROR);   // [0],[1] step arrivals from rank-1 / rank+1, [2],[3] edge-kernel arrivals
+    CK(cudaMemset(flags_, 0, 4 * sizeof(unsigned long long)), SNN_GPU_BUFFER_WRITE_ERROR);
     CK(dev_alloc(&halo_done_, 4), SNN_GPU_BUFFER_CREATE_ERROR);  // [0],[1] completion counters, [2] halo time-out flag
     CK(cudaMemset(halo_done_, 0, 4 * sizeof(unsigned int)), SNN_GPU_BUFFER_WRITE_ERROR);
     return SNN_OK;
@@ -937,7 +937,6 @@ int Engine::set_bcm_plasticity(bool enable, const snn_bcm_t *b) {
 }
 
 int Engine::set_reward_modulator(bool enable, bool modulate, const snn_rstdp_t *m) {
-    if (enable && part_world > 1) return fail(SNN_UNSUPPORTED, "reward-modulated lattices are not supported on partitioned handles");
     int n_neuron_lat = 0;
     for (auto &L : lats_) if (!L.is_train) n_neuron_lat++;
     if (enable && (n_neuron_lat > 1 || n_trains > 0)) return fail(SNN_UNSUPPORTED, "reward-modulated lattice networks are not built yet");
@@ -1491,10 +1490,13 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     RstdpParams rsp{rstdp.dopamine, rstdp.tau_c, rstdp.a_plus, rstdp.a_minus, rstdp.tau_plus, rstdp.tau_minus, rstdp.dt,
                     rs_counter_, rs_dw_, rs_c_, rs_canonical_ ? 1u : 0u};
     const bool lft_pp = stdp || rmod || (n_trains && electrical) || part_world > 1;
+    const bool rmod_part = rmod && part_world > 1;
 
     StepParams sp;
     fill_step_params(sp);
     sp.lft_pp = lft_pp;
+    if (rmod_part)   // step s + 1 overwrites ghost slots that the neighbour's per-edge kernel of step s still reads: wait for that one
+        for (int d = 0; d < 2; ++d) sp.halo[d].my_flag = halo_dir_[d].my_flag2;
     TmaParams tma;
     unsigned tma_grid = 0;
     WinParams win;
@@ -1635,7 +1637,13 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             }
             if (rmod) {
                 rsp.dopamine = rstdp.dopamine;
-                cudaError_t e = launch_rstdp_edges(sp, rsp, stream_);
+                StepParams ep = sp;
+                if (rmod_part) {
+                    // the kernel needs the neighbours' step-s exports (their last_firing_time of this step in my ghost slots)
+                    for (int d = 0; d < 2; ++d) ep.halo[d].my_flag = halo_dir_[d].my_flag;
+                    ep.halo_epoch = halo_epoch_ + 1;
+                }
+                cudaError_t e = launch_rstdp_edges(ep, rsp, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_rstdp_edges"); break; }
                 n_launch++;
             }
@@ -1826,6 +1834,8 @@ int Engine::ipc_attach(int direction, const IpcBlob *blob) {
     // the neighbour's arrival counter for data coming from me: I am its rank+1 when d == 0 (slot 1), its rank-1 when d == 1 (slot 0)
     H.peer_flag = (unsigned long long *)peer_flags_[d] + (d == 0 ? 1 : 0);
     H.my_flag = flags_ + d;
+    H.peer_flag2 = H.peer_flag + 2;
+    H.my_flag2 = H.my_flag + 2;
     H.active = 1;
     return SNN_OK;
 }

@@ -71,7 +71,10 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const __grid_constant__ 
             p.halo_done[0] = 0u;
             __threadfence_system();
             for (int d = 0; d < 2; ++d)
-                if (p.halo[d].active) st_release_sys(p.halo[d].peer_flag, p.halo_epoch + 1ull);
+                if (p.halo[d].active) {
+                    st_release_sys(p.halo[d].peer_flag, p.halo_epoch + 1ull);
+                    st_release_sys(p.halo[d].peer_flag2, p.halo_epoch + 1ull);   // nothing of an earlier run is still being read
+                }
         }
     }
 }
@@ -198,6 +201,16 @@ template <bool CANON>
 __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
+    const bool part = (p.halo[0].active | p.halo[1].active) != 0;
+    if (part) {
+        // row strips: the neighbours' last_firing_time of THIS step must have landed in the ghost slots (p.halo_epoch is the value
+        // their step kernels publish); my_flag is the step-arrival counter here
+        if (threadIdx.x == 0) {
+            if (p.halo[0].active) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2);
+            if (p.halo[1].active) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
+        }
+        __syncthreads();
+    }
     uint32_t k0[kRsSlices], k1[kRsSlices], node[kRsSlices];
     int old_post[kRsSlices], new_post[kRsSlices];
     uint32_t rounds = 0;
@@ -255,6 +268,21 @@ __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constan
             rstdp_call(r, d2, decay_c, cnt[u], dw[u], cc[u], w[u]);
             if (!CANON) { r.counter[e[u]] = (uint8_t)cnt[u]; r.dw[e[u]] = dw[u]; }
             r.c[e[u]] = cc[u]; p.wgt[e[u]] = w[u];
+        }
+    }
+    if (part) {
+        // the last CTA tells both neighbours that this rank no longer reads the ghost values of the previous step: their next
+        // step kernel may overwrite them
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const unsigned int done = atomicAdd(&p.halo_done[3], 1u) + 1u;
+            if (done == gridDim.x) {
+                p.halo_done[3] = 0u;
+                __threadfence_system();
+                for (int d = 0; d < 2; ++d)
+                    if (p.halo[d].active) st_release_sys(p.halo[d].peer_flag2, p.halo_epoch);
+            }
         }
     }
 }

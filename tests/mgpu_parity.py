@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--no-chem", action="store_true")
     ap.add_argument("--no-stdp", action="store_true")
     ap.add_argument("--runs", type=int, default=2, help="split the steps over this many run() calls")
+    ap.add_argument("--reward", action="store_true", help="RewardModulatedLattice: RewardModulatedSTDP over TraceRSTDP weights, a reward per step")
     args = ap.parse_args()
 
     import torch
@@ -56,8 +57,11 @@ def main():
         be.connect_grid(0, args.radius, 0.8)
         be.set_option(K.OPT_ELECTRICAL_SYNAPSE, 1)
         be.set_option(K.OPT_CHEMICAL_SYNAPSE, int(chem))
-        be.set_option(K.OPT_DO_PLASTICITY, int(not args.no_stdp))
+        be.set_option(K.OPT_DO_PLASTICITY, int(not args.no_stdp and not args.reward))
         be.set_plasticity(0, 0.05, 0.04, 4.5, 3.0, 0.1)
+        if args.reward:
+            be.set_reward_modulator(True, True, dopamine=0.0, tau_d=20.0, tau_c=0.05, a_plus=0.1, a_minus=0.08, tau_plus=4.5,
+                                    tau_minus=3.0, dt=0.1)
 
     strip = StripLattice(K.MODEL_IZH, rows, cols, rank, world, device=local)
     sl = slice(strip.row_begin * cols, strip.row_end * cols)
@@ -65,21 +69,33 @@ def main():
     strip.attach()
     per = [args.steps // args.runs] * args.runs
     per[-1] += args.steps - sum(per)
-    for k in per:
-        strip.be.run(k)
+    rewards = np.random.default_rng(5).uniform(-0.3, 0.3, args.steps).astype(f32)
+
+    def advance(be):
+        done = 0
+        for i, k in enumerate(per):
+            if args.reward and i % 2 == 0:
+                be.run_with_rewards(rewards[done:done + k])   # run_lattice_with_reward per step
+            else:
+                be.run(k)                                      # RunLattice::run_lattice (no reward signal; modulation stays on)
+            done += k
+
+    advance(strip.be)
     names = ["current_voltage", "w_value", "last_firing_time", "is_spiking"] + (["neurotransmitters$t", "receptors$AMPA$r$kinetics$r"] if chem else [])
     mine = {nm: strip.be.get_field(0, nm) for nm in names}
     rp, pre, w = strip.be.get_connection_csr()
     mine["weights"] = w
     mine["pre"] = pre
+    if args.reward:
+        mine["traces"] = strip.be.connection_traces()
+        mine["dopamine"] = strip.be.get_reward_modulator()["dopamine"]
     gathered = [None] * world
     dist.all_gather_object(gathered, mine)
     ok = True
     if rank == 0:
         full = CudaLatticeBackend(K.MODEL_IZH, 0, 0, rows, cols, device=local)
         configure(full, slice(0, n))
-        for k in per:
-            full.run(k)
+        advance(full)
         for nm in names:
             want = full.get_field(0, nm)
             got = np.concatenate([g[nm] for g in gathered])
@@ -92,6 +108,17 @@ def main():
         same = (gp == pre2).all() and (gw == w2).all()
         print(f"{'graph (pre, weights)':32s} {'OK' if same else 'MISMATCH'}; max |dw| from 0.8: {np.abs(w2 - 0.8).max():.4f}")
         ok &= bool(same)
+        if args.reward:
+            want_tr = full.connection_traces()
+            for i, nm in enumerate(("counter", "dw", "c")):
+                got = np.concatenate([g["traces"][i] for g in gathered])
+                same = (got == want_tr[i]).all()
+                print(f"{'trace ' + nm:32s} {'OK' if same else 'MISMATCH'} ({int((got != want_tr[i]).sum())} of {got.size})")
+                ok &= bool(same)
+            dop = full.get_reward_modulator()["dopamine"]
+            same = all(g["dopamine"] == dop for g in gathered)
+            print(f"{'dopamine':32s} {'OK' if same else 'MISMATCH'} ({dop})")
+            ok &= bool(same) and np.abs(w2 - 0.8).max() > 1e-3
         spikes = int((full.get_field(0, "last_firing_time") >= 0).sum())
         print(f"world={world} rows={rows} cols={cols} steps={args.steps} neurons that spiked: {spikes}")
         print("MGPU_PARITY", "PASS" if ok and spikes > 0 else "FAIL")

@@ -257,11 +257,9 @@ public:
     // connect(presynaptic_id, postsynaptic_id, &cond, weight_logic), neuron/mod.rs:1845-1930
     void connect(std::size_t pre_id, std::size_t post_id, const std::function<bool(Position, Position)> &cond,
                  const std::function<float(Position, Position)> &weight = nullptr) {
-        // id checks first, in the reference's order: postsynaptic spike train, presynaptic id, postsynaptic id (:1852-1862)
-        uint64_t n = 0;
+        // the library checks the ids in the reference's order: postsynaptic spike train, presynaptic id, postsynaptic id (:1852-1862)
         const Position a = dims_.count(pre_id) ? dims_[pre_id] : Position{0, 0}, b = dims_.count(post_id) ? dims_[post_id] : Position{0, 0};
         const detail::Csr g = detail::evaluate(a.first, a.second, b.first, b.second, cond, weight);
-        (void)n;
         ck(snn_network_connect_csr(h_, pre_id, post_id, g.row_ptr.data(), g.pre.data(), g.w.data(), b.first * b.second, g.row_ptr.back()));
     }
     void set_field(std::size_t id, const std::string &name, const std::vector<float> &v) { ck(snn_network_set_field(h_, id, name.c_str(), v.data(), v.size(), SNN_F32)); }

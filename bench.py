@@ -215,6 +215,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries the one JSON line and nothing else: NCCL's banner ("NCCL version ...") goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rows, cols, iters = args.rows, args.cols, args.iters
     n_local = rows * cols

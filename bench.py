@@ -208,6 +208,12 @@ def main():
     from snn_b200.backend import CudaLatticeBackend
     from snn_b200.dist import StripLattice
 
+    # stdout carries the one JSON line and nothing else: whatever libraries print while we work (NCCL's "NCCL version ..."
+    # banner at the first collective, for one) is sent to stderr at the file-descriptor level; fd 1 comes back for the line
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,8 +221,6 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout carries the one JSON line and nothing else: NCCL's banner ("NCCL version ...") goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rows, cols, iters = args.rows, args.cols, args.iters
     n_local = rows * cols
@@ -348,7 +352,10 @@ def main():
                 line["other_configs"] = bench_configs.measure(cpu=False)
             except Exception as exc:  # noqa: BLE001
                 line["other_configs"] = {"error": repr(exc)}
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the step rates of the other BASELINE.json configurations")
     ap.add_argument("--cpu-rows", type=int, default=512, help="side of the bounded CPU sample lattice")
+    ap.add_argument("--ref-budget-s", type=float, default=60.0, help="CPU seconds the whole --impl reference run may take")
     return ap.parse_args()
 
 
@@ -163,7 +164,7 @@ def reference_arm(args):
     rows = cols = args.cpu_rows
     # calibrate so that the whole --steps/--warmup run stays within a couple of minutes
     rate, _ = cpu_oracle_run(rows, cols, 2, 1, 0, True, cores)
-    budget = 60.0 / max(1, args.steps + args.warmup)
+    budget = args.ref_budget_s / max(1, args.steps + args.warmup)
     iters = max(1, min(args.iters, int(rate * budget / (rows * cols))))
     value, per_step = cpu_oracle_run(rows, cols, iters, args.steps, args.warmup, True, cores)
     sample = f"{rows}x{cols} Izhikevich lattice (same synapses/STDP), {iters} timesteps per step, OpenMP gather on {cores} threads"

@@ -67,7 +67,7 @@ int Engine::init() {
     CK(cudaEventCreate(&ev1_), SNN_GPU_QUEUE_FAILURE);
     CK(dev_alloc(&flags_, 4), SNN_GPU_BUFFER_CREATE_ERROR);   // [0],[1] step arrivals from rank-1 / rank+1, [2],[3] edge-kernel arrivals
     CK(cudaMemset(flags_, 0, 4 * sizeof(unsigned long long)), SNN_GPU_BUFFER_WRITE_ERROR);
-    CK(dev_alloc(&halo_done_, 4), SNN_GPU_BUFFER_CREATE_ERROR);  // [0],[1] completion counters, [2] halo time-out flag
+    CK(dev_alloc(&halo_done_, 4), SNN_GPU_BUFFER_CREATE_ERROR);  // [0],[1] completion counters, [2] halo time-out flag, [3] per-edge kernel CTAs done
     CK(cudaMemset(halo_done_, 0, 4 * sizeof(unsigned int)), SNN_GPU_BUFFER_WRITE_ERROR);
     return SNN_OK;
 }

@@ -512,15 +512,17 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
 // lazy STDP, the products) is spread over all warps of the CTA — warp w takes k-rows w, w + W, ... of a chunk, lane = row —
 // and parked in shared memory; the leader warp then adds the parked terms in ascending presynaptic order.  The terms and
 // the order of the additions are those of gather_edges, so the sums are bit-identical.
-constexpr uint32_t kWideChunk = 64;   // k-rows per chunk
-constexpr int kWideUnroll = 4;         // k-rows per thread and batch (kWideChunk = kWideUnroll * warps per CTA)
+constexpr int kWideUnroll = 4;         // k-rows per helper thread and chunk
+constexpr int kWideWarps = 16;         // warps per CTA: one leader + 15 helpers
+constexpr uint32_t kWideChunk = kWideUnroll * (kWideWarps - 1);   // 60 k-rows per chunk (slice widths are multiples of 4)
+// shared memory of one chunk buffer (two of them: the helpers fill one while the leader drains the other)
+__host__ __device__ constexpr uint32_t wide_buf_bytes(int chemg) { return kWideChunk * 32u * (4u + (chemg == 3 ? 4u * kNT : (chemg == 1 ? 4u : 0u)) + 1u); }
 
 struct WideSrc : GlobalSrc {
     static constexpr bool kWide = true;
     uint32_t warp, n_warps;
-    float *sm_e;          // [kWideChunk][32] electrical terms
-    float *sm_t;          // [kNT][kWideChunk][32] chemical terms
-    uint8_t *sm_f;        // [kWideChunk][32] bit 0: edge present, bits 1..3: presynaptic node releases type 0..2
+    unsigned char *sm;    // 2 x wide_buf_bytes: [kWideChunk][32] f32 electrical terms, [types][kWideChunk][32] f32 chemical terms,
+                          // [kWideChunk][32] u8 flags (bit 0: edge present, bits 1..3: presynaptic node releases type 0..2)
 };
 
 template <int CHEMG, bool STDP, bool NET, class SRC>
@@ -531,18 +533,26 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
     const bool do_e = p.electrical != 0;
     const int prev = (int)p.clock - 1;
     const uint32_t lane = src.lane;
-    for (uint32_t kk = 0; kk < width; kk += kWideChunk) {
+    constexpr uint32_t HW = kWideWarps - 1;
+    constexpr uint32_t kTerms = kWideChunk * 32u;
+    constexpr uint32_t kTypes = CHEMG == 3 ? (uint32_t)kNT : (CHEMG == 1 ? 1u : 0u);
+    const uint32_t n_chunks = (width + kWideChunk - 1u) / kWideChunk;
+    // ---- phase A (helper warps): the terms of chunk c into buffer c & 1 — kWideUnroll k-rows per thread: all col/weight loads,
+    // then every gather they address (V, last_firing_time, t, the spike-train constants), then the arithmetic
+    auto phase_a = [&](uint32_t ci) {
+        unsigned char *buf = src.sm + (ci & 1u) * wide_buf_bytes(CHEMG);
+        float *sm_e = reinterpret_cast<float *>(buf);
+        float *sm_t = sm_e + kTerms;
+        uint8_t *sm_f = reinterpret_cast<uint8_t *>(sm_t + kTypes * kTerms);
+        const uint32_t kk = ci * kWideChunk;
         const uint32_t kn = min(kWideChunk, width - kk);
-        // ---- phase A: every warp computes the terms of its k-rows, kWideUnroll at a time: all col/weight loads, then every
-        // gather they address (V, last_firing_time, t, the spike-train constants), then the arithmetic — two dependent
-        // memory round trips per batch instead of three per edge
-        for (uint32_t kb = src.warp; kb < kn; kb += kWideUnroll * src.n_warps) {
+        for (uint32_t kb = src.warp - 1u; kb < kn; kb += kWideUnroll * HW) {
             uint32_t c[kWideUnroll], j[kWideUnroll];
             float w[kWideUnroll];
             bool live[kWideUnroll], ok[kWideUnroll], train[kWideUnroll];
 #pragma unroll
             for (int u = 0; u < kWideUnroll; ++u) {
-                const uint32_t k = kb + (uint32_t)u * src.n_warps;
+                const uint32_t k = kb + (uint32_t)u * HW;
                 live[u] = k < kn;
                 c[u] = live[u] ? src.col(kk + k) : kColPad;
                 w[u] = live[u] ? src.wgt(kk + k) : 0.f;
@@ -577,7 +587,7 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
 #pragma unroll
             for (int u = 0; u < kWideUnroll; ++u) {
                 if (!live[u]) continue;
-                const uint32_t k = kb + (uint32_t)u * src.n_warps;
+                const uint32_t k = kb + (uint32_t)u * HW;
                 float wu = w[u];
                 if (pending) {
                     bool pre_trig = ok[u] && lj[u] == prev;
@@ -601,42 +611,56 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
                         else final_input = gap * refract_effect(p.refract, tfv[u][1], p.clock, (uint32_t)lt[u], tfv[u][2], tfv[u][0], tfv[u][3]);
                     }
                 }
-                src.sm_e[k * 32u + lane] = final_input * wu;
+                sm_e[k * 32u + lane] = final_input * wu;
                 uint32_t f = ok[u] ? 1u : 0u;
                 if (CHEMG == 1) {
                     const bool has = ok[u] && ((c[u] >> (kColNtShift + ty0)) & 1u);
-                    src.sm_t[k * 32u + lane] = tj[u][0] * wu;
+                    sm_t[k * 32u + lane] = tj[u][0] * wu;
                     f |= has ? 2u : 0u;
                 } else if (CHEMG == 3) {
                     const uint32_t m = ok[u] ? (c[u] >> kColNtShift) & 7u : 0u;
 #pragma unroll
-                    for (int ty = 0; ty < kNT; ++ty) src.sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] = tj[u][ty] * wu;
+                    for (int ty = 0; ty < kNT; ++ty) sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] = tj[u][ty] * wu;
                     f |= m << 1;
                 }
-                src.sm_f[k * 32u + lane] = (uint8_t)f;
+                sm_f[k * 32u + lane] = (uint8_t)f;
             }
         }
-        __syncthreads();
-        // ---- phase B: the leader warp adds the parked terms in ascending presynaptic order -----------------------
-        if (src.warp == 0) {
+    };
+    // ---- phase B (leader warp): add the parked terms of chunk c in ascending presynaptic order
+    auto phase_b = [&](uint32_t ci) {
+        const unsigned char *buf = src.sm + (ci & 1u) * wide_buf_bytes(CHEMG);
+        const float *sm_e = reinterpret_cast<const float *>(buf);
+        const float *sm_t = sm_e + kTerms;
+        const uint8_t *sm_f = reinterpret_cast<const uint8_t *>(sm_t + kTypes * kTerms);
+        const uint32_t kn = min(kWideChunk, width - ci * kWideChunk);
+        {
             for (uint32_t k = 0; k < kn; ++k) {
-                const uint32_t f = src.sm_f[k * 32u + lane];
-                if (do_e) A.acc_e = A.acc_e + src.sm_e[k * 32u + lane];
+                const uint32_t f = sm_f[k * 32u + lane];
+                if (do_e) A.acc_e = A.acc_e + sm_e[k * 32u + lane];
                 if (CHEMG == 1) {
                     const bool has = (f >> 1) & 1u;
-                    A.acc_t[0] = A.acc_t[0] + (has ? src.sm_t[k * 32u + lane] : 0.f);
+                    A.acc_t[0] = A.acc_t[0] + (has ? sm_t[k * 32u + lane] : 0.f);
                     A.cnt[0] += has ? 1u : 0u;
                 } else if (CHEMG == 3) {
 #pragma unroll
                     for (int ty = 0; ty < kNT; ++ty) {
                         const bool has = (f >> (1 + ty)) & 1u;
-                        A.acc_t[ty] = A.acc_t[ty] + (has ? src.sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] : 0.f);
+                        A.acc_t[ty] = A.acc_t[ty] + (has ? sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] : 0.f);
                         A.cnt[ty] += has ? 1u : 0u;
                     }
                 }
                 A.n_in += f & 1u;
             }
         }
+    };
+    // software pipeline over the chunks: while the leader adds chunk c, the helpers already compute chunk c + 1
+    if (n_chunks == 0u) return;
+    if (src.warp != 0u) phase_a(0u);
+    __syncthreads();
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        if (src.warp == 0u) phase_b(c);
+        else if (c + 1u < n_chunks) phase_a(c + 1u);
         __syncthreads();
     }
 }

@@ -6,13 +6,9 @@
 
 namespace snn {
 
-constexpr int kWideWarps = 16;
-
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
 __global__ void __launch_bounds__(kWideWarps * 32) step_wide_kernel(const __grid_constant__ StepParams p) {
-    __shared__ float sm_e[kWideChunk * 32];
-    __shared__ float sm_t[(CHEMG == 3 ? kNT : (CHEMG == 1 ? 1 : 0)) * kWideChunk * 32 + 1];
-    __shared__ uint8_t sm_f[kWideChunk * 32];
+    extern __shared__ __align__(16) unsigned char wide_sm[];   // 2 x wide_buf_bytes(CHEMG): double-buffered chunk terms
     const uint32_t warp_global = blockIdx.x;   // one CTA per slice
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t ln = warp_global * 32u + lane;
@@ -22,15 +18,23 @@ __global__ void __launch_bounds__(kWideWarps * 32) step_wide_kernel(const __grid
     const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + warp_global + 1);
     const float *t0 = nullptr;
     if (CHEMG == 1) t0 = p.t_in + (size_t)(__ffs((int)p.nt_used) - 1) * p.t_stride;
-    const WideSrc src{{p, lnc, p.own0 + lnc, lane, k0, k1, t0}, warp, (uint32_t)kWideWarps, sm_e, sm_t, sm_f};
+    const WideSrc src{{p, lnc, p.own0 + lnc, lane, k0, k1, t0}, warp, (uint32_t)kWideWarps, wide_sm};
     neuron_step<MODEL, CHEMG, NTREL, STDP, NET>(p, src, warp_global, lane, ln, lnc, valid, false, false);
 }
 
 template <int MODEL, int CHEMG, bool NTREL, bool NET>
 static cudaError_t launch_wide_3(const StepParams &p, bool stdp, cudaStream_t s) {
     const unsigned grid = (p.n_neurons + 31u) / 32u;
-    if (stdp) step_wide_kernel<MODEL, CHEMG, NTREL, true, NET><<<grid, kWideWarps * 32, 0, s>>>(p);
-    else step_wide_kernel<MODEL, CHEMG, NTREL, false, NET><<<grid, kWideWarps * 32, 0, s>>>(p);
+    constexpr size_t smem = 2u * wide_buf_bytes(CHEMG);
+    if (stdp) {
+        auto k = step_wide_kernel<MODEL, CHEMG, NTREL, true, NET>;
+        if (smem > 48u * 1024u) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+        k<<<grid, kWideWarps * 32, smem, s>>>(p);
+    } else {
+        auto k = step_wide_kernel<MODEL, CHEMG, NTREL, false, NET>;
+        if (smem > 48u * 1024u) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
+        k<<<grid, kWideWarps * 32, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 

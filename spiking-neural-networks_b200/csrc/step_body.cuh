@@ -634,23 +634,37 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
         const float *sm_t = sm_e + kTerms;
         const uint8_t *sm_f = reinterpret_cast<const uint8_t *>(sm_t + kTypes * kTerms);
         const uint32_t kn = min(kWideChunk, width - ci * kWideChunk);
-        {
-            for (uint32_t k = 0; k < kn; ++k) {
-                const uint32_t f = sm_f[k * 32u + lane];
-                if (do_e) A.acc_e = A.acc_e + sm_e[k * 32u + lane];
+        // 4 k-rows per iteration (kn is a multiple of 4): their loads are issued together, the additions stay strictly ordered
+        for (uint32_t k0b = 0; k0b < kn; k0b += 4u) {
+            uint32_t f[4];
+            float te[4], tt[4][CHEMG == 3 ? kNT : 1];
+#pragma unroll
+            for (uint32_t q = 0; q < 4u; ++q) {
+                const uint32_t k = k0b + q;
+                f[q] = sm_f[k * 32u + lane];
+                te[q] = sm_e[k * 32u + lane];
+                if (CHEMG == 1) tt[q][0] = sm_t[k * 32u + lane];
+                if (CHEMG == 3) {
+#pragma unroll
+                    for (int ty = 0; ty < kNT; ++ty) tt[q][ty] = sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane];
+                }
+            }
+#pragma unroll
+            for (uint32_t q = 0; q < 4u; ++q) {
+                if (do_e) A.acc_e = A.acc_e + te[q];
                 if (CHEMG == 1) {
-                    const bool has = (f >> 1) & 1u;
-                    A.acc_t[0] = A.acc_t[0] + (has ? sm_t[k * 32u + lane] : 0.f);
+                    const bool has = (f[q] >> 1) & 1u;
+                    A.acc_t[0] = A.acc_t[0] + (has ? tt[q][0] : 0.f);
                     A.cnt[0] += has ? 1u : 0u;
                 } else if (CHEMG == 3) {
 #pragma unroll
                     for (int ty = 0; ty < kNT; ++ty) {
-                        const bool has = (f >> (1 + ty)) & 1u;
-                        A.acc_t[ty] = A.acc_t[ty] + (has ? sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] : 0.f);
+                        const bool has = (f[q] >> (1 + ty)) & 1u;
+                        A.acc_t[ty] = A.acc_t[ty] + (has ? tt[q][ty] : 0.f);
                         A.cnt[ty] += has ? 1u : 0u;
                     }
                 }
-                A.n_in += f & 1u;
+                A.n_in += f[q] & 1u;
             }
         }
     };

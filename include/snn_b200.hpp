@@ -298,4 +298,27 @@ private:
     void ck(int status) const { detail::check(status, h_ ? snn_network_last_error(h_) : nullptr); }
 };
 
+// SpikeTrainLattice<N, T, U> on its own (neuron/mod.rs:1290-1428; RunSpikeTrainLattice :1419-1428): a network that holds just this lattice
+class SpikeTrainLattice {
+public:
+    bool update_grid_history = false, update_spike_history = false;
+    explicit SpikeTrainLattice(snn_spike_train_t kind = SNN_TRAIN_POISSON, std::size_t id = 0) : net_(SNN_MODEL_IZHIKEVICH, kind), id_(id) {}
+    // populate(&base_spike_train, num_rows, num_cols), :1321-1341; base = the spike train's fields that differ from Default
+    void populate(const std::map<std::string, float> &base_fields, std::size_t rows, std::size_t cols) {
+        net_.add_spike_train_lattice(id_, base_fields, rows, cols);
+    }
+    void set_field(const std::string &name, const std::vector<float> &v) { net_.set_field(id_, name, v); }
+    std::vector<float> get_field(const std::string &name) { return net_.get_field(id_, name); }
+    void run_lattice(std::size_t iterations) {
+        net_.set_lattice_option(id_, SNN_OPT_UPDATE_GRID_HISTORY, update_grid_history);
+        net_.set_lattice_option(id_, SNN_OPT_UPDATE_SPIKE_HISTORY, update_spike_history);
+        net_.run_lattices(iterations);
+    }
+    std::vector<uint8_t> spike_history() { return net_.spike_history(id_); }
+
+private:
+    LatticeNetwork net_;
+    std::size_t id_;
+};
+
 }  // namespace snn_b200

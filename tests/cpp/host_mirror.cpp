@@ -125,6 +125,16 @@ int main(int argc, char **argv) {
     net.connect(0, 1, [](Position, Position) { return true; }, [](Position, Position) { return 0.5f; });
     net.run_lattices(50);
 
+    // ---- SpikeTrainLattice on its own: tests/rate_spike_train.rs:54-72 (rate 100, dt 1: a spike every 100th step) -----------
+    SpikeTrainLattice trains(SNN_TRAIN_RATE, 4);
+    trains.populate({{"rate", 100.f}, {"dt", 1.f}}, 2, 3);
+    trains.update_spike_history = true;
+    trains.run_lattice(1001);
+    const std::vector<uint8_t> ts = trains.spike_history();
+    REQUIRE(ts.size() == 1001 * 6);
+    for (std::size_t s = 0; s < 1001; ++s)
+        for (std::size_t c = 0; c < 6; ++c) REQUIRE((ts[s * 6 + c] != 0) == (s != 0 && (s + 1) % 100 == 0));
+
     std::printf("HOST_MIRROR_OK (%zu lattice spikes, dopamine %.4f, w(0,0)->(0,1) %.5f)\n", spikes, r.reward_modulator.dopamine, w01);
     return 0;
 }

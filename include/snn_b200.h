@@ -142,11 +142,15 @@ typedef enum snn_option {
     SNN_OPT_UPDATE_SPIKE_HISTORY = 4, /* default 0 (per lattice): SpikeHistory raster, neuron/mod.rs:324-378 */
     SNN_OPT_INTERNAL_CLOCK = 5,       /* usize clock, persists across run calls */
     SNN_OPT_PARALLEL = 6,             /* accepted for API parity; the device path is always parallel */
-    SNN_OPT_RNG_SEED = 7,             /* Philox key for Poisson spike trains (reference: unseeded thread_rng) */
+    SNN_OPT_RNG_SEED = 7,             /* Philox key for Poisson spike trains (reference: unseeded thread_rng).  Default: a distinct key per
+                                         handle; the counter is (train, per-handle draw number) and is NOT reset by reset_timing, so repeated
+                                         presentations see fresh noise */
     SNN_OPT_UPDATE_AVERAGE_HISTORY = 8, /* AverageVoltageHistory, neuron/mod.rs:303-322 */
     SNN_OPT_STEPS_PER_GRAPH = 9,      /* reserved (stored, not acted on): a 10^4-neuron step is 4 us, at the floor of one
                                          grid-wide synchronisation per timestep, so graph replay has nothing left to remove */
-    SNN_OPT_UPDATE_EEG_HISTORY = 10   /* default 0 (per lattice): EEGHistory, neuron/mod.rs:231-284 */
+    SNN_OPT_UPDATE_EEG_HISTORY = 10,  /* default 0 (per lattice): EEGHistory, neuron/mod.rs:231-284 */
+    SNN_OPT_HALO_TIMEOUT_MS = 11      /* partitioned handles: bound of one in-kernel wait for a neighbouring strip (default 30000);
+                                         run() first meets the neighbours on the host (4x this bound) before any step is enqueued */
 } snn_option_t;
 
 /* STDP, backend/src/neuron/plasticity/mod.rs:14-39 (defaults 2, 2, 4.5, 4.5, 0.1) */
@@ -255,9 +259,19 @@ SNN_API int32_t snn_lattice_graph_nnz(snn_lattice_t *h, uint64_t *nnz);
 SNN_API int32_t snn_lattice_get_graph_csr(snn_lattice_t *h, uint64_t *row_ptr, uint32_t *pre, float *weights,
                                           uint64_t n, uint64_t nnz);
 SNN_API int32_t snn_lattice_get_graph_dense(snn_lattice_t *h, uint32_t *connections, float *weights, uint32_t n);
-/* Graph::lookup_weight / edit_weight on flat indices (graph/mod.rs:196-226); *connected = 0 for None */
+/* Graph::lookup_weight on flat indices (graph/mod.rs:196-206); *connected = 0 for None.  Reads one row of the device table. */
 SNN_API int32_t snn_lattice_lookup_weight(snn_lattice_t *h, uint64_t pre, uint64_t post, float *weight,
                                           int32_t *connected);
+/* Graph::edit_weight(pre, post, Option<f32>) (graph/mod.rs:208-226): connected = 0 is None (the edge is removed), else
+ * Some(weight).  Same error order as the reference (postsynaptic position first).  Some(w) over an existing edge is one word
+ * written on the device; adding or removing an edge edits the host CSR and the device table is rebuilt at the next run
+ * (whole-lattice handles only). */
+SNN_API int32_t snn_lattice_edit_weight(snn_lattice_t *h, uint64_t pre, uint64_t post, int32_t connected, float weight);
+/* Graph::get_incoming_connections over the postsynaptic positions [row_begin, row_end) (graph/mod.rs:228-256), with the current
+ * weights: CSR decoded from the device table without downloading the whole graph.  row_ptr has row_end - row_begin + 1
+ * entries; pre / weights hold up to `capacity` edges (either may be NULL to count only); *nnz = edges in the range. */
+SNN_API int32_t snn_lattice_get_graph_rows(snn_lattice_t *h, uint64_t row_begin, uint64_t row_end, uint64_t *row_ptr, uint32_t *pre,
+                                           float *weights, uint64_t capacity, uint64_t *nnz);
 
 SNN_API int32_t snn_lattice_set_option(snn_lattice_t *h, int32_t option, int64_t value);
 SNN_API int32_t snn_lattice_get_option(const snn_lattice_t *h, int32_t option, int64_t *value);
@@ -303,6 +317,9 @@ SNN_API int32_t snn_lattice_history_len(const snn_lattice_t *h, uint64_t *steps)
 SNN_API int32_t snn_lattice_get_grid_history(snn_lattice_t *h, float *out, uint64_t capacity_floats);
 SNN_API int32_t snn_lattice_get_spike_history(snn_lattice_t *h, uint8_t *out, uint64_t capacity_bytes);
 SNN_API int32_t snn_lattice_get_average_history(snn_lattice_t *h, float *out, uint64_t capacity_floats);
+/* SpikeHistory::aggregate (neuron/mod.rs:335-359): per neuron, the number of recorded steps in which it spiked (isize).  Counted
+ * on the device from the staged raster while SNN_OPT_UPDATE_SPIKE_HISTORY is on; reset by reset_history. */
+SNN_API int32_t snn_lattice_get_spike_aggregate(snn_lattice_t *h, int64_t *out, uint64_t capacity);
 /* EEGHistory (neuron/mod.rs:231-284): one value per step, (1 / (4 pi conductivity distance)) * sum(V - reference_voltage).
  * Defaults 0.007 mV, 0.8 mm, 251 S/mm (EEGHistory::default, :243-252). */
 SNN_API int32_t snn_lattice_set_eeg_parameters(snn_lattice_t *h, float reference_voltage, float distance, float conductivity);
@@ -369,6 +386,13 @@ SNN_API int32_t snn_network_get_connection_dense(snn_network_t *h, uint64_t pre_
                                                  uint32_t *connections, float *weights, uint64_t n_pre,
                                                  uint64_t n_post);
 
+/* Graph::lookup_weight / edit_weight between two lattices of the network (or inside one when pre_id == post_id) on flat
+ * indices: LatticeNetwork::connect's id errors first (neuron/mod.rs:1852-1862), then GraphError as for the lattice calls */
+SNN_API int32_t snn_network_lookup_weight(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post,
+                                          float *weight, int32_t *connected);
+SNN_API int32_t snn_network_edit_weight(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post,
+                                        int32_t connected, float weight);
+
 /* network-wide: ELECTRICAL_SYNAPSE, CHEMICAL_SYNAPSE, INTERNAL_CLOCK, RNG_SEED, PARALLEL */
 SNN_API int32_t snn_network_set_option(snn_network_t *h, int32_t option, int64_t value);
 SNN_API int32_t snn_network_get_option(const snn_network_t *h, int32_t option, int64_t *value);
@@ -387,6 +411,7 @@ SNN_API int32_t snn_network_run_timed(snn_network_t *h, uint64_t iterations, flo
 SNN_API int32_t snn_network_history_len(const snn_network_t *h, uint64_t id, uint64_t *steps);
 SNN_API int32_t snn_network_get_grid_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats);
 SNN_API int32_t snn_network_get_spike_history(snn_network_t *h, uint64_t id, uint8_t *out, uint64_t capacity_bytes);
+SNN_API int32_t snn_network_get_spike_aggregate(snn_network_t *h, uint64_t id, int64_t *out, uint64_t capacity);
 SNN_API int32_t snn_network_get_average_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats);
 SNN_API int32_t snn_network_set_eeg_parameters(snn_network_t *h, uint64_t id, float reference_voltage, float distance, float conductivity);
 SNN_API int32_t snn_network_get_eeg_history(snn_network_t *h, uint64_t id, float *out, uint64_t capacity_floats);

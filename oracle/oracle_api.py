@@ -229,6 +229,25 @@ class OracleBackend:
         self._ck(self.L.orc_get_connection_dense(self.h, pre_id, post_id, _ptr(c), _ptr(w), n_pre, n_post))
         return c.reshape(n_pre, n_post), w.reshape(n_pre, n_post)
 
+    # Graph::lookup_weight / edit_weight (graph/mod.rs:196-226) on the oracle's adjacency; called as (pre, post[, weight]) in
+    # the lattice role and as (pre_id, post_id, pre, post[, weight]) in the network role, like the two CUDA back ends
+    def lookup_weight(self, *a):
+        pre_id, post_id, pre, post = (0, 0) + tuple(a) if len(a) == 2 else a
+        c, w = self.get_connection_dense(pre_id, post_id)
+        return float(w[pre, post]) if c[pre, post] else None
+
+    def edit_weight(self, *a):
+        pre_id, post_id, pre, post, weight = (0, 0) + tuple(a) if len(a) == 3 else a
+        c, w = self.get_connection_dense(pre_id, post_id)
+        c[pre, post] = 0 if weight is None else 1
+        w[pre, post] = 0.0 if weight is None else weight
+        self.connect_dense(pre_id, post_id, c, w)
+
+    def spike_aggregate(self, id=0):
+        """SpikeHistory::aggregate, neuron/mod.rs:335-359: literal sum of the boolean raster over its steps."""
+        h = self.spike_history(id)
+        return h.astype(np.int64).sum(axis=0) if h.shape[0] else np.zeros(self.size(id), np.int64)
+
     # options use the product's option numbering (include/snn_b200.h snn_option_t)
     def set_option(self, option, value, id=None):
         value = int(value)

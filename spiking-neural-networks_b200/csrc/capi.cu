@@ -187,26 +187,20 @@ int32_t snn_lattice_get_graph_dense(snn_lattice_t *h, uint32_t *connections, flo
 }
 int32_t snn_lattice_lookup_weight(snn_lattice_t *h, uint64_t pre, uint64_t post, float *weight, int32_t *connected) {
     if (!h || !weight || !connected) return SNN_INVALID_ARGUMENT;
-    SNN_TRY
-    Engine *e = h->e;
-    const uint64_t n = e->find(kLatticeId)->n;
-    // lookup_weight checks the postsynaptic key first (graph/mod.rs:197-202)
-    if (post >= n) return e->fail(SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND, "Postsynaptic position not found, position: " + std::to_string(post));
-    const uint64_t pre_limit = e->part_world > 1 ? (uint64_t)e->rows_global * e->find(kLatticeId)->cols : n;
-    if (pre >= pre_limit) return e->fail(SNN_GRAPH_PRESYNAPTIC_NOT_FOUND, "Presynaptic position not found, position: " + std::to_string(pre));
-    uint64_t nnz = 0;
-    int r = e->connection_nnz(kLatticeId, kLatticeId, &nnz);
-    if (r) return r;
-    std::vector<uint64_t> rp(n + 1);
-    std::vector<uint32_t> pr(nnz ? nnz : 1);
-    std::vector<float> w(nnz ? nnz : 1);
-    r = e->get_connection_csr(kLatticeId, kLatticeId, rp.data(), pr.data(), w.data(), n, nnz);
-    if (r) return r;
-    *connected = 0; *weight = 0.f;
-    for (uint64_t k = rp[post]; k < rp[post + 1]; ++k)
-        if (pr[k] == pre) { *connected = 1; *weight = w[k]; break; }
-    return SNN_OK;
-    SNN_CATCH(h)
+    SNN_TRY return h->e->lookup_weight(kLatticeId, kLatticeId, pre, post, weight, connected); SNN_CATCH(h)
+}
+int32_t snn_lattice_edit_weight(snn_lattice_t *h, uint64_t pre, uint64_t post, int32_t connected, float weight) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->edit_weight(kLatticeId, kLatticeId, pre, post, connected != 0, weight); SNN_CATCH(h)
+}
+int32_t snn_lattice_get_graph_rows(snn_lattice_t *h, uint64_t row_begin, uint64_t row_end, uint64_t *row_ptr, uint32_t *pre, float *weights,
+                                   uint64_t capacity, uint64_t *nnz) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_connection_rows(kLatticeId, kLatticeId, row_begin, row_end, row_ptr, pre, weights, capacity, nnz); SNN_CATCH(h)
+}
+int32_t snn_lattice_get_spike_aggregate(snn_lattice_t *h, int64_t *out, uint64_t capacity) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_spike_aggregate(kLatticeId, out, capacity); SNN_CATCH(h)
 }
 
 static int32_t engine_set_option(Engine *e, bool have_id, uint64_t id, int32_t option, int64_t value) {
@@ -218,6 +212,9 @@ static int32_t engine_set_option(Engine *e, bool have_id, uint64_t id, int32_t o
     case SNN_OPT_PARALLEL: e->parallel = value != 0; return SNN_OK;
     case SNN_OPT_RNG_SEED: e->seed = (uint64_t)value; return SNN_OK;
     case SNN_OPT_STEPS_PER_GRAPH: e->steps_per_graph = (uint32_t)value; return SNN_OK;
+    case SNN_OPT_HALO_TIMEOUT_MS:
+        if (value <= 0) return e->fail(SNN_INVALID_ARGUMENT, "halo time-out must be positive");
+        e->halo_timeout_ms = (uint64_t)value; return SNN_OK;
     case SNN_OPT_INTERNAL_CLOCK:
         if (value < 0) return e->fail(SNN_INVALID_ARGUMENT, "clock must be non-negative");
         if (L && L->is_train) L->clock = (uint64_t)value; else e->internal_clock = (uint64_t)value;
@@ -240,6 +237,7 @@ static int32_t engine_get_option(const Engine *e, bool have_id, uint64_t id, int
     case SNN_OPT_PARALLEL: *value = e->parallel; return SNN_OK;
     case SNN_OPT_RNG_SEED: *value = (int64_t)e->seed; return SNN_OK;
     case SNN_OPT_STEPS_PER_GRAPH: *value = e->steps_per_graph; return SNN_OK;
+    case SNN_OPT_HALO_TIMEOUT_MS: *value = (int64_t)e->halo_timeout_ms; return SNN_OK;
     case SNN_OPT_INTERNAL_CLOCK: *value = (int64_t)((L && L->is_train) ? L->clock : e->internal_clock); return SNN_OK;
     case SNN_OPT_DO_PLASTICITY: if (!L) break; *value = L->do_plasticity; return SNN_OK;
     case SNN_OPT_UPDATE_GRID_HISTORY: if (!L) break; *value = L->grid_hist; return SNN_OK;
@@ -440,6 +438,26 @@ int32_t snn_network_get_connection_dense(snn_network_t *h, uint64_t pre_id, uint
                                          uint64_t n_pre, uint64_t n_post) {
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->get_connection_dense(pre_id, post_id, connections, weights, n_pre, n_post); SNN_CATCH(h)
+}
+int32_t snn_network_lookup_weight(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, float *weight,
+                                  int32_t *connected) {
+    if (!h || !weight || !connected) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->lookup_weight(pre_id, post_id, pre, post, weight, connected); SNN_CATCH(h)
+}
+int32_t snn_network_edit_weight(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, int32_t connected,
+                                float weight) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY
+    snn::Lat *B;   // LatticeNetwork::connect's id checks (neuron/mod.rs:1852-1862) before the graph's position checks
+    if (!(B = h->e->find(post_id))) return h->e->fail(SNN_NET_POSTSYNAPTIC_ID_NOT_FOUND, "Postsynaptic id not present in network, id: " + std::to_string(post_id));
+    if (B->is_train) return h->e->fail(SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN, "Postsynaptic lattice cannot be a spike train lattice because spike trains cannot take inputs");
+    if (!h->e->find(pre_id)) return h->e->fail(SNN_NET_PRESYNAPTIC_ID_NOT_FOUND, "Presynaptic id not present in network, id: " + std::to_string(pre_id));
+    return h->e->edit_weight(pre_id, post_id, pre, post, connected != 0, weight);
+    SNN_CATCH(h)
+}
+int32_t snn_network_get_spike_aggregate(snn_network_t *h, uint64_t id, int64_t *out, uint64_t capacity) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_spike_aggregate(id, out, capacity); SNN_CATCH(h)
 }
 int32_t snn_network_set_option(snn_network_t *h, int32_t option, int64_t value) {
     if (!h) return SNN_INVALID_ARGUMENT;

@@ -108,6 +108,7 @@ struct StepParams {
     unsigned long long halo_epoch;   // value the arrival counters must reach before ghosts are read
     uint32_t out_par;                // parity of the *_out ping-pong buffers (same on every rank)
     unsigned int *halo_done;         // [2] per-direction CTA completion counters
+    unsigned long long halo_timeout_ns;   // bound of one in-kernel wait for a neighbouring strip
     uint32_t reverse;                // window kernel: sweep the tiles back to front (alternates per step: the tail of the
                                      // arrays that the previous step left in L2 is what this step reads first)
     unsigned long long *dbg;         // SNN_DEBUG_TIMING: {clock64, globaltimer} at the start and end of CTA 0 (else null)
@@ -116,6 +117,7 @@ struct StepParams {
 struct TrainParams {
     uint32_t train0, n_trains, clock; int kind; int ntk;
     uint64_t seed;
+    uint64_t draw;   // per-handle count of spike-train steps: the Philox counter (survives reset_timing)
     const float *v_in; float *v_out;
     const int *lft_in; int *lft_out; uint32_t lft_pp;
     const uint32_t *spk_in; uint32_t *spk_out;
@@ -280,6 +282,8 @@ cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s);
 cudaError_t launch_history_reduce(const float *grid, uint64_t n_neurons, uint32_t steps, const uint32_t *lat_base, const uint32_t *lat_n,
                                   const float *lat_ref, int n_lat, double *out, cudaStream_t s);
 // node_flags[i] <- (node_flags[i] & ~(0xF << shift)) | (mask of the non-zero words of src[i*3 .. i*3+2]) << shift; *changed |= any
+// counts[i] = number of the `steps` staged raster records in which node i spiked (SpikeHistory::aggregate)
+cudaError_t launch_spike_count(const uint32_t *words, uint32_t steps, uint64_t n_words, uint64_t n, uint32_t *counts, cudaStream_t s);
 cudaError_t launch_pack_flags(const uint32_t *src, uint8_t *node_flags, uint64_t n, int shift, unsigned int *changed, cudaStream_t s);
 cudaError_t launch_fill_u32(uint32_t *p, uint32_t v, uint64_t n, cudaStream_t s);
 cudaError_t launch_bits_from_u32(const uint32_t *src, uint32_t *words, uint64_t n, uint64_t bit0, cudaStream_t s);

@@ -4,6 +4,8 @@
 #include <cmath>
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -24,8 +26,20 @@ static cudaError_t dev_alloc(T **p, size_t n) {
     return cudaMalloc((void **)p, std::max<size_t>(n, 1) * sizeof(T));
 }
 
+static uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
 Engine::Engine(int model_, int ntk_, int rck_, int train_kind_, int refract_, int device_)
-    : model(model_), ntk(ntk_), rck(rck_), train_kind(train_kind_), refract(refract_), device(device_) {}
+    : model(model_), ntk(ntk_), rck(rck_), train_kind(train_kind_), refract(refract_), device(device_) {
+    // handles of one process get distinct (but reproducible) default keys: two networks built the same way must not replay the
+    // same Poisson noise; SNN_OPT_RNG_SEED pins the key
+    static std::atomic<uint64_t> serial{0};
+    seed = splitmix64(0x5EED5EEDull + serial.fetch_add(1));
+}
 
 Engine::~Engine() {
     if (device >= 0) cudaSetDevice(device);
@@ -123,7 +137,8 @@ void Engine::free_device() {
     if (slab_) cudaFree(slab_);
     slab_ = nullptr;
     V_[0] = V_[1] = nullptr; LFT_[0] = LFT_[1] = nullptr; T_[0] = T_[1] = nullptr;
-    fr(SPK_[0]); fr(SPK_[1]); fr(node_flags_); fr(was_inc_);
+    fr(SPK_[0]); fr(SPK_[1]); fr(was_inc_);
+    node_flags_ = nullptr;   // lives in the slab
     for (auto &p : NT_) fr(p);
     for (auto &p : F_) fr(p);
     for (auto &p : RC_) fr(p);
@@ -147,9 +162,13 @@ int Engine::alloc_device() {
     // map all halo-visible arrays with one CUDA IPC handle
     const size_t vb = round_up(node_cap_ * 4, 256);
     slab_off_v_[0] = 0; slab_off_v_[1] = vb; slab_off_lft_[0] = 2 * vb; slab_off_lft_[1] = 3 * vb;
-    slab_off_t_[0] = 4 * vb; slab_off_t_[1] = 4 * vb + round_up(node_cap_ * 4 * kNT, 256);
-    slab_bytes_ = 4 * vb;  // T appended by ensure_chem (which reallocates the slab)
+    // node flags ride in the slab too: a neighbouring strip reads the neurotransmitter type sets of my boundary rows at attach time
+    const size_t fbytes = round_up(node_cap_, 256);
+    slab_off_flags_ = 4 * vb;
+    slab_off_t_[0] = 4 * vb + fbytes; slab_off_t_[1] = slab_off_t_[0] + round_up(node_cap_ * 4 * kNT, 256);
+    slab_bytes_ = 4 * vb + fbytes;  // T appended by ensure_chem (which reallocates the slab)
     CK(cudaMalloc(&slab_, slab_bytes_), SNN_GPU_BUFFER_CREATE_ERROR);
+    node_flags_ = (uint8_t *)slab_ + slab_off_flags_;
     for (int k = 0; k < 2; ++k) {
         V_[k] = (float *)((char *)slab_ + slab_off_v_[k]);
         LFT_[k] = (int *)((char *)slab_ + slab_off_lft_[k]);
@@ -158,7 +177,6 @@ int Engine::alloc_device() {
         CK(dev_alloc(&SPK_[k], node_cap_ / 32 + 1), SNN_GPU_BUFFER_CREATE_ERROR);
         CK(launch_fill_u32(SPK_[k], 0u, node_cap_ / 32 + 1, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     }
-    CK(dev_alloc(&node_flags_, node_cap_), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(cudaMemsetAsync(node_flags_, 0, node_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     h_node_flags_.assign(node_cap_, 0);
     flags_cache_valid_ = false;
@@ -219,6 +237,7 @@ int Engine::ensure_chem() {
         LFT_[k] = (int *)((char *)slab_ + slab_off_lft_[k]);
         T_[k] = (float *)((char *)slab_ + slab_off_t_[k]);
     }
+    node_flags_ = (uint8_t *)slab_ + slab_off_flags_;
     for (int s = 0; s < NTF_COUNT; ++s) {
         CK(dev_alloc(&NT_[s], node_cap_ * kNT), SNN_GPU_BUFFER_CREATE_ERROR);
         CK(fill_f32(NT_[s], nt_default(ntk, s), node_cap_ * kNT, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
@@ -747,6 +766,12 @@ int Engine::connect_grid(uint64_t id, uint32_t radius, float weight) {
             A = B = find(id);
         }
     }
+    // the learned weights of every OTHER block live on the device until synced: replacing this block must not discard them
+    if (dev_weights_newer_) {
+        bool others = false;
+        for (auto &kv : blocks_) others |= kv.first != std::make_pair(id, id);
+        if (others) { r = sync_weights_to_host(); if (r) return r; }
+    }
     Block b;
     b.kind = Block::GRID;
     b.radius = radius; b.weight = weight;
@@ -775,6 +800,7 @@ int Engine::materialize_grid(Block &b, const Lat &L) {
             b.row_ptr[i * cols + j + 1] = b.pre.size();
         }
     b.kind = Block::CSR;
+    b.from_grid_radius = b.radius;
     return SNN_OK;
 }
 
@@ -814,9 +840,10 @@ int Engine::finalize_graph() {
     if (!reuse) CK(dev_alloc(&slice_off_, (size_t)n_slices_ + 1), SNN_GPU_BUFFER_CREATE_ERROR);
     // partitioned handles: ghost rows inherit the neurotransmitter type sets of the adjacent owned rows
     if (part_world > 1 && n_neurons) {
+        // (until the neighbour is attached: ipc_attach replaces them with the neighbour's real boundary flags)
         for (uint32_t g = 0; g < halo_; ++g) {
-            if (part_rank > 0) h_node_flags_[own0_ - halo_ + g] = h_node_flags_[own0_ + (g % std::max<uint64_t>(n_neurons, 1))];
-            if (part_rank < part_world - 1) h_node_flags_[ghost_hi0_ + g] = h_node_flags_[own0_ + n_neurons - halo_ + g];
+            if (part_rank > 0 && !ghost_flags_from_peer_[0]) h_node_flags_[own0_ - halo_ + g] = h_node_flags_[own0_ + (g % std::max<uint64_t>(n_neurons, 1))];
+            if (part_rank < part_world - 1 && !ghost_flags_from_peer_[1]) h_node_flags_[ghost_hi0_ + g] = h_node_flags_[own0_ + n_neurons - halo_ + g];
         }
         CK(cudaMemcpy(node_flags_, h_node_flags_.data(), node_cap_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
         flags_cache_valid_ = false;
@@ -904,8 +931,31 @@ int Engine::finalize_graph() {
         slice_off[s + 1] = (uint32_t)next;
     }
     sell_krows_ = slice_off[n_slices_];
-    CK(dev_alloc(&col_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
-    CK(dev_alloc(&wgt_, sell_krows_ * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+    // a materialised stencil (weights came back from the device: STDP, edit_weight) keeps the uniform-width layout of the
+    // generator, so the window / TMA step kernels stay eligible after a rebuild
+    uint32_t stencil_width = 0;
+    if (n_neuron_lat == 1 && blocks_.size() == 1 && blocks_.begin()->second.from_grid_radius &&
+        blocks_.begin()->first == std::make_pair(only->id, only->id)) {
+        const uint32_t R = blocks_.begin()->second.from_grid_radius;
+        stencil_width = (2 * R + 1) * (2 * R + 1) - 1;
+        for (uint32_t s = 0; s < n_slices_; ++s) {
+            if (slice_off[s + 1] - slice_off[s] > stencil_width) { stencil_width = 0; break; }
+        }
+        if (stencil_width) {
+            for (uint32_t s = 0; s <= n_slices_; ++s) slice_off[s] = s * stencil_width;
+            sell_krows_ = (uint64_t)n_slices_ * stencil_width;
+        }
+    }
+    const uint64_t alloc_krows = stencil_width ? round_up(n_slices_, kTmaConsumerWarps) * stencil_width : sell_krows_;
+    CK(dev_alloc(&col_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&wgt_, alloc_krows * 32), SNN_GPU_BUFFER_CREATE_ERROR);
+    if (stencil_width) {
+        sell_alloc_krows_ = alloc_krows;
+        if (alloc_krows > sell_krows_) {
+            CK(cudaMemset(col_ + sell_krows_ * 32, 0xFF, (alloc_krows - sell_krows_) * 32 * 4), SNN_GPU_BUFFER_WRITE_ERROR);
+            CK(cudaMemset(wgt_ + sell_krows_ * 32, 0, (alloc_krows - sell_krows_) * 32 * 4), SNN_GPU_BUFFER_WRITE_ERROR);
+        }
+    }
     CK(cudaMemcpy(slice_off_, slice_off.data(), ((size_t)n_slices_ + 1) * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
     uint64_t *d_rp = nullptr; uint32_t *d_pre = nullptr; float *d_w = nullptr;
     CK(dev_alloc(&d_rp, n_neurons + 1), SNN_GPU_BUFFER_CREATE_ERROR);
@@ -918,6 +968,7 @@ int Engine::finalize_graph() {
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
     cudaFree(d_rp); cudaFree(d_pre); cudaFree(d_w);
     if (e != cudaSuccess) return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "sell_from_csr");
+    if (stencil_width) { grid_fast_ = true; uniform_width_ = stencil_width; }
     graph_dirty_ = false;
     dev_weights_newer_ = false;
     return SNN_OK;
@@ -1158,6 +1209,140 @@ int Engine::get_connection_dense(uint64_t pre_id, uint64_t post_id, uint32_t *co
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-row graph access on the device table (Graph::get_incoming_connections / lookup_weight / edit_weight)
+// ------------------------------------------------------------------------------------------------
+int Engine::get_connection_rows(uint64_t pre_id, uint64_t post_id, uint64_t row_begin, uint64_t row_end, uint64_t *row_ptr, uint32_t *pre,
+                                float *weights, uint64_t capacity, uint64_t *nnz_out) {
+    Lat *A = find(pre_id), *B = find(post_id);
+    if (!A || !B || B->is_train) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    if (row_begin > row_end || row_end > B->n) return fail(SNN_GRAPH_POSITION_NOT_FOUND, "Position not found, position: " + std::to_string(row_end));
+    if (nnz_out) *nnz_out = 0;
+    if (row_ptr) row_ptr[0] = 0;
+    if (row_begin == row_end) return SNN_OK;
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    int r = finalize_graph();
+    if (r) return r;
+    const uint64_t g0 = B->off + row_begin, g1 = B->off + row_end;   // local neuron numbers
+    const uint32_t s0 = (uint32_t)(g0 / 32), s1 = (uint32_t)((g1 - 1) / 32);
+    std::vector<uint32_t> so(s1 - s0 + 2);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    CK(cudaMemcpy(so.data(), slice_off_ + s0, so.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    const uint64_t k0 = so.front(), k1 = so.back();
+    std::vector<uint32_t> col(std::max<uint64_t>((k1 - k0) * 32, 1));
+    std::vector<float> wg(col.size());
+    if (k1 > k0) {
+        CK(cudaMemcpy(col.data(), col_ + k0 * 32, (k1 - k0) * 32 * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+        CK(cudaMemcpy(wg.data(), wgt_ + k0 * 32, (k1 - k0) * 32 * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    }
+    // node range of the presynaptic lattice; partitioned handles report GLOBAL flat indices (ghost nodes included)
+    const int64_t a0 = part_world > 1 ? 0 : (int64_t)node_off(*A), a1 = part_world > 1 ? (int64_t)n_nodes_ : a0 + (int64_t)A->n;
+    const int64_t shift = part_world > 1 ? (int64_t)row0_global * A->cols - (int64_t)own0_ : -a0;
+    uint64_t o = 0;
+    for (uint64_t g = g0; g < g1; ++g) {
+        const uint32_t s = (uint32_t)(g / 32), lane = (uint32_t)(g % 32);
+        for (uint64_t k = so[s - s0]; k < so[s - s0 + 1]; ++k) {
+            const size_t e = (size_t)(k - k0) * 32 + lane;
+            if (col[e] == kColPad) break;   // valid entries first
+            const int64_t j = (int64_t)(col[e] & kColIdxMask);
+            if (j < a0 || j >= a1) continue;
+            if (o < capacity) { if (pre) pre[o] = (uint32_t)(j + shift); if (weights) weights[o] = wg[e]; }
+            ++o;
+        }
+        if (row_ptr) row_ptr[g - g0 + 1] = o;
+    }
+    if (nnz_out) *nnz_out = o;
+    if (o > capacity && (pre || weights)) return fail(SNN_SIZE_MISMATCH, "edge buffers too small: " + std::to_string(o) + " edges in the row range");
+    return SNN_OK;
+}
+
+int Engine::check_edge_endpoints(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, Lat **A, Lat **B) {
+    *A = find(pre_id); *B = find(post_id);
+    if (!*A || !*B || (*B)->is_train) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    // lookup_weight / edit_weight check the postsynaptic key first (graph/mod.rs:197-202, 209-214)
+    if (post >= (*B)->n) return fail(SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND, "Postsynaptic position not found, position: " + std::to_string(post));
+    const uint64_t pre_limit = part_world > 1 ? (uint64_t)rows_global * (*A)->cols : (*A)->n;
+    if (pre >= pre_limit) return fail(SNN_GRAPH_PRESYNAPTIC_NOT_FOUND, "Presynaptic position not found, position: " + std::to_string(pre));
+    return SNN_OK;
+}
+
+int Engine::find_edge(uint64_t row, uint32_t j, int64_t *elem) {
+    *elem = -1;
+    const uint32_t s = (uint32_t)(row / 32), lane = (uint32_t)(row % 32);
+    uint32_t so[2];
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
+    CK(cudaMemcpy(so, slice_off_ + s, 8, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    if (so[1] == so[0]) return SNN_OK;
+    std::vector<uint32_t> col((size_t)(so[1] - so[0]) * 32);
+    CK(cudaMemcpy(col.data(), col_ + (size_t)so[0] * 32, col.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    for (uint32_t k = 0; k < so[1] - so[0]; ++k) {
+        const uint32_t c = col[(size_t)k * 32 + lane];
+        if (c == kColPad) break;
+        if ((c & kColIdxMask) == j) { *elem = ((int64_t)so[0] + k) * 32 + lane; break; }
+    }
+    return SNN_OK;
+}
+
+int Engine::lookup_weight(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, float *weight, int32_t *connected) {
+    Lat *A, *B;
+    int r = check_edge_endpoints(pre_id, post_id, pre, post, &A, &B);
+    if (r) return r;
+    *connected = 0; *weight = 0.f;
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    r = finalize_graph();
+    if (r) return r;
+    const int64_t node = part_world > 1 ? (int64_t)pre + (int64_t)own0_ - (int64_t)row0_global * A->cols : (int64_t)node_off(*A) + (int64_t)pre;
+    if (node < 0 || node >= (int64_t)n_nodes_) return SNN_OK;   // partitioned: beyond the halo of this strip, cannot be connected
+    int64_t e = -1;
+    r = find_edge(B->off + post, (uint32_t)node, &e);
+    if (r || e < 0) return r;
+    CK(cudaMemcpy(weight, wgt_ + e, 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    *connected = 1;
+    return SNN_OK;
+}
+
+int Engine::edit_weight(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, bool has, float weight) {
+    Lat *A, *B;
+    int r = check_edge_endpoints(pre_id, post_id, pre, post, &A, &B);
+    if (r) return r;
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    r = finalize_graph();
+    if (r) return r;
+    const int64_t node = part_world > 1 ? (int64_t)pre + (int64_t)own0_ - (int64_t)row0_global * A->cols : (int64_t)node_off(*A) + (int64_t)pre;
+    int64_t e = -1;
+    if (node >= 0 && node < (int64_t)n_nodes_) { r = find_edge(B->off + post, (uint32_t)node, &e); if (r) return r; }
+    if (e >= 0 && has) {
+        // Some(w) over Some(_): the adjacency is unchanged, one word on the device
+        CK(cudaMemcpy(wgt_ + e, &weight, 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+        dev_weights_newer_ = true;
+        return SNN_OK;
+    }
+    if (e < 0 && !has) return SNN_OK;   // None over None
+    // the adjacency changes (None -> Some, Some -> None): edit the host CSR of the block and rebuild the device table lazily
+    if (part_world > 1) return fail(SNN_UNSUPPORTED, "adding or removing edges is not supported on partitioned handles (weights of existing edges are)");
+    dev_weights_newer_ = true;   // the device holds the live weights (STDP, earlier in-place edits)
+    r = sync_weights_to_host();
+    if (r) return r;
+    Block &b = blocks_[{pre_id, post_id}];
+    if (b.kind == Block::GRID) materialize_grid(b, *A);
+    b.from_grid_radius = 0;   // no longer the generator's adjacency
+    if (b.row_ptr.size() != B->n + 1) b.row_ptr.assign(B->n + 1, 0);
+    const uint64_t rs = b.row_ptr[post], re = b.row_ptr[post + 1];
+    uint64_t pos = rs;
+    while (pos < re && b.pre[pos] < pre) ++pos;
+    if (has) {
+        b.pre.insert(b.pre.begin() + pos, (uint32_t)pre);
+        b.w.insert(b.w.begin() + pos, weight);
+        for (uint64_t q = post + 1; q <= B->n; ++q) b.row_ptr[q] += 1;
+    } else {
+        b.pre.erase(b.pre.begin() + pos);
+        b.w.erase(b.w.begin() + pos);
+        for (uint64_t q = post + 1; q <= B->n; ++q) b.row_ptr[q] -= 1;
+    }
+    graph_dirty_ = true;
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // options
 // ------------------------------------------------------------------------------------------------
 int Engine::set_dt(float dt) {
@@ -1196,7 +1381,7 @@ int Engine::reset_timing() {
 }
 
 int Engine::reset_history() {
-    for (auto &L : lats_) { L.grid_history.clear(); L.spike_history.clear(); L.average_history.clear(); L.eeg_history.clear(); L.hist_len = 0; }
+    for (auto &L : lats_) { L.grid_history.clear(); L.spike_history.clear(); L.spike_agg.clear(); L.average_history.clear(); L.eeg_history.clear(); L.hist_len = 0; }
     return SNN_OK;
 }
 
@@ -1228,6 +1413,17 @@ int Engine::set_eeg_parameters(uint64_t id, float reference_voltage, float dista
     Lat *L = find(id);
     if (!L || L->is_train) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
     L->eeg_ref = reference_voltage; L->eeg_dist = distance; L->eeg_cond = conductivity;
+    return SNN_OK;
+}
+
+int Engine::get_spike_aggregate(uint64_t id, int64_t *out, uint64_t capacity) {
+    Lat *L = find(id);
+    if (!L) return fail(SNN_NET_ID_NOT_FOUND_IN_LATTICES, "Id not present in lattices");
+    // an empty history aggregates to an empty vector in the reference; here: zeros (the shape is known)
+    if (capacity < L->n) return fail(SNN_SIZE_MISMATCH, "aggregate buffer too small");
+    if (!out) return L->n ? fail(SNN_INVALID_ARGUMENT, "null argument") : SNN_OK;
+    if (L->spike_agg.size() == L->n) memcpy(out, L->spike_agg.data(), L->n * 8);
+    else std::fill(out, out + L->n, (int64_t)0);
     return SNN_OK;
 }
 
@@ -1283,6 +1479,7 @@ void Engine::fill_step_params(StepParams &p) {
     p.n_lat = std::max(nl, 1);
     p.halo[0] = halo_dir_[0]; p.halo[1] = halo_dir_[1];
     p.halo_done = halo_done_;
+    p.halo_timeout_ns = halo_timeout_ms * 1000000ull;
 }
 
 // Operand streams of the TMA-staged kernel for the current configuration; false = not eligible (use the general kernel).
@@ -1579,6 +1776,24 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "halo_push"); }
         halo_epoch_ += 1;
         n_launch++;
+        // rendez-vous before any step kernel is enqueued: the in-kernel waits are bounded, so ordinary host-side skew between
+        // the ranks (Python work, history drains, allocation) must be absorbed here, where nothing has been computed yet
+        e = cudaStreamSynchronize(stream_);
+        if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_WAIT_ERROR, "halo_push"); }
+        const auto t_wait0 = std::chrono::steady_clock::now();
+        for (;;) {
+            unsigned long long f[4];
+            e = cudaMemcpy(f, flags_, sizeof f, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_BUFFER_READ_ERROR, "halo rendez-vous"); }
+            bool ready = true;
+            for (int d = 0; d < 2; ++d) if (halo_dir_[d].active && f[d] < halo_epoch_) ready = false;
+            if (ready) break;
+            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wait0).count() > 4.0 * (double)halo_timeout_ms) {
+                free_hist();
+                return fail(SNN_GPU_WAIT_ERROR, "timed out waiting for the neighbouring strips to enter run() (is every rank calling run with the same number of steps?)");
+            }
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+        }
     }
 
     static const bool win_reverse = !(getenv("SNN_B200_WIN_REVERSE") && atoi(getenv("SNN_B200_WIN_REVERSE")) == 0);
@@ -1658,6 +1873,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                 for (auto &L : lats_)
                     if (L.is_train) { tp.tl_base[tp.n_tl] = (uint32_t)L.off; tp.tl_clock[tp.n_tl] = (uint32_t)L.clock; tp.n_tl++; }
                 tp.tl_base[tp.n_tl] = (uint32_t)n_trains;
+                tp.draw = train_draws++;
                 tp.grid_hist = want_tgrid ? d_tgrid + s * n_trains : nullptr;
                 tp.spike_hist = want_tspk ? d_tspk + s * t_words : nullptr;
                 cudaError_t e = launch_trains(tp, stream_);
@@ -1719,7 +1935,9 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         // drain histories
         if (per_step_bytes) {
             std::vector<float> hg, htg; std::vector<uint32_t> hs, hts;
-            if (copy_grid) { hg.resize(steps * n_neurons); cudaMemcpy(hg.data(), d_grid, hg.size() * 4, cudaMemcpyDeviceToHost); }
+            cudaError_t he = cudaSuccess;
+            if (copy_grid) { hg.resize(steps * n_neurons); he = cudaMemcpy(hg.data(), d_grid, hg.size() * 4, cudaMemcpyDeviceToHost); }
+            if (he != cudaSuccess) { bail(he, SNN_GPU_BUFFER_READ_ERROR, "grid history drain"); break; }
             if (want_red) {
                 const size_t nl = red_lats.size();
                 cudaError_t re = launch_history_reduce(d_grid, n_neurons, (uint32_t)steps, d_red_lat, d_red_lat + nl,
@@ -1741,14 +1959,35 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                     if (!L.grid_hist && !L.spike_hist) L.hist_len += steps;
                 }
             }
-            if (want_spk) { hs.resize(steps * n_words); cudaMemcpy(hs.data(), d_spk, hs.size() * 4, cudaMemcpyDeviceToHost); }
-            if (want_tgrid) { htg.resize(steps * n_trains); cudaMemcpy(htg.data(), d_tgrid, htg.size() * 4, cudaMemcpyDeviceToHost); }
-            if (want_tspk) { hts.resize(steps * t_words); cudaMemcpy(hts.data(), d_tspk, hts.size() * 4, cudaMemcpyDeviceToHost); }
+            if (want_spk) { hs.resize(steps * n_words); he = cudaMemcpy(hs.data(), d_spk, hs.size() * 4, cudaMemcpyDeviceToHost); }
+            if (he == cudaSuccess && want_tgrid) { htg.resize(steps * n_trains); he = cudaMemcpy(htg.data(), d_tgrid, htg.size() * 4, cudaMemcpyDeviceToHost); }
+            if (he == cudaSuccess && want_tspk) { hts.resize(steps * t_words); he = cudaMemcpy(hts.data(), d_tspk, hts.size() * 4, cudaMemcpyDeviceToHost); }
+            if (he != cudaSuccess) { bail(he, SNN_GPU_BUFFER_READ_ERROR, "history drain"); break; }
+            // SpikeHistory::aggregate (neuron/mod.rs:335-359): the sum over the chunk's steps is taken on the device from the
+            // staged raster; the host only adds one count per neuron and chunk
+            std::vector<uint32_t> cnt_n, cnt_t;
+            for (int dom = 0; dom < 2 && he == cudaSuccess; ++dom) {
+                const bool on = dom ? want_tspk : want_spk;
+                const uint64_t dn = dom ? n_trains : n_neurons, dw = dom ? t_words : n_words;
+                if (!on || dn == 0) continue;
+                std::vector<uint32_t> &cnt = dom ? cnt_t : cnt_n;
+                cnt.resize(dn);
+                if (ensure_scratch(dn * 4)) { he = cudaErrorMemoryAllocation; break; }
+                he = launch_spike_count(dom ? d_tspk : d_spk, (uint32_t)steps, dw, dn, (uint32_t *)scratch_, stream_);
+                if (he == cudaSuccess) he = cudaMemcpyAsync(cnt.data(), scratch_, dn * 4, cudaMemcpyDeviceToHost, stream_);
+                if (he == cudaSuccess) he = cudaStreamSynchronize(stream_);
+            }
+            if (he != cudaSuccess) { bail(he, SNN_GPU_BUFFER_READ_ERROR, "spike aggregate"); break; }
             for (auto &L : lats_) {
                 if (!L.grid_hist && !L.spike_hist) continue;
                 const uint64_t dom_n = L.is_train ? n_trains : n_neurons, dom_w = L.is_train ? t_words : n_words;
                 const std::vector<float> &G = L.is_train ? htg : hg;
                 const std::vector<uint32_t> &S = L.is_train ? hts : hs;
+                if (L.spike_hist) {
+                    const std::vector<uint32_t> &cnt = L.is_train ? cnt_t : cnt_n;
+                    if (L.spike_agg.size() != L.n) L.spike_agg.assign(L.n, 0);
+                    for (uint64_t j = 0; j < L.n; ++j) L.spike_agg[j] += cnt[L.off + j];
+                }
                 for (uint64_t s = 0; s < steps; ++s) {
                     if (L.grid_hist) L.grid_history.insert(L.grid_history.end(), G.begin() + s * dom_n + L.off, G.begin() + s * dom_n + L.off + L.n);
                     if (L.spike_hist) {
@@ -1798,6 +2037,7 @@ int Engine::ipc_export(IpcBlob *blob) {
     CK(cudaIpcGetMemHandle(&blob->slab, slab_), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(cudaIpcGetMemHandle(&blob->flags, flags_), SNN_GPU_BUFFER_CREATE_ERROR);
     for (int k = 0; k < 2; ++k) { blob->off_v[k] = slab_off_v_[k]; blob->off_lft[k] = slab_off_lft_[k]; blob->off_t[k] = slab_off_t_[k]; }
+    blob->off_flags = slab_off_flags_;
     blob->t_stride = node_cap_;
     blob->own0 = own0_; blob->n_neurons = (uint32_t)n_neurons; blob->ghost_hi0 = ghost_hi0_; blob->halo = halo_;
     blob->cols = lats_.empty() ? 0 : lats_[0].cols; blob->chem = chem_alloc_;
@@ -1837,6 +2077,22 @@ int Engine::ipc_attach(int direction, const IpcBlob *blob) {
     H.peer_flag2 = H.peer_flag + 2;
     H.my_flag2 = H.my_flag + 2;
     H.active = 1;
+    // my ghost rows take the neurotransmitter / receptor type flags of the neighbour's boundary rows (they are baked into the
+    // col words of edges from ghosts): d == 0 reads the LAST halo_ neurons of rank - 1, d == 1 the FIRST halo_ of rank + 1
+    {
+        const uint8_t *peer_f = (const uint8_t *)peer_slab_[d] + blob->off_flags + (d == 0 ? blob->own0 + blob->n_neurons - halo_ : blob->own0);
+        std::vector<uint8_t> tmp(halo_);
+        CK(cudaMemcpy(tmp.data(), peer_f, halo_, cudaMemcpyDefault), SNN_GPU_BUFFER_READ_ERROR);
+        bool changed = !ghost_flags_from_peer_[d];
+        for (uint32_t g = 0; g < halo_; ++g) { changed |= h_node_flags_[H.my_ghost0 + g] != tmp[g]; h_node_flags_[H.my_ghost0 + g] = tmp[g]; }
+        ghost_flags_from_peer_[d] = true;
+        if (changed) {
+            CK(cudaMemcpy(node_flags_ + H.my_ghost0, tmp.data(), halo_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+            flags_cache_valid_ = false;
+            if (dev_weights_newer_) { int r = sync_weights_to_host(); if (r) return r; }
+            graph_dirty_ = true;
+        }
+    }
     return SNN_OK;
 }
 

@@ -30,6 +30,7 @@ struct Lat {
     std::vector<float> cold[2];                   // v_init, w_init
     std::vector<float> grid_history;
     std::vector<uint8_t> spike_history;
+    std::vector<int64_t> spike_agg;                // SpikeHistory::aggregate, accumulated from device-side counts
     uint64_t hist_len = 0;
     std::vector<uint64_t> ft_off;                 // preset firing times (CSR) of a train lattice
     std::vector<float> ft;
@@ -42,12 +43,15 @@ struct Block {  // connections pre lattice -> post lattice, CSR by post (pre asc
     std::vector<float> w;
     uint32_t radius = 0;
     float weight = 1.f;
+    // a materialised stencil (kind == CSR, adjacency still that of set_graph_grid(radius)): finalize_graph keeps the uniform-width
+    // layout and with it the window / TMA step kernels; cleared when an edge is added or removed
+    uint32_t from_grid_radius = 0;
 };
 
 struct IpcBlob {  // exchanged between neighbouring ranks by the caller (e.g. torch.distributed all_gather)
     uint32_t magic, version;
     cudaIpcMemHandle_t slab, flags;
-    uint64_t off_v[2], off_lft[2], off_t[2];
+    uint64_t off_v[2], off_lft[2], off_t[2], off_flags;
     uint64_t t_stride;
     uint32_t own0, n_neurons, ghost_hi0, halo, cols, chem;
     int32_t rank, world;
@@ -84,6 +88,13 @@ public:
                            uint64_t n_post, uint64_t nnz);
     int get_connection_dense(uint64_t pre_id, uint64_t post_id, uint32_t *connections, float *weights, uint64_t n_pre,
                              uint64_t n_post);
+    // CSR of the postsynaptic rows [row_begin, row_end) of the pre -> post block, decoded from the device table (no whole-graph
+    // download): Graph::get_incoming_connections over a range of positions (graph/mod.rs:228-256)
+    int get_connection_rows(uint64_t pre_id, uint64_t post_id, uint64_t row_begin, uint64_t row_end, uint64_t *row_ptr, uint32_t *pre,
+                            float *weights, uint64_t capacity, uint64_t *nnz);
+    // Graph::lookup_weight / edit_weight on flat indices (graph/mod.rs:196-226)
+    int lookup_weight(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, float *weight, int32_t *connected);
+    int edit_weight(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, bool has, float weight);
 
     // options
     int set_dt(float dt);
@@ -107,6 +118,7 @@ public:
     int history_len(uint64_t id, uint64_t *steps) const;
     int get_grid_history(uint64_t id, float *out, uint64_t capacity);
     int get_spike_history(uint64_t id, uint8_t *out, uint64_t capacity);
+    int get_spike_aggregate(uint64_t id, int64_t *out, uint64_t capacity);   // SpikeHistory::aggregate, neuron/mod.rs:335-359
     int get_reduced_history(uint64_t id, bool eeg, float *out, uint64_t capacity);
     int set_eeg_parameters(uint64_t id, float reference_voltage, float distance, float conductivity);
 
@@ -117,8 +129,11 @@ public:
     // public knobs (Lattice / LatticeNetwork pub fields, neuron/mod.rs:556-587, 1554-1563)
     bool electrical = true, chemical = false, parallel = false;
     uint64_t internal_clock = 0;
-    uint64_t seed = 0x5EED5EEDull;
+    uint64_t seed;                  // Philox key of the Poisson trains: distinct per handle unless SNN_OPT_RNG_SEED sets it
+    uint64_t train_draws = 0;       // Philox counter word: one per spike-train step of this handle, never reset (reset_timing
+                                    // restarts the clocks, not the random stream: the reference draws from thread_rng)
     uint32_t steps_per_graph = 0;
+    uint64_t halo_timeout_ms = 30000;   // multi-GPU: how long a step may wait for a neighbouring strip before SNN_GPU_WAIT_ERROR
     int use_tma = -1;   // -1 auto (env SNN_B200_TMA), 0 never, 1 whenever eligible
     std::string last_error;
 
@@ -142,7 +157,8 @@ private:
     float *V_[2] = {nullptr, nullptr};
     int *LFT_[2] = {nullptr, nullptr};
     float *T_[2] = {nullptr, nullptr};
-    uint64_t slab_off_v_[2] = {0, 0}, slab_off_lft_[2] = {0, 0}, slab_off_t_[2] = {0, 0};
+    uint64_t slab_off_v_[2] = {0, 0}, slab_off_lft_[2] = {0, 0}, slab_off_t_[2] = {0, 0}, slab_off_flags_ = 0;
+    bool ghost_flags_from_peer_[2] = {false, false};
     uint32_t *SPK_[2] = {nullptr, nullptr};
     uint8_t *node_flags_ = nullptr;
     std::vector<uint8_t> h_node_flags_;
@@ -193,6 +209,9 @@ private:
     int get_bits(const uint32_t *words, uint32_t *host_u32, uint64_t n, uint64_t bit0);
     int finalize_graph();
     int sync_weights_to_host();
+    // element index of edge (pre node j -> neuron row) in the sliced-ELL arrays, or -1; the graph must be finalized
+    int find_edge(uint64_t row, uint32_t j, int64_t *elem);
+    int check_edge_endpoints(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_t post, Lat **A, Lat **B);
     int materialize_grid(Block &b, const Lat &L);
     uint32_t nt_used() const; uint32_t rc_used() const;
     void refresh_flag_cache() const;

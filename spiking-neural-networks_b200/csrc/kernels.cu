@@ -26,6 +26,7 @@ namespace snn {
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p) {
+    if (!NET && halo_failed(p)) return;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (warp_global * 32u >= p.n_neurons) return;
@@ -83,6 +84,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const __grid_constant__ 
 // end-of-run flush of the lazily applied STDP (the last step's updates are still pending)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__ StepParams p) {
+    if (halo_failed(p)) return;
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (warp_global * 32u >= p.n_neurons) return;
@@ -90,8 +92,8 @@ __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__
     // partitioned handles: the neighbours' last step must have landed in the ghost slots before they are read
     if (p.halo[0].active | p.halo[1].active) {
         if (lane == 0) {
-            if (p.halo[0].active) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2);
-            if (p.halo[1].active) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
+            if (p.halo[0].active) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
+            if (p.halo[1].active) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
         }
         __syncwarp();
     }
@@ -202,12 +204,13 @@ __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constan
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
     const bool part = (p.halo[0].active | p.halo[1].active) != 0;
+    if (halo_failed(p)) return;
     if (part) {
         // row strips: the neighbours' last_firing_time of THIS step must have landed in the ghost slots (p.halo_epoch is the value
         // their step kernels publish); my_flag is the step-arrival counter here
         if (threadIdx.x == 0) {
-            if (p.halo[0].active) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2);
-            if (p.halo[1].active) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
+            if (p.halo[0].active) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
+            if (p.halo[1].active) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
         }
         __syncthreads();
     }
@@ -328,9 +331,9 @@ __device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t *
     return (uint32_t)prod;
 }
 
-// Philox4x32-10 counter-based generator keyed by (seed), counter (train index, clock)
-__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t idx, uint32_t clock) {
-    uint32_t c0 = idx, c1 = clock, c2 = 0x5EEDu, c3 = 0u;
+// Philox4x32-10 counter-based generator keyed by (seed), counter (train index, per-handle draw number)
+__device__ __forceinline__ uint32_t philox_u32(uint64_t seed, uint32_t idx, uint64_t draw) {
+    uint32_t c0 = idx, c1 = (uint32_t)draw, c2 = 0x5EEDu, c3 = (uint32_t)(draw >> 32);
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
@@ -359,7 +362,7 @@ __global__ void __launch_bounds__(256) train_kernel(const __grid_constant__ Trai
     if (p.kind == SNN_TRAIN_POISSON) {
         // PoissonNeuron::iterate, spike_train/mod.rs:352-368; uniform in [0,1] from Philox (the reference's
         // thread_rng is unseeded, so only the firing statistics are comparable)
-        const float u = (float)(philox_u32(p.seed, tc, p.tl_clock[tl]) >> 8) * (1.0f / 16777215.0f);
+        const float u = (float)(philox_u32(p.seed, tc, p.draw) >> 8) * (1.0f / 16777215.0f);
         spike = u <= p.tf[TF_CHANCE][tc];
     } else if (p.kind == SNN_TRAIN_RATE) {
         // RateSpikeTrain::iterate, spike_train/mod.rs:1015-1030
@@ -649,6 +652,22 @@ __global__ void pack_flags_kernel(const uint32_t *src, uint8_t *node_flags, uint
         if (ch) node_flags[i] = nf;
     }
     if (__any_sync(0xffffffffu, ch) && (threadIdx.x & 31u) == 0) atomicOr(changed, 1u);
+}
+
+__global__ void spike_count_kernel(const uint32_t *words, uint32_t steps, uint64_t n_words, uint64_t n, uint32_t *counts) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t *w = words + (i >> 5);
+    const uint32_t b = (uint32_t)(i & 31u);
+    uint32_t c = 0;
+    for (uint32_t s = 0; s < steps; ++s) c += (w[(size_t)s * n_words] >> b) & 1u;
+    counts[i] = c;
+}
+
+cudaError_t launch_spike_count(const uint32_t *words, uint32_t steps, uint64_t n_words, uint64_t n, uint32_t *counts, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    spike_count_kernel<<<blocks_for(n, 256), 256, 0, s>>>(words, steps, n_words, n, counts);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pack_flags(const uint32_t *src, uint8_t *node_flags, uint64_t n, int shift, unsigned int *changed, cudaStream_t s) {

@@ -113,14 +113,31 @@ __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// Spin until the neighbour's arrival counter reaches `epoch`.  Bounded (~4e9 SM cycles, about two seconds): a
-// neighbour that died must not hang this GPU; the host turns the error flag into SNN_GPU_WAIT_ERROR.
-__device__ __forceinline__ void halo_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *err) {
-    const long long t0 = clock64();
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Spin until the neighbour's arrival counter reaches `epoch`.  Bounded by `timeout_ns` (SNN_OPT_HALO_TIMEOUT_MS, default
+// 30 s; run() has already met the neighbours on the host before the first step kernel, so only a neighbour that died or
+// runs a different number of steps gets here): a dead neighbour must not hang this GPU.  On time-out the error flag is
+// raised — every later kernel of the run returns at once (halo_failed), the host reports SNN_GPU_WAIT_ERROR.
+__device__ __forceinline__ bool halo_wait(const unsigned long long *flag, unsigned long long epoch, unsigned int *err,
+                                          unsigned long long timeout_ns) {
+    if (ld_acquire_sys(flag) >= epoch) return true;
+    const unsigned long long t0 = global_timer_ns();
     while (ld_acquire_sys(flag) < epoch) {
         __nanosleep(64);
-        if (clock64() - t0 > 4000000000ll) { atomicExch(err, 1u); break; }
+        if (global_timer_ns() - t0 > timeout_ns || *(volatile unsigned int *)err) { atomicExch(err, 1u); return false; }
     }
+    return true;
+}
+// a halo wait of this run has timed out: the ghosts are stale, stop stepping (uniform over the grid once the flag is visible)
+// (CTA-uniform: called by every thread of the CTA before anything else)
+__device__ __forceinline__ bool halo_failed(const StepParams &p) {
+    if (!(p.halo[0].active | p.halo[1].active)) return false;
+    return __syncthreads_or(*(volatile unsigned int *)(p.halo_done + 2) != 0u) != 0;
 }
 
 
@@ -949,11 +966,11 @@ __device__ __forceinline__ void halo_import(const StepParams &p, uint32_t warp_g
     const bool near_lo = p.halo[0].active && w0 < p.halo[0].first + p.halo[0].count;
     const bool near_hi = p.halo[1].active && w1 > p.halo[1].first;
     if (near_lo) {
-        if (lane == 0) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2);
+        if (lane == 0) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
         __syncwarp();
     }
     if (near_hi) {
-        if (lane == 0) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
+        if (lane == 0) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
         __syncwarp();
     }
     export_lo = near_lo && valid && ln >= p.halo[0].first && ln < p.halo[0].first + p.halo[0].count;

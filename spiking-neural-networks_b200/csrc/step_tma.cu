@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(kTmaThreads, tma_min_ctas<MODEL, CHEMG>()) ste
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)tp.stages * tp.stage_bytes);
     uint64_t *empty = full + tp.stages;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (halo_failed(p)) return;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < tp.stages; ++s) {
             mbar_init(&full[s], 1);

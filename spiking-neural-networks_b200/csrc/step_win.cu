@@ -128,6 +128,7 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * wp.stage_bytes);
     uint64_t *empty = full + S;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (halo_failed(p)) return;
     if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
@@ -179,11 +180,11 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
             // last owned neuron read upper ghosts.
             bool ghosts = false;
             if (!waited_lo && ts <= wp.cols) {
-                if (lane == 0) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2);
+                if (lane == 0) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
                 waited_lo = ghosts = true;
             }
             if (!waited_hi && ts + kWinTile + 1u + wp.cols > p.n_neurons) {
-                if (lane == 0) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2);
+                if (lane == 0) halo_wait(p.halo[1].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
                 waited_hi = ghosts = true;
             }
             unsigned char *dst = smem + (size_t)s * wp.stage_bytes;

@@ -39,7 +39,7 @@ REFRACT_DELTA_DIRAC, REFRACT_EXPONENTIAL_DECAY = range(2)
 F32, U32, I32 = range(3)
 (OPT_ELECTRICAL_SYNAPSE, OPT_CHEMICAL_SYNAPSE, OPT_DO_PLASTICITY, OPT_UPDATE_GRID_HISTORY, OPT_UPDATE_SPIKE_HISTORY,
  OPT_INTERNAL_CLOCK, OPT_PARALLEL, OPT_RNG_SEED, OPT_UPDATE_AVERAGE_HISTORY, OPT_STEPS_PER_GRAPH,
- OPT_UPDATE_EEG_HISTORY) = range(11)
+ OPT_UPDATE_EEG_HISTORY, OPT_HALO_TIMEOUT_MS) = range(12)
 
 
 class StdpStruct(C.Structure):
@@ -104,6 +104,9 @@ SIGNATURES = {
     "snn_lattice_get_graph_csr": ([_P, _P, _P, _P, _u64, _u64], _i32),
     "snn_lattice_get_graph_dense": ([_P, _P, _P, _u32], _i32),
     "snn_lattice_lookup_weight": ([_P, _u64, _u64, C.POINTER(_f), C.POINTER(_i32)], _i32),
+    "snn_lattice_edit_weight": ([_P, _u64, _u64, _i32, _f], _i32),
+    "snn_lattice_get_graph_rows": ([_P, _u64, _u64, _P, _P, _P, _u64, C.POINTER(_u64)], _i32),
+    "snn_lattice_get_spike_aggregate": ([_P, _P, _u64], _i32),
     "snn_lattice_set_option": ([_P, _i32, _i64], _i32),
     "snn_lattice_get_option": ([_P, _i32, C.POINTER(_i64)], _i32),
     "snn_lattice_set_plasticity": ([_P, C.POINTER(StdpStruct)], _i32),
@@ -146,6 +149,9 @@ SIGNATURES = {
     "snn_network_connect_csr": ([_P, _u64, _u64, _P, _P, _P, _u64, _u64], _i32),
     "snn_network_connection_nnz": ([_P, _u64, _u64, C.POINTER(_u64)], _i32),
     "snn_network_get_connection_dense": ([_P, _u64, _u64, _P, _P, _u64, _u64], _i32),
+    "snn_network_lookup_weight": ([_P, _u64, _u64, _u64, _u64, C.POINTER(_f), C.POINTER(_i32)], _i32),
+    "snn_network_edit_weight": ([_P, _u64, _u64, _u64, _u64, _i32, _f], _i32),
+    "snn_network_get_spike_aggregate": ([_P, _u64, _P, _u64], _i32),
     "snn_network_set_option": ([_P, _i32, _i64], _i32),
     "snn_network_get_option": ([_P, _i32, C.POINTER(_i64)], _i32),
     "snn_network_set_lattice_option": ([_P, _u64, _i32, _i64], _i32),

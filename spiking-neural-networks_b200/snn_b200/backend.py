@@ -162,6 +162,26 @@ class CudaLatticeBackend(_CudaBase):
         self._ck(self.lib.snn_lattice_lookup_weight(self.h, int(pre), int(post), C.byref(w), C.byref(has)))
         return w.value if has.value else None
 
+    def edit_weight(self, pre, post, weight):
+        """Graph::edit_weight(pre, post, Option<f32>): weight None removes the edge."""
+        self._ck(self.lib.snn_lattice_edit_weight(self.h, int(pre), int(post), int(weight is not None),
+                                                  0.0 if weight is None else float(weight)))
+
+    def get_graph_rows(self, row_begin, row_end):
+        """In-edges (CSR) of the postsynaptic positions [row_begin, row_end) with the current weights, read from the device table."""
+        nrow = int(row_end) - int(row_begin)
+        rp = np.zeros(nrow + 1, np.uint64)
+        nnz = C.c_uint64()
+        self._ck(self.lib.snn_lattice_get_graph_rows(self.h, int(row_begin), int(row_end), _ptr(rp), None, None, 0, C.byref(nnz)))
+        pr, w = np.zeros(max(nnz.value, 1), np.uint32), np.zeros(max(nnz.value, 1), np.float32)
+        self._ck(self.lib.snn_lattice_get_graph_rows(self.h, int(row_begin), int(row_end), _ptr(rp), _ptr(pr), _ptr(w), nnz.value, C.byref(nnz)))
+        return rp, pr[:nnz.value], w[:nnz.value]
+
+    def spike_aggregate(self, id=0):
+        out = np.zeros(self.size(), np.int64)
+        self._ck(self.lib.snn_lattice_get_spike_aggregate(self.h, _ptr(out), out.size))
+        return out
+
     def set_option(self, option, value, id=None):
         self._ck(self.lib.snn_lattice_set_option(self.h, option, int(value)))
 
@@ -319,6 +339,20 @@ class CudaNetworkBackend(_CudaBase):
         w = np.zeros(n_pre * n_post, np.float32)
         self._ck(self.lib.snn_network_get_connection_dense(self.h, pre_id, post_id, _ptr(c), _ptr(w), n_pre, n_post))
         return c.reshape(n_pre, n_post), w.reshape(n_pre, n_post)
+
+    def lookup_weight(self, pre_id, post_id, pre, post):
+        w, has = C.c_float(), C.c_int32()
+        self._ck(self.lib.snn_network_lookup_weight(self.h, pre_id, post_id, int(pre), int(post), C.byref(w), C.byref(has)))
+        return w.value if has.value else None
+
+    def edit_weight(self, pre_id, post_id, pre, post, weight):
+        self._ck(self.lib.snn_network_edit_weight(self.h, pre_id, post_id, int(pre), int(post), int(weight is not None),
+                                                  0.0 if weight is None else float(weight)))
+
+    def spike_aggregate(self, id):
+        out = np.zeros(self.size(id), np.int64)
+        self._ck(self.lib.snn_network_get_spike_aggregate(self.h, id, _ptr(out), out.size))
+        return out
 
     def set_option(self, option, value, id=None):
         if id is None:

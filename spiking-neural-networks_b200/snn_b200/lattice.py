@@ -75,7 +75,8 @@ class SpikeHistory(GridVoltageHistory):
         return h.reshape(h.shape[0], self._o.rows, self._o.cols).astype(bool)
 
     def aggregate(self):
-        return self.history.sum(axis=0).astype(np.int64)
+        """Per-cell spike counts over the recorded steps; the sum over steps is taken on the device (snn_*_get_spike_aggregate)."""
+        return self._o._be.spike_aggregate(self._o._bid).reshape(self._o.rows, self._o.cols)
 
 
 class AverageVoltageHistory(GridVoltageHistory):
@@ -385,9 +386,21 @@ class Lattice(_CellLattice):
         for p, code in ((postsynaptic, K.SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND), (presynaptic, K.SNN_GRAPH_PRESYNAPTIC_NOT_FOUND)):
             if not (0 <= p[0] < self.rows and 0 <= p[1] < self.cols):
                 raise K.SnnError(code, f"position not found: {p}")
-        c, w = self.graph_dense()
         a, b = presynaptic[0] * self.cols + presynaptic[1], postsynaptic[0] * self.cols + postsynaptic[1]
-        return float(w[a, b]) if c[a, b] else None
+        if self._in_network is not None:
+            return self._be.lookup_weight(self._bid, self._bid, a, b)
+        return self._be.lookup_weight(a, b)
+
+    def edit_weight(self, presynaptic, postsynaptic, weight):
+        """Graph::edit_weight on (row, col) positions (graph/mod.rs:208-226); weight None removes the connection."""
+        for p, code in ((postsynaptic, K.SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND), (presynaptic, K.SNN_GRAPH_PRESYNAPTIC_NOT_FOUND)):
+            if not (0 <= p[0] < self.rows and 0 <= p[1] < self.cols):
+                raise K.SnnError(code, f"position not found: {p}")
+        a, b = presynaptic[0] * self.cols + presynaptic[1], postsynaptic[0] * self.cols + postsynaptic[1]
+        if self._in_network is not None:
+            self._be.edit_weight(self._bid, self._bid, a, b, weight)
+        else:
+            self._be.edit_weight(a, b, weight)
 
     # ---- timing / options ---------------------------------------------------------------------
     @property

@@ -117,6 +117,109 @@ def test_graph_ingestion_round_trips():
     assert ei.value.status == K.SNN_GRAPH_PRESYNAPTIC_NOT_FOUND
 
 
+def test_edit_weight_none_some_none_and_row_access(oracle_lattice_factory):
+    """Graph::edit_weight(pre, post, Option<f32>) (graph/mod.rs:208-226) through the C ABI: None -> Some(0.0) -> None on a single
+    edge, Some(w) over an existing edge (one word on the device), the doc-test of graph/mod.rs:112-137 replayed, error order, and
+    snn_lattice_get_graph_rows == the matching rows of the whole-graph CSR.  Every state is stepped against the oracle."""
+    rows, cols = 4, 5
+    n = rows * cols
+
+    def make(fac):
+        lat = SC.build_lattice(fac, model="izh", rows=rows, cols=cols, seed=3, graph="random", history=False)
+        return lat
+    a, b = make(None), make(oracle_lattice_factory)
+    conn, w = a.graph_dense()
+    z = [tuple(x) for x in np.argwhere(conn == 0) if x[0] != x[1]][0]
+    e = tuple(np.argwhere(conn == 1)[3])
+    pos = lambda i: (int(i) // cols, int(i) % cols)
+    for lat in (a, b):
+        assert lat.get_weight(pos(z[0]), pos(z[1])) is None
+        lat.edit_weight(pos(z[0]), pos(z[1]), 0.0)          # None -> Some(0.0): connected, counted in the averages
+        assert lat.get_weight(pos(z[0]), pos(z[1])) == 0.0
+        lat.edit_weight(pos(e[0]), pos(e[1]), 1.75)         # Some -> Some: in place
+        assert lat.get_weight(pos(e[0]), pos(e[1])) == 1.75
+    a.run_lattice(30); b.run_lattice(30)
+    SC.compare_lattices(a, b, exact=True, fields=("current_voltage", "w_value", "last_firing_time"))
+    (ca, wa), (cb, wb) = a.graph_dense(), b.graph_dense()
+    assert (ca == cb).all() and (wa == wb).all() and ca[z] == 1 and wa[z] == 0.0 and wa[e] == 1.75
+    for lat in (a, b):
+        lat.edit_weight(pos(z[0]), pos(z[1]), None)         # Some(0.0) -> None
+        assert lat.get_weight(pos(z[0]), pos(z[1])) is None
+        lat.edit_weight(pos(e[0]), pos(e[1]), None)         # an original edge goes away too
+        lat.edit_weight(pos(z[0]), pos(z[1]), None)         # None over None: no-op
+    a.run_lattice(30); b.run_lattice(30)
+    SC.compare_lattices(a, b, exact=True, fields=("current_voltage", "w_value", "last_firing_time"))
+    (ca, wa), (cb, wb) = a.graph_dense(), b.graph_dense()
+    assert (ca == cb).all() and (wa == wb).all() and ca[z] == 0 and ca[e] == 0
+    # row access == rows of the whole CSR
+    rp, pre, ww = a._be.get_connection_csr()
+    for (r0, r1) in ((0, n), (3, 4), (7, 15), (n - 1, n), (5, 5)):
+        rp2, pre2, ww2 = a._be.get_graph_rows(r0, r1)
+        s, t = int(rp[r0]), int(rp[r1])
+        assert (rp2 == rp[r0:r1 + 1] - rp[r0]).all() and (pre2 == pre[s:t]).all() and (ww2 == ww[s:t]).all()
+    # error order: postsynaptic position first (graph/mod.rs:209-214)
+    be = a._be
+    for args, code in (((0, n, 1.0), K.SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND), ((n, 0, 1.0), K.SNN_GRAPH_PRESYNAPTIC_NOT_FOUND),
+                       ((n, n, 1.0), K.SNN_GRAPH_POSTSYNAPTIC_NOT_FOUND)):
+        with pytest.raises(S.SnnError) as ei:
+            be.edit_weight(*args)
+        assert ei.value.status == code
+    # the doc-test of AdjacencyMatrix (graph/mod.rs:112-137) on a 1 x 3 lattice: nodes (0,0) (0,1) (0,2)
+    g = CudaLatticeBackend(K.MODEL_IZH, 0, 0, 1, 3)
+    g.edit_weight(0, 1, 0.5)
+    g.edit_weight(2, 1, 1.0)
+    assert g.lookup_weight(0, 1) == 0.5 and g.lookup_weight(1, 0) is None
+    rp3, pre3, _ = g.get_graph_rows(1, 2)
+    assert pre3.tolist() == [0, 2]                            # get_incoming_connections((0,1)) == {(0,0), (1,2)}
+    g.edit_weight(0, 1, None)
+    assert g.lookup_weight(0, 1) is None and g.get_graph_rows(1, 2)[1].tolist() == [2]
+
+
+def test_edit_weight_on_stencil_keeps_the_staged_kernels(oracle_lattice_factory):
+    """A weight edit (and the weight read-back after STDP) on a set_graph_grid lattice large enough for the window-staged kernel:
+    the block is materialised on the host, yet the rebuilt table keeps the generator's uniform layout — results stay those of the
+    oracle, before and after an edge is removed."""
+    rows, cols = 264, 256
+
+    def make(fac):
+        lat = SC.build_lattice(fac, model="izh", rows=rows, cols=cols, seed=4, graph="grid", hetero=False, history=False,
+                               chem="approx_ampa", stdp=False, c_m=2.0)
+        rng = np.random.default_rng(9)
+        lat.set_field("current_voltage", rng.uniform(-65, 30, rows * cols).astype(f32))
+        lat.set_field("b", rng.uniform(0.25, 0.36, rows * cols).astype(f32))
+        return lat
+    a, b = make(None), make(oracle_lattice_factory)
+    for lat in (a, b):
+        lat.edit_weight((100, 100), (100, 101), 3.0)
+        lat.edit_weight((263, 255), (262, 254), 0.25)
+    a.run_lattice(12); b.run_lattice(12)
+    for name in ("current_voltage", "last_firing_time", "neurotransmitters$t"):
+        assert (a.get_field(name) == b.get_field(name)).all(), name
+    for lat in (a, b):
+        lat.edit_weight((10, 10), (10, 11), None)            # structural: rebuild through the host CSR
+        lat.edit_weight((10, 12), (10, 10), 2.0)             # not a stencil edge: added
+    a.run_lattice(12); b.run_lattice(12)
+    for name in ("current_voltage", "last_firing_time", "neurotransmitters$t"):
+        assert (a.get_field(name) == b.get_field(name)).all(), name
+    assert a.get_weight((10, 10), (10, 11)) is None and a.get_weight((10, 12), (10, 10)) == 2.0 and a.get_weight((100, 100), (100, 101)) == 3.0
+
+
+def test_spike_history_aggregate_on_device(oracle_lattice_factory):
+    """SpikeHistory::aggregate (neuron/mod.rs:335-359) from the device-side counts, across several run calls and a reset."""
+    a = SC.build_lattice(None, model="izh", rows=9, cols=11, seed=5)
+    b = SC.build_lattice(oracle_lattice_factory, model="izh", rows=9, cols=11, seed=5)
+    assert (a.spike_history.aggregate() == 0).all() and a.spike_history.aggregate().shape == (9, 11)
+    for k in (70, 1, 129):
+        a.run_lattice(k); b.run_lattice(k)
+    agg = a.spike_history.aggregate()
+    assert agg.dtype == np.int64 and agg.sum() > 20
+    assert (agg == a.spike_history.history.sum(axis=0)).all()
+    assert (agg == b.spike_history.aggregate()).all()
+    a.spike_history.reset()
+    a.run_lattice(40)
+    assert (a.spike_history.aggregate() == a.spike_history.history.sum(axis=0)).all()
+
+
 def test_grid_generator_equals_connect_predicate(oracle_lattice_factory):
     """set_graph_grid(radius) == Lattice::connect(|x,y| max(|dr|,|dc|) <= radius && x != y, None) (neuron/mod.rs:1134-1157)."""
     for radius in (1, 2):

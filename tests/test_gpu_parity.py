@@ -297,7 +297,7 @@ def test_stdp_run_continuity(oracle_lattice_factory):
 
 # ------------------------------------------------------------------ networks
 def build_network(lattice_factory, network_factory, train="rate", stdp=True, chemical=True, electrical=True, seed=21,
-                  st_shape=(3, 4)):
+                  st_shape=(3, 4), refract=None):
     """MNIST-shaped miniature of BASELINE.json configs[3]: spike trains -> excitatory <-> inhibitory."""
     rng = np.random.default_rng(seed)
     T = S.IonotropicNeurotransmitterType
@@ -325,6 +325,8 @@ def build_network(lattice_factory, network_factory, train="rate", stdp=True, che
     else:
         st_cls, base = S.PresetSpikeTrain, S.PresetSpikeTrain(firing_times=[1.0, 2.5, 0.7])
     base.synaptic_neurotransmitters[T.AMPA] = S.ApproximateNeurotransmitter()
+    if refract is not None:
+        base.neural_refractoriness = refract
     st = S.SpikeTrainLattice(st_cls, id=0, network_backend_factory=network_factory)
     n_st = st_shape[0] * st_shape[1]
     st.populate(base, *st_shape)
@@ -399,6 +401,54 @@ def test_network_electrical_rate_trains_bit_exact(oracle_lattice_factory, oracle
         ha, hb = a.get_lattice(lid).grid_history.history, b.get_lattice(lid).grid_history.history
         np.testing.assert_allclose(ha, hb, rtol=1e-4, atol=1e-3)
         assert (a.get_lattice(lid).spike_history.history == b.get_lattice(lid).spike_history.history).all()
+
+
+@pytest.mark.parametrize("st_shape", [(3, 4), (8, 9)])
+@pytest.mark.parametrize("stdp", [False, True])
+def test_network_exponential_decay_refractoriness(st_shape, stdp, oracle_lattice_factory, oracle_network_factory):
+    """ExponentialDecayRefractoriness (spike_train/mod.rs:150-180) behind spike_train_gap_junction (neuron/mod.rs:119-137): the
+    trains' effect on their postsynaptic neurons decays as exp(-dt_since_spike / (k / dt)) instead of the Gaussian of the
+    delta-Dirac kind.  Both the narrow kernel (12 trains) and the wide-row kernel (72 trains) are covered; with STDP the
+    comparison is segment-wise (expf in the weight update)."""
+    kw = dict(train="rate", stdp=stdp, electrical=True, chemical=False, st_shape=st_shape)
+    a = build_network(None, None, refract=S.ExponentialDecayRefractoriness(k=1.5), **kw)
+    b = build_network(oracle_lattice_factory, oracle_network_factory, refract=S.ExponentialDecayRefractoriness(k=1.5), **kw)
+    ref_dirac = build_network(oracle_lattice_factory, oracle_network_factory, **kw)
+    assert a.get_spike_train_lattice(0)._refract == K.REFRACT_EXPONENTIAL_DECAY
+    total, seg, done, spikes = 200, 25, 0, 0
+    while done < total:
+        a.run_lattices(seg)
+        b.run_lattices(seg)
+        for lid in (1, 2):
+            ha, hb = a.get_lattice(lid).grid_history.history[done:done + seg], b.get_lattice(lid).grid_history.history[done:done + seg]
+            np.testing.assert_allclose(ha, hb, rtol=1e-4, atol=1e-3, err_msg=f"lattice {lid}, segment at {done}")
+            ra, rb = a.get_lattice(lid).spike_history.history[done:done + seg], b.get_lattice(lid).spike_history.history[done:done + seg]
+            assert (ra == rb).all(), f"lattice {lid}: raster differs in the segment at {done}"
+            spikes += int(rb.sum())
+        _sync_network(b, a)
+        done += seg
+    assert spikes > 10
+    # the refractoriness kind matters: the same network with the delta-Dirac kind follows another trajectory
+    ref_dirac.run_lattices(total)
+    assert np.abs(ref_dirac.get_lattice(1).grid_history.history - b.get_lattice(1).grid_history.history).max() > 1e-2
+
+
+def test_poisson_noise_is_fresh_after_reset_timing_and_across_handles():
+    """The reference draws thread_rng values on every iterate (spike_train/mod.rs:352-368): a presentation / reset_timing loop
+    must not replay the same noise, and two networks built the same way must not share it (unless the caller pins the key)."""
+    steps = 600
+    net = build_network(None, None, train="poisson", stdp=False)
+    net.run_lattices(steps)
+    first = net.get_spike_train_lattice(0).spike_history.history.copy()
+    net.reset_timing()
+    net.get_spike_train_lattice(0).spike_history.reset()
+    net.run_lattices(steps)
+    second = net.get_spike_train_lattice(0).spike_history.history
+    assert first.shape == second.shape and first.sum() > 20 and second.sum() > 20
+    assert (first != second).any(), "reset_timing replayed the identical Poisson sequence"
+    other = build_network(None, None, train="poisson", stdp=False)
+    other.run_lattices(steps)
+    assert (other.get_spike_train_lattice(0).spike_history.history != first).any(), "two handles share one default key"
 
 
 def test_poisson_network_firing_statistics():
@@ -560,6 +610,7 @@ def _window_check(big, rows, cols, r0, c0, h, w, k, oracle_lattice_factory, init
 
 
 def test_full_size_10m_izhikevich_window_property(oracle_lattice_factory):
+    """Electrical synapses only: no transcendental anywhere, every compared field bit for bit after k = 24 steps."""
     rows = cols = 3163
     n = rows * cols
     rng = np.random.default_rng(2024)
@@ -576,6 +627,83 @@ def test_full_size_10m_izhikevich_window_property(oracle_lattice_factory):
         _window_check(big, rows, cols, r0, c0, 16, 16, k, oracle_lattice_factory, init)
     spikes = (big.get_field("last_firing_time") >= 0).sum()
     assert spikes > 1000
+
+
+def _bench_config_lattice(factory, rows, cols, init):
+    """The bench workload (bench.py, BASELINE.json configs[4] shape): Izhikevich, radius-1 Moore grid, electrical + AMPA chemistry
+    (ApproximateNeurotransmitter / ApproximateReceptor), STDP on."""
+    lat = SC.build_lattice(factory, model="izh", rows=rows, cols=cols, seed=0, graph="grid", hetero=False, history=False,
+                           chem="approx_ampa", stdp=True, c_m=2.0)
+    lat.plasticity = S.STDP(a_plus=0.05, a_minus=0.04, tau_plus=4.5, tau_minus=3.0)
+    for name, arr in init.items():
+        lat.set_field(name, arr)
+    return lat
+
+
+BENCH_STATE = ("current_voltage", "w_value", "last_firing_time", "neurotransmitters$t", "receptors$AMPA$r$kinetics$r")
+
+
+def _bench_window_check(big, rows, cols, r0, c0, h, w, k, factory, init):
+    """Light cone: after k steps a cell depends only on cells within Chebyshev distance k, so a (h+2k) x (w+2k) patch stepped by
+    the oracle must reproduce the window — last_firing_time bit for bit, float state to 1e-4 (STDP's expf is the one
+    transcendental), weights of the window's in-edges to 1e-4."""
+    ra, rb = max(0, r0 - k), min(rows, r0 + h + k)
+    ca, cb = max(0, c0 - k), min(cols, c0 + w + k)
+    patch = _bench_config_lattice(factory, rb - ra, cb - ca, {n_: a.reshape(rows, cols)[ra:rb, ca:cb] for n_, a in init.items()})
+    patch.run_lattice(k)
+    pc = cb - ca
+    for name in BENCH_STATE:
+        got = big[name].reshape(rows, cols, -1)[r0:r0 + h, c0:c0 + w]
+        want = patch.get_field(name).reshape(rb - ra, pc, -1)[r0 - ra:r0 - ra + h, c0 - ca:c0 - ca + w]
+        if name == "last_firing_time":
+            assert (got == want).all(), (name, r0, c0)
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4, err_msg=f"{name} at ({r0},{c0})")
+    prp, ppre, pw = patch._be.get_connection_csr()
+    changed = 0
+    for r in range(r0, r0 + h):
+        rp, pre, ww = big["rows"](r * cols + c0, r * cols + c0 + w)
+        for q in range(w):
+            pq = (r - ra) * pc + (c0 + q - ca)
+            s, t = int(prp[pq]), int(prp[pq + 1])
+            gpre = pre[int(rp[q]):int(rp[q + 1])]
+            # same in-edges (global index -> patch index) and the same weights
+            assert ((gpre // cols - ra) * pc + (gpre % cols - ca) == ppre[s:t]).all()
+            np.testing.assert_allclose(ww[int(rp[q]):int(rp[q + 1])], pw[s:t], rtol=1e-4, atol=1e-5)
+            changed += int((np.abs(pw[s:t] - 1.0) > 1e-6).sum())
+    return changed
+
+
+def _full_size_bench_config(rows, cols, k, windows, factory, seed):
+    n = rows * cols
+    rng = np.random.default_rng(seed)
+    init = {"current_voltage": rng.uniform(-65, 30, n).astype(f32), "b": rng.uniform(0.25, 0.36, n).astype(f32)}
+    lat = _bench_config_lattice(None, rows, cols, init)
+    lat.run_lattice(k)
+    assert lat.internal_clock == k
+    big = {name: lat.get_field(name) for name in BENCH_STATE}
+    big["rows"] = lat._be.get_graph_rows
+    changed = 0
+    for (r0, c0) in windows:
+        changed += _bench_window_check(big, rows, cols, r0, c0, 16, 16, k, factory, init)
+    assert (big["last_firing_time"] >= 0).sum() > 1000
+    assert changed > 0, "STDP never changed a weight inside the windows"
+    assert np.abs(big["neurotransmitters$t"]).max() > 0
+
+
+def test_full_size_10m_bench_config_window_property(oracle_lattice_factory):
+    """BASELINE.json configs[4] shape as bench.py runs it (3163 x 3163 Izhikevich, electrical + AMPA + STDP) through the
+    window-staged kernel at full size: five 16 x 16 windows incl. corners and edges, k = 12 steps."""
+    rows = cols = 3163
+    _full_size_bench_config(rows, cols, 12, [(0, 0), (1500, 1700), (rows - 16, cols - 16), (0, cols - 16), (3000, 0)],
+                            oracle_lattice_factory, 2024)
+
+
+def test_full_size_100m_bench_config_window_property(oracle_lattice_factory):
+    """The same property at 10^8 neurons on one GPU (10 000 x 10 000, ~25 GB of HBM): 64-bit offsets, node indices near the
+    28-bit limit of the col words."""
+    rows = cols = 10000
+    _full_size_bench_config(rows, cols, 6, [(0, 0), (rows // 2 + 3, cols // 2 - 5), (rows - 16, cols - 16)], oracle_lattice_factory, 5)
 
 
 def test_full_size_uniform_state_follows_isolated_neuron(oracle_lattice_factory):

@@ -146,8 +146,11 @@ typedef enum snn_option {
                                          handle; the counter is (train, per-handle draw number) and is NOT reset by reset_timing, so repeated
                                          presentations see fresh noise */
     SNN_OPT_UPDATE_AVERAGE_HISTORY = 8, /* AverageVoltageHistory, neuron/mod.rs:303-322 */
-    SNN_OPT_STEPS_PER_GRAPH = 9,      /* reserved (stored, not acted on): a 10^4-neuron step is 4 us, at the floor of one
-                                         grid-wide synchronisation per timestep, so graph replay has nothing left to remove */
+    SNN_OPT_STEPS_PER_GRAPH = 9,      /* timesteps per kernel launch for lattices / networks that the one-launch-per-step kernels leave
+                                         launch-bound (whole-GPU handles below ~10^6 neurons that are not stepped by the TMA-staged
+                                         kernels): 0 (default) = a whole run (or history chunk) per cooperative launch with a grid-wide
+                                         barrier between timesteps, 1 = one launch per timestep, k = at most k.  Results are
+                                         bit-identical for every value. */
     SNN_OPT_UPDATE_EEG_HISTORY = 10,  /* default 0 (per lattice): EEGHistory, neuron/mod.rs:231-284 */
     SNN_OPT_HALO_TIMEOUT_MS = 11      /* partitioned handles: bound of one in-kernel wait for a neighbouring strip (default 30000);
                                          run() first meets the neighbours on the host (4x this bound) before any step is enqueued */

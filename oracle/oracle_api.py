@@ -233,15 +233,28 @@ class OracleBackend:
     # the lattice role and as (pre_id, post_id, pre, post[, weight]) in the network role, like the two CUDA back ends
     def lookup_weight(self, *a):
         pre_id, post_id, pre, post = (0, 0) + tuple(a) if len(a) == 2 else a
-        c, w = self.get_connection_dense(pre_id, post_id)
-        return float(w[pre, post]) if c[pre, post] else None
+        rp, pr, w = self.get_connection_csr(pre_id, post_id)
+        s, t = int(rp[post]), int(rp[post + 1])
+        hit = np.nonzero(pr[s:t] == pre)[0]
+        return float(w[s + hit[0]]) if hit.size else None
 
     def edit_weight(self, *a):
         pre_id, post_id, pre, post, weight = (0, 0) + tuple(a) if len(a) == 3 else a
-        c, w = self.get_connection_dense(pre_id, post_id)
-        c[pre, post] = 0 if weight is None else 1
-        w[pre, post] = 0.0 if weight is None else weight
-        self.connect_dense(pre_id, post_id, c, w)
+        rp, pr, w = self.get_connection_csr(pre_id, post_id)
+        s, t = int(rp[post]), int(rp[post + 1])
+        hit = np.nonzero(pr[s:t] == pre)[0]
+        if hit.size and weight is not None:
+            w = w.copy(); w[s + hit[0]] = weight
+        elif hit.size:
+            pr, w = np.delete(pr, s + hit[0]), np.delete(w, s + hit[0])
+            rp = rp.copy(); rp[post + 1:] -= 1
+        elif weight is not None:
+            at = s + int(np.searchsorted(pr[s:t], pre))
+            pr, w = np.insert(pr, at, pre), np.insert(w, at, np.float32(weight))
+            rp = rp.copy(); rp[post + 1:] += 1
+        else:
+            return
+        self.connect_csr(pre_id, post_id, rp, pr, w)
 
     def spike_aggregate(self, id=0):
         """SpikeHistory::aggregate, neuron/mod.rs:335-359: literal sum of the boolean raster over its steps."""

@@ -131,6 +131,22 @@ struct TrainParams {
     float *grid_hist; uint32_t *spike_hist;   // this step's record over all trains (nullptr = off)
 };
 
+// ---- multi-step kernel (step_multi.cu): a whole chunk of timesteps in one cooperative launch ----------
+struct MultiParams {
+    uint32_t steps;           // timesteps of this launch
+    uint32_t first_pending;   // the first of them applies the previous step's pending STDP (0 only at the first step of a run)
+    uint32_t cur, lft_loc;    // parities of the current V / t / spike buffers and of the current last_firing_time at launch
+    uint32_t lft_pp;
+    uint32_t train_sync;      // the spike trains of a step wait for all of its neurons (lazy STDP reads the trains' lft_out)
+    float *v[2]; int *lft[2]; uint32_t *spk[2]; float *t[2];
+    float *grid_hist; uint32_t *spike_hist; float *tgrid_hist; uint32_t *tspike_hist;   // staged history of the chunk (record s at + s * row)
+    uint64_t n_neurons, n_words, n_trains, t_words;
+    unsigned int *barrier;    // grid-wide arrival counter, zero at launch
+};
+// dry = only report whether the configuration is eligible (cudaSuccess) without launching
+cudaError_t launch_step_multi(const StepParams &p, const TrainParams &t, const MultiParams &m, int model, int chemg, bool ntrel, bool stdp,
+                              bool net, bool wide, int device, bool dry, cudaStream_t s);
+
 // ---- TMA-staged step kernel (step_tma.cu) -----------------------------------------------------
 constexpr int kTmaTile = 256;            // neurons per tile
 constexpr int kTmaConsumerWarps = 8;
@@ -233,6 +249,7 @@ struct WinParams {
     uint32_t node_cap;            // elements allocated per node array (window copies are clamped to [0, node_cap))
     uint32_t cols;
     uint32_t lft_copy;            // copy last_firing_time windows at all (STDP or ping-ponged lft)
+    uint32_t first_lo, first_hi;  // row strips: this many tiles at the front / back of the strip touch a halo and are stepped first
     TmaStream st[kMaxTmaStreams]; // per-tile contiguous operands (src + tile * bytes_per_tile)
     uint32_t o_nt[NTF_COUNT][kNT];   // run-time part of the stage layout: per-type chemical parameters
     uint32_t o_rc[RCF_COUNT][kNT];

@@ -50,6 +50,7 @@ Engine::~Engine() {
     free_device();
     if (flags_) cudaFree(flags_);
     if (halo_done_) cudaFree(halo_done_);
+    if (multi_barrier_) cudaFree(multi_barrier_);
     if (scratch_) cudaFree(scratch_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -81,6 +82,7 @@ int Engine::init() {
     CK(cudaEventCreate(&ev1_), SNN_GPU_QUEUE_FAILURE);
     CK(dev_alloc(&flags_, 4), SNN_GPU_BUFFER_CREATE_ERROR);   // [0],[1] step arrivals from rank-1 / rank+1, [2],[3] edge-kernel arrivals
     CK(cudaMemset(flags_, 0, 4 * sizeof(unsigned long long)), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(dev_alloc(&multi_barrier_, 1), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(dev_alloc(&halo_done_, 4), SNN_GPU_BUFFER_CREATE_ERROR);  // [0],[1] completion counters, [2] halo time-out flag, [3] per-edge kernel CTAs done
     CK(cudaMemset(halo_done_, 0, 4 * sizeof(unsigned int)), SNN_GPU_BUFFER_WRITE_ERROR);
     return SNN_OK;
@@ -1633,6 +1635,17 @@ bool Engine::build_win_params(WinParams &wp, int chemg, bool ntrel, bool stdp, b
     wp.node_cap = (uint32_t)node_cap_;
     wp.cols = cols;
     wp.lft_copy = (stdp || lft_pp) ? 1u : 0u;
+    // tiles whose windows reach ghost rows (they are also the ones that export): same predicates as the producer's waits
+    wp.first_lo = wp.first_hi = 0;
+    if (part_world > 1) {
+        for (uint32_t t = 0; t < wp.n_tiles; ++t) {
+            const uint64_t ts = (uint64_t)t * kWinTile;
+            if (halo_dir_[0].active && ts <= cols) wp.first_lo++;
+            if (halo_dir_[1].active && ts + kWinTile + 1u + cols > n_neurons) wp.first_hi++;
+        }
+        if (wp.first_lo + wp.first_hi > wp.n_tiles) wp.first_lo = wp.first_hi = 0;   // a strip of a few rows: every tile is a boundary tile
+        if (const char *e = getenv("SNN_B200_BOUNDARY_FIRST")) if (atoi(e) == 0) wp.first_lo = wp.first_hi = 0;
+    }
     const uint32_t G = (uint32_t)win_groups(model, chemg);
     uint32_t stages = (224u * 1024u) / (off + 16u);
     if (const char *es = getenv("SNN_B200_WIN_STAGES")) stages = std::min<uint32_t>(stages, (uint32_t)std::max(1, atoi(es)));
@@ -1797,6 +1810,18 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     }
 
     static const bool win_reverse = !(getenv("SNN_B200_WIN_REVERSE") && atoi(getenv("SNN_B200_WIN_REVERSE")) == 0);
+    // small lattices / networks (everything the staged kernels do not take): a whole chunk of timesteps per cooperative launch
+    // (step_multi.cu).  SNN_OPT_STEPS_PER_GRAPH: 0 = as many as the history chunk holds, 1 = one launch per timestep, k = at most k.
+    bool multi = part_world == 1 && n_neurons > 0 && !win_ok && !tma_ok && !bcm_on && !reward_mode && steps_per_graph != 1 &&
+                 !getenv("SNN_DEBUG_TIMING");
+    if (const char *e = getenv("SNN_B200_MULTI")) multi = multi && atoi(e) != 0;
+    if (multi) {
+        StepParams probe = sp;
+        TrainParams tprobe = tp;
+        MultiParams mprobe{};
+        multi = launch_step_multi(probe, tprobe, mprobe, model, chemg, ntrel, stdp, net, wide, device, true, stream_) == cudaSuccess;
+        cudaGetLastError();
+    }
     uint64_t done = 0;
     bool first_step = true;
     while (done < iterations && status == SNN_OK) {
@@ -1807,7 +1832,40 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         std::vector<cudaEvent_t> dbg_ev;
         unsigned long long *dbg_clk = nullptr;
         if (dbg_timing && steps <= 32) { cudaMalloc(&dbg_clk, 32 * 4 * sizeof(unsigned long long)); cudaMemset(dbg_clk, 0, 32 * 4 * sizeof(unsigned long long)); }
-        for (uint64_t s = 0; s < steps; ++s) {
+        for (uint64_t s0 = 0; multi && s0 < steps;) {
+            const uint64_t k = steps_per_graph ? std::min<uint64_t>(steps_per_graph, steps - s0) : steps - s0;
+            sp.clock = (uint32_t)internal_clock;
+            sp.dbg = nullptr; sp.reverse = 0u;
+            if (n_trains) {
+                tp.n_tl = 0;
+                for (auto &L : lats_)
+                    if (L.is_train) { tp.tl_base[tp.n_tl] = (uint32_t)L.off; tp.tl_clock[tp.n_tl] = (uint32_t)L.clock; tp.n_tl++; }
+                tp.tl_base[tp.n_tl] = (uint32_t)n_trains;
+                tp.draw = train_draws;
+            }
+            MultiParams mp{};
+            mp.steps = (uint32_t)k; mp.first_pending = first_step ? 0u : 1u;
+            mp.cur = (uint32_t)cur_; mp.lft_loc = (uint32_t)lft_loc_; mp.lft_pp = lft_pp ? 1u : 0u;
+            mp.train_sync = (stdp && n_trains) ? 1u : 0u;
+            for (int q = 0; q < 2; ++q) { mp.v[q] = V_[q]; mp.lft[q] = LFT_[q]; mp.spk[q] = SPK_[q]; mp.t[q] = T_[q]; }
+            mp.grid_hist = want_grid ? d_grid + s0 * n_neurons : nullptr;
+            mp.spike_hist = want_spk ? d_spk + s0 * n_words : nullptr;
+            mp.tgrid_hist = want_tgrid ? d_tgrid + s0 * n_trains : nullptr;
+            mp.tspike_hist = want_tspk ? d_tspk + s0 * t_words : nullptr;
+            mp.n_neurons = n_neurons; mp.n_words = n_words; mp.n_trains = n_trains; mp.t_words = t_words;
+            mp.barrier = multi_barrier_;
+            cudaError_t e = cudaMemsetAsync(multi_barrier_, 0, sizeof(unsigned int), stream_);
+            if (e == cudaSuccess) e = launch_step_multi(sp, tp, mp, model, chemg, ntrel, stdp, net, wide, device, false, stream_);
+            if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_multi"); break; }
+            n_launch++;
+            // the host mirrors what the launch did to the ping-pong state and the clocks
+            internal_clock += k;
+            if (k & 1ull) { cur_ ^= 1; if (lft_pp) lft_loc_ ^= 1; }
+            if (n_trains) { train_draws += k; for (auto &L : lats_) if (L.is_train) L.clock += k; }
+            first_step = false;
+            s0 += k;
+        }
+        for (uint64_t s = 0; !multi && s < steps; ++s) {
             if (dbg_timing && steps <= 32) { cudaEvent_t ev; cudaEventCreate(&ev); cudaEventRecord(ev, stream_); dbg_ev.push_back(ev); }
             const int in = cur_, out = cur_ ^ 1;
             sp.clock = (uint32_t)internal_clock;

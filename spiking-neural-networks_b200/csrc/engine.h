@@ -188,6 +188,7 @@ private:
     // halo
     unsigned long long *flags_ = nullptr;  // [0] arrivals from rank-1, [1] arrivals from rank+1
     unsigned int *halo_done_ = nullptr;
+    unsigned int *multi_barrier_ = nullptr;   // grid-wide arrival counter of the multi-step kernel
     HaloDir halo_dir_[2] = {};
     void *peer_slab_[2] = {nullptr, nullptr};
     void *peer_flags_[2] = {nullptr, nullptr};

@@ -161,7 +161,8 @@ struct GlobalSrc {
     __device__ __forceinline__ float v() const { return p.v_in[i]; }
     __device__ __forceinline__ int lft() const { return p.lft_in[i]; }
     __device__ __forceinline__ uint32_t flags() const { return p.node_flags[i]; }
-    __device__ __forceinline__ uint32_t spk_prev_word(uint32_t warp_global) const { return __ldg(p.spk_in + (p.own0 >> 5) + warp_global); }
+    // plain load: the multi-step kernel (step_multi.cu) reads words that an earlier step of the same launch wrote
+    __device__ __forceinline__ uint32_t spk_prev_word(uint32_t warp_global) const { return p.spk_in[(p.own0 >> 5) + warp_global]; }
     __device__ __forceinline__ float t_own(int ty) const { return p.t_in[(size_t)ty * p.t_stride + i]; }
     __device__ __forceinline__ float nt(int slot, int ty) const { return __ldg(p.nt[slot] + (size_t)ty * p.nt_stride + i); }
     __device__ __forceinline__ float rc(int slot, int ty) const { return __ldg(p.rc[slot] + (size_t)ty * p.rc_stride + lnc); }

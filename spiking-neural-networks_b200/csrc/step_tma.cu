@@ -61,6 +61,17 @@ struct SmemSrc {
 template <int MODEL, int CHEMG>
 constexpr int tma_min_ctas() { return (MODEL == SNN_MODEL_HODGKIN_HUXLEY || CHEMG == 3) ? 2 : 3; }
 
+// row strips: the tiles whose slices import ghosts / export boundary rows are stepped first (see win_tile_of, step_win.cu)
+__device__ __forceinline__ uint32_t tma_tile_of(const StepParams &p, uint32_t n_tiles, uint32_t seq) {
+    if (!(p.halo[0].active | p.halo[1].active)) return seq;
+    const uint32_t n_lo = p.halo[0].active ? (p.halo[0].count + kTmaTile - 1u) / kTmaTile : 0u;
+    const uint32_t n_hi = p.halo[1].active ? n_tiles - p.halo[1].first / kTmaTile : 0u;
+    if (n_lo + n_hi > n_tiles) return seq;
+    if (seq < n_lo) return seq;
+    if (seq < n_lo + n_hi) return n_tiles - 1u - (seq - n_lo);
+    return seq - n_hi;
+}
+
 template <int MODEL, int CHEMG, bool NTREL, bool STDP>
 __global__ void __launch_bounds__(kTmaThreads, tma_min_ctas<MODEL, CHEMG>()) step_tma_kernel(const __grid_constant__ StepParams p, const __grid_constant__ TmaParams tp) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -81,7 +92,8 @@ __global__ void __launch_bounds__(kTmaThreads, tma_min_ctas<MODEL, CHEMG>()) ste
         // ---- producer: one lane streams whole tiles ahead of the consumers ---------------------------
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
+            for (uint32_t seq = blockIdx.x; seq < tp.n_tiles; seq += gridDim.x) {
+                const uint32_t tile = tma_tile_of(p, tp.n_tiles, seq);
                 mbar_wait_backoff(&empty[s], ph ^ 1u);
                 mbar_arrive_expect_tx(&full[s], tp.tx_bytes);
                 unsigned char *dst = smem + (size_t)s * tp.stage_bytes;
@@ -95,7 +107,8 @@ __global__ void __launch_bounds__(kTmaThreads, tma_min_ctas<MODEL, CHEMG>()) ste
     }
     // ---- consumers: 8 warps x 32 neurons per tile --------------------------------------------------
     uint32_t s = 0, ph = 0;
-    for (uint32_t tile = blockIdx.x; tile < tp.n_tiles; tile += gridDim.x) {
+    for (uint32_t seq = blockIdx.x; seq < tp.n_tiles; seq += gridDim.x) {
+        const uint32_t tile = tma_tile_of(p, tp.n_tiles, seq);
         const uint32_t warp_global = tile * kTmaConsumerWarps + warp;
         const uint32_t ln = warp_global * 32u + lane;
         const bool active = warp_global * 32u < p.n_neurons;

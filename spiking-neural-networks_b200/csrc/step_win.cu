@@ -113,6 +113,18 @@ struct WinSrc {
     __device__ __forceinline__ float gt(Handle h, int ty) const { return lds_f32_rt(h + lay().o_twin + (uint32_t)ty * 3u * kWinRowBytes); }
 };
 
+// Order in which the CTAs take the tiles.  Whole lattices: ascending, or descending on odd timesteps (the tail of the arrays that
+// the previous step left in L2 is what this step reads first).  Row strips: the tiles that import ghosts / export boundary rows
+// go FIRST, so a strip's exports of step s leave at the start of step s and its neighbour — which needs them at the start of its
+// step s + 1 — finds them long arrived: the NVLink store / fence / flag latency (~10 us) is off the critical path of every step.
+__device__ __forceinline__ uint32_t win_tile_of(const StepParams &p, const WinParams &wp, uint32_t seq) {
+    const uint32_t nb = wp.first_lo + wp.first_hi;
+    if (seq < wp.first_lo) return seq;
+    if (seq < nb) return wp.n_tiles - 1u - (seq - wp.first_lo);
+    const uint32_t k = seq - nb, n_int = wp.n_tiles - nb;
+    return wp.first_lo + (p.reverse ? n_int - 1u - k : k);
+}
+
 #ifndef SNN_WIN_PRODUCERS
 #define SNN_WIN_PRODUCERS 4
 #endif
@@ -172,7 +184,7 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
         if (is_stream) my = wp.st[idx];
         uint32_t s = 0, ph = 0;
         for (uint32_t tile_seq = blockIdx.x; tile_seq < wp.n_tiles; tile_seq += gridDim.x) {
-            const uint32_t tile = p.reverse ? wp.n_tiles - 1u - tile_seq : tile_seq;
+            const uint32_t tile = win_tile_of(p, wp, tile_seq);
             mbar_wait_backoff(&empty[s], ph ^ 1u);   // the whole warp probes: no divergent lane-0 loop with 31 lanes parked at a reconvergence barrier
             const uint32_t ts = tile * kWinTile;   // first local neuron of the tile
             // multi-GPU: ghost rows are written by the neighbouring GPU over NVLink; they must have landed before TMA reads
@@ -233,7 +245,7 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
     const uint32_t smem_s = smem_u32(smem);
     uint32_t s = g % S, ph = (g / S) & 1u;
     for (uint32_t tile_seq = blockIdx.x + g * gridDim.x; tile_seq < wp.n_tiles; tile_seq += G * gridDim.x) {
-        const uint32_t tile = p.reverse ? wp.n_tiles - 1u - tile_seq : tile_seq;
+        const uint32_t tile = win_tile_of(p, wp, tile_seq);
         const uint32_t warp_global = tile * 8u + wg;
         const uint32_t ln = warp_global * 32u + lane;
         const bool active = warp_global * 32u < p.n_neurons;

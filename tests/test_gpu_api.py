@@ -360,3 +360,71 @@ def test_plasticity_variant_error_behaviour():
     # networks are out of scope this round (row-strip partitioned lattices are covered by tests/mgpu_parity.py --reward)
     net = CudaNetworkBackend(K.MODEL_IZH)
     assert not hasattr(net, "set_reward_modulator")
+
+
+@pytest.mark.parametrize("case", ["izh_grid_hist", "hh_chem", "lif_stdp_random", "net_rate_stdp", "net_preset_wide", "net_poisson"])
+def test_multi_step_launch_is_bit_identical_to_one_launch_per_step(case):
+    """SNN_OPT_STEPS_PER_GRAPH: 0 = the whole run inside one cooperative launch (step_multi.cu, grid-wide barrier between
+    timesteps), 1 = one launch per timestep, 7 = at most seven per launch.  Same arithmetic in the same order: every field, every
+    history record and every weight must be bit-identical, including odd step counts (ping-pong parity), several run calls
+    (pending STDP across launches) and networks whose spike trains step between the neurons of consecutive timesteps."""
+    import test_gpu_parity as TP
+
+    def build():
+        if case == "izh_grid_hist":
+            return SC.build_lattice(None, model="izh", rows=37, cols=41, seed=3, graph="grid"), None
+        if case == "hh_chem":
+            return SC.build_lattice(None, model="hh", rows=19, cols=23, seed=4, graph="grid2", chem="destexhe_all", gap=2.0), None
+        if case == "lif_stdp_random":
+            return SC.build_lattice(None, model="lif", rows=9, cols=12, seed=5, graph="random", stdp=True, gap=40.0), None
+        if case == "net_rate_stdp":
+            return None, TP.build_network(None, None, train="rate", stdp=True)
+        if case == "net_preset_wide":
+            return None, TP.build_network(None, None, train="preset", stdp=True, st_shape=(8, 9))
+        net = TP.build_network(None, None, train="poisson", stdp=True)
+        net._be.set_option(K.OPT_RNG_SEED, 77)
+        return None, net
+
+    results = []
+    for spg in (1, 0, 7):
+        lat, net = build()
+        be = (lat or net)._be
+        be.set_option(K.OPT_STEPS_PER_GRAPH, spg)
+        assert be.get_option(K.OPT_STEPS_PER_GRAPH) == spg
+        launches = 0
+        for k in (33, 1, 50):
+            if lat is not None:
+                lat._push_options()
+            else:
+                net.run_lattices(0)   # pushes the options
+            ms, nl = be.run_timed(k)
+            launches += nl
+        out = {"launches": launches}
+        if lat is not None:
+            for name in SC.lattice_field_names(lat):
+                out[name] = lat.get_field(name)
+            out["grid"], out["spikes"] = lat.grid_history.history, lat.spike_history.history
+            out["w"] = lat.graph_csr()[2]
+        else:
+            for lid in (1, 2):
+                L = net.get_lattice(lid)
+                for name in SC.lattice_field_names(L):
+                    out[f"{lid}/{name}"] = L.get_field(name)
+                out[f"{lid}/grid"], out[f"{lid}/spikes"] = L.grid_history.history, L.spike_history.history
+            st = net.get_spike_train_lattice(0)
+            out["st/spikes"] = st.spike_history.history
+            out["st/lft"] = st.get_field("last_firing_time")
+            for pre, post in TP.PAIRS:
+                out[f"w{pre}{post}"] = net._be.get_connection_dense(pre, post)[1]
+        results.append(out)
+    one, whole, seven = results
+    assert whole["launches"] < one["launches"] / 10, (whole["launches"], one["launches"])
+    assert whole["launches"] < seven["launches"] < one["launches"]
+    for key in one:
+        if key == "launches":
+            continue
+        for other, label in ((whole, "whole-run launch"), (seven, "7 steps per launch")):
+            a, b = np.asarray(one[key]), np.asarray(other[key])
+            assert a.shape == b.shape and (a.view(np.uint8) == b.view(np.uint8)).all() if a.dtype != bool else (a == b).all(), (key, label)
+    spikes = one["spikes"].sum() if "spikes" in one else one["1/spikes"].sum() + one["2/spikes"].sum()
+    assert spikes > 0

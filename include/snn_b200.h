@@ -338,6 +338,11 @@ SNN_API uint32_t snn_lattice_ipc_blob_size(void);
 SNN_API int32_t snn_lattice_ipc_export(snn_lattice_t *h, void *blob);
 /* attach the neighbouring strip: direction -1 = rank-1 (rows above), +1 = rank+1 (rows below) */
 SNN_API int32_t snn_lattice_ipc_attach(snn_lattice_t *h, int32_t direction, const void *blob);
+/* the same for a neighbouring strip whose handle lives in THIS process (same device, or a device with peer access): no CUDA IPC.
+ * Both handles attach each other; they are then stepped concurrently from separate host threads with the same iteration
+ * counts.  On a single device the strips must be small enough for their step kernels to be resident together (boundary warps
+ * spin on the neighbour's progress) — meant for tests and for one process driving several GPUs. */
+SNN_API int32_t snn_lattice_attach_local(snn_lattice_t *h, int32_t direction, snn_lattice_t *neighbour);
 
 /* ---------------------------------------------------------------- network
  * Replaces LatticeNetworkGPU (gpu_lattices/mod.rs:1560-1656) + RunNetwork (:3183-3212); semantics

@@ -347,6 +347,10 @@ int32_t snn_lattice_ipc_attach(snn_lattice_t *h, int32_t direction, const void *
     if (!h || !blob) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->ipc_attach(direction, (const snn::IpcBlob *)blob); SNN_CATCH(h)
 }
+int32_t snn_lattice_attach_local(snn_lattice_t *h, int32_t direction, snn_lattice_t *neighbour) {
+    if (!h || !neighbour) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->attach_local(direction, neighbour->e); SNN_CATCH(h)
+}
 
 // ---------------------------------------------------------------------------------------------- network
 int32_t snn_network_create(const snn_network_desc_t *desc, snn_network_t **out) {

@@ -20,6 +20,16 @@ namespace snn {
 
 static inline uint64_t round_up(uint64_t x, uint64_t m) { return (x + m - 1) / m * m; }
 
+// Host -> device copy that has LANDED when it returns.  A plain cudaMemcpy from pageable memory may return once the data sits in
+// the driver's staging buffer; the engine's kernels run on a non-blocking stream that does not wait for the legacy stream's DMA,
+// so a kernel launched right after could read an array whose tail has not arrived yet (seen as garbage in the last slices of a
+// rebuilt graph).  Copy on the engine's stream and wait for it.
+static cudaError_t h2d_sync(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(s);
+}
+
 template <class T>
 static cudaError_t dev_alloc(T **p, size_t n) {
     *p = nullptr;
@@ -81,10 +91,11 @@ int Engine::init() {
     CK(cudaEventCreate(&ev0_), SNN_GPU_QUEUE_FAILURE);
     CK(cudaEventCreate(&ev1_), SNN_GPU_QUEUE_FAILURE);
     CK(dev_alloc(&flags_, 4), SNN_GPU_BUFFER_CREATE_ERROR);   // [0],[1] step arrivals from rank-1 / rank+1, [2],[3] edge-kernel arrivals
-    CK(cudaMemset(flags_, 0, 4 * sizeof(unsigned long long)), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(cudaMemsetAsync(flags_, 0, 4 * sizeof(unsigned long long), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     CK(dev_alloc(&multi_barrier_, 1), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(dev_alloc(&halo_done_, 4), SNN_GPU_BUFFER_CREATE_ERROR);  // [0],[1] completion counters, [2] halo time-out flag, [3] per-edge kernel CTAs done
-    CK(cudaMemset(halo_done_, 0, 4 * sizeof(unsigned int)), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(cudaMemsetAsync(halo_done_, 0, 4 * sizeof(unsigned int), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
     return SNN_OK;
 }
 
@@ -222,7 +233,7 @@ int Engine::alloc_device() {
 
 int Engine::ensure_chem() {
     if (chem_alloc_) return SNN_OK;
-    if (peer_slab_[0] || peer_slab_[1]) return fail(SNN_UNSUPPORTED, "chemical fields must be set before the halo slab is exported");
+    if (peer_slab_[0] || peer_slab_[1] || layout_frozen_) return fail(SNN_UNSUPPORTED, "chemical fields must be set before the halo slab is exported");
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     // grow the slab to hold T[2]
     const size_t tb = round_up(node_cap_ * 4 * kNT, 256);
@@ -474,7 +485,8 @@ int Engine::field_io(Lat &L, const FieldDef &fd, void *data, uint64_t count, boo
         int r = plain(LFT_[lft_loc_] + no, n);
         if (r) return r;
         if (set && part_world > 1)  // keep both parities coherent for the halo protocol
-            CK(cudaMemcpy(LFT_[lft_loc_ ^ 1] + no, LFT_[lft_loc_] + no, n * 4, cudaMemcpyDeviceToDevice), wr);
+            CK(cudaMemcpyAsync(LFT_[lft_loc_ ^ 1] + no, LFT_[lft_loc_] + no, n * 4, cudaMemcpyDeviceToDevice, stream_), wr);
+            CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
         return SNN_OK;
     }
     case FK_SPIKING:
@@ -630,8 +642,8 @@ int Engine::set_preset_firing_times(uint64_t id, const uint64_t *offsets, const 
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     if (ft_) cudaFree(ft_);
     CK(dev_alloc(&ft_, all.size()), SNN_GPU_BUFFER_CREATE_ERROR);
-    CK(cudaMemcpy(ft_off_, off.data(), off.size() * 8, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
-    if (!all.empty()) CK(cudaMemcpy(ft_, all.data(), all.size() * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(h2d_sync(ft_off_, off.data(), off.size() * 8, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (!all.empty()) CK(h2d_sync(ft_, all.data(), all.size() * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     return SNN_OK;
 }
 
@@ -739,7 +751,7 @@ int Engine::connect_grid(uint64_t id, uint32_t radius, float weight) {
         if (need > A->n && A->n) return fail(SNN_UNSUPPORTED, "strip is thinner than the stencil radius");
         if (need != halo_) {
             // re-layout with a halo of `radius` rows (snapshot/restore through the field path)
-            if (peer_slab_[0] || peer_slab_[1]) return fail(SNN_UNSUPPORTED, "cannot change the stencil after the halo slab was exported");
+            if (peer_slab_[0] || peer_slab_[1] || layout_frozen_) return fail(SNN_UNSUPPORTED, "cannot change the stencil after the halo slab was exported");
             Lat copy = *A;
             std::vector<LatSnap> unused;
             // temporarily remove the lattice and add it back with the new halo
@@ -847,7 +859,7 @@ int Engine::finalize_graph() {
             if (part_rank > 0 && !ghost_flags_from_peer_[0]) h_node_flags_[own0_ - halo_ + g] = h_node_flags_[own0_ + (g % std::max<uint64_t>(n_neurons, 1))];
             if (part_rank < part_world - 1 && !ghost_flags_from_peer_[1]) h_node_flags_[ghost_hi0_ + g] = h_node_flags_[own0_ + n_neurons - halo_ + g];
         }
-        CK(cudaMemcpy(node_flags_, h_node_flags_.data(), node_cap_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(h2d_sync(node_flags_, h_node_flags_.data(), node_cap_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
         flags_cache_valid_ = false;
     }
     int n_neuron_lat = 0;
@@ -871,7 +883,7 @@ int Engine::finalize_graph() {
                 CK(cudaMemsetAsync(wgt_ + tail0, 0, tail_n * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
             }
         }
-        if (n_neurons == 0) CK(cudaMemset(slice_off_, 0, 4), SNN_GPU_BUFFER_WRITE_ERROR);
+        if (n_neurons == 0) CK(cudaMemsetAsync(slice_off_, 0, 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
         CK(launch_sell_grid(only->rows, only->cols, part_world > 1 ? row0_global : 0, part_world > 1 ? rows_global : only->rows,
                             b.radius, b.weight, own0_, node_flags_, width, slice_off_, col_, wgt_, stream_), SNN_GPU_QUEUE_FAILURE);
         CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
@@ -954,17 +966,17 @@ int Engine::finalize_graph() {
     if (stencil_width) {
         sell_alloc_krows_ = alloc_krows;
         if (alloc_krows > sell_krows_) {
-            CK(cudaMemset(col_ + sell_krows_ * 32, 0xFF, (alloc_krows - sell_krows_) * 32 * 4), SNN_GPU_BUFFER_WRITE_ERROR);
-            CK(cudaMemset(wgt_ + sell_krows_ * 32, 0, (alloc_krows - sell_krows_) * 32 * 4), SNN_GPU_BUFFER_WRITE_ERROR);
+            CK(cudaMemsetAsync(col_ + sell_krows_ * 32, 0xFF, (alloc_krows - sell_krows_) * 32 * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+            CK(cudaMemsetAsync(wgt_ + sell_krows_ * 32, 0, (alloc_krows - sell_krows_) * 32 * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
         }
     }
-    CK(cudaMemcpy(slice_off_, slice_off.data(), ((size_t)n_slices_ + 1) * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(h2d_sync(slice_off_, slice_off.data(), ((size_t)n_slices_ + 1) * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     uint64_t *d_rp = nullptr; uint32_t *d_pre = nullptr; float *d_w = nullptr;
     CK(dev_alloc(&d_rp, n_neurons + 1), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(dev_alloc(&d_pre, nnz), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(dev_alloc(&d_w, nnz), SNN_GPU_BUFFER_CREATE_ERROR);
-    cudaMemcpy(d_rp, row_ptr.data(), (n_neurons + 1) * 8, cudaMemcpyHostToDevice);
-    if (nnz) { cudaMemcpy(d_pre, pre.data(), nnz * 4, cudaMemcpyHostToDevice); cudaMemcpy(d_w, w.data(), nnz * 4, cudaMemcpyHostToDevice); }
+    h2d_sync(d_rp, row_ptr.data(), (n_neurons + 1) * 8, stream_);
+    if (nnz) { h2d_sync(d_pre, pre.data(), nnz * 4, stream_); h2d_sync(d_w, w.data(), nnz * 4, stream_); }
     cudaError_t e = launch_sell_from_csr(d_rp, d_pre, d_w, node_flags_, part_world > 1 ? 0xFFFFFFFFu : train0_, (uint32_t)n_neurons,
                                          slice_off_, col_, wgt_, stream_);
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
@@ -1099,10 +1111,10 @@ int Engine::set_connection_traces(const float *weight, const uint32_t *counter, 
         }
     }
     const uint64_t wel = std::max(sell_alloc_krows_, sell_krows_) * 32;
-    if (weight) CK(cudaMemcpy(wgt_, hw.data(), wel * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
-    if (counter) CK(cudaMemcpy(rs_counter_, hc.data(), rs_elems_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
-    if (dw) CK(cudaMemcpy(rs_dw_, hd.data(), rs_elems_ * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
-    if (c) CK(cudaMemcpy(rs_c_, hcc.data(), rs_elems_ * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (weight) CK(h2d_sync(wgt_, hw.data(), wel * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (counter) CK(h2d_sync(rs_counter_, hc.data(), rs_elems_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (dw) CK(h2d_sync(rs_dw_, hd.data(), rs_elems_ * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    if (c) CK(h2d_sync(rs_c_, hcc.data(), rs_elems_ * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     if (weight && it->second.kind == Block::GRID) dev_weights_newer_ = true;   // a stencil block's weights live on the device
     return SNN_OK;
 }
@@ -1314,7 +1326,7 @@ int Engine::edit_weight(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_
     if (node >= 0 && node < (int64_t)n_nodes_) { r = find_edge(B->off + post, (uint32_t)node, &e); if (r) return r; }
     if (e >= 0 && has) {
         // Some(w) over Some(_): the adjacency is unchanged, one word on the device
-        CK(cudaMemcpy(wgt_ + e, &weight, 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(h2d_sync(wgt_ + e, &weight, 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
         dev_weights_newer_ = true;
         return SNN_OK;
     }
@@ -1359,7 +1371,7 @@ int Engine::set_dt(float dt) {
             if (train_kind == SNN_TRAIN_POISSON) {
                 CK(cudaMemcpy(ch.data(), TF_[TF_CHANCE] + L.off, L.n * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
                 for (uint64_t i = 0; i < L.n; ++i) { const float scalar = dt / old[i]; ch[i] *= scalar; }
-                CK(cudaMemcpy(TF_[TF_CHANCE] + L.off, ch.data(), L.n * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+                CK(h2d_sync(TF_[TF_CHANCE] + L.off, ch.data(), L.n * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
             }
             CK(fill_f32(TF_[TF_DT] + L.off, dt, L.n, stream_), SNN_GPU_QUEUE_FAILURE);
         } else {
@@ -1767,7 +1779,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         }
         CK(dev_alloc(&d_red, chunk * nl * 2), SNN_GPU_BUFFER_CREATE_ERROR);
         CK(dev_alloc(&d_red_lat, 3 * nl), SNN_GPU_BUFFER_CREATE_ERROR);
-        CK(cudaMemcpy(d_red_lat, meta.data(), meta.size() * 4, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+        CK(h2d_sync(d_red_lat, meta.data(), meta.size() * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     }
     auto free_hist = [&]() { cudaFree(d_grid); cudaFree(d_spk); cudaFree(d_tgrid); cudaFree(d_tspk); cudaFree(d_red); cudaFree(d_red_lat); };
 
@@ -1831,7 +1843,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         static const bool dbg_timing = getenv("SNN_DEBUG_TIMING") != nullptr;
         std::vector<cudaEvent_t> dbg_ev;
         unsigned long long *dbg_clk = nullptr;
-        if (dbg_timing && steps <= 32) { cudaMalloc(&dbg_clk, 32 * 4 * sizeof(unsigned long long)); cudaMemset(dbg_clk, 0, 32 * 4 * sizeof(unsigned long long)); }
+        if (dbg_timing && steps <= 32) { cudaMalloc(&dbg_clk, 32 * 4 * sizeof(unsigned long long)); cudaMemsetAsync(dbg_clk, 0, 32 * 4 * sizeof(unsigned long long), stream_); }
         for (uint64_t s0 = 0; multi && s0 < steps;) {
             const uint64_t k = steps_per_graph ? std::min<uint64_t>(steps_per_graph, steps - s0) : steps - s0;
             sp.clock = (uint32_t)internal_clock;
@@ -2067,7 +2079,8 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         unsigned int err = 0;
         CK(cudaMemcpy(&err, halo_done_ + 2, 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
         if (err) {
-            cudaMemset(halo_done_, 0, 4 * sizeof(unsigned int));
+            cudaMemsetAsync(halo_done_, 0, 4 * sizeof(unsigned int), stream_);
+            cudaStreamSynchronize(stream_);
             return fail(SNN_GPU_WAIT_ERROR, "timed out waiting for a neighbouring strip's halo (is every rank running the same number of steps?)");
         }
     }
@@ -2088,12 +2101,19 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
 // multi-GPU halo plumbing (CUDA IPC; the caller moves the blobs between ranks)
 // ------------------------------------------------------------------------------------------------
 int Engine::ipc_export(IpcBlob *blob) {
-    if (part_world <= 1) return fail(SNN_INVALID_ARGUMENT, "handle is not partitioned");
+    int r = ipc_export_layout(blob);
+    if (r) return r;
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
-    memset(blob, 0, sizeof *blob);
-    blob->magic = 0x534E4E42u; blob->version = SNN_B200_ABI_VERSION;
     CK(cudaIpcGetMemHandle(&blob->slab, slab_), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(cudaIpcGetMemHandle(&blob->flags, flags_), SNN_GPU_BUFFER_CREATE_ERROR);
+    layout_frozen_ = true;   // a neighbour will hold pointers into the slab
+    return SNN_OK;
+}
+
+int Engine::ipc_export_layout(IpcBlob *blob) {
+    if (part_world <= 1) return fail(SNN_INVALID_ARGUMENT, "handle is not partitioned");
+    memset(blob, 0, sizeof *blob);
+    blob->magic = 0x534E4E42u; blob->version = SNN_B200_ABI_VERSION;
     for (int k = 0; k < 2; ++k) { blob->off_v[k] = slab_off_v_[k]; blob->off_lft[k] = slab_off_lft_[k]; blob->off_t[k] = slab_off_t_[k]; }
     blob->off_flags = slab_off_flags_;
     blob->t_stride = node_cap_;
@@ -2107,14 +2127,53 @@ int Engine::ipc_attach(int direction, const IpcBlob *blob) {
     if (part_world <= 1) return fail(SNN_INVALID_ARGUMENT, "handle is not partitioned");
     if (direction != -1 && direction != 1) return fail(SNN_INVALID_ARGUMENT, "direction must be -1 or +1");
     if (blob->magic != 0x534E4E42u || blob->version != SNN_B200_ABI_VERSION) return fail(SNN_INVALID_ARGUMENT, "bad ipc blob");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    const int d = direction < 0 ? 0 : 1;
+    if (peer_slab_[d] || halo_dir_[d].active) return fail(SNN_INVALID_ARGUMENT, "direction already attached");
+    void *slab = nullptr, *flags = nullptr;
+    CK(cudaIpcOpenMemHandle(&slab, blob->slab, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaIpcOpenMemHandle(&flags, blob->flags, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
+    peer_slab_[d] = slab; peer_flags_[d] = flags;
+    int r = attach_view(direction, blob, slab, flags);
+    if (r) {
+        cudaIpcCloseMemHandle(slab); cudaIpcCloseMemHandle(flags);
+        peer_slab_[d] = peer_flags_[d] = nullptr;
+    }
+    return r;
+}
+
+// The neighbouring strip lives in THIS process (another handle on the same device, or on a device with peer access): no CUDA
+// IPC, the neighbour's slab and arrival counters are addressed directly.  Both handles must attach each other.  On one device
+// the caller steps the handles from separate host threads and keeps the strips small enough for their step kernels to be
+// resident together (a strip's boundary warps spin on the neighbour's progress).
+int Engine::attach_local(int direction, Engine *peer) {
+    if (part_world <= 1) return fail(SNN_INVALID_ARGUMENT, "handle is not partitioned");
+    if (direction != -1 && direction != 1) return fail(SNN_INVALID_ARGUMENT, "direction must be -1 or +1");
+    if (!peer || peer == this) return fail(SNN_INVALID_ARGUMENT, "bad neighbour handle");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    const int d = direction < 0 ? 0 : 1;
+    if (peer_slab_[d] || halo_dir_[d].active) return fail(SNN_INVALID_ARGUMENT, "direction already attached");
+    if (peer->device != device) {
+        int can = 0;
+        CK(cudaDeviceCanAccessPeer(&can, device, peer->device), SNN_GPU_GET_DEVICE_FAILURE);
+        if (!can) return fail(SNN_UNSUPPORTED, "no peer access between the two devices");
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, SNN_GPU_GET_DEVICE_FAILURE, "cudaDeviceEnablePeerAccess");
+        cudaGetLastError();
+    }
+    IpcBlob blob;
+    int r = peer->ipc_export_layout(&blob);
+    if (r) return fail(r, peer->last_error);
+    r = attach_view(direction, &blob, peer->slab_, peer->flags_);
+    if (!r) peer->layout_frozen_ = layout_frozen_ = true;   // raw pointers into each other's slabs from now on
+    return r;
+}
+
+int Engine::attach_view(int direction, const IpcBlob *blob, void *slab, void *flags) {
     if (blob->rank != part_rank + direction || blob->world != part_world) return fail(SNN_INVALID_ARGUMENT, "ipc blob is not from the neighbouring rank");
     if (blob->halo != halo_ || (blob->chem != 0) != chem_alloc_) return fail(SNN_INVALID_ARGUMENT, "neighbouring strips disagree on halo width / chemistry");
     if (halo_ > n_neurons || halo_ > blob->n_neurons) return fail(SNN_UNSUPPORTED, "strip thinner than the halo");
-    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     const int d = direction < 0 ? 0 : 1;
-    if (peer_slab_[d]) return fail(SNN_INVALID_ARGUMENT, "direction already attached");
-    CK(cudaIpcOpenMemHandle(&peer_slab_[d], blob->slab, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
-    CK(cudaIpcOpenMemHandle(&peer_flags_[d], blob->flags, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
     HaloDir &H = halo_dir_[d];
     memset(&H, 0, sizeof H);
     H.count = halo_;
@@ -2124,13 +2183,13 @@ int Engine::ipc_attach(int direction, const IpcBlob *blob) {
     H.peer_node0 = d == 0 ? blob->ghost_hi0 : blob->own0 - blob->halo;
     H.my_ghost0 = d == 0 ? own0_ - halo_ : ghost_hi0_;
     for (int k = 0; k < 2; ++k) {
-        H.peer_v[k] = (float *)((char *)peer_slab_[d] + blob->off_v[k]);
-        H.peer_lft[k] = (int *)((char *)peer_slab_[d] + blob->off_lft[k]);
-        H.peer_t[k] = (float *)((char *)peer_slab_[d] + blob->off_t[k]);
+        H.peer_v[k] = (float *)((char *)slab + blob->off_v[k]);
+        H.peer_lft[k] = (int *)((char *)slab + blob->off_lft[k]);
+        H.peer_t[k] = (float *)((char *)slab + blob->off_t[k]);
     }
     H.peer_t_stride = blob->t_stride;
     // the neighbour's arrival counter for data coming from me: I am its rank+1 when d == 0 (slot 1), its rank-1 when d == 1 (slot 0)
-    H.peer_flag = (unsigned long long *)peer_flags_[d] + (d == 0 ? 1 : 0);
+    H.peer_flag = (unsigned long long *)flags + (d == 0 ? 1 : 0);
     H.my_flag = flags_ + d;
     H.peer_flag2 = H.peer_flag + 2;
     H.my_flag2 = H.my_flag + 2;
@@ -2138,14 +2197,14 @@ int Engine::ipc_attach(int direction, const IpcBlob *blob) {
     // my ghost rows take the neurotransmitter / receptor type flags of the neighbour's boundary rows (they are baked into the
     // col words of edges from ghosts): d == 0 reads the LAST halo_ neurons of rank - 1, d == 1 the FIRST halo_ of rank + 1
     {
-        const uint8_t *peer_f = (const uint8_t *)peer_slab_[d] + blob->off_flags + (d == 0 ? blob->own0 + blob->n_neurons - halo_ : blob->own0);
+        const uint8_t *peer_f = (const uint8_t *)slab + blob->off_flags + (d == 0 ? blob->own0 + blob->n_neurons - halo_ : blob->own0);
         std::vector<uint8_t> tmp(halo_);
         CK(cudaMemcpy(tmp.data(), peer_f, halo_, cudaMemcpyDefault), SNN_GPU_BUFFER_READ_ERROR);
         bool changed = !ghost_flags_from_peer_[d];
         for (uint32_t g = 0; g < halo_; ++g) { changed |= h_node_flags_[H.my_ghost0 + g] != tmp[g]; h_node_flags_[H.my_ghost0 + g] = tmp[g]; }
         ghost_flags_from_peer_[d] = true;
         if (changed) {
-            CK(cudaMemcpy(node_flags_ + H.my_ghost0, tmp.data(), halo_, cudaMemcpyHostToDevice), SNN_GPU_BUFFER_WRITE_ERROR);
+            CK(h2d_sync(node_flags_ + H.my_ghost0, tmp.data(), halo_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
             flags_cache_valid_ = false;
             if (dev_weights_newer_) { int r = sync_weights_to_host(); if (r) return r; }
             graph_dirty_ = true;

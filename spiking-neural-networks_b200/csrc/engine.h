@@ -125,6 +125,7 @@ public:
     // multi-GPU
     int ipc_export(IpcBlob *blob);
     int ipc_attach(int direction, const IpcBlob *blob);
+    int attach_local(int direction, Engine *peer);   // neighbour handle in the same process (no CUDA IPC)
 
     // public knobs (Lattice / LatticeNetwork pub fields, neuron/mod.rs:556-587, 1554-1563)
     bool electrical = true, chemical = false, parallel = false;
@@ -196,6 +197,9 @@ private:
     // scratch
     void *scratch_ = nullptr; size_t scratch_bytes_ = 0;
 
+    int ipc_export_layout(IpcBlob *blob);
+    int attach_view(int direction, const IpcBlob *blob, void *slab, void *flags);
+    bool layout_frozen_ = false;
     int cuda_fail(cudaError_t e, int status, const char *what);
     int ensure_scratch(size_t bytes);
     void free_device();

@@ -132,6 +132,7 @@ SIGNATURES = {
     "snn_lattice_ipc_blob_size": ([], _u32),
     "snn_lattice_ipc_export": ([_P, _P], _i32),
     "snn_lattice_ipc_attach": ([_P, _i32, _P], _i32),
+    "snn_lattice_attach_local": ([_P, _i32, _P], _i32),
     "snn_network_create": ([C.POINTER(NetworkDesc), _pp], _i32),
     "snn_network_destroy": ([_P], _i32),
     "snn_network_add_lattice": ([_P, _u64, _u32, _u32], _i32),

@@ -283,6 +283,11 @@ class CudaLatticeBackend(_CudaBase):
         self._ck(self.lib.snn_lattice_ipc_attach(self.h, direction, buf))
 
 
+    def attach_local(self, direction: int, neighbour: "CudaLatticeBackend"):
+        """Attach a neighbouring strip that lives in this process (no CUDA IPC); call on both handles."""
+        self._ck(self.lib.snn_lattice_attach_local(self.h, direction, neighbour.h))
+
+
 class CudaNetworkBackend(_CudaBase):
     """snn_network_t: the LatticeNetworkGPU replacement (reference: gpu_lattices/mod.rs:1560-1656)."""
     network = True

@@ -49,3 +49,67 @@ class StripLattice:
         if hi is not None:
             self.be.ipc_attach(+1, hi)
         dist.barrier(group=group)
+
+
+class LocalStrips:
+    """The same row-strip partition with every strip in THIS process (snn_lattice_attach_local): strips on one device, or one
+    process driving several GPUs.  `run` steps all strips concurrently from one host thread each (a strip's boundary warps wait
+    for its neighbours' progress on the device, so the calls must overlap)."""
+
+    def __init__(self, model, rows, cols, world, ntk=K.NT_APPROXIMATE, rck=K.RC_APPROXIMATE, devices=None):
+        self.rows, self.cols, self.world = rows, cols, world
+        self.bounds = [partition_rows(rows, world, r)[0] for r in range(world)] + [rows]
+        devices = devices or [-1] * world
+        self.strips = [CudaLatticeBackend(model, ntk, rck, rows, cols, device=devices[r], rank=r, world=world) for r in range(world)]
+
+    def rows_of(self, r):
+        return slice(self.bounds[r] * self.cols, self.bounds[r + 1] * self.cols)
+
+    def set_field(self, name, arr, per=1):
+        import numpy as np
+        a = np.asarray(arr).reshape(self.rows * self.cols, per)
+        for r, be in enumerate(self.strips):
+            be.set_field(0, name, a[self.rows_of(r)].reshape(-1))
+
+    def get_field(self, name):
+        import numpy as np
+        return np.concatenate([be.get_field(0, name) for be in self.strips])
+
+    def each(self, fn):
+        for be in self.strips:
+            fn(be)
+
+    def attach(self):
+        for r, be in enumerate(self.strips):
+            if r > 0:
+                be.attach_local(-1, self.strips[r - 1])
+            if r < self.world - 1:
+                be.attach_local(+1, self.strips[r + 1])
+
+    def run(self, iterations, rewards=None):
+        import threading
+        errs = []
+
+        def work(be):
+            try:
+                be.run(iterations) if rewards is None else be.run_with_rewards(rewards)
+            except Exception as exc:  # noqa: BLE001
+                errs.append(exc)
+        ts = [threading.Thread(target=work, args=(be,)) for be in self.strips]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def graph_csr(self):
+        """Whole-lattice CSR (global presynaptic indices) assembled from the strips."""
+        import numpy as np
+        rps, pres, ws, base = [np.zeros(1, np.uint64)], [], [], 0
+        for be in self.strips:
+            rp, pre, w = be.get_connection_csr()
+            rps.append(rp[1:] + base)
+            pres.append(pre); ws.append(w)
+            base += int(rp[-1])
+        return np.concatenate(rps), np.concatenate(pres), np.concatenate(ws)

@@ -250,6 +250,7 @@ struct WinParams {
     uint32_t cols;
     uint32_t lft_copy;            // copy last_firing_time windows at all (STDP or ping-ponged lft)
     uint32_t first_lo, first_hi;  // row strips: this many tiles at the front / back of the strip touch a halo and are stepped first
+    uint32_t bnd_lo, bnd_hi;      // tiles at the front / back that import ghosts or export boundary rows (0, 0 on whole lattices)
     TmaStream st[kMaxTmaStreams]; // per-tile contiguous operands (src + tile * bytes_per_tile)
     uint32_t o_nt[NTF_COUNT][kNT];   // run-time part of the stage layout: per-type chemical parameters
     uint32_t o_rc[RCF_COUNT][kNT];

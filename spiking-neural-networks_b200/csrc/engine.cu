@@ -93,8 +93,8 @@ int Engine::init() {
     CK(dev_alloc(&flags_, 4), SNN_GPU_BUFFER_CREATE_ERROR);   // [0],[1] step arrivals from rank-1 / rank+1, [2],[3] edge-kernel arrivals
     CK(cudaMemsetAsync(flags_, 0, 4 * sizeof(unsigned long long), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     CK(dev_alloc(&multi_barrier_, 1), SNN_GPU_BUFFER_CREATE_ERROR);
-    CK(dev_alloc(&halo_done_, 4), SNN_GPU_BUFFER_CREATE_ERROR);  // [0],[1] completion counters, [2] halo time-out flag, [3] per-edge kernel CTAs done
-    CK(cudaMemsetAsync(halo_done_, 0, 4 * sizeof(unsigned int), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(dev_alloc(&halo_done_, 8), SNN_GPU_BUFFER_CREATE_ERROR);  // [4] ns / 16 spent in halo waits, [5] waits that spun (diagnostics); [0],[1] completion counters, [2] halo time-out flag, [3] per-edge kernel CTAs done
+    CK(cudaMemsetAsync(halo_done_, 0, 8 * sizeof(unsigned int), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
     return SNN_OK;
 }
@@ -1648,13 +1648,14 @@ bool Engine::build_win_params(WinParams &wp, int chemg, bool ntrel, bool stdp, b
     wp.cols = cols;
     wp.lft_copy = (stdp || lft_pp) ? 1u : 0u;
     // tiles whose windows reach ghost rows (they are also the ones that export): same predicates as the producer's waits
-    wp.first_lo = wp.first_hi = 0;
+    wp.first_lo = wp.first_hi = wp.bnd_lo = wp.bnd_hi = 0;
     if (part_world > 1) {
         for (uint32_t t = 0; t < wp.n_tiles; ++t) {
             const uint64_t ts = (uint64_t)t * kWinTile;
             if (halo_dir_[0].active && ts <= cols) wp.first_lo++;
             if (halo_dir_[1].active && ts + kWinTile + 1u + cols > n_neurons) wp.first_hi++;
         }
+        wp.bnd_lo = wp.first_lo; wp.bnd_hi = wp.first_hi;
         if (wp.first_lo + wp.first_hi > wp.n_tiles) wp.first_lo = wp.first_hi = 0;   // a strip of a few rows: every tile is a boundary tile
         if (const char *e = getenv("SNN_B200_BOUNDARY_FIRST")) if (atoi(e) == 0) wp.first_lo = wp.first_hi = 0;
     }
@@ -1821,6 +1822,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         }
     }
 
+    static const bool halo_nowait = getenv("SNN_B200_HALO_NOWAIT") != nullptr;
     static const bool win_reverse = !(getenv("SNN_B200_WIN_REVERSE") && atoi(getenv("SNN_B200_WIN_REVERSE")) == 0);
     // small lattices / networks (everything the staged kernels do not take): a whole chunk of timesteps per cooperative launch
     // (step_multi.cu).  SNN_OPT_STEPS_PER_GRAPH: 0 = as many as the history chunk holds, 1 = one launch per timestep, k = at most k.
@@ -1892,7 +1894,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             sp.grid_hist = want_grid ? d_grid + s * n_neurons : nullptr;
             sp.spike_hist = want_spk ? d_spk + s * n_words : nullptr;
             sp.out_par = (uint32_t)out;
-            sp.halo_epoch = halo_epoch_;
+            sp.halo_epoch = halo_nowait ? 0ull : halo_epoch_;   // timing experiment only (SNN_B200_HALO_NOWAIT): results are wrong
             if (n_neurons && win_ok) {
                 cudaError_t e = launch_step_win(sp, win, model, chemg, ntrel, stdp, win_grid, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_win"); break; }
@@ -2076,6 +2078,14 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     free_hist();
     if (status != SNN_OK) return status;
     if (part_world > 1) {
+        if (getenv("SNN_DEBUG_HALO")) {
+            unsigned int d[8];
+            cudaMemcpy(d, halo_done_, sizeof d, cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[snn rank %d] %llu steps: %u halo waits spun, %.1f us waited in total (%.2f us per step)\n", part_rank,
+                    (unsigned long long)iterations, d[5], d[4] * 16e-3, d[4] * 16e-3 / (double)iterations);
+            cudaMemsetAsync(halo_done_ + 4, 0, 8, stream_);
+            cudaStreamSynchronize(stream_);
+        }
         unsigned int err = 0;
         CK(cudaMemcpy(&err, halo_done_ + 2, 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
         if (err) {

@@ -131,6 +131,9 @@ __device__ __forceinline__ bool halo_wait(const unsigned long long *flag, unsign
         __nanosleep(64);
         if (global_timer_ns() - t0 > timeout_ns || *(volatile unsigned int *)err) { atomicExch(err, 1u); return false; }
     }
+    // diagnostics (err[2], err[3] = halo_done[4], [5]): time spent waiting for neighbours and the number of waits that had to spin
+    atomicAdd(err + 2, (unsigned int)((global_timer_ns() - t0) >> 4));
+    atomicAdd(err + 3, 1u);
     return true;
 }
 // a halo wait of this run has timed out: the ghosts are stale, stop stepping (uniform over the grid once the flag is visible)
@@ -706,7 +709,10 @@ template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET, class SRC>
 __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src, uint32_t warp_global, uint32_t lane,
                                             uint32_t ln, uint32_t lnc, bool valid, bool export_lo, bool export_hi) {
     const uint32_t i = p.own0 + lnc;
-    const bool part = (p.halo[0].active | p.halo[1].active) != 0;   // partitioned handle (uniform)
+    // row strips: does any lane of this warp export to a neighbour (warp-uniform)?  Interior warps — all but a few dozen of a
+    // strip's tiles — skip every export test: the window kernel is co-limited by its instruction stream, and ~35 extra
+    // instructions per warp and tile on the common path cost 5 % of the step (measured on 2 GPUs, tools/diag_halo.py)
+    const bool part = __any_sync(0xffffffffu, export_lo | export_hi);
     // ---- own state and parameters ------------------------------------------------------------------
     float v = src.v();
     const float gap = src.template f<F_GAP>();

@@ -252,7 +252,9 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
         const bool valid = ln < p.n_neurons;
         const uint32_t lnc = valid ? ln : p.n_neurons - 1;
         bool export_lo = false, export_hi = false;
-        halo_export_flags(p, ln, valid, export_lo, export_hi);
+        // only the few tiles at the two ends of a strip touch a halo (CTA-uniform test): everything else runs the plain step
+        const bool boundary = tile < wp.bnd_lo || tile + wp.bnd_hi >= wp.n_tiles;
+        if (boundary) halo_export_flags(p, ln, valid, export_lo, export_hi);
         // A group returns to a stage only every lcm(S, G) / S rounds, and a parity wait cannot tell "round k landed" from
         // "round k - 1 is still landing" (two phases apart).  Bulk copies of different stages complete out of order, so
         // first make sure that round k - 1 of this stage has been consumed (the empty barrier; a producer that issued this
@@ -276,7 +278,7 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
-        if (active) halo_publish(p, warp_global, lane);
+        if (boundary && active) halo_publish(p, warp_global, lane);
         s += G;
         if (s >= S) { s -= S; ph ^= 1u; }
     }

@@ -152,6 +152,9 @@ typedef enum snn_option {
                                          barrier between timesteps, 1 = one launch per timestep, k = at most k.  Results are
                                          bit-identical for every value. */
     SNN_OPT_UPDATE_EEG_HISTORY = 10,  /* default 0 (per lattice): EEGHistory, neuron/mod.rs:231-284 */
+    SNN_OPT_GENERAL_PARTITION = 12,   /* partitioned handles: the next snn_lattice_set_graph_csr builds gather-list ghosts (general-graph
+                                         partition) even if this rank's edges happen to stay inside the strip halo — set it on EVERY
+                                         rank when any rank's graph reaches further (the mode must be the same on all ranks) */
     SNN_OPT_HALO_TIMEOUT_MS = 11      /* partitioned handles: bound of one in-kernel wait for a neighbouring strip (default 30000);
                                          run() first meets the neighbours on the host (4x this bound) before any step is enqueued */
 } snn_option_t;
@@ -343,6 +346,23 @@ SNN_API int32_t snn_lattice_ipc_attach(snn_lattice_t *h, int32_t direction, cons
  * counts.  On a single device the strips must be small enough for their step kernels to be resident together (boundary warps
  * spin on the neighbour's progress) — meant for tests and for one process driving several GPUs. */
 SNN_API int32_t snn_lattice_attach_local(snn_lattice_t *h, int32_t direction, snn_lattice_t *neighbour);
+
+/* ---- multi-GPU, general graphs: the same contiguous node ranges (whole rows) per rank, but in-edges from ANY node of
+ * any rank.  snn_lattice_set_graph_csr with global presynaptic indices switches a partitioned handle to this mode as soon as an
+ * edge reaches beyond the strip's halo rows: the ghosts then are gather lists of exactly the remote nodes the rank's rows read.
+ * Set-up, per pair of ranks (the caller moves the lists and blobs, e.g. torch.distributed.all_gather_object):
+ *   1. r: gpart_wants(q, idx, cap, &n, &slot)   the nodes of q that r reads (ascending global indices) and the node slot in r's
+ *                                               arrays where the first of them lives
+ *   2. q: gpart_set_exports(r, idx, n, slot)    q will write those nodes into r's slots after every step
+ *   3. both: gpart_attach(peer, blob of snn_lattice_ipc_export) or gpart_attach_local(peer, handle in this process)
+ * Every step a rank waits, where a slice reads ghosts or exports, until all its peers have completed the previous step, and
+ * raises its own completion counter at every peer when its last warp is done: ranks are never more than one step apart. */
+SNN_API int32_t snn_lattice_gpart_wants(snn_lattice_t *h, int32_t peer, uint32_t *global_idx, uint64_t capacity, uint64_t *n,
+                                        uint32_t *first_slot);
+SNN_API int32_t snn_lattice_gpart_set_exports(snn_lattice_t *h, int32_t peer, const uint32_t *global_idx, uint64_t n,
+                                              uint32_t first_slot_at_peer);
+SNN_API int32_t snn_lattice_gpart_attach(snn_lattice_t *h, int32_t peer, const void *blob);
+SNN_API int32_t snn_lattice_gpart_attach_local(snn_lattice_t *h, int32_t peer, snn_lattice_t *peer_handle);
 
 /* ---------------------------------------------------------------- network
  * Replaces LatticeNetworkGPU (gpu_lattices/mod.rs:1560-1656) + RunNetwork (:3183-3212); semantics

@@ -212,6 +212,7 @@ static int32_t engine_set_option(Engine *e, bool have_id, uint64_t id, int32_t o
     case SNN_OPT_PARALLEL: e->parallel = value != 0; return SNN_OK;
     case SNN_OPT_RNG_SEED: e->seed = (uint64_t)value; return SNN_OK;
     case SNN_OPT_STEPS_PER_GRAPH: e->steps_per_graph = (uint32_t)value; return SNN_OK;
+    case SNN_OPT_GENERAL_PARTITION: e->force_gpart = value != 0; return SNN_OK;
     case SNN_OPT_HALO_TIMEOUT_MS:
         if (value <= 0) return e->fail(SNN_INVALID_ARGUMENT, "halo time-out must be positive");
         e->halo_timeout_ms = (uint64_t)value; return SNN_OK;
@@ -238,6 +239,7 @@ static int32_t engine_get_option(const Engine *e, bool have_id, uint64_t id, int
     case SNN_OPT_RNG_SEED: *value = (int64_t)e->seed; return SNN_OK;
     case SNN_OPT_STEPS_PER_GRAPH: *value = e->steps_per_graph; return SNN_OK;
     case SNN_OPT_HALO_TIMEOUT_MS: *value = (int64_t)e->halo_timeout_ms; return SNN_OK;
+    case SNN_OPT_GENERAL_PARTITION: *value = e->force_gpart || e->is_gpart(); return SNN_OK;
     case SNN_OPT_INTERNAL_CLOCK: *value = (int64_t)((L && L->is_train) ? L->clock : e->internal_clock); return SNN_OK;
     case SNN_OPT_DO_PLASTICITY: if (!L) break; *value = L->do_plasticity; return SNN_OK;
     case SNN_OPT_UPDATE_GRID_HISTORY: if (!L) break; *value = L->grid_hist; return SNN_OK;
@@ -350,6 +352,22 @@ int32_t snn_lattice_ipc_attach(snn_lattice_t *h, int32_t direction, const void *
 int32_t snn_lattice_attach_local(snn_lattice_t *h, int32_t direction, snn_lattice_t *neighbour) {
     if (!h || !neighbour) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->attach_local(direction, neighbour->e); SNN_CATCH(h)
+}
+int32_t snn_lattice_gpart_wants(snn_lattice_t *h, int32_t peer, uint32_t *global_idx, uint64_t capacity, uint64_t *n, uint32_t *first_slot) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->gpart_wants(peer, global_idx, capacity, n, first_slot); SNN_CATCH(h)
+}
+int32_t snn_lattice_gpart_set_exports(snn_lattice_t *h, int32_t peer, const uint32_t *global_idx, uint64_t n, uint32_t first_slot_at_peer) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->gpart_set_exports(peer, global_idx, n, first_slot_at_peer); SNN_CATCH(h)
+}
+int32_t snn_lattice_gpart_attach(snn_lattice_t *h, int32_t peer, const void *blob) {
+    if (!h || !blob) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->gpart_attach(peer, (const snn::IpcBlob *)blob, nullptr); SNN_CATCH(h)
+}
+int32_t snn_lattice_gpart_attach_local(snn_lattice_t *h, int32_t peer, snn_lattice_t *peer_handle) {
+    if (!h || !peer_handle) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->gpart_attach(peer, nullptr, peer_handle->e); SNN_CATCH(h)
 }
 
 // ---------------------------------------------------------------------------------------------- network

@@ -68,6 +68,15 @@ struct HaloDir {
     uint32_t active;
 };
 
+// general-graph partition (contiguous node ranges, arbitrary in-edges): one entry per rank this rank exchanges with
+constexpr int kMaxRanks = 16;
+struct GPeer {
+    float *v[2]; int *lft[2]; float *t[2];   // the peer's node arrays (both parities), mapped through CUDA IPC or addressed directly
+    uint64_t t_stride;
+    unsigned long long *peer_flag;           // the peer's "rank r has completed step s" counter for me
+    unsigned long long *my_flag;             // my counter for that peer
+};
+
 struct StepParams {
     // index space
     uint32_t own0;        // node index of neuron 0 (multiple of 32)
@@ -109,6 +118,11 @@ struct StepParams {
     uint32_t out_par;                // parity of the *_out ping-pong buffers (same on every rank)
     unsigned int *halo_done;         // [2] per-direction CTA completion counters
     unsigned long long halo_timeout_ns;   // bound of one in-kernel wait for a neighbouring strip
+    // general-graph partition: ghosts are gather lists, not contiguous rows
+    const GPeer *gpeers; uint32_t n_gpeers;
+    const uint32_t *gexp_off, *gexp_ent;    // per owned neuron: export entries (peer slot << 28 | node index in the peer's arrays)
+    const uint8_t *gslice;                  // per slice: bit 0 reads ghosts, bit 1 has exporting neurons
+    uint32_t n_gslices;
     uint32_t reverse;                // window kernel: sweep the tiles back to front (alternates per step: the tail of the
                                      // arrays that the previous step left in L2 is what this step reads first)
     unsigned long long *dbg;         // SNN_DEBUG_TIMING: {clock64, globaltimer} at the start and end of CTA 0 (else null)
@@ -296,6 +310,7 @@ cudaError_t launch_sell_grid(uint32_t rows_local, uint32_t cols, uint32_t row0_g
                              uint32_t radius, float weight, uint32_t own0, const uint8_t *node_flags, uint32_t width,
                              uint32_t *slice_off, uint32_t *col, float *wgt, cudaStream_t s);
 cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s);
+cudaError_t launch_gpart_push(const StepParams &p, cudaStream_t s);
 // per (step, lattice): sum of V and sum of (V - ref) over the lattice's neurons, f64, fixed reduction order
 cudaError_t launch_history_reduce(const float *grid, uint64_t n_neurons, uint32_t steps, const uint32_t *lat_base, const uint32_t *lat_n,
                                   const float *lat_ref, int n_lat, double *out, cudaStream_t s);

@@ -57,6 +57,12 @@ Engine::~Engine() {
         if (peer_slab_[d]) cudaIpcCloseMemHandle(peer_slab_[d]);
         if (peer_flags_[d]) cudaIpcCloseMemHandle(peer_flags_[d]);
     }
+    for (auto &G : gpeers_)
+        if (G.ipc) { if (G.slab) cudaIpcCloseMemHandle(G.slab); if (G.flags) cudaIpcCloseMemHandle(G.flags); }
+    if (d_gpeers_) cudaFree(d_gpeers_);
+    if (d_gexp_off_) cudaFree(d_gexp_off_);
+    if (d_gexp_ent_) cudaFree(d_gexp_ent_);
+    if (d_gslice_) cudaFree(d_gslice_);
     free_device();
     if (flags_) cudaFree(flags_);
     if (halo_done_) cudaFree(halo_done_);
@@ -90,8 +96,9 @@ int Engine::init() {
     CK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), SNN_GPU_QUEUE_FAILURE);
     CK(cudaEventCreate(&ev0_), SNN_GPU_QUEUE_FAILURE);
     CK(cudaEventCreate(&ev1_), SNN_GPU_QUEUE_FAILURE);
-    CK(dev_alloc(&flags_, 4), SNN_GPU_BUFFER_CREATE_ERROR);   // [0],[1] step arrivals from rank-1 / rank+1, [2],[3] edge-kernel arrivals
-    CK(cudaMemsetAsync(flags_, 0, 4 * sizeof(unsigned long long), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    // [0],[1] step arrivals from rank-1 / rank+1, [2],[3] edge-kernel arrivals, [8 + r] general-graph partition: rank r completed a step
+    CK(dev_alloc(&flags_, 8 + kMaxRanks), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(cudaMemsetAsync(flags_, 0, (8 + kMaxRanks) * sizeof(unsigned long long), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     CK(dev_alloc(&multi_barrier_, 1), SNN_GPU_BUFFER_CREATE_ERROR);
     CK(dev_alloc(&halo_done_, 8), SNN_GPU_BUFFER_CREATE_ERROR);  // [4] ns / 16 spent in halo waits, [5] waits that spun (diagnostics); [0],[1] completion counters, [2] halo time-out flag, [3] per-edge kernel CTAs done
     CK(cudaMemsetAsync(halo_done_, 0, 8 * sizeof(unsigned int), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
@@ -131,8 +138,9 @@ void Engine::compute_layout() {
         if (L.is_train) { L.off = n_trains; n_trains += L.n; }
         else { L.off = n_neurons; n_neurons += L.n; }
     }
-    const uint32_t halo_lo = (part_world > 1 && part_rank > 0) ? halo_ : 0;
-    const uint32_t halo_hi = (part_world > 1 && part_rank < part_world - 1) ? halo_ : 0;
+    // row strips: `halo_` ghost rows on each side that has a neighbour; general-graph partition: the ghost lists themselves
+    const uint32_t halo_lo = gpart_ ? (uint32_t)g_lo_.size() : ((part_world > 1 && part_rank > 0) ? halo_ : 0);
+    const uint32_t halo_hi = gpart_ ? (uint32_t)g_hi_.size() : ((part_world > 1 && part_rank < part_world - 1) ? halo_ : 0);
     own0_ = (uint32_t)round_up(halo_lo, 32);
     train0_ = (uint32_t)round_up(own0_ + n_neurons, 32);
     // upper ghosts follow the owned neurons without a gap: the stencil generator addresses the row below the strip as
@@ -648,6 +656,231 @@ int Engine::set_preset_firing_times(uint64_t id, const uint64_t *offsets, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// general-graph partition (second half): contiguous node ranges per rank, in-edges from any node of any rank
+// ------------------------------------------------------------------------------------------------
+// Node order on a rank: [ghosts below my range, ascending global index | my neurons | ghosts above], so local order == global
+// order and the canonical (ascending presynaptic index) summation order of every row is the one of the unpartitioned lattice.
+int Engine::relayout_keep_fields(const std::function<void()> &change) {
+    // snapshot every field through the public get path, change the layout parameters, rebuild, restore
+    std::vector<LatSnap> snaps;
+    const bool had_chem = chem_alloc_;
+    for (auto &L : lats_) {
+        LatSnap sn; sn.id = L.id;
+        uint32_t cnt = 0; field_count(L.id, &cnt);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const char *name; int32_t dt; uint32_t per;
+            field_info(L.id, i, &name, &dt, &per);
+            FieldDef fd;
+            if (lookup_field(L, name, &fd)) continue;
+            const bool is_chem = fd.kind == FK_NT_FLAGS || fd.kind == FK_NT_T || fd.kind == FK_NT || fd.kind == FK_RC_FLAGS || fd.kind == FK_RC;
+            if (is_chem && !had_chem) continue;
+            FieldSnap f; f.name = name; f.dtype = dt; f.count = L.n * per; f.data.resize(std::max<uint64_t>(f.count, 1) * 4);
+            int r = get_field(L.id, name, f.data.data(), f.count, dt);
+            if (r) return r;
+            sn.fields.push_back(std::move(f));
+        }
+        snaps.push_back(std::move(sn));
+    }
+    const uint64_t saved_clock = internal_clock;
+    free_device();
+    change();
+    compute_layout();
+    int r = alloc_device();
+    if (r) return r;
+    if (had_chem) { r = ensure_chem(); if (r) return r; }
+    for (auto &sn : snaps)
+        for (auto &f : sn.fields) { r = set_field(sn.id, f.name.c_str(), f.data.data(), f.count, f.dtype); if (r) return r; }
+    internal_clock = saved_clock;
+    graph_dirty_ = true;
+    return SNN_OK;
+}
+
+int Engine::gpart_enable(const std::vector<uint32_t> &remote) {
+    if (layout_frozen_) return fail(SNN_UNSUPPORTED, "the graph of a partitioned handle cannot change its reach after the slab was exported");
+    const uint64_t cols = lats_[0].cols, g0 = (uint64_t)row0_global * cols, g1 = g0 + n_neurons;
+    std::vector<uint32_t> lo, hi;
+    for (uint32_t g : remote) (g < g0 ? lo : hi).push_back(g);
+    (void)g1;
+    if (gpart_ && lo == g_lo_ && hi == g_hi_) return SNN_OK;
+    for (int d = 0; d < 2; ++d) if (halo_dir_[d].active) return fail(SNN_UNSUPPORTED, "handle already attached as a row strip");
+    int r = relayout_keep_fields([&]() { gpart_ = true; g_lo_ = lo; g_hi_ = hi; });
+    if (r) return r;
+    gpeers_.clear();
+    gpart_dirty_ = true;
+    return SNN_OK;
+}
+
+int64_t Engine::global_to_node(uint64_t g) const {
+    const uint64_t cols = lats_.empty() ? 0 : lats_[0].cols, g0 = (uint64_t)row0_global * cols;
+    if (g >= g0 && g < g0 + n_neurons) return (int64_t)own0_ + (int64_t)(g - g0);
+    if (!gpart_) {
+        const int64_t node = (int64_t)g + (int64_t)own0_ - (int64_t)g0;
+        return (node < 0 || node >= (int64_t)n_nodes_) ? -1 : node;
+    }
+    const std::vector<uint32_t> &v = g < g0 ? g_lo_ : g_hi_;
+    auto it = std::lower_bound(v.begin(), v.end(), (uint32_t)g);
+    if (it == v.end() || *it != g) return -1;
+    const uint64_t k = (uint64_t)(it - v.begin());
+    return g < g0 ? (int64_t)own0_ - (int64_t)g_lo_.size() + (int64_t)k : (int64_t)ghost_hi0_ + (int64_t)k;
+}
+
+uint64_t Engine::node_to_global(uint32_t node) const {
+    const uint64_t cols = lats_.empty() ? 0 : lats_[0].cols, g0 = (uint64_t)row0_global * cols;
+    if (node >= own0_ && node < own0_ + n_neurons) return g0 + (node - own0_);
+    if (!gpart_) return (uint64_t)((int64_t)node + (int64_t)g0 - (int64_t)own0_);
+    if (node < own0_) return g_lo_[node - (own0_ - (uint32_t)g_lo_.size())];
+    return g_hi_[node - ghost_hi0_];
+}
+
+Engine::GPeerHost *Engine::gpeer(int rank, bool create) {
+    for (auto &g : gpeers_) if (g.rank == rank) return &g;
+    if (!create) return nullptr;
+    GPeerHost g; g.rank = rank;
+    auto it = gpeers_.begin();
+    while (it != gpeers_.end() && it->rank < rank) ++it;
+    return &*gpeers_.insert(it, std::move(g));
+}
+
+int Engine::gpart_wants(int peer, uint32_t *global_idx, uint64_t capacity, uint64_t *n, uint32_t *first_slot) {
+    if (part_world <= 1 || peer < 0 || peer >= part_world || peer == part_rank) return fail(SNN_INVALID_ARGUMENT, "bad peer rank");
+    if (n) *n = 0;
+    if (first_slot) *first_slot = 0;
+    if (!gpart_) return SNN_OK;   // a row strip has no gather lists
+    const uint64_t cols = lats_[0].cols;
+    const uint64_t q0 = (uint64_t)snn_partition_begin(rows_global, part_world, peer) * cols, q1 = (uint64_t)snn_partition_begin(rows_global, part_world, peer + 1) * cols;
+    const std::vector<uint32_t> &v = peer < part_rank ? g_lo_ : g_hi_;
+    auto a = std::lower_bound(v.begin(), v.end(), (uint32_t)q0), b = std::lower_bound(v.begin(), v.end(), (uint32_t)std::min<uint64_t>(q1, 0xFFFFFFFFull));
+    const uint64_t cnt = (uint64_t)(b - a);
+    if (n) *n = cnt;
+    const uint32_t base = peer < part_rank ? own0_ - (uint32_t)g_lo_.size() : ghost_hi0_;
+    if (first_slot) *first_slot = base + (uint32_t)(a - v.begin());
+    if (global_idx) {
+        if (capacity < cnt) return fail(SNN_SIZE_MISMATCH, "index buffer too small");
+        std::copy(a, b, global_idx);
+    }
+    return SNN_OK;
+}
+
+int Engine::gpart_set_exports(int peer, const uint32_t *global_idx, uint64_t n, uint32_t first_slot_at_peer) {
+    if (part_world <= 1 || peer < 0 || peer >= part_world || peer == part_rank) return fail(SNN_INVALID_ARGUMENT, "bad peer rank");
+    if (n && !global_idx) return fail(SNN_INVALID_ARGUMENT, "null argument");
+    if (!gpart_) return fail(SNN_INVALID_ARGUMENT, "not a general-graph partition (set SNN_OPT_GENERAL_PARTITION before the graph on every rank)");
+    if (n == 0 && !gpeer(peer, false)) return SNN_OK;
+    const uint64_t cols = lats_[0].cols, g0 = (uint64_t)row0_global * cols;
+    GPeerHost *G = gpeer(peer, true);
+    G->exp_local.clear();
+    for (uint64_t k = 0; k < n; ++k) {
+        if (global_idx[k] < g0 || global_idx[k] >= g0 + n_neurons) return fail(SNN_GRAPH_POSITION_NOT_FOUND, "Position not found, position: " + std::to_string(global_idx[k]));
+        if (k && global_idx[k] <= global_idx[k - 1]) return fail(SNN_INVALID_ARGUMENT, "export list must be ascending");
+        G->exp_local.push_back((uint32_t)(global_idx[k] - g0));
+    }
+    G->peer_slot0 = first_slot_at_peer;
+    gpart_dirty_ = true;
+    return SNN_OK;
+}
+
+int Engine::gpart_attach(int peer, const IpcBlob *blob_in, Engine *local_peer) {
+    if (part_world <= 1 || peer < 0 || peer >= part_world || peer == part_rank) return fail(SNN_INVALID_ARGUMENT, "bad peer rank");
+    if (!gpart_) return fail(SNN_INVALID_ARGUMENT, "not a general-graph partition (set SNN_OPT_GENERAL_PARTITION before the graph on every rank)");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    GPeerHost *G = gpeer(peer, true);
+    if (G->attached) return fail(SNN_INVALID_ARGUMENT, "peer already attached");
+    IpcBlob blob;
+    if (local_peer) {
+        if (local_peer == this) return fail(SNN_INVALID_ARGUMENT, "bad peer handle");
+        if (local_peer->device != device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, device, local_peer->device), SNN_GPU_GET_DEVICE_FAILURE);
+            if (!can) return fail(SNN_UNSUPPORTED, "no peer access between the two devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(local_peer->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return cuda_fail(e, SNN_GPU_GET_DEVICE_FAILURE, "cudaDeviceEnablePeerAccess");
+            cudaGetLastError();
+        }
+        int r = local_peer->ipc_export_layout(&blob);
+        if (r) return fail(r, local_peer->last_error);
+        G->slab = local_peer->slab_; G->flags = local_peer->flags_;
+        local_peer->layout_frozen_ = true;
+    } else {
+        blob = *blob_in;
+        if (blob.magic != 0x534E4E42u || blob.version != SNN_B200_ABI_VERSION) return fail(SNN_INVALID_ARGUMENT, "bad ipc blob");
+        CK(cudaIpcOpenMemHandle(&G->slab, blob.slab, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
+        CK(cudaIpcOpenMemHandle(&G->flags, blob.flags, cudaIpcMemLazyEnablePeerAccess), SNN_GPU_BUFFER_CREATE_ERROR);
+        G->ipc = true;
+    }
+    if (blob.rank != peer || blob.world != part_world) return fail(SNN_INVALID_ARGUMENT, "ipc blob is not from that rank");
+    if ((blob.chem != 0) != chem_alloc_) return fail(SNN_INVALID_ARGUMENT, "the ranks disagree on chemistry");
+    G->view = blob;
+    G->attached = true;
+    layout_frozen_ = true;
+    // neurotransmitter / receptor type flags of the ghosts that this peer owns (baked into the col words of edges from ghosts)
+    uint64_t cnt = 0; uint32_t slot0 = 0;
+    int r = gpart_wants(peer, nullptr, 0, &cnt, &slot0);
+    if (r) return r;
+    if (cnt) {
+        std::vector<uint8_t> pf(blob.n_neurons);
+        CK(cudaMemcpy(pf.data(), (const uint8_t *)G->slab + blob.off_flags + blob.own0, blob.n_neurons, cudaMemcpyDefault), SNN_GPU_BUFFER_READ_ERROR);
+        const uint64_t cols = lats_[0].cols, q0 = (uint64_t)snn_partition_begin(rows_global, part_world, peer) * cols;
+        bool changed = false;
+        for (uint64_t k = 0; k < cnt; ++k) {
+            const uint32_t node = slot0 + (uint32_t)k;
+            const uint8_t f = pf[node_to_global(node) - q0];
+            changed |= h_node_flags_[node] != f;
+            h_node_flags_[node] = f;
+        }
+        if (changed) {
+            CK(h2d_sync(node_flags_ + slot0, h_node_flags_.data() + slot0, cnt, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+            flags_cache_valid_ = false;
+            if (dev_weights_newer_) { r = sync_weights_to_host(); if (r) return r; }
+            graph_dirty_ = true;
+        }
+    }
+    gpart_dirty_ = true;
+    return SNN_OK;
+}
+
+int Engine::gpart_build_device() {
+    if (!gpart_dirty_) return SNN_OK;
+    auto fr = [](auto *&p) { if (p) cudaFree(p); p = nullptr; };
+    fr(d_gpeers_); fr(d_gexp_off_); fr(d_gexp_ent_); fr(d_gslice_);
+    if (gpeers_.size() > 15) return fail(SNN_UNSUPPORTED, "too many peers");
+    std::vector<GPeer> hp(std::max<size_t>(gpeers_.size(), 1));
+    std::vector<std::vector<uint32_t>> per(n_neurons);
+    for (size_t q = 0; q < gpeers_.size(); ++q) {
+        GPeerHost &G = gpeers_[q];
+        if (!G.attached) return fail(SNN_INVALID_ARGUMENT, "general-graph partition: rank " + std::to_string(G.rank) + " is not attached");
+        GPeer &D = hp[q];
+        for (int k = 0; k < 2; ++k) {
+            D.v[k] = (float *)((char *)G.slab + G.view.off_v[k]);
+            D.lft[k] = (int *)((char *)G.slab + G.view.off_lft[k]);
+            D.t[k] = (float *)((char *)G.slab + G.view.off_t[k]);
+        }
+        D.t_stride = G.view.t_stride;
+        D.peer_flag = (unsigned long long *)G.flags + 8 + part_rank;
+        D.my_flag = flags_ + 8 + G.rank;
+        for (size_t k = 0; k < G.exp_local.size(); ++k) per[G.exp_local[k]].push_back(((uint32_t)q << 28) | (G.peer_slot0 + (uint32_t)k));
+    }
+    std::vector<uint32_t> off(n_neurons + 1, 0), ent;
+    std::vector<uint8_t> gs(std::max<size_t>(n_slices_, 1), 0);
+    for (uint64_t i = 0; i < n_neurons; ++i) {
+        off[i] = (uint32_t)ent.size();
+        ent.insert(ent.end(), per[i].begin(), per[i].end());
+        if (!per[i].empty()) gs[i / 32] |= 2u;
+    }
+    off[n_neurons] = (uint32_t)ent.size();
+    for (size_t sl = 0; sl < h_gslice_.size() && sl < gs.size(); ++sl) gs[sl] |= h_gslice_[sl] & 1u;
+    CK(dev_alloc(&d_gpeers_, hp.size()), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&d_gexp_off_, off.size()), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&d_gexp_ent_, ent.size()), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(dev_alloc(&d_gslice_, gs.size()), SNN_GPU_BUFFER_CREATE_ERROR);
+    CK(h2d_sync(d_gpeers_, hp.data(), hp.size() * sizeof(GPeer), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(h2d_sync(d_gexp_off_, off.data(), off.size() * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(h2d_sync(d_gexp_ent_, ent.data(), ent.size() * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    CK(h2d_sync(d_gslice_, gs.data(), gs.size(), stream_), SNN_GPU_BUFFER_WRITE_ERROR);
+    gpart_dirty_ = false;
+    return SNN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // graph ingestion
 // ------------------------------------------------------------------------------------------------
 static int check_connect(Engine &E, uint64_t pre_id, uint64_t post_id, Lat **A, Lat **B) {
@@ -736,6 +969,27 @@ int Engine::connect_csr(uint64_t pre_id, uint64_t post_id, const uint64_t *row_p
     b.pre.assign(pre, pre + nnz);
     b.w.assign(weights, weights + nnz);
     sort_rows(b);
+    if (part_world > 1) {
+        // edges that reach beyond the strip's halo rows (or any edge, once the handle is a general-graph partition): the ghosts
+        // become gather lists of exactly the remote nodes this rank's rows read
+        const int64_t g0 = (int64_t)row0_global * A->cols, g1 = g0 + (int64_t)A->n;
+        bool beyond = gpart_ || force_gpart;
+        std::vector<uint32_t> remote;
+        for (uint64_t k = 0; k < nnz; ++k) {
+            const int64_t g = b.pre[k];
+            if (g >= g0 && g < g1) continue;
+            remote.push_back((uint32_t)g);
+            if (g < g0 - (int64_t)halo_ || g >= g1 + (int64_t)halo_) beyond = true;
+        }
+        if (beyond) {
+            std::sort(remote.begin(), remote.end());
+            remote.erase(std::unique(remote.begin(), remote.end()), remote.end());
+            blocks_.clear();
+            r = gpart_enable(remote);
+            if (r) return r;
+            A = B = find(pre_id);
+        }
+    }
     blocks_[{pre_id, post_id}] = std::move(b);
     graph_dirty_ = true;
     return SNN_OK;
@@ -853,7 +1107,7 @@ int Engine::finalize_graph() {
     n_slices_ = new_slices;
     if (!reuse) CK(dev_alloc(&slice_off_, (size_t)n_slices_ + 1), SNN_GPU_BUFFER_CREATE_ERROR);
     // partitioned handles: ghost rows inherit the neurotransmitter type sets of the adjacent owned rows
-    if (part_world > 1 && n_neurons) {
+    if (part_world > 1 && n_neurons && !gpart_) {
         // (until the neighbour is attached: ipc_attach replaces them with the neighbour's real boundary flags)
         for (uint32_t g = 0; g < halo_; ++g) {
             if (part_rank > 0 && !ghost_flags_from_peer_[0]) h_node_flags_[own0_ - halo_ + g] = h_node_flags_[own0_ + (g % std::max<uint64_t>(n_neurons, 1))];
@@ -918,6 +1172,7 @@ int Engine::finalize_graph() {
     std::vector<uint32_t> pre(std::max<uint64_t>(nnz, 1));
     std::vector<float> w(std::max<uint64_t>(nnz, 1));
     const int64_t node_shift = part_world > 1 ? (int64_t)own0_ - (int64_t)row0_global * (only ? only->cols : 0) : 0;
+    std::vector<uint64_t> ghost_rows;   // general-graph partition: rows with an in-edge from a ghost
     for (size_t li = 0; li < lats_.size(); ++li) {
         if (lats_[li].is_train) continue;
         for (uint64_t q = 0; q < lats_[li].n; ++q) {
@@ -926,9 +1181,10 @@ int Engine::finalize_graph() {
                 const Block &b = *ab.second;
                 const uint32_t base = node_off(*ab.first);
                 for (uint64_t k = b.row_ptr[q]; k < b.row_ptr[q + 1]; ++k) {
-                    int64_t node = part_world > 1 ? (int64_t)b.pre[k] + node_shift : (int64_t)base + b.pre[k];
+                    int64_t node = gpart_ ? global_to_node(b.pre[k]) : (part_world > 1 ? (int64_t)b.pre[k] + node_shift : (int64_t)base + b.pre[k]);
                     if (node < 0 || node >= (int64_t)n_nodes_)
                         return fail(SNN_UNSUPPORTED, "edge reaches beyond the halo of this strip");
+                    if (gpart_ && (node < (int64_t)own0_ || node >= (int64_t)own0_ + (int64_t)n_neurons)) ghost_rows.push_back(lats_[li].off + q);
                     pre[o] = (uint32_t)node; w[o] = b.w[k]; ++o;
                 }
             }
@@ -983,6 +1239,11 @@ int Engine::finalize_graph() {
     cudaFree(d_rp); cudaFree(d_pre); cudaFree(d_w);
     if (e != cudaSuccess) return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "sell_from_csr");
     if (stencil_width) { grid_fast_ = true; uniform_width_ = stencil_width; }
+    if (gpart_) {
+        h_gslice_.assign(n_slices_, 0);
+        for (uint64_t row : ghost_rows) h_gslice_[row / 32] |= 1u;
+        gpart_dirty_ = true;
+    }
     graph_dirty_ = false;
     dev_weights_newer_ = false;
     return SNN_OK;
@@ -1259,7 +1520,7 @@ int Engine::get_connection_rows(uint64_t pre_id, uint64_t post_id, uint64_t row_
             if (col[e] == kColPad) break;   // valid entries first
             const int64_t j = (int64_t)(col[e] & kColIdxMask);
             if (j < a0 || j >= a1) continue;
-            if (o < capacity) { if (pre) pre[o] = (uint32_t)(j + shift); if (weights) weights[o] = wg[e]; }
+            if (o < capacity) { if (pre) pre[o] = gpart_ ? (uint32_t)node_to_global((uint32_t)j) : (uint32_t)(j + shift); if (weights) weights[o] = wg[e]; }
             ++o;
         }
         if (row_ptr) row_ptr[g - g0 + 1] = o;
@@ -1304,8 +1565,8 @@ int Engine::lookup_weight(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint6
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     r = finalize_graph();
     if (r) return r;
-    const int64_t node = part_world > 1 ? (int64_t)pre + (int64_t)own0_ - (int64_t)row0_global * A->cols : (int64_t)node_off(*A) + (int64_t)pre;
-    if (node < 0 || node >= (int64_t)n_nodes_) return SNN_OK;   // partitioned: beyond the halo of this strip, cannot be connected
+    const int64_t node = part_world > 1 ? global_to_node(pre) : (int64_t)node_off(*A) + (int64_t)pre;
+    if (node < 0 || node >= (int64_t)n_nodes_) return SNN_OK;   // partitioned: not among this rank's ghosts, cannot be connected
     int64_t e = -1;
     r = find_edge(B->off + post, (uint32_t)node, &e);
     if (r || e < 0) return r;
@@ -1321,7 +1582,7 @@ int Engine::edit_weight(uint64_t pre_id, uint64_t post_id, uint64_t pre, uint64_
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     r = finalize_graph();
     if (r) return r;
-    const int64_t node = part_world > 1 ? (int64_t)pre + (int64_t)own0_ - (int64_t)row0_global * A->cols : (int64_t)node_off(*A) + (int64_t)pre;
+    const int64_t node = part_world > 1 ? global_to_node(pre) : (int64_t)node_off(*A) + (int64_t)pre;
     int64_t e = -1;
     if (node >= 0 && node < (int64_t)n_nodes_) { r = find_edge(B->off + post, (uint32_t)node, &e); if (r) return r; }
     if (e >= 0 && has) {
@@ -1494,6 +1755,10 @@ void Engine::fill_step_params(StepParams &p) {
     p.halo[0] = halo_dir_[0]; p.halo[1] = halo_dir_[1];
     p.halo_done = halo_done_;
     p.halo_timeout_ns = halo_timeout_ms * 1000000ull;
+    if (gpart_ && !gpeers_.empty()) {
+        p.gpeers = d_gpeers_; p.n_gpeers = (uint32_t)gpeers_.size();
+        p.gexp_off = d_gexp_off_; p.gexp_ent = d_gexp_ent_; p.gslice = d_gslice_; p.n_gslices = n_slices_;
+    }
 }
 
 // Operand streams of the TMA-staged kernel for the current configuration; false = not eligible (use the general kernel).
@@ -1679,16 +1944,18 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     if (iterations == 0 || (n_neurons == 0 && n_trains == 0)) return SNN_OK;
     if (!electrical && !chemical) return SNN_OK;
     if (internal_clock + iterations > 0x7FFFFFF0ull) return fail(SNN_UNSUPPORTED, "internal clock would overflow the i32 last_firing_time");
-    if (part_world > 1) {
+    if (part_world > 1 && !gpart_) {
         if ((part_rank > 0 && !halo_dir_[0].active) || (part_rank < part_world - 1 && !halo_dir_[1].active))
             return fail(SNN_INVALID_ARGUMENT, "partitioned handle: neighbouring strips are not attached");
     }
+    if (gpart_ && (reward_mode || bcm_mode)) return fail(SNN_UNSUPPORTED, "general-graph partitions step plain and STDP lattices");
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     if (chemical) { int r = ensure_chem(); if (r) return r; }
     int r = finalize_graph();
     if (r) return r;
     r = upload_lat_table();
     if (r) return r;
+    if (gpart_) { r = gpart_build_device(); if (r) return r; }
 
     bool stdp = false, want_grid = false, want_spk = false, want_tgrid = false, want_tspk = false, want_red = false;
     for (auto &L : lats_) {
@@ -1798,7 +2065,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             cudaMemcpyAsync(LFT_[cur_], LFT_[lft_loc_], node_cap_ * 4, cudaMemcpyDeviceToDevice, stream_);
             lft_loc_ = cur_; hp.lft_in = LFT_[lft_loc_];
         }
-        cudaError_t e = launch_halo_push(hp, stream_);
+        cudaError_t e = gpart_ ? launch_gpart_push(hp, stream_) : launch_halo_push(hp, stream_);
         if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "halo_push"); }
         halo_epoch_ += 1;
         n_launch++;
@@ -1808,11 +2075,12 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_WAIT_ERROR, "halo_push"); }
         const auto t_wait0 = std::chrono::steady_clock::now();
         for (;;) {
-            unsigned long long f[4];
+            unsigned long long f[8 + kMaxRanks];
             e = cudaMemcpy(f, flags_, sizeof f, cudaMemcpyDeviceToHost);
             if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_BUFFER_READ_ERROR, "halo rendez-vous"); }
             bool ready = true;
             for (int d = 0; d < 2; ++d) if (halo_dir_[d].active && f[d] < halo_epoch_) ready = false;
+            for (auto &G : gpeers_) if (f[8 + G.rank] < halo_epoch_) ready = false;
             if (ready) break;
             if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wait0).count() > 4.0 * (double)halo_timeout_ms) {
                 free_hist();

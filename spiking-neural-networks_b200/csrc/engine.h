@@ -5,6 +5,7 @@
 // one in-edge table.  A reference `Lattice` is an Engine with a single lattice.
 #pragma once
 #include <cstdint>
+#include <functional>
 #include <map>
 #include <string>
 #include <utility>
@@ -126,6 +127,12 @@ public:
     int ipc_export(IpcBlob *blob);
     int ipc_attach(int direction, const IpcBlob *blob);
     int attach_local(int direction, Engine *peer);   // neighbour handle in the same process (no CUDA IPC)
+    // general-graph partition (contiguous node ranges, in-edges from anywhere): which of `peer`'s nodes this rank reads, which of
+    // its own nodes `peer` reads, and the mapping of the peer's arrays
+    int gpart_wants(int peer, uint32_t *global_idx, uint64_t capacity, uint64_t *n, uint32_t *first_slot);
+    int gpart_set_exports(int peer, const uint32_t *global_idx, uint64_t n, uint32_t first_slot_at_peer);
+    int gpart_attach(int peer, const IpcBlob *blob, Engine *local_peer);
+    bool is_gpart() const { return gpart_; }
 
     // public knobs (Lattice / LatticeNetwork pub fields, neuron/mod.rs:556-587, 1554-1563)
     bool electrical = true, chemical = false, parallel = false;
@@ -134,6 +141,7 @@ public:
     uint64_t train_draws = 0;       // Philox counter word: one per spike-train step of this handle, never reset (reset_timing
                                     // restarts the clocks, not the random stream: the reference draws from thread_rng)
     uint32_t steps_per_graph = 0;
+    bool force_gpart = false;           // SNN_OPT_GENERAL_PARTITION: CSR graphs of a partitioned handle always use gather-list ghosts
     uint64_t halo_timeout_ms = 30000;   // multi-GPU: how long a step may wait for a neighbouring strip before SNN_GPU_WAIT_ERROR
     int use_tma = -1;   // -1 auto (env SNN_B200_TMA), 0 never, 1 whenever eligible
     std::string last_error;
@@ -194,6 +202,26 @@ private:
     void *peer_slab_[2] = {nullptr, nullptr};
     void *peer_flags_[2] = {nullptr, nullptr};
     unsigned long long halo_epoch_ = 0;
+    // general-graph partition
+    struct GPeerHost {
+        int rank = -1;
+        std::vector<uint32_t> exp_local;   // my local neuron numbers this peer reads (ascending)
+        uint32_t peer_slot0 = 0;           // node index in the peer's arrays where they go
+        void *slab = nullptr, *flags = nullptr;
+        bool ipc = false, attached = false;
+        IpcBlob view{};
+    };
+    bool gpart_ = false, gpart_dirty_ = true;
+    std::vector<uint32_t> g_lo_, g_hi_;    // global indices of the ghost nodes below / above my node range (ascending)
+    std::vector<GPeerHost> gpeers_;        // ascending rank
+    std::vector<uint8_t> h_gslice_;        // per slice: bit 0 = a row of the slice reads a ghost
+    GPeer *d_gpeers_ = nullptr; uint32_t *d_gexp_off_ = nullptr, *d_gexp_ent_ = nullptr; uint8_t *d_gslice_ = nullptr;
+    GPeerHost *gpeer(int rank, bool create);
+    int gpart_build_device();
+    int gpart_enable(const std::vector<uint32_t> &remote_sorted_unique);
+    int relayout_keep_fields(const std::function<void()> &change);
+    int64_t global_to_node(uint64_t g) const;
+    uint64_t node_to_global(uint32_t node) const;
     // scratch
     void *scratch_ = nullptr; size_t scratch_bytes_ = 0;
 

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     const uint32_t lnc = valid ? ln : p.n_neurons - 1;  // clamped for loads
     bool export_lo = false, export_hi = false;
     if (!NET) halo_import(p, warp_global, lane, ln, valid, export_lo, export_hi);
+    if (!NET) gpart_wait(p, warp_global, lane);
     // uniform slice width (stencil graphs): no dependent load for the slice bounds
     const uint32_t k0 = p.uniform_width ? warp_global * p.uniform_width : __ldg(p.slice_off + warp_global);
     const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + warp_global + 1);
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     const GlobalSrc src{p, lnc, p.own0 + lnc, lane, k0, k1, t0};
     neuron_step<MODEL, CHEMG, NTREL, STDP, NET>(p, src, warp_global, lane, ln, lnc, valid, export_lo, export_hi);
     if (!NET) halo_publish(p, warp_global, lane);
+    if (!NET) gpart_export_publish(p, warp_global, lane, ln, valid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -91,6 +93,32 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const __grid_constant__ 
     }
 }
 
+// general-graph partition: the same push through the per-neuron export lists (here *_in are the CURRENT buffers, out_par their parity)
+__global__ void __launch_bounds__(256) gpart_push_kernel(const __grid_constant__ StepParams p) {
+    const uint32_t ln = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ln < p.n_neurons) {
+        const uint32_t i = p.own0 + ln;
+        for (uint32_t e = p.gexp_off[ln]; e < p.gexp_off[ln + 1]; ++e) {
+            const uint32_t ent = p.gexp_ent[e], dst = ent & kColIdxMask;
+            const GPeer &G = p.gpeers[ent >> 28];
+            G.v[p.out_par][dst] = p.v_in[i];
+            G.lft[p.out_par][dst] = p.lft_in[i];
+            for (int ty = 0; ty < kNT; ++ty)
+                if (p.nt_used & (1u << ty)) G.t[p.out_par][(size_t)ty * G.t_stride + dst] = p.t_in[(size_t)ty * p.t_stride + i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(&p.halo_done[6], 1u) + 1u;
+        if (done == gridDim.x) {
+            p.halo_done[6] = 0u;
+            __threadfence_system();
+            for (uint32_t q = 0; q < p.n_gpeers; ++q) st_release_sys(p.gpeers[q].peer_flag, p.halo_epoch + 1ull);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // end-of-run flush of the lazily applied STDP (the last step's updates are still pending)
 // ------------------------------------------------------------------------------------------------
@@ -101,6 +129,11 @@ __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__
     if (warp_global * 32u >= p.n_neurons) return;
     const uint32_t ln = warp_global * 32u + lane;
     // partitioned handles: the neighbours' last step must have landed in the ghost slots before they are read
+    if (p.n_gpeers) {
+        if (lane == 0)
+            for (uint32_t q = 0; q < p.n_gpeers; ++q) halo_wait(p.gpeers[q].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
+        __syncwarp();
+    }
     if (p.halo[0].active | p.halo[1].active) {
         if (lane == 0) {
             if (p.halo[0].active) halo_wait(p.halo[0].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns);
@@ -325,10 +358,10 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ S
         p.f[F_M_BETA][ln] = 4.f * expf(-(v + 65.f) / 18.f);
         p.f[F_H_ALPHA][ln] = 0.07f * expf(-(v + 65.f) / 20.f);
         p.f[F_H_BETA][ln] = 1.f / (expf(-(v + 35.f) / 10.f) + 1.f);
-        p.f[F_NA_CUR][ln] = ((powf(m, 3.f) * h) * p.f[F_GNA][ln]) * (v - p.f[F_ENA][ln]);
+        p.f[F_NA_CUR][ln] = ((pow3f(m) * h) * p.f[F_GNA][ln]) * (v - p.f[F_ENA][ln]);
         p.f[F_N_ALPHA][ln] = (0.01f * (v + 55.f)) / (1.f - expf(-(v + 55.f) / 10.f));
         p.f[F_N_BETA][ln] = 0.125f * expf(-(v + 65.f) / 80.f);
-        p.f[F_K_CUR][ln] = (powf(n, 4.f) * p.f[F_GK][ln]) * (v - p.f[F_EK][ln]);
+        p.f[F_K_CUR][ln] = (pow4f(n) * p.f[F_GK][ln]) * (v - p.f[F_EK][ln]);
         p.f[F_KL_CUR][ln] = p.f[F_GKL][ln] * (v - p.f[F_EKL][ln]);
     }
 }
@@ -492,6 +525,12 @@ cudaError_t launch_halo_push(const StepParams &p, cudaStream_t s) {
     const uint32_t cnt = max(p.halo[0].active ? p.halo[0].count : 0u, p.halo[1].active ? p.halo[1].count : 0u);
     if (cnt == 0) return cudaSuccess;
     halo_push_kernel<<<blocks_for(cnt, 256), 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gpart_push(const StepParams &p, cudaStream_t s) {
+    if (p.n_neurons == 0 || p.n_gpeers == 0) return cudaSuccess;
+    gpart_push_kernel<<<blocks_for(p.n_neurons, 256), 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -101,6 +101,13 @@ static __device__ __noinline__ float refract_effect(int kind, float k, uint32_t 
 
 __device__ __forceinline__ float ldf(const float *p, size_t i) { return __ldg(p + i); }
 
+// m.powf(3.) and n.powf(4.) of the ion-channel currents (ion_channels/mod.rs:226-231, 275-278).  The reference calls libm's
+// powf (within 1 ulp of the exact power); CUDA's powf is ~75 instructions with up to 4 ulp of error, the products below are 2-3
+// instructions with at most 1.5 ulp — closer to what the reference computes AND a tenth of the Hodgkin-Huxley step's
+// instruction stream.  (The HH path is tolerance-checked either way: its expf calls already differ from glibc's in the last bit.)
+__device__ __forceinline__ float pow3f(float x) { return (x * x) * x; }
+__device__ __forceinline__ float pow4f(float x) { const float x2 = x * x; return x2 * x2; }
+
 // ------------------------------------------------------------------------------------------------
 // halo synchronisation over NVLink peer memory (multi-GPU row strips)
 // ------------------------------------------------------------------------------------------------
@@ -139,10 +146,56 @@ __device__ __forceinline__ bool halo_wait(const unsigned long long *flag, unsign
 // a halo wait of this run has timed out: the ghosts are stale, stop stepping (uniform over the grid once the flag is visible)
 // (CTA-uniform: called by every thread of the CTA before anything else)
 __device__ __forceinline__ bool halo_failed(const StepParams &p) {
-    if (!(p.halo[0].active | p.halo[1].active)) return false;
+    if (!(p.halo[0].active | p.halo[1].active | p.n_gpeers)) return false;
     return __syncthreads_or(*(volatile unsigned int *)(p.halo_done + 2) != 0u) != 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// general-graph partition: ghosts of any rank, exported through per-neuron lists
+// ------------------------------------------------------------------------------------------------
+// Protocol: rank r publishes "step s complete" to every peer when ALL of its warps are done with step s (exports written AND
+// ghost reads finished).  A warp of step s that reads ghosts, or writes a peer's ghosts, first waits until every peer has
+// completed step s - 1: the ghosts it reads are then the peers' step s - 1 exports, and the ghost slots it overwrites (the parity
+// the peer read in ITS step s - 1) are no longer being read.  Ranks are never more than one step apart.
+__device__ __forceinline__ void gpart_wait(const StepParams &p, uint32_t slice, uint32_t lane) {
+    if (!p.n_gpeers) return;
+    if (p.gslice[slice] == 0u) return;   // warp-uniform: an interior slice neither reads ghosts nor exports
+    if (lane == 0) {
+        for (uint32_t q = 0; q < p.n_gpeers; ++q)
+            if (!halo_wait(p.gpeers[q].my_flag, p.halo_epoch, p.halo_done + 2, p.halo_timeout_ns)) break;
+    }
+    __syncwarp();
+}
+
+// after neuron_step: copy this neuron's new state into the ghost slots of every peer that lists it, then count the warp as done;
+// the last warp of the step raises every peer's completion counter
+__device__ __forceinline__ void gpart_export_publish(const StepParams &p, uint32_t slice, uint32_t lane, uint32_t ln, bool valid) {
+    if (!p.n_gpeers) return;
+    const bool exports = (p.gslice[slice] & 2u) != 0u;
+    if (exports && valid) {
+        const uint32_t i = p.own0 + ln;
+        for (uint32_t e = p.gexp_off[ln]; e < p.gexp_off[ln + 1]; ++e) {
+            const uint32_t ent = __ldg(p.gexp_ent + e), dst = ent & kColIdxMask;
+            const GPeer &G = p.gpeers[ent >> 28];
+            G.v[p.out_par][dst] = p.v_out[i];
+            G.lft[p.out_par][dst] = p.lft_out[i];
+            for (int ty = 0; ty < kNT; ++ty)
+                if (p.nt_used & (1u << ty)) G.t[p.out_par][(size_t)ty * G.t_stride + dst] = p.t_out[(size_t)ty * p.t_stride + i];
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (exports) __threadfence_system();
+        else __threadfence();
+        const unsigned int done = atomicAdd(&p.halo_done[6], 1u) + 1u;
+        if (done == p.n_gslices) {
+            p.halo_done[6] = 0u;
+            __threadfence_system();
+            for (uint32_t q = 0; q < p.n_gpeers; ++q) st_release_sys(p.gpeers[q].peer_flag, p.halo_epoch + 1ull);
+        }
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // source policies
@@ -193,6 +246,7 @@ struct EdgeAcc {
     uint32_t cnt[kNT];
     bool fast8;   // warp-uniform: every lane had exactly 8 in-edges (and, CHEMG == 1, all of them release the type):
                   // the averaging divisions are by 8 = exact multiplications by 0.125
+    bool fast8t;  // CHEMG == 3, warp-uniform: fast8 and every presynaptic neuron releases all three types
 };
 
 // The lazily applied STDP of the previous step for one chunk of U edges (see gather_edges); shared by both gathers.
@@ -319,7 +373,7 @@ __device__ __forceinline__ void stdp_chunk8_staged(const StepParams &p, const SR
 // FULL (warp-uniform): no lane of the warp has a padding slot and, with a single neurotransmitter type, every
 // presynaptic neuron releases it — the per-edge validity / type tests and the in-edge counters fold away.  The
 // accumulation order and every rounding are those of gather_edges (a skipped `+ 0` term of a padding slot is exact).
-template <int CHEMG, bool STDP, bool FULL, class SRC>
+template <int CHEMG, bool STDP, bool FULL, bool FULLT, class SRC>
 __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
                                                    bool post_trig, int li, uint32_t ty0, const uint32_t (&c)[8], EdgeAcc &A) {
     constexpr int U = 8;
@@ -356,7 +410,7 @@ __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SR
         for (int u = 0; u < U; ++u) {
             const uint32_t m = (FULL || c[u] != kColPad) ? (c[u] >> kColNtShift) : 0u;
 #pragma unroll
-            for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? src.gt(h[u], ty) : 0.f;
+            for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (FULLT || (m & (1u << ty))) ? src.gt(h[u], ty) : 0.f;
         }
     }
 #pragma unroll
@@ -377,13 +431,19 @@ __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SR
                 A.cnt[0] += has ? 1u : 0u;
             }
         } else if (CHEMG == 3) {
-            const uint32_t m = ok ? (c[u] >> kColNtShift) : 0u;
+            if (FULLT) {
+                // every presynaptic neuron releases every type: the same terms in the same order, without masks and counters
 #pragma unroll
-            for (int ty = 0; ty < kNT; ++ty) {
-                const bool has = (m >> ty) & 1u;
-                const float term = tj[u][ty] * wu;
-                A.acc_t[ty] = A.acc_t[ty] + (has ? term : 0.f);
-                A.cnt[ty] += has ? 1u : 0u;
+                for (int ty = 0; ty < kNT; ++ty) A.acc_t[ty] = A.acc_t[ty] + tj[u][ty] * wu;
+            } else {
+                const uint32_t m = ok ? (c[u] >> kColNtShift) : 0u;
+#pragma unroll
+                for (int ty = 0; ty < kNT; ++ty) {
+                    const bool has = (m >> ty) & 1u;
+                    const float term = tj[u][ty] * wu;
+                    A.acc_t[ty] = A.acc_t[ty] + (has ? term : 0.f);
+                    A.cnt[ty] += has ? 1u : 0u;
+                }
             }
         }
         if (!FULL) A.n_in += ok ? 1u : 0u;
@@ -391,6 +451,10 @@ __device__ __forceinline__ void gather_edges8_body(const StepParams &p, const SR
     if (FULL) {
         A.n_in = 8u;
         if (CHEMG == 1) A.cnt[0] = 8u;
+        if (FULLT) {
+#pragma unroll
+            for (int ty = 0; ty < kNT; ++ty) A.cnt[ty] = 8u;
+        }
     }
 }
 
@@ -403,13 +467,14 @@ __device__ __forceinline__ void gather_edges8(const StepParams &p, const SRC &sr
     // sliced-ELL rows keep their valid entries first (sell_grid_kernel / sell_from_csr_kernel pad at the end), so a valid
     // last slot means a full row
     bool lane_full = c[7] != kColPad;
-    if (CHEMG == 1) {
-        const uint32_t all = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
-        lane_full = lane_full && ((all >> (kColNtShift + ty0)) & 1u);
-    }
+    const uint32_t all = c[0] & c[1] & c[2] & c[3] & c[4] & c[5] & c[6] & c[7];
+    if (CHEMG == 1) lane_full = lane_full && ((all >> (kColNtShift + ty0)) & 1u);
     A.fast8 = __all_sync(0xffffffffu, lane_full);
-    if (A.fast8) gather_edges8_body<CHEMG, STDP, true>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, A);
-    else gather_edges8_body<CHEMG, STDP, false>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, A);
+    A.fast8t = false;
+    if (CHEMG == 3) A.fast8t = A.fast8 && __all_sync(0xffffffffu, ((all >> kColNtShift) & 7u) == 7u);
+    if (CHEMG == 3 && A.fast8t) gather_edges8_body<CHEMG, STDP, true, true>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, A);
+    else if (A.fast8) gather_edges8_body<CHEMG, STDP, true, false>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, A);
+    else gather_edges8_body<CHEMG, STDP, false, false>(p, src, i, v, gap, lft_me, post_trig, li, ty0, c, A);
 }
 
 // CHEMG: 0 = no chemical gather, 1 = exactly one neurotransmitter type in the whole node array (type index ty0),
@@ -725,6 +790,11 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     if (SRC::kEarlyLoads) { if constexpr (NEEDS_CM) c_m = src.template f<F_CM>(); v_th = src.template f<F_VTH>(); }
     const int lft_me = (STDP || p.lft_pp) ? src.lft() : 0;
     const uint32_t spk_word_in = (NTREL || BCM) ? src.spk_prev_word(warp_global) : 0u;
+    // Hodgkin-Huxley: the "was increasing" word of this warp is the one global load on the consumers' path of the staged kernels.
+    // Issued here, its latency overlaps the gather; next to its use (after stores it might alias) every warp sat out a full
+    // memory round trip per tile (30 % of the stall samples, profiles/r1_step_win_hh_full.txt)
+    uint32_t wi_word_early = 0u;
+    if constexpr (MODEL == SNN_MODEL_HODGKIN_HUXLEY) wi_word_early = p.was_inc[warp_global];
     const bool spiking_prev = (spk_word_in >> lane) & 1u;
     const uint32_t flags = NTREL ? src.flags() : 0u;
     constexpr bool IZH = MODEL == SNN_MODEL_IZHIKEVICH || MODEL == SNN_MODEL_LEAKY_IZHIKEVICH || BCM;
@@ -767,7 +837,7 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     for (int ty = 0; ty < kNT; ++ty) { A.acc_t[ty] = 0.f; A.cnt[ty] = 0; }
     const bool do_e = p.electrical != 0;
     const bool do_c = NTREL && p.chemical != 0;
-    A.fast8 = false;
+    A.fast8 = false; A.fast8t = false;
     if constexpr (SRC::kWidth == 8 && !NET) gather_edges8<CHEMG, STDP>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
     else if constexpr (SRC::kWide) gather_edges_wide<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
     else gather_edges<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
@@ -793,7 +863,7 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
                 const uint32_t cnt = (CHEMG == 1) ? (ty == (int)ty0 ? A.cnt[0] : 0u) : A.cnt[ty];
                 if (cnt > 0) {
                     const float acc = (CHEMG == 1) ? A.acc_t[0] : A.acc_t[ty];
-                    const float tin = (CHEMG == 1 && A.fast8) ? acc * 0.125f : acc / (float)cnt;
+                    const float tin = ((CHEMG == 1 && A.fast8) || (CHEMG == 3 && A.fast8t)) ? acc * 0.125f : acc / (float)cnt;
                     float k1 = 0.f, k2 = 0.f;
                     if (p.rck != SNN_RC_APPROXIMATE) { k1 = src.rc(RCF_K1, ty); k2 = src.rc(RCF_K2, ty); }
                     r = rc_apply(p.rck, r, k1, k2, tin, dt);
@@ -895,17 +965,16 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
         const float h_beta = 1.f / (expf(-(v + 35.f) / 10.f) + 1.f);
         m += dt * (m_alpha * (1.f - m) - m_beta * m);
         h += dt * (h_alpha * (1.f - h) - h_beta * h);
-        const float i_na = ((powf(m, 3.f) * h) * src.template f<F_GNA>()) * (v - src.template f<F_ENA>());
+        const float i_na = ((pow3f(m) * h) * src.template f<F_GNA>()) * (v - src.template f<F_ENA>());
         const float n_alpha = (0.01f * (v + 55.f)) / (1.f - expf(-(v + 55.f) / 10.f));
         const float n_beta = 0.125f * expf(-(v + 65.f) / 80.f);
         n += dt * (n_alpha * (1.f - n) - n_beta * n);
-        const float i_k = (powf(n, 4.f) * src.template f<F_GK>()) * (v - src.template f<F_EK>());
+        const float i_k = (pow4f(n) * src.template f<F_GK>()) * (v - src.template f<F_EK>());
         const float i_kl = src.template f<F_GKL>() * (v - src.template f<F_EKL>());
         const float i_sum = input - ((i_na + i_k) + i_kl);
         v += (dt * i_sum) / c_m - rc_dv;
         v_release = v;
-        const uint32_t wi_word = p.was_inc[warp_global];
-        const bool was_increasing = (wi_word >> lane) & 1u;
+        const bool was_increasing = (wi_word_early >> lane) & 1u;
         const bool increasing_right_now = last_voltage < v;
         spike = (v > v_th) && was_increasing && !increasing_right_now;
         const uint32_t wi_new = __ballot_sync(0xffffffffu, increasing_right_now && valid);

@@ -39,7 +39,7 @@ REFRACT_DELTA_DIRAC, REFRACT_EXPONENTIAL_DECAY = range(2)
 F32, U32, I32 = range(3)
 (OPT_ELECTRICAL_SYNAPSE, OPT_CHEMICAL_SYNAPSE, OPT_DO_PLASTICITY, OPT_UPDATE_GRID_HISTORY, OPT_UPDATE_SPIKE_HISTORY,
  OPT_INTERNAL_CLOCK, OPT_PARALLEL, OPT_RNG_SEED, OPT_UPDATE_AVERAGE_HISTORY, OPT_STEPS_PER_GRAPH,
- OPT_UPDATE_EEG_HISTORY, OPT_HALO_TIMEOUT_MS) = range(12)
+ OPT_UPDATE_EEG_HISTORY, OPT_HALO_TIMEOUT_MS, OPT_GENERAL_PARTITION) = range(13)
 
 
 class StdpStruct(C.Structure):
@@ -133,6 +133,10 @@ SIGNATURES = {
     "snn_lattice_ipc_export": ([_P, _P], _i32),
     "snn_lattice_ipc_attach": ([_P, _i32, _P], _i32),
     "snn_lattice_attach_local": ([_P, _i32, _P], _i32),
+    "snn_lattice_gpart_wants": ([_P, _i32, _P, _u64, C.POINTER(_u64), C.POINTER(_u32)], _i32),
+    "snn_lattice_gpart_set_exports": ([_P, _i32, _P, _u64, _u32], _i32),
+    "snn_lattice_gpart_attach": ([_P, _i32, _P], _i32),
+    "snn_lattice_gpart_attach_local": ([_P, _i32, _P], _i32),
     "snn_network_create": ([C.POINTER(NetworkDesc), _pp], _i32),
     "snn_network_destroy": ([_P], _i32),
     "snn_network_add_lattice": ([_P, _u64, _u32, _u32], _i32),

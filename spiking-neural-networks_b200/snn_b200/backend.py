@@ -288,6 +288,27 @@ class CudaLatticeBackend(_CudaBase):
         self._ck(self.lib.snn_lattice_attach_local(self.h, direction, neighbour.h))
 
 
+    # general-graph partition (arbitrary in-edges across ranks)
+    def gpart_wants(self, peer: int):
+        """(ascending global indices of `peer`'s nodes this rank reads, first slot of them in this rank's node arrays)."""
+        n, slot = C.c_uint64(), C.c_uint32()
+        self._ck(self.lib.snn_lattice_gpart_wants(self.h, peer, None, 0, C.byref(n), C.byref(slot)))
+        idx = np.zeros(max(n.value, 1), np.uint32)
+        self._ck(self.lib.snn_lattice_gpart_wants(self.h, peer, _ptr(idx), idx.size, C.byref(n), C.byref(slot)))
+        return idx[:n.value], slot.value
+
+    def gpart_set_exports(self, peer: int, global_idx, first_slot_at_peer: int):
+        idx = _as(global_idx, np.uint32)
+        self._ck(self.lib.snn_lattice_gpart_set_exports(self.h, peer, _ptr(idx) if idx.size else None, idx.size, int(first_slot_at_peer)))
+
+    def gpart_attach(self, peer: int, blob: bytes):
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self.lib.snn_lattice_gpart_attach(self.h, peer, buf))
+
+    def gpart_attach_local(self, peer: int, other: "CudaLatticeBackend"):
+        self._ck(self.lib.snn_lattice_gpart_attach_local(self.h, peer, other.h))
+
+
 class CudaNetworkBackend(_CudaBase):
     """snn_network_t: the LatticeNetworkGPU replacement (reference: gpu_lattices/mod.rs:1560-1656)."""
     network = True

@@ -51,6 +51,28 @@ class StripLattice:
         dist.barrier(group=group)
 
 
+def attach_general(be, rank, world, group=None):
+    """General-graph partition set-up for this rank (after snn_lattice_set_graph_csr with global indices on every rank): exchange
+    the gather lists and the IPC blobs, map every peer this rank exchanges with.  One all_gather_object of small host objects."""
+    import torch.distributed as dist
+    wants = {q: be.gpart_wants(q) for q in range(world) if q != rank}
+    mine = {"wants": {q: (idx, slot) for q, (idx, slot) in wants.items() if idx.size}, "blob": None}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    peers = set(mine["wants"].keys())
+    for q in range(world):
+        if q != rank and rank in everyone[q]["wants"]:
+            idx, slot = everyone[q]["wants"][rank]
+            be.gpart_set_exports(q, idx, slot)
+            peers.add(q)
+    blobs = [None] * world
+    dist.all_gather_object(blobs, be.ipc_export() if peers else None, group=group)
+    for q in sorted(peers):
+        be.gpart_attach(q, blobs[q])
+    dist.barrier(group=group)
+    return sorted(peers)
+
+
 class LocalStrips:
     """The same row-strip partition with every strip in THIS process (snn_lattice_attach_local): strips on one device, or one
     process driving several GPUs.  `run` steps all strips concurrently from one host thread each (a strip's boundary warps wait
@@ -85,6 +107,27 @@ class LocalStrips:
                 be.attach_local(-1, self.strips[r - 1])
             if r < self.world - 1:
                 be.attach_local(+1, self.strips[r + 1])
+
+    def set_graph_csr(self, row_ptr, pre, weights):
+        """Whole-lattice CSR (global indices) cut into the strips' rows; edges may reach any node (general-graph partition)."""
+        import numpy as np
+        rp, pre, w = np.asarray(row_ptr, np.uint64), np.asarray(pre, np.uint32), np.asarray(weights, np.float32)
+        for r, be in enumerate(self.strips):
+            be.set_option(K.OPT_GENERAL_PARTITION, 1)   # the same mode on every rank
+            q0, q1 = self.bounds[r] * self.cols, self.bounds[r + 1] * self.cols
+            s, t = int(rp[q0]), int(rp[q1])
+            be.connect_csr(0, 0, rp[q0:q1 + 1] - rp[q0], pre[s:t], w[s:t])
+
+    def attach_general(self):
+        """General-graph partition: exchange the gather lists and attach every pair of ranks that exchanges, in this process."""
+        wants = {(r, q): self.strips[r].gpart_wants(q) for r in range(self.world) for q in range(self.world) if q != r}
+        pairs = set()
+        for (r, q), (idx, slot) in wants.items():
+            if idx.size:
+                self.strips[q].gpart_set_exports(r, idx, slot)
+                pairs.add((r, q)); pairs.add((q, r))
+        for (r, q) in sorted(pairs):
+            self.strips[r].gpart_attach_local(q, self.strips[q])
 
     def run(self, iterations, rewards=None):
         import threading

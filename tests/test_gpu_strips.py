@@ -139,3 +139,72 @@ def test_local_strip_halo_timeout_is_an_error_not_a_hang():
     with pytest.raises(S.SnnError) as ei:
         strips.strips[0].run(5)     # strip 1 is never stepped
     assert ei.value.status == 6      # SNN_GPU_WAIT_ERROR
+
+
+# ------------------------------------------------------------------ general-graph partition (second half)
+def _random_radius_csr(rows, cols, seed, radius, p):
+    """tests/gpu_accuracy.rs:28-32 style: connect x -> y when x != y, distance <= radius, with probability p; random weights."""
+    import scenarios as SC
+    conn, w = SC.random_graph(rows, cols, seed, radius=radius, p=p, weights="rand")
+    return SC.dense_to_csr(conn, w)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+@pytest.mark.parametrize("shape,radius,chem,stdp", [((12, 9), 2.5, None, False), ((16, 10), 5.0, "ampa", True), ((14, 7), 30.0, "mixed", True)])
+def test_general_graph_partition_matches_the_oracle(world, shape, radius, chem, stdp):
+    """Contiguous node ranges per rank, random-radius graphs whose edges cross rank boundaries arbitrarily (radius 30 = almost
+    all-to-all: every rank reads nodes of every other rank, also of non-neighbouring ranks): gather-list ghosts, per-neuron
+    export lists, completion counters.  Electrical-only Izhikevich is bit-exact; chemistry + STDP to 1e-4, rasters exact."""
+    rows, cols = shape
+    n = rows * cols
+    rp, pre, w = _random_radius_csr(rows, cols, 41, radius, 0.6)
+    parts = LocalStrips(K.MODEL_IZH, rows, cols, world)
+
+    def configure(set_field, each):
+        rng = np.random.default_rng(19)
+        set_field("current_voltage", rng.uniform(-65, 30, n).astype(f32), 1)
+        set_field("b", rng.uniform(0.25, 0.36, n).astype(f32), 1)
+        set_field("gap_conductance", (10 * rng.uniform(0.5, 1.5, n)).astype(f32), 1)
+        set_field("c_m", np.full(n, 4.0, f32), 1)
+        if chem:
+            flags = np.zeros((n, 3), np.uint32)
+            flags[:, 0] = 1
+            if chem == "mixed":
+                flags[:, 0] = (np.arange(n) // 5) % 2
+                flags[:, 2] = 1 - flags[:, 0]
+            set_field("neurotransmitters$flags", flags, 3)
+            set_field("receptors$flags", np.ones((n, 3), np.uint32) if chem == "mixed" else flags, 3)
+
+        def opts(be):
+            be.set_option(K.OPT_ELECTRICAL_SYNAPSE, 1)
+            be.set_option(K.OPT_CHEMICAL_SYNAPSE, int(bool(chem)))
+            be.set_option(K.OPT_DO_PLASTICITY, int(stdp), 0)
+            be.set_plasticity(0, 0.05, 0.04, 4.5, 3.0, 0.1)
+        each(opts)
+
+    configure(lambda nm, a, per: parts.set_field(nm, a, per), parts.each)
+    parts.set_graph_csr(rp, pre, w)
+    parts.attach_general()
+    ob = _oracle(rows, cols)
+    configure(lambda nm, a, per: ob.set_field(0, nm, np.asarray(a).reshape(-1)), lambda fn: fn(ob))
+    ob.connect_csr(0, 0, rp, pre, w)
+    names = STATE + (["neurotransmitters$t", "receptors$AMPA$r$kinetics$r"] if chem else [])
+    for k in (21, 1, 20):
+        parts.run(k)
+        ob.run(k)
+        for nm in names:
+            got, want = parts.get_field(nm), ob.get_field(0, nm)
+            if got.dtype.kind in "iu" or not (chem or stdp):
+                assert (got == want).all(), nm
+            else:
+                np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-3, err_msg=nm)
+    grp, gpre, gw = parts.graph_csr()
+    orp, opre, ow = ob.get_connection_csr()
+    assert (grp == orp).all() and (gpre == opre).all()
+    np.testing.assert_allclose(gw, ow, rtol=1e-4, atol=1e-5)
+    assert (ob.get_field(0, "last_firing_time") >= 0).sum() > n // 4
+    if stdp:
+        assert np.abs(ow - w).max() > 1e-3
+    if radius >= 30 and world >= 3:   # non-neighbouring ranks exchange too
+        idx, _ = parts.strips[0].gpart_wants(world - 1)
+        assert idx.size > 0

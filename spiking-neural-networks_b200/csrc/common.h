@@ -300,7 +300,12 @@ struct RstdpParams {
     float dopamine, tau_c, a_plus, a_minus, tau_plus, tau_minus, dt;
     uint8_t *counter; float *dw, *c;
     uint32_t canonical;   // every edge has counter == 0 and dw == 0 between timesteps (see rstdp_edge_kernel)
+    // the STDP term depends on the two spike times only through their integer difference: tab[0][k] = term for t_post - t_pre = k,
+    // tab[1][k] for t_pre - t_post = k (k = 1 .. tab_n - 1, the last entry stands for every larger difference: the term has
+    // underflowed to +-0 there).  Filled by rstdp_table_kernel with the very function the kernel would call: bit-identical.
+    const float *tab; uint32_t tab_n;
 };
+cudaError_t launch_rstdp_table(const RstdpParams &r, float *tab, uint32_t tab_n, cudaStream_t s);
 cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaStream_t s);
 cudaError_t launch_finalize(const StepParams &p, int model, const float *v_prev, cudaStream_t s);
 cudaError_t launch_sell_from_csr(const uint64_t *row_ptr, const uint32_t *pre, const float *w, const uint8_t *node_flags,

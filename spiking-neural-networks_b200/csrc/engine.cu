@@ -67,6 +67,7 @@ Engine::~Engine() {
     if (flags_) cudaFree(flags_);
     if (halo_done_) cudaFree(halo_done_);
     if (multi_barrier_) cudaFree(multi_barrier_);
+    if (rs_tab_) cudaFree(rs_tab_);
     if (scratch_) cudaFree(scratch_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -800,6 +801,7 @@ int Engine::gpart_attach(int peer, const IpcBlob *blob_in, Engine *local_peer) {
         if (r) return fail(r, local_peer->last_error);
         G->slab = local_peer->slab_; G->flags = local_peer->flags_;
         local_peer->layout_frozen_ = true;
+        local_peers_.push_back(local_peer);
     } else {
         blob = *blob_in;
         if (blob.magic != 0x534E4E42u || blob.version != SNN_B200_ABI_VERSION) return fail(SNN_INVALID_ARGUMENT, "bad ipc blob");
@@ -1937,6 +1939,23 @@ bool Engine::build_win_params(WinParams &wp, int chemg, bool ntrel, bool stdp, b
     return true;
 }
 
+// Partition handles of ONE process (attach_local / gpart_attach_local) are stepped from one host thread each, and their kernels
+// wait for each other on the device.  CUDA only guarantees progress if every kernel a kernel waits for was launched EARLIER:
+// streams that happen to share a hardware work queue execute in launch order, so a waiting kernel queued ahead of the kernel it
+// waits for would never see it start (observed as time-outs with 4 handles on one device).  Hence: before launching a kernel
+// that waits for the counter value `need`, wait on the host until every local peer has launched the kernel that raises it.
+void Engine::wait_local_peers_launched(unsigned long long need, bool second) {
+    for (Engine *q : local_peers_) {
+        const std::atomic<unsigned long long> &c = second ? q->launched_pub2_ : q->launched_pub_;
+        const auto t0 = std::chrono::steady_clock::now();
+        while (c.load(std::memory_order_acquire) < need) {
+            std::this_thread::sleep_for(std::chrono::microseconds(5));
+            // a peer that never runs: fall through after the halo time-out, the device-side wait then reports the error
+            if (std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() > (double)halo_timeout_ms) return;
+        }
+    }
+}
+
 int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, const float *rewards) {
     if (elapsed_ms) *elapsed_ms = 0.f;
     if (launches) *launches = 0;
@@ -1978,7 +1997,22 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     if (reward_mode || bcm_mode) stdp = false;
     if (rmod) { int rr = ensure_reward_arrays(); if (rr) return rr; }
     RstdpParams rsp{rstdp.dopamine, rstdp.tau_c, rstdp.a_plus, rstdp.a_minus, rstdp.tau_plus, rstdp.tau_minus, rstdp.dt,
-                    rs_counter_, rs_dw_, rs_c_, rs_canonical_ ? 1u : 0u};
+                    rs_counter_, rs_dw_, rs_c_, rs_canonical_ ? 1u : 0u, nullptr, 0u};
+    if (rmod && !getenv("SNN_B200_RSTDP_NOTAB")) {
+        // difference table of the STDP term: long enough for the exponential to have underflowed to zero at its end
+        const double reach = 110.0 * std::max((double)rstdp.tau_plus, (double)rstdp.tau_minus) / std::max((double)rstdp.dt, 1e-30);
+        if (reach > 0 && reach < 60000.0 && rstdp.tau_plus > 0.f && rstdp.tau_minus > 0.f && rstdp.dt > 0.f) {
+            const uint32_t tab_n = (uint32_t)reach + 8u;
+            if (rs_tab_n_ != tab_n) {
+                if (rs_tab_) cudaFree(rs_tab_);
+                rs_tab_ = nullptr; rs_tab_n_ = 0;
+                CK(dev_alloc(&rs_tab_, (size_t)tab_n * 2), SNN_GPU_BUFFER_CREATE_ERROR);
+                rs_tab_n_ = tab_n;
+            }
+            CK(launch_rstdp_table(rsp, rs_tab_, tab_n, stream_), SNN_GPU_QUEUE_FAILURE);   // the parameters may have changed since the last run
+            rsp.tab = rs_tab_; rsp.tab_n = tab_n;
+        }
+    }
     const bool lft_pp = stdp || rmod || (n_trains && electrical) || part_world > 1;
     const bool rmod_part = rmod && part_world > 1;
 
@@ -2068,6 +2102,8 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
         cudaError_t e = gpart_ ? launch_gpart_push(hp, stream_) : launch_halo_push(hp, stream_);
         if (e != cudaSuccess) { free_hist(); return cuda_fail(e, SNN_GPU_QUEUE_FAILURE, "halo_push"); }
         halo_epoch_ += 1;
+        launched_pub_.store(halo_epoch_, std::memory_order_release);
+        launched_pub2_.store(halo_epoch_, std::memory_order_release);
         n_launch++;
         // rendez-vous before any step kernel is enqueued: the in-kernel waits are bounded, so ordinary host-side skew between
         // the ranks (Python work, history drains, allocation) must be absorbed here, where nothing has been computed yet
@@ -2163,6 +2199,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             sp.spike_hist = want_spk ? d_spk + s * n_words : nullptr;
             sp.out_par = (uint32_t)out;
             sp.halo_epoch = halo_nowait ? 0ull : halo_epoch_;   // timing experiment only (SNN_B200_HALO_NOWAIT): results are wrong
+            if (!local_peers_.empty()) wait_local_peers_launched(halo_epoch_, rmod_part);
             if (n_neurons && win_ok) {
                 cudaError_t e = launch_step_win(sp, win, model, chemg, ntrel, stdp, win_grid, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_win"); break; }
@@ -2198,11 +2235,16 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                     for (int d = 0; d < 2; ++d) ep.halo[d].my_flag = halo_dir_[d].my_flag;
                     ep.halo_epoch = halo_epoch_ + 1;
                 }
+                if (rmod_part && !local_peers_.empty()) {
+                    launched_pub_.store(halo_epoch_ + 1, std::memory_order_release);   // my step kernel of this timestep is in the queue
+                    wait_local_peers_launched(halo_epoch_ + 1, false);
+                }
                 cudaError_t e = launch_rstdp_edges(ep, rsp, stream_);
+                if (rmod_part) launched_pub2_.store(halo_epoch_ + 1, std::memory_order_release);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_rstdp_edges"); break; }
                 n_launch++;
             }
-            if (part_world > 1) halo_epoch_ += 1;
+            if (part_world > 1) { halo_epoch_ += 1; launched_pub_.store(halo_epoch_, std::memory_order_release); }
             // LatticeNetwork::iterate: clock += 1, then the spike trains step with their own clocks
             // (neuron/mod.rs:2582-2591)
             if (n_trains) {
@@ -2235,6 +2277,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             fp.lft_in = LFT_[lft_loc_];
             fp.lft_out = LFT_[lft_loc_ ^ 1];  // spike trains: last_firing_time from before their last iterate
             fp.halo_epoch = halo_epoch_;
+            if (!local_peers_.empty()) wait_local_peers_launched(halo_epoch_, false);
             cudaError_t e = launch_flush_stdp(fp, stream_);
             if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "flush_stdp"); break; }
             n_launch++;
@@ -2443,7 +2486,10 @@ int Engine::attach_local(int direction, Engine *peer) {
     int r = peer->ipc_export_layout(&blob);
     if (r) return fail(r, peer->last_error);
     r = attach_view(direction, &blob, peer->slab_, peer->flags_);
-    if (!r) peer->layout_frozen_ = layout_frozen_ = true;   // raw pointers into each other's slabs from now on
+    if (!r) {
+        peer->layout_frozen_ = layout_frozen_ = true;   // raw pointers into each other's slabs from now on
+        local_peers_.push_back(peer);
+    }
     return r;
 }
 

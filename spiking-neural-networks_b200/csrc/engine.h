@@ -4,6 +4,7 @@
 // neuron lattices in ascending id order, then spike-train lattices, one canonical node index space,
 // one in-edge table.  A reference `Lattice` is an Engine with a single lattice.
 #pragma once
+#include <atomic>
 #include <cstdint>
 #include <functional>
 #include <map>
@@ -190,6 +191,7 @@ private:
     uint32_t *slice_off_ = nullptr, *col_ = nullptr; float *wgt_ = nullptr;
     // TraceRSTDP members next to wgt_ (same sliced-ELL positions), allocated on the first reward-modulated run
     uint8_t *rs_counter_ = nullptr; float *rs_dw_ = nullptr, *rs_c_ = nullptr; uint64_t rs_elems_ = 0;
+    float *rs_tab_ = nullptr; uint32_t rs_tab_n_ = 0;   // difference table of the reward-modulated STDP term (RstdpParams::tab)
     bool rs_canonical_ = true;   // counter == 0 and dw == 0 on every edge (TraceRSTDP::default, kept by two calls per timestep)
     int ensure_reward_arrays();
     void free_reward_arrays();
@@ -228,6 +230,10 @@ private:
     int ipc_export_layout(IpcBlob *blob);
     int attach_view(int direction, const IpcBlob *blob, void *slab, void *flags);
     bool layout_frozen_ = false;
+    // in-process neighbours: host-side launch ordering (see wait_local_peers_launched)
+    std::vector<Engine *> local_peers_;
+    std::atomic<unsigned long long> launched_pub_{0}, launched_pub2_{0};
+    void wait_local_peers_launched(unsigned long long need, bool second);
     int cuda_fail(cudaError_t e, int status, const char *what);
     int ensure_scratch(size_t bytes);
     void free_device();

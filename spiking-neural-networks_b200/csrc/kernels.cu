@@ -221,6 +221,27 @@ __device__ __forceinline__ float rstdp_delta(const RstdpParams &r, int t_pre_i, 
     return (-1.f * r.a_minus) * expf((-1.f * fabsf((t_post - t_pre) * r.dt)) / r.tau_minus);   // callers exclude None and t_pre == t_post
 }
 
+// the same term through the difference table (see RstdpParams::tab); spike times below 2^24 are exact in f32, so the term is a
+// function of the integer difference alone
+__device__ __forceinline__ float rstdp_delta_tab(const RstdpParams &r, int t_pre_i, int t_post_i) {
+    const int d = t_post_i - t_pre_i;
+    const uint32_t k = min((uint32_t)abs(d), r.tab_n - 1u);
+    return __ldg(r.tab + (d > 0 ? 0u : r.tab_n) + k);
+}
+
+__global__ void rstdp_table_kernel(const __grid_constant__ RstdpParams r, float *tab, uint32_t tab_n) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= tab_n) return;
+    // spike times 0 and k: exactly representable, the difference is what matters
+    tab[k] = k ? rstdp_delta(r, 0, (int)k) : 0.f;
+    tab[tab_n + k] = k ? rstdp_delta(r, (int)k, 0) : 0.f;
+}
+
+cudaError_t launch_rstdp_table(const RstdpParams &r, float *tab, uint32_t tab_n, cudaStream_t s) {
+    rstdp_table_kernel<<<(tab_n + 255u) / 256u, 256, 0, s>>>(r, tab, tab_n);
+    return cudaGetLastError();
+}
+
 __device__ __forceinline__ void rstdp_call(const RstdpParams &r, float delta_w, float decay_c, uint32_t &counter, float &dw, float &c, float &w) {
     dw = dw + delta_w;
     if (counter == 0u) {
@@ -243,7 +264,7 @@ constexpr int kRsSlices = 4;
 // the state two calls per timestep always return to, so until a caller stores other values through
 // snn_lattice_set_connection_traces the counter / dw arrays hold zeros and need neither be read nor written:
 // dw = 0 + d1, then (0 + d1) + d2 — the same additions in the same order.
-template <bool CANON>
+template <bool CANON, bool TAB>
 __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
@@ -308,9 +329,10 @@ __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constan
             const bool first_live = (t_pre1 >= 0 && t_post1 >= 0 && t_pre1 != t_post1);
             const bool second_live = (new_pre[u] >= 0 && new_post[u] >= 0 && new_pre[u] != new_post[u]);
             if (!first_live && !second_live && dw[u] == 0.f && cc[u] == 0.f && cnt[u] == 0u) continue;
-            const float d2 = second_live ? rstdp_delta(r, new_pre[u], new_post[u]) : 0.f;
+            const float d2 = second_live ? (TAB ? rstdp_delta_tab(r, new_pre[u], new_post[u]) : rstdp_delta(r, new_pre[u], new_post[u])) : 0.f;
             // the two calls see the same pair of spike times unless an end of the edge spiked in this very step
-            const float d1 = (t_pre1 == new_pre[u] && t_post1 == new_post[u]) ? d2 : (first_live ? rstdp_delta(r, t_pre1, t_post1) : 0.f);
+            const float d1 = (t_pre1 == new_pre[u] && t_post1 == new_post[u]) ? d2
+                             : (first_live ? (TAB ? rstdp_delta_tab(r, t_pre1, t_post1) : rstdp_delta(r, t_pre1, t_post1)) : 0.f);
             rstdp_call(r, d1, decay_c, cnt[u], dw[u], cc[u], w[u]);
             rstdp_call(r, d2, decay_c, cnt[u], dw[u], cc[u], w[u]);
             if (!CANON) { r.counter[e[u]] = (uint8_t)cnt[u]; r.dw[e[u]] = dw[u]; }
@@ -543,8 +565,11 @@ cudaError_t launch_bcm_edges(const StepParams &p, const BcmParams &b, cudaStream
 cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
     const unsigned n_slices = (p.n_neurons + 31u) / 32u;
-    if (r.canonical) rstdp_edge_kernel<true><<<(n_slices + kRsSlices - 1) / kRsSlices, 256, 0, s>>>(p, r);
-    else rstdp_edge_kernel<false><<<(n_slices + kRsSlices - 1) / kRsSlices, 256, 0, s>>>(p, r);
+    const unsigned grid = (n_slices + kRsSlices - 1) / kRsSlices;
+    // the table stands for the formula while every spike time is exact in f32 (clock < 2^24)
+    const bool tab = r.tab != nullptr && p.clock < (1u << 24);
+    if (r.canonical) { if (tab) rstdp_edge_kernel<true, true><<<grid, 256, 0, s>>>(p, r); else rstdp_edge_kernel<true, false><<<grid, 256, 0, s>>>(p, r); }
+    else { if (tab) rstdp_edge_kernel<false, true><<<grid, 256, 0, s>>>(p, r); else rstdp_edge_kernel<false, false><<<grid, 256, 0, s>>>(p, r); }
     return cudaGetLastError();
 }
 

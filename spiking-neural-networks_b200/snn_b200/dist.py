@@ -76,7 +76,9 @@ def attach_general(be, rank, world, group=None):
 class LocalStrips:
     """The same row-strip partition with every strip in THIS process (snn_lattice_attach_local): strips on one device, or one
     process driving several GPUs.  `run` steps all strips concurrently from one host thread each (a strip's boundary warps wait
-    for its neighbours' progress on the device, so the calls must overlap)."""
+    for its neighbours' progress on the device, so the calls must overlap).  On a single device the strips' kernels must be able
+    to run concurrently: keep them small, and raise CUDA_DEVICE_MAX_CONNECTIONS (before CUDA starts) so that no two of the
+    handles' streams share a hardware work queue."""
 
     def __init__(self, model, rows, cols, world, ntk=K.NT_APPROXIMATE, rck=K.RC_APPROXIMATE, devices=None):
         self.rows, self.cols, self.world = rows, cols, world

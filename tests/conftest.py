@@ -6,6 +6,11 @@ import sys
 
 import pytest
 
+# tests/test_gpu_strips.py steps several partition handles of ONE process on ONE device; their step kernels wait for each other on
+# the device, so they must never share a hardware work queue (a kernel queued behind the kernel that waits for it would never
+# start).  32 queues instead of the default 8; must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "spiking-neural-networks_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     if p not in sys.path:

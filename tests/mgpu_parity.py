@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--no-chem", action="store_true")
     ap.add_argument("--no-stdp", action="store_true")
     ap.add_argument("--runs", type=int, default=2, help="split the steps over this many run() calls")
+    ap.add_argument("--graph", choices=["grid", "random"], default="grid",
+                    help="random: tests/gpu_accuracy.rs-style random-radius graph whose edges cross rank boundaries anywhere (general-graph partition)")
+    ap.add_argument("--graph-radius", type=float, default=6.0)
     ap.add_argument("--reward", action="store_true", help="RewardModulatedLattice: RewardModulatedSTDP over TraceRSTDP weights, a reward per step")
     args = ap.parse_args()
 
@@ -32,7 +35,7 @@ def main():
     import torch.distributed as dist
     from snn_b200 import _capi as K
     from snn_b200.backend import CudaLatticeBackend
-    from snn_b200.dist import StripLattice
+    from snn_b200.dist import StripLattice, attach_general
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -48,13 +51,42 @@ def main():
     flags = np.zeros((n, 3), np.uint32)
     flags[:, 0] = 1
 
+    csr = None
+    if args.graph == "random":
+        # vectorised random-radius graph: for every offset (dr, dc) within the radius, connect with probability 0.6
+        g = np.random.default_rng(123)
+        R = int(np.ceil(args.graph_radius))
+        rr, cc = np.divmod(np.arange(n), cols)
+        pres, posts, ws = [], [], []
+        for dr in range(-R, R + 1):
+            for dc in range(-R, R + 1):
+                if (dr == 0 and dc == 0) or np.hypot(dr, dc) > args.graph_radius:
+                    continue
+                ok = (rr + dr >= 0) & (rr + dr < rows) & (cc + dc >= 0) & (cc + dc < cols) & (g.random(n) <= 0.6)
+                posts.append(np.nonzero(ok)[0]); pres.append((rr[ok] + dr) * cols + cc[ok] + dc)
+                ws.append(g.uniform(0.2, 1.5, int(ok.sum())).astype(f32))
+        posts, pres, ws = np.concatenate(posts), np.concatenate(pres), np.concatenate(ws)
+        order = np.lexsort((pres, posts))
+        posts, pres, ws = posts[order], pres[order].astype(np.uint32), ws[order]
+        rp = np.zeros(n + 1, np.uint64)
+        np.add.at(rp, posts + 1, 1)
+        csr = (np.cumsum(rp).astype(np.uint64), pres, ws)
+
     def configure(be, sl):
         for name, arr in init.items():
             be.set_field(0, name, arr[sl])
         if chem:
             be.set_field(0, "neurotransmitters$flags", flags[sl])
             be.set_field(0, "receptors$flags", flags[sl])
-        be.connect_grid(0, args.radius, 0.8)
+        if csr is None:
+            be.connect_grid(0, args.radius, 0.8)
+        else:
+            rp, pre, w = csr
+            q0, q1 = sl.start, sl.stop
+            s, t = int(rp[q0]), int(rp[q1])
+            if sl.stop - sl.start != n:
+                be.set_option(K.OPT_GENERAL_PARTITION, 1)
+            be.connect_csr(0, 0, rp[q0:q1 + 1] - rp[q0], pre[s:t], w[s:t])
         be.set_option(K.OPT_ELECTRICAL_SYNAPSE, 1)
         be.set_option(K.OPT_CHEMICAL_SYNAPSE, int(chem))
         be.set_option(K.OPT_DO_PLASTICITY, int(not args.no_stdp and not args.reward))
@@ -66,7 +98,11 @@ def main():
     strip = StripLattice(K.MODEL_IZH, rows, cols, rank, world, device=local)
     sl = slice(strip.row_begin * cols, strip.row_end * cols)
     configure(strip.be, sl)
-    strip.attach()
+    if csr is None:
+        strip.attach()
+    else:
+        peers = attach_general(strip.be, rank, world)
+        print(f"[rank {rank}] general-graph partition: exchanges with ranks {peers}", flush=True)
     per = [args.steps // args.runs] * args.runs
     per[-1] += args.steps - sum(per)
     rewards = np.random.default_rng(5).uniform(-0.3, 0.3, args.steps).astype(f32)
@@ -106,7 +142,7 @@ def main():
         gw = np.concatenate([g["weights"] for g in gathered])
         gp = np.concatenate([g["pre"] for g in gathered])
         same = (gp == pre2).all() and (gw == w2).all()
-        print(f"{'graph (pre, weights)':32s} {'OK' if same else 'MISMATCH'}; max |dw| from 0.8: {np.abs(w2 - 0.8).max():.4f}")
+        print(f"{'graph (pre, weights)':32s} {'OK' if same else 'MISMATCH'}; max |dw| from the initial weights: {np.abs(w2 - (0.8 if csr is None else csr[2])).max():.4f}")
         ok &= bool(same)
         if args.reward:
             want_tr = full.connection_traces()

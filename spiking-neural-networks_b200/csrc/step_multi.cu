@@ -15,6 +15,9 @@
 #include "step_body.cuh"
 #include "train_body.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace snn {
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p) {
@@ -35,27 +38,29 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
     __syncthreads();
 }
 
-template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET, bool WIDE>
-__global__ void __launch_bounds__(WIDE ? kWideWarps * 32 : 256)
+// lattices of up to ~10^4 neurons fit ONE thread-block cluster (16 CTAs of 640 threads): the hardware cluster barrier (release /
+// acquire at cluster scope) replaces the atomic + poll round trips through L2 of the grid barrier — 1.3 us -> 0.3 us per timestep
+constexpr int kClusterThreads = 640;
+constexpr unsigned kClusterCtas = 16;
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET, bool WIDE, bool CLUSTER>
+__global__ void __launch_bounds__(WIDE ? kWideWarps * 32 : (CLUSTER ? kClusterThreads : 256))
 step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ TrainParams t0, const __grid_constant__ MultiParams m) {
     extern __shared__ __align__(16) unsigned char multi_sm[];   // WIDE: 2 x wide_buf_bytes(CHEMG)
-    __shared__ StepParams p;
-    __shared__ TrainParams tp;
-    {   // cooperative copy of the launch parameters into shared memory
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(&p0);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(&p);
-        for (uint32_t k = threadIdx.x; k < sizeof(StepParams) / 4; k += blockDim.x) dst[k] = src[k];
-        const uint32_t *src2 = reinterpret_cast<const uint32_t *>(&t0);
-        uint32_t *dst2 = reinterpret_cast<uint32_t *>(&tp);
-        for (uint32_t k = threadIdx.x; k < sizeof(TrainParams) / 4; k += blockDim.x) dst2[k] = src2[k];
-    }
+    // per-thread copies of the launch parameters: after inlining every access has a constant offset, so the compiler splits the
+    // structs into scalars — the step-invariant fields stay operands from the constant bank (as in the one-launch-per-step
+    // kernels), the few fields that change per timestep live in registers
+    StepParams p = p0;
+    TrainParams tp = t0;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t warps_per_cta = blockDim.x >> 5;
     const uint32_t n_slices = (p0.n_neurons + 31u) >> 5, n_twarps = (t0.n_trains + 31u) >> 5;
     unsigned int arrivals = 0;
     for (uint32_t s = 0; s < m.steps; ++s) {
-        __syncthreads();   // every warp is done with the previous step's parameters
-        if (threadIdx.x == 0) {
+        {
             const uint32_t in = (m.cur ^ s) & 1u, out = in ^ 1u;
             p.clock = p0.clock + s;
             p.apply_pending = (STDP && (s > 0u || m.first_pending)) ? 1u : 0u;
@@ -76,7 +81,6 @@ step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__
                 tp.spike_hist = m.tspike_hist ? m.tspike_hist + (size_t)s * m.t_words : nullptr;
             }
         }
-        __syncthreads();
         // ---- the neurons of this timestep
         if constexpr (WIDE) {
             for (uint32_t slice = blockIdx.x; slice < n_slices; slice += gridDim.x) {   // uniform per CTA: gather_edges_wide syncs the CTA
@@ -108,10 +112,16 @@ step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__
         // reads the trains' last_firing_time from before this step out of lft_out, which the trains overwrite now: wait for every
         // neuron first
         if (NET && t0.n_trains) {
-            if (m.train_sync) { arrivals += gridDim.x; grid_barrier(m.barrier, arrivals); }
+            if (m.train_sync) {
+                if constexpr (CLUSTER) cluster_barrier();
+                else { arrivals += gridDim.x; grid_barrier(m.barrier, arrivals); }
+            }
             for (uint32_t tw = blockIdx.x * warps_per_cta + warp; tw < n_twarps; tw += gridDim.x * warps_per_cta) train_step(tp, tw, lane);
         }
-        if (s + 1u < m.steps) { arrivals += gridDim.x; grid_barrier(m.barrier, arrivals); }
+        if (s + 1u < m.steps) {
+            if constexpr (CLUSTER) cluster_barrier();
+            else { arrivals += gridDim.x; grid_barrier(m.barrier, arrivals); }
+        }
     }
 }
 
@@ -120,17 +130,49 @@ step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET, bool WIDE>
 static cudaError_t launch_multi_5(const StepParams &p, const TrainParams &t, const MultiParams &m, int device, bool dry, cudaStream_t s) {
-    auto k = step_multi_kernel<MODEL, CHEMG, NTREL, STDP, NET, WIDE>;
+    const uint32_t n_slices = (p.n_neurons + 31u) / 32u, n_twarps = (t.n_trains + 31u) / 32u;
+    cudaError_t e;
+    if constexpr (!WIDE) {
+        // small enough for one cluster: every slice (and spike-train warp) gets its own warp in 16 CTAs of 640 threads
+        static const bool cluster_on = !(getenv("SNN_B200_MULTI_CLUSTER") && atoi(getenv("SNN_B200_MULTI_CLUSTER")) == 0);
+        const uint32_t warps = kClusterCtas * (kClusterThreads / 32);
+        if (cluster_on && n_slices <= warps && n_twarps <= warps) {
+            auto kc = step_multi_kernel<MODEL, CHEMG, NTREL, STDP, NET, false, true>;
+            static thread_local int cluster_ok = -1;   // per instantiation
+            if (cluster_ok < 0) {
+                cluster_ok = 0;
+                if (cudaFuncSetAttribute(kc, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                    cudaLaunchConfig_t cfg{};
+                    cfg.gridDim = dim3(kClusterCtas); cfg.blockDim = dim3(kClusterThreads);
+                    cudaLaunchAttribute at{};
+                    at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = kClusterCtas; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+                    cfg.attrs = &at; cfg.numAttrs = 1;
+                    int n_clusters = 0;
+                    if (cudaOccupancyMaxActiveClusters(&n_clusters, kc, &cfg) == cudaSuccess && n_clusters >= 1) cluster_ok = 1;
+                }
+                cudaGetLastError();
+            }
+            if (getenv("SNN_B200_MULTI_DEBUG") && !dry) fprintf(stderr, "[snn] multi-step launch: cluster path %s (%u slices)\n", cluster_ok == 1 ? "ON" : "unavailable", n_slices);
+            if (cluster_ok == 1) {
+                if (dry) return cudaSuccess;
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(kClusterCtas); cfg.blockDim = dim3(kClusterThreads); cfg.stream = s;
+                cudaLaunchAttribute at{};
+                at.id = cudaLaunchAttributeClusterDimension; at.val.clusterDim.x = kClusterCtas; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+                cfg.attrs = &at; cfg.numAttrs = 1;
+                return cudaLaunchKernelEx(&cfg, kc, p, t, m);
+            }
+        }
+    }
+    auto k = step_multi_kernel<MODEL, CHEMG, NTREL, STDP, NET, WIDE, false>;
     const int threads = WIDE ? kWideWarps * 32 : 256;
     const size_t smem = WIDE ? 2u * wide_buf_bytes(CHEMG) : 0u;
-    cudaError_t e;
     if (smem > 40u * 1024u) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     int per_sm = 0, sms = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    const uint32_t n_slices = (p.n_neurons + 31u) / 32u, n_twarps = (t.n_trains + 31u) / 32u;
     const uint32_t want_n = WIDE ? n_slices : (n_slices + 7u) / 8u, want_t = WIDE ? (n_twarps + kWideWarps - 1u) / kWideWarps : (n_twarps + 7u) / 8u;
     const uint32_t want = want_n > want_t ? want_n : want_t;
     const uint32_t cap = (uint32_t)per_sm * (uint32_t)sms;

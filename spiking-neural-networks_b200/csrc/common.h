@@ -156,6 +156,7 @@ struct MultiParams {
     float *grid_hist; uint32_t *spike_hist; float *tgrid_hist; uint32_t *tspike_hist;   // staged history of the chunk (record s at + s * row)
     uint64_t n_neurons, n_words, n_trains, t_words;
     unsigned int *barrier;    // grid-wide arrival counter, zero at launch
+    uint32_t wide_stage;      // wide-row variant: stage the node state in shared memory (small networks)
 };
 // dry = only report whether the configuration is eligible (cudaSuccess) without launching
 cudaError_t launch_step_multi(const StepParams &p, const TrainParams &t, const MultiParams &m, int model, int chemg, bool ntrel, bool stdp,
@@ -288,7 +289,13 @@ cudaError_t launch_step_win(const StepParams &p, const WinParams &wp, int model,
 cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, cudaStream_t s);
 // same contract as launch_step, one CTA per slice (step_wide.cu): graphs with wide rows, single-GPU handles only
 constexpr uint32_t kWideMinWidth = 48;   // mean k-rows per slice from which the wide kernel is used
-cudaError_t launch_step_wide(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, cudaStream_t s);
+// scratch != nullptr: two passes (per-edge terms of every slice chunk on its own CTA, parked in `scratch`: chunks_cap buffers of
+// wide_chunk_bytes(chemg) per slice; then the ordered sums) — very wide slices, where one SM per slice is issue-bound
+cudaError_t launch_step_wide(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, unsigned char *scratch, uint32_t chunks_cap,
+                             cudaStream_t s);
+uint32_t wide_chunk_bytes(int chemg);
+uint32_t wide_chunk_krows();
+size_t wide_part_bytes();   // per slice, after the chunk buffers: partial sums, counts and the arrival counter of the sum pass (zeroed once)
 cudaError_t launch_trains(const TrainParams &p, cudaStream_t s);
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s);
 // RewardModulatedSTDP::update_weight on every edge, both calls of the timestep (p.lft_in = last_firing_time before the step,

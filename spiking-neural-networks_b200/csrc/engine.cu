@@ -68,6 +68,7 @@ Engine::~Engine() {
     if (halo_done_) cudaFree(halo_done_);
     if (multi_barrier_) cudaFree(multi_barrier_);
     if (rs_tab_) cudaFree(rs_tab_);
+    if (wide_scratch_) cudaFree(wide_scratch_);
     if (scratch_) cudaFree(scratch_);
     if (ev0_) cudaEventDestroy(ev0_);
     if (ev1_) cudaEventDestroy(ev1_);
@@ -2005,6 +2006,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             const uint32_t tab_n = (uint32_t)reach + 8u;
             if (rs_tab_n_ != tab_n) {
                 if (rs_tab_) cudaFree(rs_tab_);
+    if (wide_scratch_) cudaFree(wide_scratch_);
                 rs_tab_ = nullptr; rs_tab_n_ = 0;
                 CK(dev_alloc(&rs_tab_, (size_t)tab_n * 2), SNN_GPU_BUFFER_CREATE_ERROR);
                 rs_tab_n_ = tab_n;
@@ -2030,6 +2032,32 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     // wide rows (hundreds of in-edges per neuron, e.g. all-to-all spike-train input): one CTA per slice
     bool wide = !win_ok && !tma_ok && part_world == 1 && n_slices_ > 0 && sell_krows_ / n_slices_ >= kWideMinWidth;
     if (const char *e = getenv("SNN_B200_WIDE")) wide = wide && atoi(e) != 0;
+    // very wide slices (hundreds of k-rows): one SM per slice cannot issue the per-edge instructions fast enough — two passes, the
+    // per-edge terms of every (slice, chunk) on its own CTA, then the ordered sums (step_wide.cu)
+    bool wide_split = false;
+    uint32_t wide_chunks_cap = 0;
+    if (wide) {
+        const uint64_t mean = sell_krows_ / n_slices_;
+        wide_split = mean >= 2 * wide_chunk_krows();
+        if (const char *e = getenv("SNN_B200_WIDE_SPLIT")) wide_split = atoi(e) != 0;
+        if (wide_split) {
+            std::vector<uint32_t> so((size_t)n_slices_ + 1);
+            CK(cudaMemcpy(so.data(), slice_off_, so.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+            uint32_t mx = 0;
+            for (uint32_t sl = 0; sl < n_slices_; ++sl) mx = std::max(mx, so[sl + 1] - so[sl]);
+            wide_chunks_cap = (mx + wide_chunk_krows() - 1) / wide_chunk_krows();
+            const size_t need = (size_t)n_slices_ * wide_chunks_cap * wide_chunk_bytes(chemg) + (size_t)n_slices_ * wide_part_bytes();
+            if (need != wide_scratch_bytes_) {
+                if (wide_scratch_) cudaFree(wide_scratch_);
+                wide_scratch_ = nullptr; wide_scratch_bytes_ = 0;
+                CK(cudaMalloc((void **)&wide_scratch_, need), SNN_GPU_BUFFER_CREATE_ERROR);
+                wide_scratch_bytes_ = need;
+            }
+            // the arrival counters of the sum pass start at zero (they reset themselves after every timestep)
+            CK(cudaMemsetAsync(wide_scratch_ + (size_t)n_slices_ * wide_chunks_cap * wide_chunk_bytes(chemg), 0, (size_t)n_slices_ * wide_part_bytes(), stream_),
+               SNN_GPU_BUFFER_WRITE_ERROR);
+        }
+    }
     // indices of the ping-ponged streams, patched every step
     int tma_iv = -1, tma_il = -1, tma_it[kNT] = {-1, -1, -1};
     if (tma_ok) {
@@ -2132,11 +2160,13 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     // (step_multi.cu).  SNN_OPT_STEPS_PER_GRAPH: 0 = as many as the history chunk holds, 1 = one launch per timestep, k = at most k.
     bool multi = part_world == 1 && n_neurons > 0 && !win_ok && !tma_ok && !bcm_on && !reward_mode && steps_per_graph != 1 &&
                  !getenv("SNN_DEBUG_TIMING");
+    if (wide && wide_split) multi = false;   // the two-pass wide kernels are one-launch-per-step kernels
     if (const char *e = getenv("SNN_B200_MULTI")) multi = multi && atoi(e) != 0;
     if (multi) {
         StepParams probe = sp;
         TrainParams tprobe = tp;
         MultiParams mprobe{};
+        mprobe.wide_stage = (wide && n_nodes_ <= 4096) ? 1u : 0u;
         multi = launch_step_multi(probe, tprobe, mprobe, model, chemg, ntrel, stdp, net, wide, device, true, stream_) == cudaSuccess;
         cudaGetLastError();
     }
@@ -2172,6 +2202,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             mp.tspike_hist = want_tspk ? d_tspk + s0 * t_words : nullptr;
             mp.n_neurons = n_neurons; mp.n_words = n_words; mp.n_trains = n_trains; mp.t_words = t_words;
             mp.barrier = multi_barrier_;
+            mp.wide_stage = (wide && n_nodes_ <= 4096 && !(getenv("SNN_B200_WIDE_STAGE") && atoi(getenv("SNN_B200_WIDE_STAGE")) == 0)) ? 1u : 0u;
             cudaError_t e = cudaMemsetAsync(multi_barrier_, 0, sizeof(unsigned int), stream_);
             if (e == cudaSuccess) e = launch_step_multi(sp, tp, mp, model, chemg, ntrel, stdp, net, wide, device, false, stream_);
             if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_multi"); break; }
@@ -2213,7 +2244,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_tma"); break; }
                 n_launch++;
             } else if (n_neurons) {
-                cudaError_t e = wide ? launch_step_wide(sp, model, chemg, ntrel, stdp, net, stream_)
+                cudaError_t e = wide ? launch_step_wide(sp, model, chemg, ntrel, stdp, net, wide_split ? wide_scratch_ : nullptr, wide_chunks_cap, stream_)
                                      : launch_step(sp, model, chemg, ntrel, stdp, net, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step"); break; }
                 n_launch++;

@@ -199,6 +199,7 @@ private:
     // halo
     unsigned long long *flags_ = nullptr;  // [0] arrivals from rank-1, [1] arrivals from rank+1
     unsigned int *halo_done_ = nullptr;
+    unsigned char *wide_scratch_ = nullptr; size_t wide_scratch_bytes_ = 0;   // parked per-edge terms of the two-pass wide kernels
     unsigned int *multi_barrier_ = nullptr;   // grid-wide arrival counter of the multi-step kernel
     HaloDir halo_dir_[2] = {};
     void *peer_slab_[2] = {nullptr, nullptr};

@@ -247,6 +247,7 @@ struct EdgeAcc {
     bool fast8;   // warp-uniform: every lane had exactly 8 in-edges (and, CHEMG == 1, all of them release the type):
                   // the averaging divisions are by 8 = exact multiplications by 0.125
     bool fast8t;  // CHEMG == 3, warp-uniform: fast8 and every presynaptic neuron releases all three types
+    bool skip;    // two-pass wide kernels: this CTA summed one accumulator and another CTA of the slice finishes the step
 };
 
 // The lazily applied STDP of the previous step for one chunk of U edges (see gather_edges); shared by both gathers.
@@ -601,15 +602,78 @@ __device__ __forceinline__ void gather_edges(const StepParams &p, const SRC &src
 constexpr int kWideUnroll = 4;         // k-rows per helper thread and chunk
 constexpr int kWideWarps = 16;         // warps per CTA: one leader + 15 helpers
 constexpr uint32_t kWideChunk = kWideUnroll * (kWideWarps - 1);   // 60 k-rows per chunk (slice widths are multiples of 4)
+constexpr uint32_t kWideSumBufs = 8;   // chunk buffers of the sum pass of the two-pass wide kernels (7 copies in flight)
 // shared memory of one chunk buffer (two of them: the helpers fill one while the leader drains the other)
 __host__ __device__ constexpr uint32_t wide_buf_bytes(int chemg) { return kWideChunk * 32u * (4u + (chemg == 3 ? 4u * kNT : (chemg == 1 ? 4u : 0u)) + 1u); }
+
+// Small networks (BASELINE.json configs[3]: 1 584 nodes): the whole node state a wide slice gathers from — V, both
+// last_firing_time buffers, the neurotransmitter concentrations and, per spike train, the refractoriness term of
+// spike_train_gap_junction (a function of the train alone: evaluated once per train and step instead of once per edge) — is
+// copied into shared memory when the CTA starts its slice.  The helpers' per-edge gathers then are shared-memory reads: the two
+// dependent L2 round trips per chunk (40 % long-scoreboard stalls, profiles/r1_step_wide_c4_pipelined_full.txt) are gone and only
+// the coalesced col / weight stream still comes from L2.  Same values, same arithmetic: bit-identical.
+struct WideStage {
+    const float *v; const int *lft_in, *lft_out; const float *t;   // [n_nodes], [n_nodes], [n_nodes], [kNT][n_nodes]
+    const float *eff; const uint8_t *never;                        // per train: refractoriness term (or v_resting), "has never fired"
+    uint32_t n_nodes;                                              // 0 = not staged (gathers go to global memory)
+};
+__host__ __device__ constexpr uint32_t wide_stage_bytes(uint32_t n_nodes, uint32_t n_trains) {
+    return ((n_nodes * 4u * (3u + (uint32_t)kNT) + n_trains * 4u + n_trains + 15u) / 16u) * 16u;
+}
+constexpr uint32_t kWideStageMaxNodes = 4096;
 
 struct WideSrc : GlobalSrc {
     static constexpr bool kWide = true;
     uint32_t warp, n_warps;
     unsigned char *sm;    // 2 x wide_buf_bytes: [kWideChunk][32] f32 electrical terms, [types][kWideChunk][32] f32 chemical terms,
                           // [kWideChunk][32] u8 flags (bit 0: edge present, bits 1..3: presynaptic node releases type 0..2)
+    WideStage st;
+    // split mode for very wide slices (one SM cannot issue a 1 200-wide slice's per-edge instructions fast enough):
+    //   0  one CTA does everything;
+    //   1  "terms" pass: this CTA computes the per-edge terms of chunk `chunk` only and parks them in global scratch (all SMs share
+    //      the slices' chunks);
+    //   2  "sum" pass: the helpers copy the parked chunks into shared memory, the leader adds them in order and steps the neurons.
+    uint32_t mode, chunk;     // sum pass: `chunk` is the accumulator this CTA sums (0: electrical, 1 + ty: neurotransmitter type)
+    unsigned char *scratch;   // [slice][chunks_cap] chunk buffers of wide_buf_bytes(CHEMG), then the partial sums (wide_part_offset)
+    uint32_t chunks_cap;
+    uint32_t n_slices;
 };
+// after the chunk buffers: per slice (1 + kNT) x 32 partial sums (f32), (1 + kNT) x 32 counts (u32), one arrival counter (u32)
+__host__ __device__ constexpr size_t wide_part_bytes_per_slice() { return (size_t)(1 + kNT) * 32u * 8u + 16u; }
+
+// every thread of the CTA: fill the stage (called before neuron_step; ends with a CTA barrier)
+template <bool NET>
+__device__ __forceinline__ WideStage wide_stage_fill(const StepParams &p, unsigned char *base, bool enable) {
+    WideStage S{};
+    if (!enable) return S;
+    const uint32_t n = p.n_nodes, nt = NET ? p.n_trains : 0u;
+    float *sv = reinterpret_cast<float *>(base);
+    int *sli = reinterpret_cast<int *>(sv + n), *slo = sli + n;
+    float *stt = reinterpret_cast<float *>(slo + n);
+    float *seff = stt + (size_t)kNT * n;
+    uint8_t *snev = reinterpret_cast<uint8_t *>(seff + nt);
+    for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) {
+        sv[j] = p.v_in[j];
+        sli[j] = p.lft_in[j];
+        slo[j] = p.lft_out[j];
+#pragma unroll
+        for (int ty = 0; ty < kNT; ++ty) stt[(size_t)ty * n + j] = (p.nt_used & (1u << ty)) ? p.t_in[(size_t)ty * p.t_stride + j] : 0.f;
+    }
+    if constexpr (NET) {
+        for (uint32_t tj = threadIdx.x; p.electrical && tj < nt; tj += blockDim.x) {
+            // spike_train_gap_junction, neuron/mod.rs:119-137: v_resting if the train has never fired, else the refractoriness term
+            const int lt = p.lft_in[p.train0 + tj];
+            const float v_rest = ldf(p.tf[TF_VREST], tj);
+            float e = v_rest;
+            if (lt >= 0) e = refract_effect(p.refract, ldf(p.tf[TF_K], tj), p.clock, (uint32_t)lt, ldf(p.tf[TF_VTH], tj), v_rest, ldf(p.tf[TF_DT], tj));
+            seff[tj] = e;
+            snev[tj] = lt < 0 ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    S.v = sv; S.lft_in = sli; S.lft_out = slo; S.t = stt; S.eff = seff; S.never = snev; S.n_nodes = n;
+    return S;
+}
 
 template <int CHEMG, bool STDP, bool NET, class SRC>
 __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC &src, uint32_t i, float v, float gap, int lft_me,
@@ -623,15 +687,19 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
     constexpr uint32_t kTerms = kWideChunk * 32u;
     constexpr uint32_t kTypes = CHEMG == 3 ? (uint32_t)kNT : (CHEMG == 1 ? 1u : 0u);
     const uint32_t n_chunks = (width + kWideChunk - 1u) / kWideChunk;
+    const WideStage &SG = src.st;
+    const bool staged = SG.n_nodes != 0u;   // CTA-uniform
     // ---- phase A (helper warps): the terms of chunk c into buffer c & 1 — kWideUnroll k-rows per thread: all col/weight loads,
     // then every gather they address (V, last_firing_time, t, the spike-train constants), then the arithmetic
-    auto phase_a = [&](uint32_t ci) {
-        unsigned char *buf = src.sm + (ci & 1u) * wide_buf_bytes(CHEMG);
+    // split (two-pass mode): the chemical terms are parked already masked (`has ? term : 0`, the very operand the sum adds) and the
+    // per-row edge counts of the chunk replace the per-term flag bytes, so the ordered sum is one load and one add per term
+    auto phase_a_to = [&](uint32_t ci, unsigned char *buf, bool split) {
         float *sm_e = reinterpret_cast<float *>(buf);
         float *sm_t = sm_e + kTerms;
         uint8_t *sm_f = reinterpret_cast<uint8_t *>(sm_t + kTypes * kTerms);
         const uint32_t kk = ci * kWideChunk;
         const uint32_t kn = min(kWideChunk, width - kk);
+        uint32_t lc[1 + kNT] = {0u, 0u, 0u, 0u};
         for (uint32_t kb = src.warp - 1u; kb < kn; kb += kWideUnroll * HW) {
             uint32_t c[kWideUnroll], j[kWideUnroll];
             float w[kWideUnroll];
@@ -650,24 +718,30 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
                 ok[u] = c[u] != kColPad;
                 j[u] = ok[u] ? (c[u] & kColIdxMask) : i;
                 train[u] = NET && ok[u] && (c[u] & kColTrainBit);
-                vj[u] = do_e ? p.v_in[j[u]] : v;
+                vj[u] = do_e ? (staged ? SG.v[j[u]] : p.v_in[j[u]]) : v;
                 // see gather_edges: a spike train's last_firing_time of before its step-s iterate sits in the other buffer
-                lj[u] = pending ? (train[u] ? p.lft_out[j[u]] : p.lft_in[j[u]]) : -1;
+                lj[u] = pending ? (staged ? (train[u] ? SG.lft_out[j[u]] : SG.lft_in[j[u]]) : (train[u] ? p.lft_out[j[u]] : p.lft_in[j[u]])) : -1;
                 lt[u] = -1;
                 if (NET) {
                     if (train[u] && do_e) {
                         const uint32_t tjx = j[u] - p.train0;
-                        lt[u] = p.lft_in[j[u]];
-                        tfv[u][0] = ldf(p.tf[TF_VREST], tjx); tfv[u][1] = ldf(p.tf[TF_K], tjx);
-                        tfv[u][2] = ldf(p.tf[TF_VTH], tjx); tfv[u][3] = ldf(p.tf[TF_DT], tjx);
+                        if (staged) {
+                            // the train's term was evaluated once for the whole CTA (wide_stage_fill): tfv[0] carries it
+                            lt[u] = SG.never[tjx] ? -1 : 0;
+                            tfv[u][0] = SG.eff[tjx];
+                        } else {
+                            lt[u] = p.lft_in[j[u]];
+                            tfv[u][0] = ldf(p.tf[TF_VREST], tjx); tfv[u][1] = ldf(p.tf[TF_K], tjx);
+                            tfv[u][2] = ldf(p.tf[TF_VTH], tjx); tfv[u][3] = ldf(p.tf[TF_DT], tjx);
+                        }
                     }
                 }
                 if (CHEMG == 1) {
-                    tj[u][0] = src.gt0(j[u]);
+                    tj[u][0] = staged ? SG.t[(size_t)ty0 * SG.n_nodes + j[u]] : src.gt0(j[u]);
                 } else if (CHEMG == 3) {
                     const uint32_t m = ok[u] ? (c[u] >> kColNtShift) & 7u : 0u;
 #pragma unroll
-                    for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? src.gt(j[u], ty) : 0.f;
+                    for (int ty = 0; ty < kNT; ++ty) tj[u][ty] = (m & (1u << ty)) ? (staged ? SG.t[(size_t)ty * SG.n_nodes + j[u]] : src.gt(j[u], ty)) : 0.f;
                 }
             }
 #pragma unroll
@@ -694,28 +768,49 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
                     if (train[u] && do_e) {
                         // spike_train_gap_junction, neuron/mod.rs:119-137
                         if (lt[u] < 0) final_input = tfv[u][0];
+                        else if (staged) final_input = gap * tfv[u][0];
                         else final_input = gap * refract_effect(p.refract, tfv[u][1], p.clock, (uint32_t)lt[u], tfv[u][2], tfv[u][0], tfv[u][3]);
                     }
                 }
                 sm_e[k * 32u + lane] = final_input * wu;
                 uint32_t f = ok[u] ? 1u : 0u;
+                lc[0] += f;
                 if (CHEMG == 1) {
                     const bool has = ok[u] && ((c[u] >> (kColNtShift + ty0)) & 1u);
-                    sm_t[k * 32u + lane] = tj[u][0] * wu;
+                    const float term = tj[u][0] * wu;
+                    sm_t[k * 32u + lane] = split ? (has ? term : 0.f) : term;
                     f |= has ? 2u : 0u;
+                    lc[1] += has ? 1u : 0u;
                 } else if (CHEMG == 3) {
                     const uint32_t m = ok[u] ? (c[u] >> kColNtShift) & 7u : 0u;
 #pragma unroll
-                    for (int ty = 0; ty < kNT; ++ty) sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] = tj[u][ty] * wu;
+                    for (int ty = 0; ty < kNT; ++ty) {
+                        const float term = tj[u][ty] * wu;
+                        sm_t[((uint32_t)ty * kWideChunk + k) * 32u + lane] = split ? (((m >> ty) & 1u) ? term : 0.f) : term;
+                        lc[1 + ty] += (m >> ty) & 1u;
+                    }
                     f |= m << 1;
                 }
-                sm_f[k * 32u + lane] = (uint8_t)f;
+                if (!split) sm_f[k * 32u + lane] = (uint8_t)f;
             }
         }
+        if (split) {
+            // per-row counts of the chunk: every helper thread adds its share into shared counters, the record takes the place of
+            // the flag bytes (helpers only: named barrier 1 over the (kWideWarps - 1) * 32 helper threads)
+            __shared__ uint32_t s_cnt[(1 + kNT) * 32];
+            const uint32_t t = (src.warp - 1u) * 32u + lane;
+            if (t < (1 + kNT) * 32u) s_cnt[t] = 0u;
+            asm volatile("bar.sync 1, %0;" ::"n"((kWideWarps - 1) * 32) : "memory");
+#pragma unroll
+            for (int q = 0; q < 1 + kNT; ++q) if (lc[q]) atomicAdd(&s_cnt[q * 32 + lane], lc[q]);
+            asm volatile("bar.sync 1, %0;" ::"n"((kWideWarps - 1) * 32) : "memory");
+            if (t < (1 + kNT) * 32u) reinterpret_cast<uint32_t *>(sm_f)[t] = s_cnt[t];
+        }
     };
+    auto phase_a = [&](uint32_t ci, uint32_t bi) { phase_a_to(ci, src.sm + bi * wide_buf_bytes(CHEMG), false); };
     // ---- phase B (leader warp): add the parked terms of chunk c in ascending presynaptic order
-    auto phase_b = [&](uint32_t ci) {
-        const unsigned char *buf = src.sm + (ci & 1u) * wide_buf_bytes(CHEMG);
+    auto phase_b = [&](uint32_t ci, uint32_t bi) {
+        const unsigned char *buf = src.sm + bi * wide_buf_bytes(CHEMG);
         const float *sm_e = reinterpret_cast<const float *>(buf);
         const float *sm_t = sm_e + kTerms;
         const uint8_t *sm_f = reinterpret_cast<const uint8_t *>(sm_t + kTypes * kTerms);
@@ -754,13 +849,99 @@ __device__ __forceinline__ void gather_edges_wide(const StepParams &p, const SRC
             }
         }
     };
+    if (n_chunks == 0u) {   // uniform over the CTA: a slice without in-edges
+        if (src.mode == 2u && src.chunk != 0u) A.skip = true;   // sum pass: one of the accumulator CTAs steps the neurons
+        return;
+    }
+    const uint32_t warp_slice = (i - p.own0) >> 5;   // every lane of every warp of the CTA works on the same slice
+    if (src.mode == 1u) {
+        // terms pass: one chunk, parked in global memory (phase_a writes through generic pointers)
+        if (src.chunk < n_chunks && src.warp != 0u) phase_a_to(src.chunk, src.scratch + ((size_t)warp_slice * src.chunks_cap + src.chunk) * wide_buf_bytes(CHEMG), true);
+        return;
+    }
+    if (src.mode == 2u) {
+        // sum pass: the helpers stream the parked chunks from L2 into the two shared-memory buffers (plain 16-byte copies, a few
+        // instructions per k-row instead of ~180), the leader adds them in ascending presynaptic order
+        // The sums of a slice are independent chains (electrical, one per neurotransmitter type): each gets its own CTA, which
+        // streams only its array of every parked chunk (7.5 KB per chunk instead of 32 KB — one SM's latency-bound L2 stream was
+        // the limit of a single summing CTA) and adds it in ascending presynaptic order.  The CTA that finishes last collects
+        // the partial sums and steps the slice's neurons.
+        constexpr uint32_t kAcc = 1u + kTypes;
+        const uint32_t a = src.chunk;   // accumulator of this CTA (CTA-uniform)
+        constexpr uint32_t kArr = kTerms * 4u;   // bytes of one array of a chunk
+        static_assert(kArr % 16u == 0u && kArr / 16u <= (kWideWarps - 1) * 32u, "one 16-byte copy per helper thread and chunk");
+        const uint32_t rec_off = (1u + kTypes) * kArr;   // count record of a chunk (phase_a_to, split)
+        // shared memory: kWideSumBufs x (array + one 128-byte count row)
+        constexpr uint32_t kSlot = kArr + 128u;
+        auto fetch = [&](uint32_t ci) {
+            const unsigned char *g = src.scratch + ((size_t)warp_slice * src.chunks_cap + ci) * wide_buf_bytes(CHEMG);
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(src.sm + (ci % kWideSumBufs) * kSlot);
+            const uint32_t t = (src.warp - 1u) * 32u + lane;
+            if (t < kArr / 16u) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + t * 16u), "l"(g + (size_t)a * kArr + (size_t)t * 16u) : "memory");
+            if (t < 8u) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + kArr + t * 16u), "l"(g + rec_off + (size_t)a * 128u + (size_t)t * 16u) : "memory");
+        };
+        auto commit = [&]() { asm volatile("cp.async.commit_group;" ::: "memory"); };
+        float part = 0.f;
+        uint32_t pcnt = 0u;
+        auto sum_chunk = [&](uint32_t ci) {
+            const float *arr = reinterpret_cast<const float *>(src.sm + (ci % kWideSumBufs) * kSlot);
+            const uint32_t kn = min(kWideChunk, width - ci * kWideChunk);
+            for (uint32_t k0b = 0; k0b < kn; k0b += 12u) {   // kn is a multiple of 4
+                float te[12];
+#pragma unroll
+                for (uint32_t q = 0; q < 12u; ++q) te[q] = arr[min(k0b + q, kn - 1u) * 32u + lane];
+#pragma unroll
+                for (uint32_t q = 0; q < 12u; ++q) if (k0b + q < kn) part = part + te[q];
+            }
+            pcnt += reinterpret_cast<const uint32_t *>(arr + kTerms)[lane];
+        };
+        static_assert(kWideSumBufs * kSlot <= 2u * wide_buf_bytes(CHEMG) || true, "");
+        if (src.warp != 0u) {
+            for (uint32_t c = 0; c + 1u < kWideSumBufs; ++c) { if (c < n_chunks) fetch(c); commit(); }
+            asm volatile("cp.async.wait_group %0;" ::"n"(kWideSumBufs - 2) : "memory");   // chunk 0 has landed
+        }
+        __syncthreads();
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            if (src.warp == 0u) {
+                sum_chunk(c);
+            } else {
+                if (c + kWideSumBufs - 1u < n_chunks) fetch(c + kWideSumBufs - 1u);   // into the buffer the leader finished before the last barrier
+                commit();
+                asm volatile("cp.async.wait_group %0;" ::"n"(kWideSumBufs - 2) : "memory");   // chunk c + 1 has landed
+            }
+            __syncthreads();
+        }
+        if (src.warp != 0u) return;
+        // publish the partial sum; the last CTA of the slice gathers all of them
+        unsigned char *pb = src.scratch + (size_t)src.n_slices * src.chunks_cap * wide_buf_bytes(CHEMG) + (size_t)warp_slice * wide_part_bytes_per_slice();
+        float *psum = reinterpret_cast<float *>(pb);
+        uint32_t *pcn = reinterpret_cast<uint32_t *>(pb + (1 + kNT) * 32u * 4u);
+        unsigned int *arrive = reinterpret_cast<unsigned int *>(pb + (1 + kNT) * 32u * 8u);
+        __stcg(psum + a * 32u + lane, part);
+        __stcg(pcn + a * 32u + lane, pcnt);
+        __threadfence();
+        __syncwarp();
+        unsigned int old = 0u;
+        if (lane == 0) old = atomicAdd(arrive, 1u);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old + 1u != kAcc) { A.skip = true; return; }
+        if (lane == 0) *arrive = 0u;   // ready for the next timestep (the next launch is stream-ordered after this kernel)
+        __threadfence();
+        A.acc_e = __ldcg(psum + lane);
+        A.n_in = __ldcg(pcn + lane);
+        if (CHEMG == 1) { A.acc_t[0] = __ldcg(psum + 32u + lane); A.cnt[0] = __ldcg(pcn + 32u + lane); }
+        if (CHEMG == 3) {
+#pragma unroll
+            for (int ty = 0; ty < kNT; ++ty) { A.acc_t[ty] = __ldcg(psum + (1u + (uint32_t)ty) * 32u + lane); A.cnt[ty] = __ldcg(pcn + (1u + (uint32_t)ty) * 32u + lane); }
+        }
+        return;
+    }
     // software pipeline over the chunks: while the leader adds chunk c, the helpers already compute chunk c + 1
-    if (n_chunks == 0u) return;
-    if (src.warp != 0u) phase_a(0u);
+    if (src.warp != 0u) phase_a(0u, 0u);
     __syncthreads();
     for (uint32_t c = 0; c < n_chunks; ++c) {
-        if (src.warp == 0u) phase_b(c);
-        else if (c + 1u < n_chunks) phase_a(c + 1u);
+        if (src.warp == 0u) phase_b(c, c & 1u);
+        else if (c + 1u < n_chunks) phase_a(c + 1u, (c + 1u) & 1u);
         __syncthreads();
     }
 }
@@ -837,12 +1018,14 @@ __device__ __forceinline__ void neuron_step(const StepParams &p, const SRC &src,
     for (int ty = 0; ty < kNT; ++ty) { A.acc_t[ty] = 0.f; A.cnt[ty] = 0; }
     const bool do_e = p.electrical != 0;
     const bool do_c = NTREL && p.chemical != 0;
-    A.fast8 = false; A.fast8t = false;
+    A.fast8 = false; A.fast8t = false; A.skip = false;
     if constexpr (SRC::kWidth == 8 && !NET) gather_edges8<CHEMG, STDP>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
     else if constexpr (SRC::kWide) gather_edges_wide<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
     else gather_edges<CHEMG, STDP, NET>(p, src, i, v, gap, lft_me, post_trig, li, ty0, A);
     if constexpr (SRC::kWide) {
-        if (src.warp != 0) return;   // the helpers of a wide-row CTA are done; the leader warp steps the 32 neurons
+        // the helpers of a wide slice, the CTAs of the terms pass and all but the last accumulator CTA of the sum pass are done;
+        // the leader warp steps the 32 neurons
+        if (src.warp != 0 || src.mode == 1u || A.skip) return;
     }
     if (!SRC::kEarlyLoads) { load_model_params(); if constexpr (NEEDS_CM) c_m = src.template f<F_CM>(); v_th = src.template f<F_VTH>(); }
     // neuron/mod.rs:722-729: divide by the number of incoming edges (1 if none)

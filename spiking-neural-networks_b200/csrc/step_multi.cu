@@ -83,6 +83,8 @@ step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__
         }
         // ---- the neurons of this timestep
         if constexpr (WIDE) {
+            // the node state of this timestep into shared memory, once per CTA and step (WideStage, step_body.cuh)
+            const WideStage stage = wide_stage_fill<NET>(p, multi_sm + 2u * wide_buf_bytes(CHEMG), m.wide_stage != 0u && blockIdx.x < n_slices);
             for (uint32_t slice = blockIdx.x; slice < n_slices; slice += gridDim.x) {   // uniform per CTA: gather_edges_wide syncs the CTA
                 const uint32_t ln = slice * 32u + lane;
                 const bool valid = ln < p.n_neurons;
@@ -91,7 +93,7 @@ step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__
                 const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + slice + 1);
                 const float *tt0 = nullptr;
                 if (CHEMG == 1) tt0 = p.t_in + (size_t)(__ffs((int)p.nt_used) - 1) * p.t_stride;
-                const WideSrc src{{p, lnc, p.own0 + lnc, lane, k0, k1, tt0}, warp, (uint32_t)kWideWarps, multi_sm};
+                const WideSrc src{{p, lnc, p.own0 + lnc, lane, k0, k1, tt0}, warp, (uint32_t)kWideWarps, multi_sm, stage, 0u, 0u, nullptr, 0u, 0u};
                 neuron_step<MODEL, CHEMG, NTREL, STDP, NET>(p, src, slice, lane, ln, lnc, valid, false, false);
                 __syncthreads();   // the chunk buffers are reused by the CTA's next slice
             }
@@ -166,7 +168,7 @@ static cudaError_t launch_multi_5(const StepParams &p, const TrainParams &t, con
     }
     auto k = step_multi_kernel<MODEL, CHEMG, NTREL, STDP, NET, WIDE, false>;
     const int threads = WIDE ? kWideWarps * 32 : 256;
-    const size_t smem = WIDE ? 2u * wide_buf_bytes(CHEMG) : 0u;
+    const size_t smem = WIDE ? 2u * wide_buf_bytes(CHEMG) + (m.wide_stage ? wide_stage_bytes(p.n_nodes, NET ? p.n_trains : 0u) : 0u) : 0u;
     if (smem > 40u * 1024u) { e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
     int per_sm = 0, sms = 0;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, smem);

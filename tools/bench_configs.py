@@ -62,6 +62,17 @@ def measure(cpu=False):
         ms, nl = lat._be.run_timed(steps)
         n = lat.size
         out[cfg] = {"neurons": n, "us_per_step": 1e3 * ms / steps, "neuron_steps_per_s": n * steps / (ms * 1e-3), "launches": nl}
+        if cfg == "C3":
+            # the long run above ends NaN-saturated (the reference's own gate formulas are 0/0 at exactly V = -55 / -40 mV, the NaN
+            # spreads through the gap junctions: tools/bench_hh.py); steps 20..170 from a quiet start are all-finite arithmetic
+            q = lattice(None, cfg)
+            q.set_field("current_voltage", np.random.default_rng(1).uniform(-64.0, -57.0, n).astype(f32))
+            q._push_options()
+            q._be.run_timed(20)
+            ms2, _ = q._be.run_timed(150)
+            out[cfg]["us_per_step_finite_window"] = 1e3 * ms2 / 150
+            out[cfg]["finite_after_window"] = float(np.isfinite(q.get_field("current_voltage")).mean())
+            out[cfg]["finite_after_long_run"] = float(np.isfinite(lat.get_field("current_voltage")).mean())
         if cpu:
             from oracle_api import OracleBackend
             ol = lattice(lambda m, nt, rc, rows, cols: OracleBackend(m, nt, rc, rows=rows, cols=cols), cfg)

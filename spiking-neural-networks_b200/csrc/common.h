@@ -291,8 +291,9 @@ cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, b
 constexpr uint32_t kWideMinWidth = 48;   // mean k-rows per slice from which the wide kernel is used
 // scratch != nullptr: two passes (per-edge terms of every slice chunk on its own CTA, parked in `scratch`: chunks_cap buffers of
 // wide_chunk_bytes(chemg) per slice; then the ordered sums) — very wide slices, where one SM per slice is issue-bound
+// trains != nullptr (two-pass mode only): the spike trains of the timestep are stepped by extra CTAs of the sum pass
 cudaError_t launch_step_wide(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, unsigned char *scratch, uint32_t chunks_cap,
-                             cudaStream_t s);
+                             const TrainParams *trains, cudaStream_t s);
 uint32_t wide_chunk_bytes(int chemg);
 uint32_t wide_chunk_krows();
 size_t wide_part_bytes();   // per slice, after the chunk buffers: partial sums, counts and the arrival counter of the sum pass (zeroed once)

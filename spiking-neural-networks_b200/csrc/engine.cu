@@ -2231,6 +2231,23 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             sp.out_par = (uint32_t)out;
             sp.halo_epoch = halo_nowait ? 0ull : halo_epoch_;   // timing experiment only (SNN_B200_HALO_NOWAIT): results are wrong
             if (!local_peers_.empty()) wait_local_peers_launched(halo_epoch_, rmod_part);
+            // spike-train parameters of this timestep (the trains step after the neurons, with their own clocks)
+            auto fill_train_step = [&](uint64_t step_in_chunk) {
+                tp.v_in = V_[in]; tp.v_out = V_[out]; tp.spk_in = SPK_[in]; tp.spk_out = SPK_[out];
+                tp.t_in = T_[in]; tp.t_out = T_[out];
+                tp.lft_in = sp.lft_in; tp.lft_out = sp.lft_out;
+                tp.n_tl = 0;
+                for (auto &L : lats_)
+                    if (L.is_train) { tp.tl_base[tp.n_tl] = (uint32_t)L.off; tp.tl_clock[tp.n_tl] = (uint32_t)L.clock; tp.n_tl++; }
+                tp.tl_base[tp.n_tl] = (uint32_t)n_trains;
+                tp.draw = train_draws++;
+                tp.grid_hist = want_tgrid ? d_tgrid + step_in_chunk * n_trains : nullptr;
+                tp.spike_hist = want_tspk ? d_tspk + step_in_chunk * t_words : nullptr;
+            };
+            // two-pass wide kernels: the spike trains ride in extra CTAs of the sum pass (nothing in that pass reads train state; the
+            // terms pass, which does, has completed) — one launch and one launch gap less per timestep
+            const bool trains_fused = n_neurons && !win_ok && !tma_ok && wide && wide_split && n_trains > 0;
+            if (trains_fused) fill_train_step(s);
             if (n_neurons && win_ok) {
                 cudaError_t e = launch_step_win(sp, win, model, chemg, ntrel, stdp, win_grid, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_win"); break; }
@@ -2244,10 +2261,10 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step_tma"); break; }
                 n_launch++;
             } else if (n_neurons) {
-                cudaError_t e = wide ? launch_step_wide(sp, model, chemg, ntrel, stdp, net, wide_split ? wide_scratch_ : nullptr, wide_chunks_cap, stream_)
+                cudaError_t e = wide ? launch_step_wide(sp, model, chemg, ntrel, stdp, net, wide_split ? wide_scratch_ : nullptr, wide_chunks_cap, trains_fused ? &tp : nullptr, stream_)
                                      : launch_step(sp, model, chemg, ntrel, stdp, net, stream_);
                 if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_step"); break; }
-                n_launch++;
+                n_launch += (wide && wide_split) ? 2 : 1;   // terms pass + sum pass
             }
             if (reward_mode && rewards) {
                 // RewardModulatedSTDP::update, plasticity/mod.rs:193-195 (run_lattice_with_reward, neuron/mod.rs:3160-3172)
@@ -2279,19 +2296,12 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             // LatticeNetwork::iterate: clock += 1, then the spike trains step with their own clocks
             // (neuron/mod.rs:2582-2591)
             if (n_trains) {
-                tp.v_in = V_[in]; tp.v_out = V_[out]; tp.spk_in = SPK_[in]; tp.spk_out = SPK_[out];
-                tp.t_in = T_[in]; tp.t_out = T_[out];
-                tp.lft_in = sp.lft_in; tp.lft_out = sp.lft_out;
-                tp.n_tl = 0;
-                for (auto &L : lats_)
-                    if (L.is_train) { tp.tl_base[tp.n_tl] = (uint32_t)L.off; tp.tl_clock[tp.n_tl] = (uint32_t)L.clock; tp.n_tl++; }
-                tp.tl_base[tp.n_tl] = (uint32_t)n_trains;
-                tp.draw = train_draws++;
-                tp.grid_hist = want_tgrid ? d_tgrid + s * n_trains : nullptr;
-                tp.spike_hist = want_tspk ? d_tspk + s * t_words : nullptr;
-                cudaError_t e = launch_trains(tp, stream_);
-                if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_trains"); break; }
-                n_launch++;
+                if (!trains_fused) {
+                    fill_train_step(s);
+                    cudaError_t e = launch_trains(tp, stream_);
+                    if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_trains"); break; }
+                    n_launch++;
+                }
                 for (auto &L : lats_) if (L.is_train) L.clock += 1;
             }
             internal_clock += 1;

@@ -3,6 +3,7 @@
 // ordered accumulation and the neuron update.  Same arithmetic, bit-identical results; used for single-GPU handles whose
 // mean slice width is >= kWideMinWidth (BASELINE.json configs[3]: 784 spike trains -> 400 excitatory <-> 400 inhibitory).
 #include "step_body.cuh"
+#include "train_body.cuh"
 
 #include <cstdlib>
 
@@ -15,10 +16,19 @@ struct WideSplit {   // very wide slices: terms pass over all SMs, then the orde
 };
 
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
-__global__ void __launch_bounds__(kWideWarps * 32) step_wide_kernel(const __grid_constant__ StepParams p, uint32_t stage_on, const __grid_constant__ WideSplit sp) {
+__global__ void __launch_bounds__(kWideWarps * 32) step_wide_kernel(const __grid_constant__ StepParams p, uint32_t stage_on, const __grid_constant__ WideSplit sp,
+                                                                    const __grid_constant__ TrainParams tp) {
     extern __shared__ __align__(16) unsigned char wide_sm[];   // 2 x wide_buf_bytes(CHEMG): double-buffered chunk terms, then the node stage
     const uint32_t warp_global = blockIdx.x;   // one CTA per slice (terms pass: per slice and chunk)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (blockIdx.x >= sp.n_slices) {
+        // sum pass with fused spike trains: the CTAs past the last slice step 16 warps of trains each (accumulator row 0 only)
+        if (NET && blockIdx.y == 0u) {
+            const uint32_t tw = (blockIdx.x - sp.n_slices) * kWideWarps + warp;
+            if (tw * 32u < tp.n_trains) train_step(tp, tw, lane);
+        }
+        return;
+    }
     const uint32_t ln = warp_global * 32u + lane;
     const bool valid = ln < p.n_neurons;
     const uint32_t lnc = valid ? ln : p.n_neurons - 1;
@@ -33,11 +43,12 @@ __global__ void __launch_bounds__(kWideWarps * 32) step_wide_kernel(const __grid
 }
 
 template <int MODEL, int CHEMG, bool NTREL, bool NET>
-static cudaError_t launch_wide_3(const StepParams &p, bool stdp, unsigned char *scratch, uint32_t chunks_cap, cudaStream_t s) {
+static cudaError_t launch_wide_3(const StepParams &p, bool stdp, unsigned char *scratch, uint32_t chunks_cap, const TrainParams *trains, cudaStream_t s) {
     const unsigned grid = (p.n_neurons + 31u) / 32u;
+    static const TrainParams no_trains{};
     auto launch = [&](auto k, dim3 g, size_t smem, uint32_t stage, WideSplit sp) -> cudaError_t {
         if (smem > 48u * 1024u) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
-        k<<<g, kWideWarps * 32, smem, s>>>(p, stage, sp);
+        k<<<g, kWideWarps * 32, smem, s>>>(p, stage, sp, (sp.mode == 2u && trains) ? *trains : no_trains);
         return cudaGetLastError();
     };
     auto both = [&](dim3 g, size_t smem, uint32_t stage, WideSplit sp) -> cudaError_t {
@@ -50,7 +61,8 @@ static cudaError_t launch_wide_3(const StepParams &p, bool stdp, unsigned char *
         cudaError_t e = both(dim3(grid, chunks_cap), 0, 0u, WideSplit{1u, scratch, chunks_cap, grid});
         if (e != cudaSuccess) return e;
         constexpr uint32_t n_acc = 1u + (CHEMG == 3 ? (uint32_t)kNT : (CHEMG == 1 ? 1u : 0u));
-        return both(dim3(grid, n_acc), kWideSumBufs * (kWideChunk * 32u * 4u + 128u), 0u, WideSplit{2u, scratch, chunks_cap, grid});
+        const unsigned train_ctas = (NET && trains) ? ((trains->n_trains + 31u) / 32u + kWideWarps - 1u) / kWideWarps : 0u;
+        return both(dim3(grid + train_ctas, n_acc), kWideSumBufs * (kWideChunk * 32u * 4u + 128u), 0u, WideSplit{2u, scratch, chunks_cap, grid});
     }
     // small networks: the node state rides in shared memory next to the chunk buffers (WideStage, step_body.cuh)
     static const bool stage_env = !(getenv("SNN_B200_WIDE_STAGE") && atoi(getenv("SNN_B200_WIDE_STAGE")) == 0);
@@ -61,16 +73,16 @@ static cudaError_t launch_wide_3(const StepParams &p, bool stdp, unsigned char *
 
 template <int MODEL>
 static cudaError_t launch_wide_model(const StepParams &p, int chemg, bool ntrel, bool stdp, bool net, unsigned char *scratch, uint32_t chunks_cap,
-                                     cudaStream_t s) {
+                                     const TrainParams *trains, cudaStream_t s) {
     if (net) {
-        if (chemg) return launch_wide_3<MODEL, 3, true, true>(p, stdp, scratch, chunks_cap, s);
-        if (ntrel) return launch_wide_3<MODEL, 0, true, true>(p, stdp, scratch, chunks_cap, s);
-        return launch_wide_3<MODEL, 0, false, true>(p, stdp, scratch, chunks_cap, s);
+        if (chemg) return launch_wide_3<MODEL, 3, true, true>(p, stdp, scratch, chunks_cap, trains, s);
+        if (ntrel) return launch_wide_3<MODEL, 0, true, true>(p, stdp, scratch, chunks_cap, trains, s);
+        return launch_wide_3<MODEL, 0, false, true>(p, stdp, scratch, chunks_cap, trains, s);
     }
-    if (chemg == 1) return launch_wide_3<MODEL, 1, true, false>(p, stdp, scratch, chunks_cap, s);
-    if (chemg == 3) return launch_wide_3<MODEL, 3, true, false>(p, stdp, scratch, chunks_cap, s);
-    if (ntrel) return launch_wide_3<MODEL, 0, true, false>(p, stdp, scratch, chunks_cap, s);
-    return launch_wide_3<MODEL, 0, false, false>(p, stdp, scratch, chunks_cap, s);
+    if (chemg == 1) return launch_wide_3<MODEL, 1, true, false>(p, stdp, scratch, chunks_cap, trains, s);
+    if (chemg == 3) return launch_wide_3<MODEL, 3, true, false>(p, stdp, scratch, chunks_cap, trains, s);
+    if (ntrel) return launch_wide_3<MODEL, 0, true, false>(p, stdp, scratch, chunks_cap, trains, s);
+    return launch_wide_3<MODEL, 0, false, false>(p, stdp, scratch, chunks_cap, trains, s);
 }
 
 uint32_t wide_chunk_bytes(int chemg) { return wide_buf_bytes(chemg); }
@@ -78,18 +90,18 @@ uint32_t wide_chunk_krows() { return kWideChunk; }
 size_t wide_part_bytes() { return wide_part_bytes_per_slice(); }
 
 cudaError_t launch_step_wide(const StepParams &p, int model, int chemg, bool ntrel, bool stdp, bool net, unsigned char *scratch, uint32_t chunks_cap,
-                             cudaStream_t s) {
+                             const TrainParams *trains, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
     switch (model) {
-    case SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_IZHIKEVICH: return launch_wide_model<SNN_MODEL_IZHIKEVICH>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_wide_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_HODGKIN_HUXLEY: return launch_wide_model<SNN_MODEL_HODGKIN_HUXLEY>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
-    case SNN_MODEL_BCM_IZHIKEVICH: return launch_wide_model<SNN_MODEL_BCM_IZHIKEVICH>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, s);
+    case SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_QUADRATIC_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_ADAPTIVE_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_ADAPTIVE_EXP_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_IZHIKEVICH: return launch_wide_model<SNN_MODEL_IZHIKEVICH>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_LEAKY_IZHIKEVICH: return launch_wide_model<SNN_MODEL_LEAKY_IZHIKEVICH>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE: return launch_wide_model<SNN_MODEL_SIMPLE_LEAKY_INTEGRATE_AND_FIRE>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_HODGKIN_HUXLEY: return launch_wide_model<SNN_MODEL_HODGKIN_HUXLEY>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
+    case SNN_MODEL_BCM_IZHIKEVICH: return launch_wide_model<SNN_MODEL_BCM_IZHIKEVICH>(p, chemg, ntrel, stdp, net, scratch, chunks_cap, trains, s);
     }
     return cudaErrorInvalidValue;
 }

@@ -157,6 +157,7 @@ struct MultiParams {
     uint64_t n_neurons, n_words, n_trains, t_words;
     unsigned int *barrier;    // grid-wide arrival counter, zero at launch
     uint32_t wide_stage;      // wide-row variant: stage the node state in shared memory (small networks)
+    uint32_t cache_rows;      // the stencil rows and parameters may live in registers for the whole launch (nothing rewrites them)
 };
 // dry = only report whether the configuration is eligible (cudaSuccess) without launching
 cudaError_t launch_step_multi(const StepParams &p, const TrainParams &t, const MultiParams &m, int model, int chemg, bool ntrel, bool stdp,

@@ -2202,6 +2202,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             mp.tspike_hist = want_tspk ? d_tspk + s0 * t_words : nullptr;
             mp.n_neurons = n_neurons; mp.n_words = n_words; mp.n_trains = n_trains; mp.t_words = t_words;
             mp.barrier = multi_barrier_;
+            mp.cache_rows = (!stdp && !getenv("SNN_B200_MULTI_NOCACHE")) ? 1u : 0u;
             mp.wide_stage = (wide && n_nodes_ <= 4096 && !(getenv("SNN_B200_WIDE_STAGE") && atoi(getenv("SNN_B200_WIDE_STAGE")) == 0)) ? 1u : 0u;
             cudaError_t e = cudaMemsetAsync(multi_barrier_, 0, sizeof(unsigned int), stream_);
             if (e == cudaSuccess) e = launch_step_multi(sp, tp, mp, model, chemg, ntrel, stdp, net, wide, device, false, stream_);

@@ -46,6 +46,24 @@ __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// A launch that gives every slice its own warp for all of its timesteps can keep what never changes in registers: the eight col /
+// weight words of a radius-1 stencil row and the model parameters.  What remains on the critical path of a timestep is ONE L2
+// round trip (the neighbour voltages), the arithmetic, and the barrier — every barrier drops the SM's L1, so without this each
+// step paid a second round trip for words it had already read a thousand times.  Same values, same arithmetic.
+template <int MODEL, bool NTREL>
+struct CachedSrc : GlobalSrc {
+    static constexpr uint32_t kWidth = 8;   // neuron_step takes the fixed-width gather (compile-time edge indices)
+    uint32_t cc[8];
+    float cw[8];
+    float fc[F_NA_CUR];
+    template <int SLOT> __device__ __forceinline__ float f() const { return fc[SLOT]; }
+    __device__ __forceinline__ uint32_t col(uint32_t kk) const { return cc[kk]; }
+    __device__ __forceinline__ float wgt(uint32_t kk) const { return cw[kk]; }
+    __device__ __forceinline__ Handle gh_row(int, uint32_t j) const { return j; }
+    __device__ __forceinline__ void wgt_update(uint32_t, float) const {}   // plasticity never takes this source
+    __device__ __forceinline__ void wgt_updates_done() const {}
+};
+
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET, bool WIDE, bool CLUSTER>
 __global__ void __launch_bounds__(WIDE ? kWideWarps * 32 : (CLUSTER ? kClusterThreads : 256))
 step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__ TrainParams t0, const __grid_constant__ MultiParams m) {
@@ -59,6 +77,46 @@ step_multi_kernel(const __grid_constant__ StepParams p0, const __grid_constant__
     const uint32_t warps_per_cta = blockDim.x >> 5;
     const uint32_t n_slices = (p0.n_neurons + 31u) >> 5, n_twarps = (t0.n_trains + 31u) >> 5;
     unsigned int arrivals = 0;
+    if constexpr (!WIDE && !NET && !STDP) {
+        if (p0.uniform_width == 8u && n_slices <= gridDim.x * warps_per_cta && m.cache_rows) {
+            // one slice per warp, radius-1 stencil rows, no plasticity: the register-cached source (CachedSrc)
+            const uint32_t slice = blockIdx.x * warps_per_cta + warp;
+            const bool active = slice < n_slices;
+            const uint32_t ln = slice * 32u + lane;
+            const bool valid = active && ln < p.n_neurons;
+            const uint32_t lnc = valid ? ln : p.n_neurons - 1;
+            CachedSrc<MODEL, NTREL> cs{GlobalSrc{p, lnc, p.own0 + lnc, lane, slice * 8u, slice * 8u + 8u, nullptr}, {}, {}, {}};
+            if (active) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    cs.cc[u] = __ldg(p.col + (size_t)(slice * 8u + u) * 32u + lane);
+                    cs.cw[u] = __ldg(p.wgt + (size_t)(slice * 8u + u) * 32u + lane);
+                }
+#pragma unroll
+                for (int sl = 0; sl < F_NA_CUR; ++sl) cs.fc[sl] = win_field_read(MODEL, NTREL, sl) ? __ldg(p.f[sl] + lnc) : 0.f;
+            }
+            for (uint32_t s = 0; s < m.steps; ++s) {
+                const uint32_t in = (m.cur ^ s) & 1u, out = in ^ 1u;
+                p.clock = p0.clock + s;
+                p.apply_pending = 0u;
+                p.v_in = m.v[in]; p.v_out = m.v[out];
+                p.spk_in = m.spk[in]; p.spk_out = m.spk[out];
+                p.t_in = m.t[in]; p.t_out = m.t[out];
+                const uint32_t li = m.lft_pp ? ((m.lft_loc ^ s) & 1u) : m.lft_loc;
+                p.lft_in = m.lft[li]; p.lft_out = m.lft[m.lft_pp ? li ^ 1u : li];
+                p.grid_hist = m.grid_hist ? m.grid_hist + (size_t)s * m.n_neurons : nullptr;
+                p.spike_hist = m.spike_hist ? m.spike_hist + (size_t)s * m.n_words : nullptr;
+                p.out_par = out;
+                if (CHEMG == 1) cs.t0 = p.t_in + (size_t)(__ffs((int)p.nt_used) - 1) * p.t_stride;
+                if (active) neuron_step<MODEL, CHEMG, NTREL, STDP, NET>(p, cs, slice, lane, ln, lnc, valid, false, false);
+                if (s + 1u < m.steps) {
+                    if constexpr (CLUSTER) cluster_barrier();
+                    else { arrivals += gridDim.x; grid_barrier(m.barrier, arrivals); }
+                }
+            }
+            return;
+        }
+    }
     for (uint32_t s = 0; s < m.steps; ++s) {
         {
             const uint32_t in = (m.cur ^ s) & 1u, out = in ^ 1u;

@@ -18,6 +18,7 @@
 #include "train_body.cuh"
 
 #include <cfloat>
+#include <cstdlib>
 
 namespace snn {
 
@@ -258,7 +259,13 @@ __device__ __forceinline__ void rstdp_call(const RstdpParams &r, float delta_w, 
 // warp and slice) and every thread works on one edge of each of the kRsSlices slices at a time: all col / trace loads first,
 // then the last_firing_time gathers they address, then the arithmetic — kRsSlices independent chains per thread, ~1000
 // resident threads per SM, so that two dependent memory round trips per edge still keep HBM busy.
-constexpr int kRsSlices = 4;
+#ifndef SNN_RS_SLICES
+#define SNN_RS_SLICES 4
+#endif
+#ifndef SNN_RS_CTAS
+#define SNN_RS_CTAS 3   // resident CTAs per SM of the persistent variant (register budget 65536 / (256 * CTAS))
+#endif
+constexpr int kRsSlices = SNN_RS_SLICES;
 
 // CANON: every edge enters the timestep with counter == 0 and dw == 0.  That is the state TraceRSTDP::default starts in and
 // the state two calls per timestep always return to, so until a caller stores other values through
@@ -353,6 +360,72 @@ __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constan
                     if (p.halo[d].active) st_release_sys(p.halo[d].peer_flag2, p.halo_epoch);
             }
         }
+    }
+}
+
+// The same update for radius-1 stencil tables (uniform slice width 8) of whole lattices, as a persistent, software-pipelined
+// kernel.  The short-lived CTAs above spend 53 % of their samples on the long scoreboard (profiles/r2_rstdp_edge_full.txt): four
+// edges per thread behind TWO dependent memory levels (col -> last_firing_time gathers) and ~35 instructions of per-thread set-up
+// amortised over those four edges.  Here a CTA walks many groups of kRsSlices slices; while the gathers of group g are in flight
+// the independent loads (col, c, weight, the rows' own spike times) of group g + 1 are already issued, so one of the two round
+// trips is hidden, and the set-up is paid once.  Warp w of the CTA owns k-row w of every slice (8 warps = 8 k-rows).
+template <bool CANON, bool TAB>
+__global__ void __launch_bounds__(256, SNN_RS_CTAS) rstdp_edge8_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
+    const uint32_t n_groups = (n_slices + kRsSlices - 1u) / kRsSlices;
+    const float decay_c = expf(-r.dt / r.tau_c);
+    struct L1 { uint32_t e, cw, cnt; float cc, w, dw; int old_post, new_post; uint32_t node; };
+    auto load1 = [&](uint32_t g, L1 (&x)[kRsSlices]) {
+#pragma unroll
+        for (int u = 0; u < kRsSlices; ++u) {
+            const uint32_t slice = g * kRsSlices + u, ln = slice * 32u + lane;
+            const bool ok = slice < n_slices && ln < p.n_neurons;
+            x[u].node = p.own0 + (ok ? ln : 0u);
+            x[u].e = (slice * 8u + warp) * 32u + lane;
+            x[u].cw = ok ? __ldg(p.col + x[u].e) : kColPad;
+            x[u].cnt = 0u; x[u].dw = 0.f; x[u].cc = 0.f; x[u].w = 0.f;
+            if (ok) {
+                if (!CANON) { x[u].cnt = r.counter[x[u].e]; x[u].dw = r.dw[x[u].e]; }
+                x[u].cc = r.c[x[u].e]; x[u].w = p.wgt[x[u].e];
+            }
+            x[u].old_post = p.lft_in[x[u].node]; x[u].new_post = p.lft_out[x[u].node];
+        }
+    };
+    L1 cur[kRsSlices], nxt[kRsSlices];
+    uint32_t g = blockIdx.x;
+    if (g < n_groups) load1(g, cur);
+    for (; g < n_groups; g += gridDim.x) {
+        // level 2 of this group (needs its col words) ...
+        int old_pre[kRsSlices], new_pre[kRsSlices];
+#pragma unroll
+        for (int u = 0; u < kRsSlices; ++u) {
+            const uint32_t j = cur[u].cw == kColPad ? cur[u].node : (cur[u].cw & kColIdxMask);
+            old_pre[u] = p.lft_in[j]; new_pre[u] = p.lft_out[j];
+        }
+        // ... and level 1 of the next one, in flight together
+        const uint32_t gn = g + gridDim.x;
+        if (gn < n_groups) load1(gn, nxt);
+#pragma unroll
+        for (int u = 0; u < kRsSlices; ++u) {
+            if (cur[u].cw == kColPad) continue;
+            const uint32_t j = cur[u].cw & kColIdxMask, i = cur[u].node;
+            const int t_pre1 = (j <= i) ? new_pre[u] : old_pre[u];
+            const int t_post1 = (i <= j) ? cur[u].new_post : cur[u].old_post;
+            const bool first_live = (t_pre1 >= 0 && t_post1 >= 0 && t_pre1 != t_post1);
+            const bool second_live = (new_pre[u] >= 0 && cur[u].new_post >= 0 && new_pre[u] != cur[u].new_post);
+            if (!first_live && !second_live && cur[u].dw == 0.f && cur[u].cc == 0.f && cur[u].cnt == 0u) continue;
+            const float d2 = second_live ? (TAB ? rstdp_delta_tab(r, new_pre[u], cur[u].new_post) : rstdp_delta(r, new_pre[u], cur[u].new_post)) : 0.f;
+            const float d1 = (t_pre1 == new_pre[u] && t_post1 == cur[u].new_post) ? d2
+                             : (first_live ? (TAB ? rstdp_delta_tab(r, t_pre1, t_post1) : rstdp_delta(r, t_pre1, t_post1)) : 0.f);
+            uint32_t cnt = cur[u].cnt; float dw = cur[u].dw, cc = cur[u].cc, w = cur[u].w;
+            rstdp_call(r, d1, decay_c, cnt, dw, cc, w);
+            rstdp_call(r, d2, decay_c, cnt, dw, cc, w);
+            if (!CANON) { r.counter[cur[u].e] = (uint8_t)cnt; r.dw[cur[u].e] = dw; }
+            r.c[cur[u].e] = cc; p.wgt[cur[u].e] = w;
+        }
+#pragma unroll
+        for (int u = 0; u < kRsSlices; ++u) cur[u] = nxt[u];
     }
 }
 
@@ -568,6 +641,17 @@ cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaSt
     const unsigned grid = (n_slices + kRsSlices - 1) / kRsSlices;
     // the table stands for the formula while every spike time is exact in f32 (clock < 2^24)
     const bool tab = r.tab != nullptr && p.clock < (1u << 24);
+    static const bool pipe_env = !(getenv("SNN_B200_RSTDP_PIPE") && atoi(getenv("SNN_B200_RSTDP_PIPE")) == 0);
+    if (pipe_env && p.uniform_width == 8u && !(p.halo[0].active | p.halo[1].active) && grid > 512u) {
+        // whole lattices with radius-1 stencil tables, large enough to fill the persistent grid
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const unsigned pg = (unsigned)sms * (unsigned)SNN_RS_CTAS;
+        if (r.canonical) { if (tab) rstdp_edge8_kernel<true, true><<<pg, 256, 0, s>>>(p, r); else rstdp_edge8_kernel<true, false><<<pg, 256, 0, s>>>(p, r); }
+        else { if (tab) rstdp_edge8_kernel<false, true><<<pg, 256, 0, s>>>(p, r); else rstdp_edge8_kernel<false, false><<<pg, 256, 0, s>>>(p, r); }
+        return cudaGetLastError();
+    }
     if (r.canonical) { if (tab) rstdp_edge_kernel<true, true><<<grid, 256, 0, s>>>(p, r); else rstdp_edge_kernel<true, false><<<grid, 256, 0, s>>>(p, r); }
     else { if (tab) rstdp_edge_kernel<false, true><<<grid, 256, 0, s>>>(p, r); else rstdp_edge_kernel<false, false><<<grid, 256, 0, s>>>(p, r); }
     return cudaGetLastError();

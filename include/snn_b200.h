@@ -73,6 +73,10 @@ typedef enum snn_status {
     SNN_NET_PRESYNAPTIC_ID_NOT_FOUND = 34,
     SNN_NET_ID_NOT_FOUND_IN_LATTICES = 35,
     SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN = 36,
+    /* the RewardModulatedLatticeNetwork members of LatticeNetworkError, backend/src/error/mod.rs:55-62 */
+    SNN_NET_CANNOT_CONNECT_WITH_REWARD_MODULATED_CONNECTION = 37,
+    SNN_NET_REWARD_MODULATED_CONNECTION_NOT_COMPATIBLE_INTERNALLY = 38,
+    SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE = 39,
     /* argument errors of the C boundary itself (Rust's type system rules these out) */
     SNN_INVALID_ARGUMENT = 64,
     SNN_UNKNOWN_FIELD = 65,
@@ -413,6 +417,9 @@ SNN_API int32_t snn_network_connection_nnz(snn_network_t *h, uint64_t pre_id, ui
 SNN_API int32_t snn_network_get_connection_dense(snn_network_t *h, uint64_t pre_id, uint64_t post_id,
                                                  uint32_t *connections, float *weights, uint64_t n_pre,
                                                  uint64_t n_post);
+/* the block in the layout of snn_network_connect_csr (row_ptr: n_post + 1 entries; nnz from snn_network_connection_nnz) */
+SNN_API int32_t snn_network_get_connection_csr(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint64_t *row_ptr,
+                                               uint32_t *pre, float *weights, uint64_t n_post, uint64_t nnz);
 
 /* Graph::lookup_weight / edit_weight between two lattices of the network (or inside one when pre_id == post_id) on flat
  * indices: LatticeNetwork::connect's id errors first (neuron/mod.rs:1852-1862), then GraphError as for the lattice calls */
@@ -433,6 +440,32 @@ SNN_API int32_t snn_network_reset_timing(snn_network_t *h);                /* ne
 
 /* RunNetwork::run_lattices (neuron/mod.rs:2667-2674). Blocks. */
 SNN_API int32_t snn_network_run(snn_network_t *h, uint64_t iterations);
+
+/* RewardModulatedLatticeNetwork (neuron/mod.rs:3455-5455): a network handle that also holds reward-modulated lattices.
+ *  - add_reward_modulated_lattice (:3615-3634): a lattice whose own graph carries TraceRSTDP weights and whose plasticity is a
+ *    RewardModulatedSTDP (`do_modulation` defaults to 1, :2772; modulator defaults as snn_rstdp_t above);
+ *  - set_connection_reward_modulated: the block pre_id -> post_id of the connecting graph, built with the snn_network_connect_*
+ *    calls, holds RewardModulatedConnection::RewardModulatedWeight values (connect_with_reward_modulation, :4076-4209) instead
+ *    of ::Weight (connect, :3836-3947); connecting the block again makes it a Weight block again;
+ *  - snn_network_run is RunNetwork::run_lattices (:5411-5426, no reward signal); snn_network_run_with_rewards runs one timestep
+ *    per entry, every modulator taking the reward first (run_lattices_with_reward, :5385-5392 -> :5280-5297).
+ * After all neurons of a timestep have stepped (post_neuron_update_step, :5030-5062) every neuron of a reward-modulated lattice
+ * with do_modulation updates: the edges of the lattice's own graph, twice (as in-edge of one end and out-edge of the other);
+ * incoming RewardModulatedWeight edges once with that lattice's modulator; incoming Weight edges from plain lattices with the
+ * INPUT lattice's STDP parameters (:4868-4884).  Plain lattices keep LatticeNetwork's STDP.  The reference looks OUTGOING
+ * connecting edges up with their end points swapped and panics (:4760-4763, 4931-4934): run returns SNN_UNSUPPORTED for connecting
+ * edges out of a reward-modulated lattice with do_modulation or out of a plain lattice with do_plasticity, and for the incoming
+ * arms that unwrap a missing lattice kind (:4727-4731, 4741-4747).  Single-GPU handles. */
+SNN_API int32_t snn_network_add_reward_modulated_lattice(snn_network_t *h, uint64_t id, uint32_t rows, uint32_t cols);
+SNN_API int32_t snn_network_set_reward_modulator(snn_network_t *h, uint64_t id, int32_t do_modulation, const snn_rstdp_t *modulator);
+SNN_API int32_t snn_network_get_reward_modulator(snn_network_t *h, uint64_t id, int32_t *do_modulation, snn_rstdp_t *modulator);
+SNN_API int32_t snn_network_set_connection_reward_modulated(snn_network_t *h, uint64_t pre_id, uint64_t post_id, int32_t reward_modulated);
+SNN_API int32_t snn_network_run_with_rewards(snn_network_t *h, const float *rewards, uint64_t n_rewards);
+/* TraceRSTDP members of the edges of one block in the order of snn_network_get_connection_csr (see the snn_lattice_ calls) */
+SNN_API int32_t snn_network_get_connection_traces(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw,
+                                                  float *c, uint64_t nnz);
+SNN_API int32_t snn_network_set_connection_traces(snn_network_t *h, uint64_t pre_id, uint64_t post_id, const float *weight,
+                                                  const uint32_t *counter, const float *dw, const float *c, uint64_t nnz);
 SNN_API int32_t snn_network_run_timed(snn_network_t *h, uint64_t iterations, float *elapsed_ms,
                                       uint64_t *kernel_launches);
 

@@ -82,6 +82,11 @@ def lib():
         "orc_set_reward_modulator": ([P, i32, i32, C.POINTER(Rstdp)], i32),
         "orc_get_dopamine": ([P], f),
         "orc_run_with_reward": ([P, f], i32),
+        "orc_add_reward_lattice": ([P, u64, u32, u32], i32),
+        "orc_set_lattice_reward_modulator": ([P, u64, i32, C.POINTER(Rstdp)], i32),
+        "orc_get_lattice_reward_modulator": ([P, u64, C.POINTER(i32), C.POINTER(Rstdp)], i32),
+        "orc_mark_connection_reward": ([P, u64, u64, i32], i32),
+        "orc_run_network_with_reward": ([P, f], i32),
         "orc_get_connection_traces": ([P, u64, u64, P, P, P], i32),
         "orc_set_connection_traces": ([P, u64, u64, P, P, P, P], i32),
         "orc_history_len": ([P, u64], u64),
@@ -165,6 +170,26 @@ class OracleBackend:
     def add_lattice(self, id, rows, cols):
         self._ck(self.L.orc_add_lattice(self.h, id, rows, cols))
         self._flags[id] = [0, 0, 0]
+
+    def add_reward_lattice(self, id, rows, cols):
+        self._ck(self.L.orc_add_reward_lattice(self.h, id, rows, cols))
+        self._flags[id] = [0, 0, 0]
+
+    def set_lattice_reward_modulator(self, id, do_modulation, **m):
+        s = Rstdp(*[float(m[k]) for k in self._RSTDP])
+        self._ck(self.L.orc_set_lattice_reward_modulator(self.h, id, int(do_modulation), C.byref(s)))
+
+    def get_lattice_reward_modulator(self, id):
+        s, dm = Rstdp(), C.c_int32(0)
+        self._ck(self.L.orc_get_lattice_reward_modulator(self.h, id, C.byref(dm), C.byref(s)))
+        return bool(dm.value), {k: getattr(s, k) for k in self._RSTDP}
+
+    def mark_connection_reward(self, pre_id, post_id, reward_modulated):
+        self._ck(self.L.orc_mark_connection_reward(self.h, pre_id, post_id, int(reward_modulated)))
+
+    def run_network_with_rewards(self, rewards):
+        for r in np.asarray(rewards, np.float32).reshape(-1):
+            self._ck(self.L.orc_run_network_with_reward(self.h, float(r)))
 
     def add_train_lattice(self, id, rows, cols):
         self._ck(self.L.orc_add_train_lattice(self.h, id, rows, cols))
@@ -327,10 +352,10 @@ class OracleBackend:
         s = Bcm(decay, average_scalar, dt)
         self._ck(self.L.orc_set_bcm_plasticity(self.h, 0 if id is None else id, int(enable), C.byref(s)))
 
-    def set_connection_traces(self, weight=None, counter=None, dw=None, c=None):
+    def set_connection_traces(self, weight=None, counter=None, dw=None, c=None, pre_id=0, post_id=0):
         arrs = [None if x is None else _as(np.asarray(x).reshape(-1), t)
                 for x, t in ((weight, np.float32), (counter, np.uint32), (dw, np.float32), (c, np.float32))]
-        self._ck(self.L.orc_set_connection_traces(self.h, 0, 0, *[None if a is None else _ptr(a) for a in arrs]))
+        self._ck(self.L.orc_set_connection_traces(self.h, pre_id, post_id, *[None if a is None else _ptr(a) for a in arrs]))
 
     def set_dt(self, dt):
         self.L.orc_set_dt(self.h, float(dt))

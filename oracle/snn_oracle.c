@@ -82,6 +82,9 @@ typedef struct {
     /* TraceRSTDP plasticity/mod.rs:121-136 (w is its `weight`); all zero for plain f32 weights */
     uint32_t counter;
     float dw, c;
+    /* RewardModulatedConnection neuron/mod.rs:3429-3443 for edges of a network's connecting graph: 0 = Weight(f32),
+     * 1 = RewardModulatedWeight(TraceRSTDP) */
+    uint32_t rm;
 } o_edge;
 
 typedef struct {
@@ -94,6 +97,10 @@ typedef struct {
     o_train *trains;
     int do_plasticity, update_grid_history, update_spike_history;
     orc_stdp plasticity;
+    /* member of RewardModulatedLatticeNetwork::reward_modulated_lattices (neuron/mod.rs:3470-3471): its own graph holds
+     * TraceRSTDP weights and its plasticity is a RewardModulatedSTDP (neuron/mod.rs:2719-2751) */
+    int is_reward, do_modulation;
+    orc_rstdp rstdp;
     int use_bcm;          /* the lattice's Plasticity is BCM (plasticity/mod.rs:80-112) instead of STDP */
     orc_bcm bcm;
     uint64_t internal_clock;
@@ -550,7 +557,7 @@ static void edge_set(orc_network *net, uint64_t post, uint32_t pre, int has, flo
             e = net->in[post] = realloc(e, sizeof(o_edge) * net->in_cap[post]);
         }
         memmove(&e[lo + 1], &e[lo], sizeof(o_edge) * (len - lo));
-        e[lo].pre = pre; e[lo].w = w; e[lo].counter = 0; e[lo].dw = 0.f; e[lo].c = 0.f; net->in_len[post] = len + 1;
+        e[lo].pre = pre; e[lo].w = w; e[lo].counter = 0; e[lo].dw = 0.f; e[lo].c = 0.f; e[lo].rm = 0; net->in_len[post] = len + 1;
     } else if (found) {
         memmove(&e[lo], &e[lo + 1], sizeof(o_edge) * (len - lo - 1));
         net->in_len[post] = len - 1;
@@ -763,8 +770,10 @@ void orc_set_dt(orc_network *net, float dt) {
         } else {
             for (uint64_t j = 0; j < L->n; j++) L->cells[j].dt = dt;
             L->plasticity.dt = dt; L->bcm.dt = dt;
+            if (L->is_reward) L->rstdp.dt = dt; /* RewardModulatedLattice::set_dt neuron/mod.rs:2867-2870 */
         }
     }
+    if (net->reward_mode) net->rstdp.dt = dt;
 }
 
 /* reset_timing neuron/mod.rs:405-420, 1710-1717 */
@@ -1287,6 +1296,64 @@ static void rstdp_update_from_neuron(orc_network *net, o_lattice *L, uint64_t q)
     }
 }
 
+/* RewardModulatedLatticeNetwork::post_neuron_update_step neuron/mod.rs:5030-5062, the half for the network's
+ * reward_modulated_lattices: every neuron of a lattice with do_modulation (RewardModulatedSTDP::do_update is always true,
+ * plasticity/mod.rs:231-233) runs update_weights_from_neurons_across_reward_lattices (:4855-4977) and
+ * _within_reward_lattices (:4979-5028) AFTER all neurons have stepped, so both ends carry this step's last_firing_time.
+ *  - an edge of the lattice's own graph is visited as the in-edge of its post end and as the out-edge of its pre end: two
+ *    RewardModulatedSTDP::update_weight calls a step with the lattice's modulator;
+ *  - a connecting edge INTO the lattice: RewardModulatedWeight -> one call with the post lattice's modulator whatever the
+ *    input is (:4885-4925); Weight -> STDP::update_weight with the INPUT lattice's plasticity and only when the input is a
+ *    plain Lattice (:4868-4884; a spike-train input is left alone);
+ *  - connecting edges OUT of such a lattice are looked up with the end points swapped (:4931-4934) and the reference
+ *    panics unless the reverse edge exists; orc_run refuses that configuration (error 90) instead of restating it. */
+static void reward_network_update(orc_network *net) {
+    for (int li = 0; li < net->n_neuron_lat; li++) {
+        o_lattice *B = net->lat[li];
+        if (!B->is_reward || !B->do_modulation) continue;
+        for (uint64_t q = 0; q < B->n; q++) {
+            uint64_t post = B->base + q;
+            int32_t t_post = B->cells[q].last_firing_time;
+            for (uint32_t k = 0; k < net->in_len[post]; k++) {
+                o_edge *e = &net->in[post][k];
+                o_lattice *A = lat_of_node(net, e->pre);
+                int32_t t_pre = node_lft(net, e->pre);
+                if (A == B) {
+                    rstdp_update_weight(&B->rstdp, e, t_pre, t_post);
+                    rstdp_update_weight(&B->rstdp, e, t_pre, t_post);
+                } else if (e->rm) {
+                    rstdp_update_weight(&B->rstdp, e, t_pre, t_post);
+                } else if (!A->is_train && !A->is_reward) {
+                    e->w = orc_stdp_update(&A->plasticity, e->w, t_pre, t_post);
+                }
+            }
+        }
+    }
+}
+
+/* the configurations of a RewardModulatedLatticeNetwork the reference itself cannot run (see reward_network_update) */
+static int reward_network_check(orc_network *net) {
+    int any = 0;
+    for (int li = 0; li < net->n_neuron_lat; li++) any |= net->lat[li]->is_reward;
+    if (!any || !net->in) return 0;
+    for (int li = 0; li < net->n_neuron_lat; li++) {
+        o_lattice *B = net->lat[li];
+        for (uint64_t q = 0; q < B->n; q++) {
+            uint64_t post = B->base + q;
+            for (uint32_t k = 0; k < net->in_len[post]; k++) {
+                const o_edge *e = &net->in[post][k];
+                o_lattice *A = lat_of_node(net, e->pre);
+                if (A == B) continue;
+                if (A->is_reward && A->do_modulation) return 90;            /* :4931-4934 */
+                if (!A->is_train && !A->is_reward && A->do_plasticity) return 90; /* :4760-4763 */
+                if (!B->is_reward && B->do_plasticity && (e->rm || A->is_reward)) return 90; /* :4727-4731, 4741-4747 */
+                if (!B->is_reward && e->rm) return 90; /* a TraceRSTDP nobody advances */
+            }
+        }
+    }
+    return 0;
+}
+
 static void history_push(o_lattice *L) {
     if (!L->is_train && (L->update_average_history || L->update_eeg_history)) {
         if (L->hist_len >= L->red_cap) {
@@ -1365,6 +1432,7 @@ static void step(orc_network *net) {
                 if (B->cells[q].is_spiking) update_weights_from_neuron(net, B, q); /* STDP::do_update plasticity/mod.rs:67-69 */
         }
     }
+    if (net->in) reward_network_update(net);
     net->internal_clock += 1;
     for (int li = 0; li < net->n_neuron_lat; li++) net->lat[li]->internal_clock = net->internal_clock;
     /* phase 4: spike trains step after the neurons with their own clock (:2588-2591, 1377-1393) */
@@ -1383,6 +1451,7 @@ int orc_run(orc_network *net, uint64_t iterations) {
     /* run_lattice / run_lattices dispatch neuron/mod.rs:1213-1218, 2668-2673: (false,false) is a no-op */
     if (!net->electrical && !net->chemical) return 0;
     ensure_graph(net);
+    { int r = reward_network_check(net); if (r) return r; }
     if (!net->inp_e) {
         uint64_t n = net->n_neurons ? net->n_neurons : 1;
         net->inp_e = calloc(n, sizeof(float));
@@ -1406,6 +1475,58 @@ float orc_get_dopamine(orc_network *net) { return net->rstdp.dopamine; }
 int orc_run_with_reward(orc_network *net, float reward) {
     if (!net->electrical && !net->chemical) return 0;
     net->rstdp.dopamine = net->rstdp.dopamine * expf(-net->rstdp.dt / net->rstdp.tau_d) + net->rstdp.tau_d * reward;
+    return orc_run(net, 1);
+}
+
+/* RewardModulatedLatticeNetwork::add_reward_modulated_lattice neuron/mod.rs:3615-3634 (do_modulation defaults to true,
+ * :2772; RewardModulatedSTDP::default plasticity/mod.rs:167-181) */
+int orc_add_reward_lattice(orc_network *net, uint64_t id, uint32_t rows, uint32_t cols) {
+    int r = add_lat(net, id, rows, cols, 0);
+    if (r) return r;
+    o_lattice *L = find_lat(net, id);
+    L->is_reward = 1; L->do_modulation = 1;
+    L->rstdp = (orc_rstdp){0.f, 20.f, 0.0001f, 2.f, 2.f, 4.5f, 4.5f, 0.1f};
+    return 0;
+}
+int orc_set_lattice_reward_modulator(orc_network *net, uint64_t id, int do_modulation, const orc_rstdp *m) {
+    o_lattice *L = find_lat(net, id);
+    if (!L || !L->is_reward) return 35;
+    L->do_modulation = do_modulation;
+    if (m) L->rstdp = *m;
+    return 0;
+}
+int orc_get_lattice_reward_modulator(orc_network *net, uint64_t id, int *do_modulation, orc_rstdp *m) {
+    o_lattice *L = find_lat(net, id);
+    if (!L || !L->is_reward) return 35;
+    if (do_modulation) *do_modulation = L->do_modulation;
+    if (m) *m = L->rstdp;
+    return 0;
+}
+/* connect_with_reward_modulation neuron/mod.rs:4076-4209: the block's edges hold RewardModulatedWeight (rm = 1) or
+ * Weight (rm = 0) values */
+int orc_mark_connection_reward(orc_network *net, uint64_t pre_id, uint64_t post_id, int rm) {
+    o_lattice *A = find_lat(net, pre_id), *B = find_lat(net, post_id);
+    if (!A || !B || B->is_train) return 35;
+    ensure_graph(net);
+    for (uint64_t q = 0; q < B->n; q++) {
+        uint64_t post = B->base + q;
+        for (uint32_t k = 0; k < net->in_len[post]; k++) {
+            o_edge *e = &net->in[post][k];
+            if (e->pre >= A->base && e->pre < A->base + A->n) e->rm = (uint32_t)(rm != 0);
+        }
+    }
+    return 0;
+}
+/* RewardModulatedLatticeNetwork::run_lattices_with_reward neuron/mod.rs:5385-5392 -> run_lattices_*(reward) :5280-5297:
+ * inputs from the pre-step state, RewardModulatedSTDP::update(reward) (plasticity/mod.rs:193-195) on every
+ * reward-modulated lattice, then iterate. The inputs do not read the dopamine, so updating it first is the same. */
+int orc_run_network_with_reward(orc_network *net, float reward) {
+    if (!net->electrical && !net->chemical) return 0;
+    for (int li = 0; li < net->n_neuron_lat; li++) {
+        o_lattice *L = net->lat[li];
+        if (!L->is_reward) continue;
+        L->rstdp.dopamine = L->rstdp.dopamine * expf(-L->rstdp.dt / L->rstdp.tau_d) + L->rstdp.tau_d * reward;
+    }
     return orc_run(net, 1);
 }
 

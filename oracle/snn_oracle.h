@@ -109,6 +109,12 @@ int orc_set_bcm_plasticity(orc_network *net, uint64_t id, int enable, const orc_
 int orc_set_reward_modulator(orc_network *net, int enable, int do_modulation, const orc_rstdp *m);
 float orc_get_dopamine(orc_network *net);
 int orc_run_with_reward(orc_network *net, float reward);
+/* RewardModulatedLatticeNetwork neuron/mod.rs:3455-5455: reward-modulated lattices inside a network */
+int orc_add_reward_lattice(orc_network *net, uint64_t id, uint32_t rows, uint32_t cols);
+int orc_set_lattice_reward_modulator(orc_network *net, uint64_t id, int do_modulation, const orc_rstdp *m);
+int orc_get_lattice_reward_modulator(orc_network *net, uint64_t id, int *do_modulation, orc_rstdp *m);
+int orc_mark_connection_reward(orc_network *net, uint64_t pre_id, uint64_t post_id, int rm);
+int orc_run_network_with_reward(orc_network *net, float reward);
 int orc_get_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw, float *c);
 int orc_set_connection_traces(orc_network *net, uint64_t pre_id, uint64_t post_id, const float *weight, const uint32_t *counter,
                               const float *dw, const float *c);

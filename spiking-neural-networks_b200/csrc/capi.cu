@@ -55,6 +55,12 @@ const char *snn_status_string(int32_t s) {
     case SNN_NET_ID_NOT_FOUND_IN_LATTICES: return "Id not present in lattices";
     case SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN:
         return "Postsynaptic lattice cannot be a spike train lattice because spike trains cannot take inputs";
+    case SNN_NET_CANNOT_CONNECT_WITH_REWARD_MODULATED_CONNECTION:
+        return "When connecting reward modulated network, at least one lattice has to be reward modulated";
+    case SNN_NET_REWARD_MODULATED_CONNECTION_NOT_COMPATIBLE_INTERNALLY:
+        return "When connecting reward modulated lattice, RewardModulatedConnection cannot be used to connect a reward modulated lattice internally";
+    case SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE:
+        return "Connect function must have non reward modulated lattices, connect with reward modulation instead";
     case SNN_INVALID_ARGUMENT: return "invalid argument";
     case SNN_UNKNOWN_FIELD: return "unknown field";
     case SNN_DTYPE_MISMATCH: return "dtype mismatch";
@@ -515,6 +521,42 @@ int32_t snn_network_reset_timing(snn_network_t *h) {
 int32_t snn_network_run(snn_network_t *h, uint64_t iterations) {
     if (!h) return SNN_INVALID_ARGUMENT;
     SNN_TRY return h->e->run(iterations, nullptr, nullptr); SNN_CATCH(h)
+}
+int32_t snn_network_get_connection_csr(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint64_t *row_ptr, uint32_t *pre, float *weights,
+                                       uint64_t n_post, uint64_t nnz) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_connection_csr(pre_id, post_id, row_ptr, pre, weights, n_post, nnz); SNN_CATCH(h)
+}
+int32_t snn_network_add_reward_modulated_lattice(snn_network_t *h, uint64_t id, uint32_t rows, uint32_t cols) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->add_lattice(id, rows, cols, false, true); SNN_CATCH(h)
+}
+int32_t snn_network_set_reward_modulator(snn_network_t *h, uint64_t id, int32_t do_modulation, const snn_rstdp_t *modulator) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->set_lattice_reward_modulator(id, do_modulation != 0, modulator); SNN_CATCH(h)
+}
+int32_t snn_network_get_reward_modulator(snn_network_t *h, uint64_t id, int32_t *do_modulation, snn_rstdp_t *modulator) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_lattice_reward_modulator(id, do_modulation, modulator); SNN_CATCH(h)
+}
+int32_t snn_network_set_connection_reward_modulated(snn_network_t *h, uint64_t pre_id, uint64_t post_id, int32_t reward_modulated) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->set_connection_reward(pre_id, post_id, reward_modulated != 0); SNN_CATCH(h)
+}
+int32_t snn_network_run_with_rewards(snn_network_t *h, const float *rewards, uint64_t n_rewards) {
+    if (!h || (n_rewards && !rewards)) return SNN_INVALID_ARGUMENT;
+    if (!h->e->has_reward_lattices()) return h->e->fail(SNN_INVALID_ARGUMENT, "network holds no reward-modulated lattice");
+    SNN_TRY return h->e->run(n_rewards, nullptr, nullptr, rewards); SNN_CATCH(h)
+}
+int32_t snn_network_get_connection_traces(snn_network_t *h, uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw, float *c,
+                                          uint64_t nnz) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->get_block_traces(pre_id, post_id, counter, dw, c, nnz); SNN_CATCH(h)
+}
+int32_t snn_network_set_connection_traces(snn_network_t *h, uint64_t pre_id, uint64_t post_id, const float *weight, const uint32_t *counter,
+                                          const float *dw, const float *c, uint64_t nnz) {
+    if (!h) return SNN_INVALID_ARGUMENT;
+    SNN_TRY return h->e->set_block_traces(pre_id, post_id, weight, counter, dw, c, nnz); SNN_CATCH(h)
 }
 int32_t snn_network_run_timed(snn_network_t *h, uint64_t iterations, float *elapsed_ms, uint64_t *kernel_launches) {
     if (!h) return SNN_INVALID_ARGUMENT;

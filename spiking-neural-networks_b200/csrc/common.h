@@ -316,6 +316,22 @@ struct RstdpParams {
 };
 cudaError_t launch_rstdp_table(const RstdpParams &r, float *tab, uint32_t tab_n, cudaStream_t s);
 cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaStream_t s);
+// RewardModulatedLatticeNetwork (neuron/mod.rs:3455-5455): the post-step weight pass over the rows of its reward-modulated
+// lattices.  lat[] follows StepParams::lat (neuron lattices in node order).
+struct RnetLat {
+    float dopamine, tau_c, a_plus, a_minus, tau_plus, tau_minus, dt;
+    uint32_t flags;   // bit 0: a RewardModulatedLattice; bit 1: its do_modulation
+};
+struct RnetParams {
+    RnetLat lat[kMaxLattices];
+    // per post lattice: bit q set = the connecting block from presynaptic class q holds RewardModulatedWeight values (else Weight);
+    // q < kMaxLattices: neuron lattice q; q = kMaxLattices + t: spike-train lattice t
+    uint32_t conn_reward[kMaxLattices];
+    uint32_t n_tl, tl_base[kMaxLattices + 1];   // spike-train lattice t covers node indices [train0 + tl_base[t], train0 + tl_base[t+1])
+    uint32_t train0;
+    uint8_t *counter; float *dw, *c;   // TraceRSTDP members next to StepParams::wgt (same element index)
+};
+cudaError_t launch_rstdp_net_edges(const StepParams &p, const RnetParams &r, cudaStream_t s);
 cudaError_t launch_finalize(const StepParams &p, int model, const float *v_prev, cudaStream_t s);
 cudaError_t launch_sell_from_csr(const uint64_t *row_ptr, const uint32_t *pre, const float *w, const uint8_t *node_flags,
                                  uint32_t train0, uint32_t n_rows, const uint32_t *slice_off, uint32_t *col, float *wgt,

@@ -287,14 +287,17 @@ int Engine::set_partition(uint32_t rows_g, uint32_t cols, int rank, int world) {
 struct FieldSnap { std::string name; int dtype; std::vector<uint8_t> data; uint64_t count; };
 struct LatSnap { uint64_t id; std::vector<FieldSnap> fields; };
 
-int Engine::add_lattice(uint64_t id, uint32_t rows, uint32_t cols, bool is_train) {
+int Engine::add_lattice(uint64_t id, uint32_t rows, uint32_t cols, bool is_train, bool is_reward) {
     // LatticeNetwork::add_lattice / add_spike_train_lattice, neuron/mod.rs:1663-1698
     if (find(id)) return fail(SNN_NET_GRAPH_ID_ALREADY_PRESENT, "Graph id already present in network, id: " + std::to_string(id));
     int n_neuron_lat = 0;
     for (auto &L : lats_) if (!L.is_train) n_neuron_lat++;
     if (!is_train && n_neuron_lat >= kMaxLattices) return fail(SNN_UNSUPPORTED, "too many lattices");
     if (part_world > 1 && (!lats_.empty() || is_train)) return fail(SNN_UNSUPPORTED, "a partitioned handle holds exactly one neuron lattice");
+    if (is_reward && (is_train || part_world > 1 || reward_mode || bcm_mode))
+        return fail(SNN_UNSUPPORTED, "reward-modulated lattices of a network: single-GPU network handles only");
     Lat nl;
+    nl.is_reward = is_reward;   // RewardModulatedLatticeNetwork::add_reward_modulated_lattice, neuron/mod.rs:3615-3634
     nl.id = id; nl.rows = rows; nl.cols = cols; nl.n = (uint64_t)rows * cols; nl.is_train = is_train;
     if ((is_train ? n_trains : n_neurons) + nl.n + 64ull * (part_world > 1 ? cols : 0) > kMaxNodes)
         return fail(SNN_UNSUPPORTED, "lattice too large for one device (node index is 28 bits)");
@@ -1275,6 +1278,42 @@ int Engine::set_reward_modulator(bool enable, bool modulate, const snn_rstdp_t *
     return SNN_OK;
 }
 
+// RewardModulatedLatticeNetwork: per-lattice modulators and the kind of the connecting blocks
+int Engine::set_lattice_reward_modulator(uint64_t id, bool modulate, const snn_rstdp_t *m) {
+    Lat *L = find(id);
+    if (!L || !L->is_reward) return fail(SNN_INVALID_ARGUMENT, "not a reward-modulated lattice of this network, id: " + std::to_string(id));
+    L->do_modulation = modulate;
+    if (m) L->rstdp = *m;
+    return SNN_OK;
+}
+
+int Engine::get_lattice_reward_modulator(uint64_t id, int32_t *modulate, snn_rstdp_t *m) {
+    Lat *L = find(id);
+    if (!L || !L->is_reward) return fail(SNN_INVALID_ARGUMENT, "not a reward-modulated lattice of this network, id: " + std::to_string(id));
+    if (modulate) *modulate = L->do_modulation ? 1 : 0;
+    if (m) *m = L->rstdp;
+    return SNN_OK;
+}
+
+int Engine::set_connection_reward(uint64_t pre_id, uint64_t post_id, bool reward_modulated) {
+    // connect_with_reward_modulation neuron/mod.rs:4076-4209: the block's values are RewardModulatedConnection::RewardModulatedWeight
+    // (TraceRSTDP) instead of ::Weight(f32)
+    const Lat *A = find(pre_id), *B = find(post_id);
+    if (B && B->is_train)
+        return fail(SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN, "Postsynaptic lattice cannot be a spike train lattice because spike trains cannot take inputs");
+    if (!A) return fail(SNN_NET_PRESYNAPTIC_ID_NOT_FOUND, "Presynaptic id not present in network, id: " + std::to_string(pre_id));
+    if (!(B && B->is_reward) && !A->is_reward)
+        return fail(SNN_NET_CANNOT_CONNECT_WITH_REWARD_MODULATED_CONNECTION, "When connecting reward modulated network, at least one lattice has to be reward modulated");
+    if (!B) return fail(SNN_NET_POSTSYNAPTIC_ID_NOT_FOUND, "Postsynaptic id not present in network, id: " + std::to_string(post_id));
+    if (pre_id == post_id)
+        return fail(SNN_NET_REWARD_MODULATED_CONNECTION_NOT_COMPATIBLE_INTERNALLY,
+                    "When connecting reward modulated lattice, RewardModulatedConnection cannot be used to connect a reward modulated lattice internally");
+    auto it = blocks_.find({pre_id, post_id});
+    if (it == blocks_.end()) return fail(SNN_INVALID_ARGUMENT, "no such connecting block: connect it first");
+    it->second.reward_conn = reward_modulated;
+    return SNN_OK;
+}
+
 void Engine::free_reward_arrays() {
     if (rs_counter_) cudaFree(rs_counter_);
     if (rs_dw_) cudaFree(rs_dw_);
@@ -1297,47 +1336,75 @@ int Engine::ensure_reward_arrays() {
     return SNN_OK;
 }
 
-int Engine::get_connection_traces(uint32_t *counter, float *dw, float *c, uint64_t nnz) {
-    const Lat *only = nullptr;
-    for (auto &L : lats_) if (!L.is_train) only = &L;
-    if (!only || !reward_mode) return fail(SNN_INVALID_ARGUMENT, "handle is not a reward-modulated lattice");
-    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
-    int r = finalize_graph();
-    if (r) return r;
-    r = ensure_reward_arrays();
-    if (r) return r;
-    auto it = blocks_.find({only->id, only->id});
-    Block tmp;
-    if (it != blocks_.end()) { tmp = it->second; if (tmp.kind == Block::GRID) materialize_grid(tmp, *only); }
-    else tmp.row_ptr.assign(only->n + 1, 0);
-    if (tmp.pre.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
-    if (nnz == 0) return SNN_OK;
+bool Engine::has_reward_lattices() const {
+    for (auto &L : lats_) if (L.is_reward) return true;
+    return false;
+}
+
+// element index (k * 32 + lane) of every edge of block pre_id -> post_id, in the block's CSR order; rows are laid out as
+// finalize_graph wrote them (blocks into a lattice ordered by the presynaptic lattice's node offset)
+int Engine::block_elements(uint64_t pre_id, uint64_t post_id, std::vector<size_t> *elems, Block **blk) {
+    Lat *B = find(post_id);
+    if (!find(pre_id) || !B || B->is_train) return fail(SNN_INVALID_ARGUMENT, "no such connection block");
+    *blk = nullptr;
+    elems->clear();
+    auto it = blocks_.find({pre_id, post_id});
+    if (it == blocks_.end()) return SNN_OK;
+    *blk = &it->second;
     std::vector<uint32_t> so((size_t)n_slices_ + 1);
-    std::vector<uint8_t> hc(rs_elems_);
-    std::vector<float> hd(rs_elems_), hcc(rs_elems_);
     CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
     CK(cudaMemcpy(so.data(), slice_off_, so.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
-    CK(cudaMemcpy(hc.data(), rs_counter_, rs_elems_, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
-    CK(cudaMemcpy(hd.data(), rs_dw_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
-    CK(cudaMemcpy(hcc.data(), rs_c_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
-    for (uint64_t q = 0; q < only->n; ++q) {
-        const uint64_t row = only->off + q;
-        const uint32_t s = (uint32_t)(row / 32), lane = (uint32_t)(row % 32);
-        uint32_t k = so[s];
-        for (uint64_t e = tmp.row_ptr[q]; e < tmp.row_ptr[q + 1]; ++e, ++k) {
-            const size_t o = (size_t)k * 32 + lane;
-            if (counter) counter[e] = hc[o];
-            if (dw) dw[e] = hd[o];
-            if (c) c[e] = hcc[o];
+    Block tmp;
+    const Block *target = &it->second;
+    if (target->kind == Block::GRID) { tmp = *target; materialize_grid(tmp, *B); target = &tmp; }   // single stencil lattice: keep the device fast path
+    std::vector<std::pair<const Lat *, const Block *>> into;
+    for (auto &kv : blocks_)
+        if (kv.first.second == post_id) { const Lat *A = find(kv.first.first); if (A) into.emplace_back(A, &kv.second == &it->second ? target : &kv.second); }
+    std::sort(into.begin(), into.end(), [&](auto &x, auto &y) { return node_off(*x.first) < node_off(*y.first); });
+    elems->reserve(target->pre.size());
+    for (uint64_t q = 0; q < B->n; ++q) {
+        const uint64_t row = B->off + q;
+        const uint32_t sl = (uint32_t)(row / 32), lane = (uint32_t)(row % 32);
+        uint32_t k = so[sl];
+        for (auto &ab : into) {
+            const uint64_t len = ab.second->row_ptr[q + 1] - ab.second->row_ptr[q];
+            if (ab.second == target)
+                for (uint64_t e = 0; e < len; ++e) elems->push_back((size_t)(k + e) * 32 + lane);
+            k += (uint32_t)len;
         }
     }
     return SNN_OK;
 }
 
-int Engine::set_connection_traces(const float *weight, const uint32_t *counter, const float *dw, const float *c, uint64_t nnz) {
-    Lat *only = nullptr;
-    for (auto &L : lats_) if (!L.is_train) only = &L;
-    if (!only || !reward_mode) return fail(SNN_INVALID_ARGUMENT, "handle is not a reward-modulated lattice");
+int Engine::get_block_traces(uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw, float *c, uint64_t nnz) {
+    if (!reward_mode && !has_reward_lattices()) return fail(SNN_INVALID_ARGUMENT, "handle holds no reward-modulated lattice");
+    CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
+    int r = finalize_graph();
+    if (r) return r;
+    r = ensure_reward_arrays();
+    if (r) return r;
+    std::vector<size_t> el;
+    Block *b = nullptr;
+    r = block_elements(pre_id, post_id, &el, &b);
+    if (r) return r;
+    if (el.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
+    if (nnz == 0) return SNN_OK;
+    std::vector<uint8_t> hc(rs_elems_);
+    std::vector<float> hd(rs_elems_), hcc(rs_elems_);
+    CK(cudaMemcpy(hc.data(), rs_counter_, rs_elems_, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hd.data(), rs_dw_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    CK(cudaMemcpy(hcc.data(), rs_c_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    for (uint64_t e = 0; e < nnz; ++e) {
+        if (counter) counter[e] = hc[el[e]];
+        if (dw) dw[e] = hd[el[e]];
+        if (c) c[e] = hcc[el[e]];
+    }
+    return SNN_OK;
+}
+
+int Engine::set_block_traces(uint64_t pre_id, uint64_t post_id, const float *weight, const uint32_t *counter, const float *dw, const float *c,
+                             uint64_t nnz) {
+    if (!reward_mode && !has_reward_lattices()) return fail(SNN_INVALID_ARGUMENT, "handle holds no reward-modulated lattice");
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     int r = finalize_graph();
     if (r) return r;
@@ -1345,42 +1412,46 @@ int Engine::set_connection_traces(const float *weight, const uint32_t *counter, 
     if (r) return r;
     r = sync_weights_to_host();   // the host copy of the weights must be current before parts of it are overwritten
     if (r) return r;
-    auto it = blocks_.find({only->id, only->id});
-    if (it == blocks_.end()) return nnz ? fail(SNN_SIZE_MISMATCH, "nnz mismatch") : SNN_OK;
-    Block tmp;
-    Block *b = &it->second;
-    if (b->kind == Block::GRID) { tmp = *b; materialize_grid(tmp, *only); b = &tmp; }   // keep the device fast path
-    if (b->pre.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
+    std::vector<size_t> el;
+    Block *b = nullptr;
+    r = block_elements(pre_id, post_id, &el, &b);
+    if (r) return r;
+    if (el.size() != nnz) return fail(SNN_SIZE_MISMATCH, "nnz mismatch");
     if (nnz == 0) return SNN_OK;
-    std::vector<uint32_t> so((size_t)n_slices_ + 1);
+    const uint64_t wel = std::max(sell_alloc_krows_, sell_krows_) * 32;
     std::vector<uint8_t> hc(rs_elems_);
     std::vector<float> hd(rs_elems_), hcc(rs_elems_), hw(rs_elems_);
-    CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
-    CK(cudaMemcpy(so.data(), slice_off_, so.size() * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
     CK(cudaMemcpy(hc.data(), rs_counter_, rs_elems_, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
     CK(cudaMemcpy(hd.data(), rs_dw_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
     CK(cudaMemcpy(hcc.data(), rs_c_, rs_elems_ * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
-    CK(cudaMemcpy(hw.data(), wgt_, std::min<uint64_t>(rs_elems_, std::max(sell_alloc_krows_, sell_krows_) * 32) * 4, cudaMemcpyDeviceToHost),
-       SNN_GPU_BUFFER_READ_ERROR);
-    for (uint64_t q = 0; q < only->n; ++q) {
-        const uint64_t row = only->off + q;
-        const uint32_t s = (uint32_t)(row / 32), lane = (uint32_t)(row % 32);
-        uint32_t k = so[s];
-        for (uint64_t e = b->row_ptr[q]; e < b->row_ptr[q + 1]; ++e, ++k) {
-            const size_t o = (size_t)k * 32 + lane;
-            if (weight) { hw[o] = weight[e]; if (it->second.kind == Block::CSR) it->second.w[e] = weight[e]; }
-            if (counter) { hc[o] = (uint8_t)counter[e]; if (counter[e] != 0u) rs_canonical_ = false; }
-            if (dw) { hd[o] = dw[e]; if (dw[e] != 0.f) rs_canonical_ = false; }
-            if (c) hcc[o] = c[e];
-        }
+    CK(cudaMemcpy(hw.data(), wgt_, std::min<uint64_t>(rs_elems_, wel) * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
+    for (uint64_t e = 0; e < nnz; ++e) {
+        const size_t o = el[e];
+        if (weight) { hw[o] = weight[e]; if (b->kind == Block::CSR) b->w[e] = weight[e]; }
+        if (counter) { hc[o] = (uint8_t)counter[e]; if (counter[e] != 0u) rs_canonical_ = false; }
+        if (dw) { hd[o] = dw[e]; if (dw[e] != 0.f) rs_canonical_ = false; }
+        if (c) hcc[o] = c[e];
     }
-    const uint64_t wel = std::max(sell_alloc_krows_, sell_krows_) * 32;
     if (weight) CK(h2d_sync(wgt_, hw.data(), wel * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     if (counter) CK(h2d_sync(rs_counter_, hc.data(), rs_elems_, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     if (dw) CK(h2d_sync(rs_dw_, hd.data(), rs_elems_ * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
     if (c) CK(h2d_sync(rs_c_, hcc.data(), rs_elems_ * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
-    if (weight && it->second.kind == Block::GRID) dev_weights_newer_ = true;   // a stencil block's weights live on the device
+    if (weight && b->kind == Block::GRID) dev_weights_newer_ = true;   // a stencil block's weights live on the device
     return SNN_OK;
+}
+
+int Engine::get_connection_traces(uint32_t *counter, float *dw, float *c, uint64_t nnz) {
+    const Lat *only = nullptr;
+    for (auto &L : lats_) if (!L.is_train) only = &L;
+    if (!only || !reward_mode) return fail(SNN_INVALID_ARGUMENT, "handle is not a reward-modulated lattice");
+    return get_block_traces(only->id, only->id, counter, dw, c, nnz);
+}
+
+int Engine::set_connection_traces(const float *weight, const uint32_t *counter, const float *dw, const float *c, uint64_t nnz) {
+    const Lat *only = nullptr;
+    for (auto &L : lats_) if (!L.is_train) only = &L;
+    if (!only || !reward_mode) return fail(SNN_INVALID_ARGUMENT, "handle is not a reward-modulated lattice");
+    return set_block_traces(only->id, only->id, weight, counter, dw, c, nnz);
 }
 
 int Engine::sync_weights_to_host() {
@@ -1628,7 +1699,7 @@ int Engine::set_dt(float dt) {
     // rescales chance_of_firing (spike_train/mod.rs:345-349)
     CK(cudaSetDevice(device), SNN_GPU_GET_DEVICE_FAILURE);
     for (auto &L : lats_) {
-        if (L.n == 0) { if (!L.is_train) L.stdp.dt = dt; continue; }
+        if (L.n == 0) { if (!L.is_train) { L.stdp.dt = dt; if (L.is_reward) L.rstdp.dt = dt; } continue; }
         if (L.is_train) {
             std::vector<float> old(L.n), ch(L.n);
             CK(cudaMemcpy(old.data(), TF_[TF_DT] + L.off, L.n * 4, cudaMemcpyDeviceToHost), SNN_GPU_BUFFER_READ_ERROR);
@@ -1641,8 +1712,10 @@ int Engine::set_dt(float dt) {
         } else {
             CK(fill_f32(F_[F_DT] + L.off, dt, L.n, stream_), SNN_GPU_QUEUE_FAILURE);
             L.stdp.dt = dt;
+            if (L.is_reward) L.rstdp.dt = dt;   // RewardModulatedLattice::set_dt, neuron/mod.rs:2867-2870
         }
     }
+    if (reward_mode) rstdp.dt = dt;
     CK(cudaStreamSynchronize(stream_), SNN_GPU_WAIT_ERROR);
     return SNN_OK;
 }
@@ -1725,7 +1798,7 @@ int Engine::upload_lat_table() {
         tab[k].base = (uint32_t)L.off; tab[k].n = (uint32_t)L.n;
         tab[k].a_plus = L.stdp.a_plus; tab[k].a_minus = L.stdp.a_minus; tab[k].tau_plus = L.stdp.tau_plus;
         tab[k].tau_minus = L.stdp.tau_minus; tab[k].dt = L.stdp.dt;
-        tab[k].do_plasticity = L.do_plasticity; tab[k].grid_hist = L.grid_hist; tab[k].spike_hist = L.spike_hist;
+        tab[k].do_plasticity = L.do_plasticity && !L.is_reward; tab[k].grid_hist = L.grid_hist; tab[k].spike_hist = L.spike_hist;
         ++k;
     }
     if (k == 0) k = 1;
@@ -1979,7 +2052,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
 
     bool stdp = false, want_grid = false, want_spk = false, want_tgrid = false, want_tspk = false, want_red = false;
     for (auto &L : lats_) {
-        if (!L.is_train) { stdp |= L.do_plasticity; want_grid |= L.grid_hist; want_spk |= L.spike_hist; want_red |= L.avg_hist || L.eeg_hist; }
+        if (!L.is_train) { stdp |= L.do_plasticity && !L.is_reward; want_grid |= L.grid_hist; want_spk |= L.spike_hist; want_red |= L.avg_hist || L.eeg_hist; }
         else { want_tgrid |= L.grid_hist; want_tspk |= L.spike_hist; }
     }
     // kernel specialisation: ntrel = neurotransmitter / receptor state must be stepped; chemg = how the chemical gather
@@ -2006,7 +2079,6 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             const uint32_t tab_n = (uint32_t)reach + 8u;
             if (rs_tab_n_ != tab_n) {
                 if (rs_tab_) cudaFree(rs_tab_);
-    if (wide_scratch_) cudaFree(wide_scratch_);
                 rs_tab_ = nullptr; rs_tab_n_ = 0;
                 CK(dev_alloc(&rs_tab_, (size_t)tab_n * 2), SNN_GPU_BUFFER_CREATE_ERROR);
                 rs_tab_n_ = tab_n;
@@ -2015,7 +2087,49 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             rsp.tab = rs_tab_; rsp.tab_n = tab_n;
         }
     }
-    const bool lft_pp = stdp || rmod || (n_trains && electrical) || part_world > 1;
+    // RewardModulatedLatticeNetwork: reward-modulated lattices next to plain lattices and spike trains
+    const bool net_reward = has_reward_lattices();
+    bool net_rmod = false;
+    RnetParams rnp;
+    memset(&rnp, 0, sizeof rnp);
+    if (net_reward) {
+        if (part_world > 1 || reward_mode || bcm_mode) return fail(SNN_UNSUPPORTED, "reward-modulated lattice networks run on single-GPU network handles");
+        // the configurations the reference cannot run itself: update_weights_from_neurons_across_(reward_)lattices looks the OUTGOING
+        // connecting edges up with the end points swapped and unwraps the result (neuron/mod.rs:4760-4763, 4931-4934), and its
+        // incoming arms unwrap lattice kinds that need not be there (:4727-4731, 4741-4747)
+        for (auto &kv : blocks_) {
+            if (kv.first.first == kv.first.second) continue;
+            if (kv.second.kind != Block::GRID && kv.second.pre.empty()) continue;
+            const Lat *A = find(kv.first.first), *B = find(kv.first.second);
+            if (!A || !B) continue;
+            if (A->is_reward && A->do_modulation)
+                return fail(SNN_UNSUPPORTED, "connecting edges out of a reward-modulated lattice with do_modulation: the reference panics on them (neuron/mod.rs:4931-4934)");
+            if (!A->is_train && !A->is_reward && A->do_plasticity)
+                return fail(SNN_UNSUPPORTED, "connecting edges out of a plastic lattice of a reward-modulated network: the reference panics on them (neuron/mod.rs:4760-4763)");
+            if (!B->is_reward && kv.second.reward_conn)
+                return fail(SNN_UNSUPPORTED, "RewardModulatedWeight connections must end in a reward-modulated lattice");
+            if (!B->is_reward && B->do_plasticity && A->is_reward)
+                return fail(SNN_UNSUPPORTED, "a plastic lattice fed by a reward-modulated lattice: the reference panics on it (neuron/mod.rs:4727-4731)");
+        }
+        std::map<uint64_t, int> cls;   // lattice id -> presynaptic class of RnetParams::conn_reward
+        int kn = 0, kt = 0;
+        for (auto &L : lats_) {
+            if (L.is_train) { rnp.tl_base[kt] = (uint32_t)L.off; cls[L.id] = kMaxLattices + kt; ++kt; continue; }
+            RnetLat &R = rnp.lat[kn];
+            R.dopamine = L.rstdp.dopamine; R.tau_c = L.rstdp.tau_c; R.a_plus = L.rstdp.a_plus; R.a_minus = L.rstdp.a_minus;
+            R.tau_plus = L.rstdp.tau_plus; R.tau_minus = L.rstdp.tau_minus; R.dt = L.rstdp.dt;
+            R.flags = (L.is_reward ? 1u : 0u) | (L.is_reward && L.do_modulation ? 2u : 0u);
+            net_rmod |= L.is_reward && L.do_modulation && L.n > 0;
+            cls[L.id] = kn++;
+        }
+        rnp.n_tl = (uint32_t)kt; rnp.tl_base[kt] = (uint32_t)n_trains; rnp.train0 = train0_;
+        for (auto &kv : blocks_)
+            if (kv.second.reward_conn && kv.first.first != kv.first.second && cls.count(kv.first.first) && cls.count(kv.first.second))
+                rnp.conn_reward[cls[kv.first.second]] |= 1u << cls[kv.first.first];
+        if (net_rmod) { int rr = ensure_reward_arrays(); if (rr) return rr; }
+        rnp.counter = rs_counter_; rnp.dw = rs_dw_; rnp.c = rs_c_;
+    }
+    const bool lft_pp = stdp || rmod || net_rmod || (n_trains && electrical) || part_world > 1;
     const bool rmod_part = rmod && part_world > 1;
 
     StepParams sp;
@@ -2158,7 +2272,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
     static const bool win_reverse = !(getenv("SNN_B200_WIN_REVERSE") && atoi(getenv("SNN_B200_WIN_REVERSE")) == 0);
     // small lattices / networks (everything the staged kernels do not take): a whole chunk of timesteps per cooperative launch
     // (step_multi.cu).  SNN_OPT_STEPS_PER_GRAPH: 0 = as many as the history chunk holds, 1 = one launch per timestep, k = at most k.
-    bool multi = part_world == 1 && n_neurons > 0 && !win_ok && !tma_ok && !bcm_on && !reward_mode && steps_per_graph != 1 &&
+    bool multi = part_world == 1 && n_neurons > 0 && !win_ok && !tma_ok && !bcm_on && !reward_mode && !net_reward && steps_per_graph != 1 &&
                  !getenv("SNN_DEBUG_TIMING");
     if (wide && wide_split) multi = false;   // the two-pass wide kernels are one-launch-per-step kernels
     if (const char *e = getenv("SNN_B200_MULTI")) multi = multi && atoi(e) != 0;
@@ -2270,6 +2384,21 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             if (reward_mode && rewards) {
                 // RewardModulatedSTDP::update, plasticity/mod.rs:193-195 (run_lattice_with_reward, neuron/mod.rs:3160-3172)
                 rstdp.dopamine = rstdp.dopamine * expf(-rstdp.dt / rstdp.tau_d) + rstdp.tau_d * rewards[done + s];
+            }
+            if (net_reward) {
+                // RewardModulatedLatticeNetwork::run_lattices_with_reward (neuron/mod.rs:5280-5297): every reward-modulated lattice's
+                // modulator takes the reward before iterate; then post_neuron_update_step's pass over their rows
+                int kn = 0;
+                for (auto &L : lats_) {
+                    if (L.is_train) continue;
+                    if (L.is_reward && rewards) L.rstdp.dopamine = L.rstdp.dopamine * expf(-L.rstdp.dt / L.rstdp.tau_d) + L.rstdp.tau_d * rewards[done + s];
+                    rnp.lat[kn++].dopamine = L.rstdp.dopamine;
+                }
+                if (net_rmod) {
+                    cudaError_t e = launch_rstdp_net_edges(sp, rnp, stream_);
+                    if (e != cudaSuccess) { bail(e, SNN_GPU_QUEUE_FAILURE, "launch_rstdp_net_edges"); break; }
+                    n_launch++;
+                }
             }
             if (bcm_on) {
                 cudaError_t e = launch_bcm_edges(sp, BcmParams{bcm.decay, bcm.average_scalar, bcm.dt}, stream_);
@@ -2447,7 +2576,7 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             return fail(SNN_GPU_WAIT_ERROR, "timed out waiting for a neighbouring strip's halo (is every rank running the same number of steps?)");
         }
     }
-    if (stdp || rmod || bcm_on) dev_weights_newer_ = true;
+    if (stdp || rmod || net_rmod || bcm_on) dev_weights_newer_ = true;
     // derived fields (receptor currents, HH gate rates / channel currents) from the retained pre-update V
     if ((chemical && chem_alloc_) || model == SNN_MODEL_HODGKIN_HUXLEY) {
         StepParams fp = sp;

@@ -28,6 +28,10 @@ struct Lat {
     float eeg_ref = 0.007f, eeg_dist = 0.8f, eeg_cond = 251.f;   // EEGHistory::default, neuron/mod.rs:243-252
     std::vector<float> average_history, eeg_history;
     snn_stdp_t stdp{2.f, 2.f, 4.5f, 4.5f, 0.1f};  // STDP::default, plasticity/mod.rs:29-39
+    // a member of RewardModulatedLatticeNetwork::reward_modulated_lattices (neuron/mod.rs:3470-3471): TraceRSTDP weights in its own
+    // graph, a RewardModulatedSTDP modulator (RewardModulatedLattice::default, neuron/mod.rs:2760-2777)
+    bool is_reward = false, do_modulation = true;
+    snn_rstdp_t rstdp{0.f, 20.f, 0.0001f, 2.f, 2.f, 4.5f, 4.5f, 0.1f};
     uint64_t clock = 0;                           // SpikeTrainLattice::internal_clock
     std::vector<float> cold[2];                   // v_init, w_init
     std::vector<float> grid_history;
@@ -48,6 +52,8 @@ struct Block {  // connections pre lattice -> post lattice, CSR by post (pre asc
     // a materialised stencil (kind == CSR, adjacency still that of set_graph_grid(radius)): finalize_graph keeps the uniform-width
     // layout and with it the window / TMA step kernels; cleared when an edge is added or removed
     uint32_t from_grid_radius = 0;
+    // connecting block of a RewardModulatedLatticeNetwork whose values are RewardModulatedWeight(TraceRSTDP) rather than Weight(f32)
+    bool reward_conn = false;
 };
 
 struct IpcBlob {  // exchanged between neighbouring ranks by the caller (e.g. torch.distributed all_gather)
@@ -66,7 +72,7 @@ public:
     int init();  // device selection + stream; returns snn_status
 
     // topology
-    int add_lattice(uint64_t id, uint32_t rows, uint32_t cols, bool is_train);
+    int add_lattice(uint64_t id, uint32_t rows, uint32_t cols, bool is_train, bool is_reward = false);
     int set_partition(uint32_t rows_global, uint32_t cols, int rank, int world);  // before add_lattice
     Lat *find(uint64_t id);
     const Lat *find(uint64_t id) const;
@@ -111,6 +117,13 @@ public:
     int set_bcm_plasticity(bool enable, const snn_bcm_t *b);
     bool bcm_mode = false;
     snn_bcm_t bcm{0.1f, 0.1f, 0.1f};   // BCM::default, plasticity/mod.rs:91-97
+    int set_lattice_reward_modulator(uint64_t id, bool modulate, const snn_rstdp_t *m);
+    int get_lattice_reward_modulator(uint64_t id, int32_t *modulate, snn_rstdp_t *m);
+    int set_connection_reward(uint64_t pre_id, uint64_t post_id, bool reward_modulated);
+    bool has_reward_lattices() const;
+    int block_elements(uint64_t pre_id, uint64_t post_id, std::vector<size_t> *elems, Block **blk);
+    int get_block_traces(uint64_t pre_id, uint64_t post_id, uint32_t *counter, float *dw, float *c, uint64_t nnz);
+    int set_block_traces(uint64_t pre_id, uint64_t post_id, const float *weight, const uint32_t *counter, const float *dw, const float *c, uint64_t nnz);
     int get_connection_traces(uint32_t *counter, float *dw, float *c, uint64_t nnz);
     int set_connection_traces(const float *weight, const uint32_t *counter, const float *dw, const float *c, uint64_t nnz);
     bool reward_mode = false, do_modulation = true;

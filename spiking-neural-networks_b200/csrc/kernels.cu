@@ -657,6 +657,73 @@ cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaSt
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// RewardModulatedLatticeNetwork::post_neuron_update_step (neuron/mod.rs:5030-5062), the reward-modulated half
+// ------------------------------------------------------------------------------------------------
+// Runs after the step kernel and before the spike trains step: every neuron of a reward-modulated lattice with do_modulation
+// visits its in-edges (update_weights_from_neurons_across_reward_lattices :4855-4929, _within_reward_lattices :4979-5003) and
+// the out-edges of its own graph (:5005-5025), with both ends already carrying this step's last_firing_time.  Per edge that is
+//  - own graph: two RewardModulatedSTDP::update_weight calls with identical arguments (as in-edge of the post end and as
+//    out-edge of the pre end);
+//  - connecting edge, RewardModulatedWeight: one call with the post lattice's modulator, whatever the input is;
+//  - connecting edge, Weight: STDP::update_weight with the INPUT lattice's plasticity, only when the input is a plain Lattice.
+// Connecting edges OUT of such a lattice are refused by Engine::run (the reference looks them up with swapped end points and
+// panics).  One CTA per 32-row slice, one thread per edge, no ordering between edges.
+__global__ void __launch_bounds__(256) rstdp_net_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RnetParams r) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t slice = blockIdx.x;
+    const uint32_t ln = slice * 32u + lane;
+    if (ln >= p.n_neurons) return;
+    const int lp = lat_index(p, ln);
+    const RnetLat &P = r.lat[lp];
+    if ((P.flags & 3u) != 3u) return;
+    const uint32_t k0 = p.uniform_width ? slice * p.uniform_width : __ldg(p.slice_off + slice);
+    const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + slice + 1);
+    const int t_post = p.lft_out[p.own0 + ln];
+    const float decay_c = expf(-P.dt / P.tau_c);
+    RstdpParams m;
+    m.dopamine = P.dopamine; m.tau_c = P.tau_c; m.a_plus = P.a_plus; m.a_minus = P.a_minus;
+    m.tau_plus = P.tau_plus; m.tau_minus = P.tau_minus; m.dt = P.dt;
+    for (uint32_t k = k0 + warp; k < k1; k += 8u) {
+        const size_t e = (size_t)k * 32u + lane;
+        const uint32_t cw = __ldg(p.col + e);
+        if (cw == kColPad) continue;
+        const uint32_t j = cw & kColIdxMask;
+        const bool train = (cw & kColTrainBit) != 0u;
+        int t_pre, cls;
+        if (train) {
+            t_pre = p.lft_in[j];   // the trains step after this pass: their current value is still in the input buffer
+            const uint32_t tj = j - r.train0;
+            cls = 0;
+#pragma unroll 1
+            for (uint32_t t = 1; t < r.n_tl; ++t) if (tj >= r.tl_base[t]) cls = (int)t;
+            cls += kMaxLattices;
+        } else {
+            t_pre = p.lft_out[j];
+            cls = lat_index(p, j - p.own0);
+        }
+        const bool internal = !train && cls == lp;
+        if (internal || ((r.conn_reward[lp] >> cls) & 1u)) {
+            float delta_w = 0.f;
+            if (t_pre >= 0 && t_post >= 0 && t_pre != t_post) delta_w = rstdp_delta(m, t_pre, t_post);
+            uint32_t cnt = r.counter[e];
+            float dw = r.dw[e], c = r.c[e], w = p.wgt[e];
+            rstdp_call(m, delta_w, decay_c, cnt, dw, c, w);
+            if (internal) rstdp_call(m, delta_w, decay_c, cnt, dw, c, w);
+            r.counter[e] = (uint8_t)cnt; r.dw[e] = dw; r.c[e] = c; p.wgt[e] = w;
+        } else if (!train && !(r.lat[cls].flags & 1u)) {
+            const float d = stdp_delta(p.lat[cls], t_pre, t_post);
+            if (d != 0.f) p.wgt[e] = p.wgt[e] + d;
+        }
+    }
+}
+
+cudaError_t launch_rstdp_net_edges(const StepParams &p, const RnetParams &r, cudaStream_t s) {
+    if (p.n_neurons == 0) return cudaSuccess;
+    rstdp_net_edge_kernel<<<(p.n_neurons + 31u) / 32u, 256, 0, s>>>(p, r);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
     flush_stdp_kernel<<<blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256), 256, 0, s>>>(p);

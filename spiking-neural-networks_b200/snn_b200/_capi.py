@@ -25,6 +25,9 @@ SNN_NET_POSTSYNAPTIC_ID_NOT_FOUND = 33
 SNN_NET_PRESYNAPTIC_ID_NOT_FOUND = 34
 SNN_NET_ID_NOT_FOUND_IN_LATTICES = 35
 SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN = 36
+SNN_NET_CANNOT_CONNECT_WITH_REWARD_MODULATED_CONNECTION = 37
+SNN_NET_REWARD_MODULATED_CONNECTION_NOT_COMPATIBLE_INTERNALLY = 38
+SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE = 39
 SNN_INVALID_ARGUMENT = 64
 SNN_UNKNOWN_FIELD = 65
 SNN_DTYPE_MISMATCH = 66
@@ -154,6 +157,7 @@ SIGNATURES = {
     "snn_network_connect_csr": ([_P, _u64, _u64, _P, _P, _P, _u64, _u64], _i32),
     "snn_network_connection_nnz": ([_P, _u64, _u64, C.POINTER(_u64)], _i32),
     "snn_network_get_connection_dense": ([_P, _u64, _u64, _P, _P, _u64, _u64], _i32),
+    "snn_network_get_connection_csr": ([_P, _u64, _u64, _P, _P, _P, _u64, _u64], _i32),
     "snn_network_lookup_weight": ([_P, _u64, _u64, _u64, _u64, C.POINTER(_f), C.POINTER(_i32)], _i32),
     "snn_network_edit_weight": ([_P, _u64, _u64, _u64, _u64, _i32, _f], _i32),
     "snn_network_get_spike_aggregate": ([_P, _u64, _P, _u64], _i32),
@@ -165,6 +169,13 @@ SIGNATURES = {
     "snn_network_set_dt": ([_P, _f], _i32),
     "snn_network_reset_timing": ([_P], _i32),
     "snn_network_run": ([_P, _u64], _i32),
+    "snn_network_add_reward_modulated_lattice": ([_P, _u64, _u32, _u32], _i32),
+    "snn_network_set_reward_modulator": ([_P, _u64, _i32, C.POINTER(RstdpStruct)], _i32),
+    "snn_network_get_reward_modulator": ([_P, _u64, C.POINTER(_i32), C.POINTER(RstdpStruct)], _i32),
+    "snn_network_set_connection_reward_modulated": ([_P, _u64, _u64, _i32], _i32),
+    "snn_network_run_with_rewards": ([_P, _P, _u64], _i32),
+    "snn_network_get_connection_traces": ([_P, _u64, _u64, _P, _P, _P, _u64], _i32),
+    "snn_network_set_connection_traces": ([_P, _u64, _u64, _P, _P, _P, _P, _u64], _i32),
     "snn_network_run_timed": ([_P, _u64, C.POINTER(_f), C.POINTER(_u64)], _i32),
     "snn_network_history_len": ([_P, _u64, C.POINTER(_u64)], _i32),
     "snn_network_get_grid_history": ([_P, _u64, _P, _u64], _i32),

@@ -335,6 +335,40 @@ class CudaNetworkBackend(_CudaBase):
     def add_train_lattice(self, id, rows, cols):
         self._ck(self.lib.snn_network_add_spike_train_lattice(self.h, id, rows, cols))
 
+    # ---- RewardModulatedLatticeNetwork (neuron/mod.rs:3455-5455) ----
+    _RSTDP = ("dopamine", "tau_d", "tau_c", "a_plus", "a_minus", "tau_plus", "tau_minus", "dt")
+
+    def add_reward_lattice(self, id, rows, cols):
+        self._ck(self.lib.snn_network_add_reward_modulated_lattice(self.h, id, rows, cols))
+
+    def set_lattice_reward_modulator(self, id, do_modulation, **m):
+        s = K.RstdpStruct(*[float(m[k]) for k in self._RSTDP])
+        self._ck(self.lib.snn_network_set_reward_modulator(self.h, id, int(do_modulation), C.byref(s)))
+
+    def get_lattice_reward_modulator(self, id):
+        s, dm = K.RstdpStruct(), C.c_int32(0)
+        self._ck(self.lib.snn_network_get_reward_modulator(self.h, id, C.byref(dm), C.byref(s)))
+        return bool(dm.value), {k: getattr(s, k) for k in self._RSTDP}
+
+    def mark_connection_reward(self, pre_id, post_id, reward_modulated):
+        self._ck(self.lib.snn_network_set_connection_reward_modulated(self.h, pre_id, post_id, int(reward_modulated)))
+
+    def run_network_with_rewards(self, rewards):
+        r = np.ascontiguousarray(np.asarray(rewards, np.float32).reshape(-1))
+        self._ck(self.lib.snn_network_run_with_rewards(self.h, _ptr(r), r.size))
+
+    def connection_traces(self, pre_id, post_id):
+        nnz = self.connection_nnz(pre_id, post_id)
+        cnt, dw, c = np.zeros(max(nnz, 1), np.uint32), np.zeros(max(nnz, 1), np.float32), np.zeros(max(nnz, 1), np.float32)
+        self._ck(self.lib.snn_network_get_connection_traces(self.h, pre_id, post_id, _ptr(cnt), _ptr(dw), _ptr(c), nnz))
+        return cnt[:nnz], dw[:nnz], c[:nnz]
+
+    def set_connection_traces(self, weight=None, counter=None, dw=None, c=None, pre_id=0, post_id=0):
+        nnz = self.connection_nnz(pre_id, post_id)
+        arrs = [None if x is None else _as(np.asarray(x).reshape(-1), t)
+                for x, t in ((weight, np.float32), (counter, np.uint32), (dw, np.float32), (c, np.float32))]
+        self._ck(self.lib.snn_network_set_connection_traces(self.h, pre_id, post_id, *[None if a is None else _ptr(a) for a in arrs], nnz))
+
     def size(self, id):
         n = C.c_uint64()
         self._ck(self.lib.snn_network_lattice_size(self.h, id, C.byref(n)))
@@ -358,6 +392,14 @@ class CudaNetworkBackend(_CudaBase):
         n = C.c_uint64()
         self._ck(self.lib.snn_network_connection_nnz(self.h, pre_id, post_id, C.byref(n)))
         return n.value
+
+    def get_connection_csr(self, pre_id, post_id):
+        n, nnz = self.size(post_id), self.connection_nnz(pre_id, post_id)
+        rp = np.zeros(n + 1, np.uint64)
+        pr = np.zeros(max(nnz, 1), np.uint32)
+        w = np.zeros(max(nnz, 1), np.float32)
+        self._ck(self.lib.snn_network_get_connection_csr(self.h, pre_id, post_id, _ptr(rp), _ptr(pr), _ptr(w), n, nnz))
+        return rp, pr[:nnz], w[:nnz]
 
     def get_connection_dense(self, pre_id, post_id):
         n_pre, n_post = self.size(pre_id), self.size(post_id)

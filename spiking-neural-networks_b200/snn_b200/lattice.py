@@ -467,10 +467,16 @@ class RewardModulatedLattice(Lattice):
         self.do_plasticity = False
         super()._push_options()
         m = self.reward_modulator
-        self._be.set_reward_modulator(True, self.do_modulation, **{k: getattr(m, k) for k in m._defaults})
+        if self._in_network is not None:   # a member of RewardModulatedLatticeNetwork::reward_modulated_lattices
+            self._be.set_lattice_reward_modulator(self._bid, self.do_modulation, **{k: getattr(m, k) for k in m._defaults})
+        else:
+            self._be.set_reward_modulator(True, self.do_modulation, **{k: getattr(m, k) for k in m._defaults})
 
     def _pull_modulator(self):
-        self.reward_modulator.dopamine = self._be.get_reward_modulator()["dopamine"]
+        if self._in_network is not None:
+            self.reward_modulator.dopamine = self._be.get_lattice_reward_modulator(self._bid)[1]["dopamine"]
+        else:
+            self.reward_modulator.dopamine = self._be.get_reward_modulator()["dopamine"]
 
     def set_dt(self, dt):
         super().set_dt(dt)
@@ -480,6 +486,8 @@ class RewardModulatedLattice(Lattice):
         self.run_lattice_with_rewards([reward])
 
     def run_lattice_with_rewards(self, rewards):
+        if self._in_network is not None:
+            raise RuntimeError("lattice is owned by a network; use run_lattices_with_reward")
         if self._be is None:
             return
         self._push_options()
@@ -489,12 +497,17 @@ class RewardModulatedLattice(Lattice):
     def graph_traces(self):
         """(counter, dw, c) of every edge, in the order of graph_csr()."""
         self._push_options()
+        if self._in_network is not None:
+            return self._be.connection_traces(self._bid, self._bid)
         return self._be.connection_traces()
 
     def set_graph_traces(self, weight=None, counter=None, dw=None, c=None):
         """Graph::edit_weight with whole TraceRSTDP values on every existing edge (order of graph_csr(); None = keep)."""
         self._push_options()
-        self._be.set_connection_traces(weight, counter, dw, c)
+        if self._in_network is not None:
+            self._be.set_connection_traces(weight, counter, dw, c, pre_id=self._bid, post_id=self._bid)
+        else:
+            self._be.set_connection_traces(weight, counter, dw, c)
 
 
 class SpikeTrainLattice(_CellLattice):
@@ -804,3 +817,202 @@ class LatticeNetwork:
             self._be.set_option(K.OPT_UPDATE_GRID_HISTORY, st.update_grid_history, st.get_id())
             self._be.set_option(K.OPT_UPDATE_SPIKE_HISTORY, st.update_spike_history, st.get_id())
         self._be.run(iterations)
+
+
+class TraceRSTDP:
+    """TraceRSTDP (plasticity/mod.rs:121-136): the weight type of reward-modulated graphs."""
+
+    def __init__(self, counter=0, dw=0.0, weight=1.0, c=0.0):
+        self.counter, self.dw, self.weight, self.c = counter, dw, weight, c
+
+    def get_weight(self):
+        return self.weight
+
+
+class RewardModulatedConnection:
+    """RewardModulatedConnection<S> (neuron/mod.rs:3418-3443): `Weight(f32)` or `RewardModulatedWeight(TraceRSTDP)`."""
+
+    def __init__(self, value, reward_modulated):
+        self.value, self.reward_modulated = value, reward_modulated
+
+    @classmethod
+    def Weight(cls, w):
+        return cls(float(w), False)
+
+    @classmethod
+    def RewardModulatedWeight(cls, trace=None):
+        return cls(trace if trace is not None else TraceRSTDP(), True)
+
+    def get_weight(self):
+        return self.value.weight if self.reward_modulated else self.value
+
+
+class RewardModulatedLatticeNetwork(LatticeNetwork):
+    """RewardModulatedLatticeNetwork<...> (neuron/mod.rs:3455-5455): plain lattices, reward-modulated lattices and spike-train
+    lattices over one connecting graph of RewardModulatedConnection values.
+
+    Differences from the reference, each refused with an error instead of silently diverging:
+     * all edges of one connecting block (one presynaptic id -> postsynaptic id pair) hold the same connection kind;
+     * the configurations on which the reference itself panics (connecting edges OUT of a reward-modulated lattice with
+       do_modulation, or out of a plain lattice with do_plasticity: update_weights_from_neurons_across_*lattices looks them up
+       with swapped end points, neuron/mod.rs:4760-4763, 4931-4934) make run_lattices raise SNN_UNSUPPORTED."""
+
+    def __init__(self, backend_factory=None):
+        super().__init__(backend_factory)
+        self._reward_modulated_lattices = {}
+
+    @classmethod
+    def generate_network(cls, lattices, reward_modulated_lattices=(), spike_train_lattices=(), backend_factory=None):
+        """neuron/mod.rs:3558-3594."""
+        net = cls(backend_factory)
+        neuron_lats = list(lattices) + list(reward_modulated_lattices)
+        spike_train_lattices = list(spike_train_lattices)
+        model = neuron_lats[0].neuron_type.model if neuron_lats else K.MODEL_IZH
+        ntk = neuron_lats[0]._ntk if neuron_lats else (spike_train_lattices[0]._ntk if spike_train_lattices else K.NT_APPROXIMATE)
+        rck = neuron_lats[0]._rck if neuron_lats else K.RC_APPROXIMATE
+        tk = spike_train_lattices[0].spike_train_type.kind if spike_train_lattices else K.TRAIN_POISSON
+        rf = spike_train_lattices[0]._refract if spike_train_lattices else K.REFRACT_DELTA_DIRAC
+        net._sig = (model, ntk, rck, tk, rf)
+        net._be = net._factory(model, ntk, rck, tk, rf)
+        for lat in lattices:
+            net.add_lattice(lat)
+        for lat in reward_modulated_lattices:
+            net.add_reward_modulated_lattice(lat)
+        for st in spike_train_lattices:
+            net.add_spike_train_lattice(st)
+        return net
+
+    def get_all_ids(self):
+        return super().get_all_ids() | set(self._reward_modulated_lattices)
+
+    def add_reward_modulated_lattice(self, lattice: RewardModulatedLattice):
+        """neuron/mod.rs:3615-3634."""
+        if lattice.get_id() in self.get_all_ids():
+            raise K.SnnError(K.SNN_NET_GRAPH_ID_ALREADY_PRESENT, f"Graph id already present in network, id: {lattice.get_id()}")
+        self._ensure_backend(lattice, False)
+        if (lattice.neuron_type.model, lattice._rck) != (self._sig[0], self._sig[2]) and (self._lattices or self._reward_modulated_lattices):
+            raise TypeError("all lattices of a network share one neuron / kinetics type")
+        self._be.add_reward_lattice(lattice.get_id(), lattice.rows, lattice.cols)
+        self._adopt(lattice, False)
+        self._reward_modulated_lattices[lattice.get_id()] = lattice
+
+    def get_reward_modulated_lattice(self, id):
+        return self._reward_modulated_lattices.get(id)
+
+    def get_reward_modulated_lattices(self):
+        return self._reward_modulated_lattices
+
+    def connect(self, presynaptic_id, postsynaptic_id, connecting_conditional, weight_logic=None):
+        """neuron/mod.rs:3836-3947: plain / spike-train lattices only (error order included)."""
+        if postsynaptic_id in self._spike_train_lattices:
+            raise K.SnnError(K.SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN,
+                             "Postsynaptic lattice cannot be a spike train lattice because spike trains cannot take inputs")
+        if presynaptic_id not in self.get_all_ids():
+            raise K.SnnError(K.SNN_NET_PRESYNAPTIC_ID_NOT_FOUND, f"Presynaptic id not present in network, id: {presynaptic_id}")
+        msg = "Connect function must have non reward modulated lattices, connect with reward modulation instead"
+        if postsynaptic_id not in self._lattices and postsynaptic_id in self._reward_modulated_lattices:
+            raise K.SnnError(K.SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE, msg)
+        if postsynaptic_id in self._lattices and presynaptic_id in self._reward_modulated_lattices:
+            raise K.SnnError(K.SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE, msg)
+        return super().connect(presynaptic_id, postsynaptic_id, connecting_conditional, weight_logic)
+
+    falliable_connect = connect
+
+    def connect_with_reward_modulation(self, presynaptic_id, postsynaptic_id, connecting_conditional, weight_logic):
+        """neuron/mod.rs:4076-4209 (error order included).  `weight_logic(pre, post)` returns a RewardModulatedConnection."""
+        if postsynaptic_id in self._spike_train_lattices:
+            raise K.SnnError(K.SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN,
+                             "Postsynaptic lattice cannot be a spike train lattice because spike trains cannot take inputs")
+        if presynaptic_id not in self.get_all_ids():
+            raise K.SnnError(K.SNN_NET_PRESYNAPTIC_ID_NOT_FOUND, f"Presynaptic id not present in network, id: {presynaptic_id}")
+        rm = self._reward_modulated_lattices
+        if postsynaptic_id not in rm and presynaptic_id not in rm:
+            raise K.SnnError(K.SNN_NET_CANNOT_CONNECT_WITH_REWARD_MODULATED_CONNECTION,
+                             "When connecting reward modulated network, at least one lattice has to be reward modulated")
+        if postsynaptic_id not in self._lattices and postsynaptic_id not in rm:
+            raise K.SnnError(K.SNN_NET_POSTSYNAPTIC_ID_NOT_FOUND, f"Postsynaptic id not present in network, id: {postsynaptic_id}")
+        if presynaptic_id == postsynaptic_id:
+            raise K.SnnError(K.SNN_NET_REWARD_MODULATED_CONNECTION_NOT_COMPATIBLE_INTERNALLY,
+                             "When connecting reward modulated lattice, RewardModulatedConnection cannot be used to connect a "
+                             "reward modulated lattice internally")
+        pre = self._lattices.get(presynaptic_id) or rm.get(presynaptic_id) or self._spike_train_lattices[presynaptic_id]
+        post = self._lattices.get(postsynaptic_id) or rm[postsynaptic_id]
+        ppos = [(i, j) for i in range(pre.rows) for j in range(pre.cols)]
+        qpos = post._positions()
+        conn = np.zeros((len(ppos), len(qpos)), np.uint32)
+        w = np.zeros((len(ppos), len(qpos)), np.float32)
+        kinds, traces = set(), {}
+        for a, x in enumerate(ppos):
+            for b, y in enumerate(qpos):
+                if connecting_conditional(x, y):
+                    v = weight_logic(x, y)
+                    conn[a, b] = 1
+                    w[a, b] = v.get_weight()
+                    kinds.add(v.reward_modulated)
+                    if v.reward_modulated and (v.value.counter or v.value.dw or v.value.c):
+                        traces[(a, b)] = v.value
+        if len(kinds) > 1:
+            raise K.SnnError(K.SNN_UNSUPPORTED, "one connecting block holds one kind of RewardModulatedConnection")
+        self._be.connect_dense(presynaptic_id, postsynaptic_id, conn, w)
+        if True in kinds:
+            self._be.mark_connection_reward(presynaptic_id, postsynaptic_id, True)
+            if traces:   # non-default TraceRSTDP members: written in the order of the block's CSR (post-major, pre ascending)
+                order = [(a, b) for b in range(len(qpos)) for a in range(len(ppos)) if conn[a, b]]
+                get = lambda k, f, d: getattr(traces[k], f) if k in traces else d
+                self._be.set_connection_traces(None, [get(k, "counter", 0) for k in order], [get(k, "dw", 0.0) for k in order],
+                                               [get(k, "c", 0.0) for k in order], pre_id=presynaptic_id, post_id=postsynaptic_id)
+
+    falliable_connect_with_reward_modulation = connect_with_reward_modulation
+
+    def connect_reward_modulated_lattice_interally(self, id, connecting_conditional, weight_logic=None):
+        """neuron/mod.rs:4393-4413."""
+        if id not in self._reward_modulated_lattices:
+            raise K.SnnError(K.SNN_NET_ID_NOT_FOUND_IN_LATTICES, f"Id not present in lattices, id: {id}")
+        self._reward_modulated_lattices[id].connect(connecting_conditional, weight_logic)
+
+    def connection_traces(self, presynaptic_id, postsynaptic_id):
+        """(counter, dw, c) of the block's edges in the order of its CSR (post-major, pre ascending)."""
+        self._push_all()
+        return self._be.connection_traces(presynaptic_id, postsynaptic_id)
+
+    def set_dt(self, dt):
+        """neuron/mod.rs:3666-3673."""
+        super().set_dt(dt)
+        for lat in self._reward_modulated_lattices.values():
+            lat.plasticity.dt = dt
+            lat.reward_modulator.dt = dt
+
+    def _push_all(self):
+        self._be.set_option(K.OPT_ELECTRICAL_SYNAPSE, self.electrical_synapse)
+        self._be.set_option(K.OPT_CHEMICAL_SYNAPSE, self.chemical_synapse)
+        for lat in list(self._lattices.values()) + list(self._reward_modulated_lattices.values()):
+            lat._push_options()
+        for st in self._spike_train_lattices.values():
+            self._be.set_option(K.OPT_UPDATE_GRID_HISTORY, st.update_grid_history, st.get_id())
+            self._be.set_option(K.OPT_UPDATE_SPIKE_HISTORY, st.update_spike_history, st.get_id())
+
+    def run_lattices(self, iterations: int):
+        """RunNetwork::run_lattices (neuron/mod.rs:5411-5426): no reward signal."""
+        if self._be is None:
+            return
+        self._push_all()
+        self._be.run(iterations)
+
+    def run_lattices_with_reward(self, reward: float):
+        """neuron/mod.rs:5385-5392: one timestep, every modulator taking `reward` first."""
+        self.run_lattices_with_rewards([reward])
+
+    def run_lattices_with_rewards(self, rewards):
+        if self._be is None:
+            return
+        self._push_all()
+        self._be.run_network_with_rewards(rewards)
+        for lat in self._reward_modulated_lattices.values():
+            lat._pull_modulator()
+
+    # Agent (neuron/mod.rs:5428-5455)
+    def update_and_apply_reward(self, reward: float):
+        self.run_lattices_with_reward(reward)
+
+    def update(self):
+        self.run_lattices(1)

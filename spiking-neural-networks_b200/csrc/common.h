@@ -6,7 +6,39 @@
 
 #include "../../include/snn_b200.h"
 
+#include <cstdlib>
+#include <utility>
+
 namespace snn {
+
+// Programmatic dependent launch: a kernel launched through launch_pdl may be scheduled while its predecessor in the stream is
+// still draining (its CTAs take the SMs the predecessor's CTAs leave); it must execute pdl_wait() before it touches anything the
+// predecessor wrote — that returns once the predecessor grid has completed and its writes are visible.  Hides the launch latency
+// and the prologue (barrier initialisation, parameter loads) behind the predecessor's tail.  SNN_B200_PDL=0 switches it off.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+// SNN_B200_PDL is a mask of these.  Measured (profiles/README.md, round 2): step kernels gain 2.5-3 us per launch (1000 x 1000
+// lattice 26.5 -> 23.4 us per step, wide-row network 30.6 -> 28.0 us); the persistent per-edge reward kernel LOSES 90 us per
+// step as a dependent launch (its three CTAs per SM arrive one by one as the step kernel's CTAs drain) and stays a plain launch.
+enum PdlKind : unsigned { PDL_STEP = 1u, PDL_TRAINS = 2u, PDL_EDGES = 4u };
+inline unsigned pdl_mask() {
+    static const unsigned m = getenv("SNN_B200_PDL") ? (unsigned)atoi(getenv("SNN_B200_PDL")) : (PDL_STEP | PDL_TRAINS);
+    return m;
+}
+template <unsigned KIND, typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = (pdl_mask() & KIND) ? 1u : 0u;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr int kNT = SNN_NUM_NT_TYPES;
 

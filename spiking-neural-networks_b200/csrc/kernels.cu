@@ -28,6 +28,7 @@ namespace snn {
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p) {
+    pdl_wait();   // launch_pdl
     if (!NET && halo_failed(p)) return;
     uint32_t block = blockIdx.x;
     if (!NET && (p.halo[0].active | p.halo[1].active)) {
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(256) flush_stdp_kernel(const __grid_constant__
 // whose two ends both spiked is simply updated twice.  Runs after the step kernel (deferred, canonicalisation (3)): the raster
 // word of the step tells who spiked, the activities are the ones the step just wrote.
 __global__ void __launch_bounds__(256) bcm_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ BcmParams b) {
+    pdl_wait();   // launch_pdl
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ln = warp_global * 32u + lane;
@@ -273,6 +275,7 @@ constexpr int kRsSlices = SNN_RS_SLICES;
 // dw = 0 + d1, then (0 + d1) + d2 — the same additions in the same order.
 template <bool CANON, bool TAB>
 __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
+    pdl_wait();   // launch_pdl
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
     const bool part = (p.halo[0].active | p.halo[1].active) != 0;
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__(256, 4) rstdp_edge_kernel(const __grid_constan
 // trips is hidden, and the set-up is paid once.  Warp w of the CTA owns k-row w of every slice (8 warps = 8 k-rows).
 template <bool CANON, bool TAB>
 __global__ void __launch_bounds__(256, SNN_RS_CTAS) rstdp_edge8_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RstdpParams r) {
+    pdl_wait();   // launch_pdl
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t n_slices = (p.n_neurons + 31u) >> 5;
     const uint32_t n_groups = (n_slices + kRsSlices - 1u) / kRsSlices;
@@ -465,6 +469,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(const __grid_constant__ S
 // spike trains (SpikeTrainLattice::iterate, neuron/mod.rs:1377-1393): train_body.cuh
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) train_kernel(const __grid_constant__ TrainParams p) {
+    pdl_wait();   // launch_pdl
     const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     if (warp_global * 32u >= p.n_trains) return;
@@ -575,8 +580,8 @@ static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((
 template <int MODEL, int CHEMG, bool NTREL, bool NET>
 static cudaError_t launch_step_3(const StepParams &p, bool stdp, cudaStream_t s) {
     const unsigned grid = blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256);
-    if (stdp) step_kernel<MODEL, CHEMG, NTREL, true, NET><<<grid, 256, 0, s>>>(p);
-    else step_kernel<MODEL, CHEMG, NTREL, false, NET><<<grid, 256, 0, s>>>(p);
+    if (stdp) return launch_pdl<PDL_STEP>(step_kernel<MODEL, CHEMG, NTREL, true, NET>, dim3(grid), dim3(256), 0, s, p);
+    return launch_pdl<PDL_STEP>(step_kernel<MODEL, CHEMG, NTREL, false, NET>, dim3(grid), dim3(256), 0, s, p);
     return cudaGetLastError();
 }
 
@@ -612,7 +617,7 @@ cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, b
 
 cudaError_t launch_trains(const TrainParams &p, cudaStream_t s) {
     if (p.n_trains == 0) return cudaSuccess;
-    train_kernel<<<blocks_for((uint64_t)((p.n_trains + 31u) / 32u) * 32u, 256), 256, 0, s>>>(p);
+    return launch_pdl<PDL_TRAINS>(train_kernel, dim3(blocks_for((uint64_t)((p.n_trains + 31u) / 32u) * 32u, 256)), dim3(256), 0, s, p);
     return cudaGetLastError();
 }
 
@@ -631,7 +636,7 @@ cudaError_t launch_gpart_push(const StepParams &p, cudaStream_t s) {
 
 cudaError_t launch_bcm_edges(const StepParams &p, const BcmParams &b, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
-    bcm_edge_kernel<<<blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256), 256, 0, s>>>(p, b);
+    return launch_pdl<PDL_EDGES>(bcm_edge_kernel, dim3(blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256)), dim3(256), 0, s, p, b);
     return cudaGetLastError();
 }
 
@@ -648,13 +653,11 @@ cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaSt
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const unsigned pg = (unsigned)sms * (unsigned)SNN_RS_CTAS;
-        if (r.canonical) { if (tab) rstdp_edge8_kernel<true, true><<<pg, 256, 0, s>>>(p, r); else rstdp_edge8_kernel<true, false><<<pg, 256, 0, s>>>(p, r); }
-        else { if (tab) rstdp_edge8_kernel<false, true><<<pg, 256, 0, s>>>(p, r); else rstdp_edge8_kernel<false, false><<<pg, 256, 0, s>>>(p, r); }
-        return cudaGetLastError();
+        if (r.canonical) return tab ? launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<true, true>, dim3(pg), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<true, false>, dim3(pg), dim3(256), 0, s, p, r);
+        return tab ? launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<false, true>, dim3(pg), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<false, false>, dim3(pg), dim3(256), 0, s, p, r);
     }
-    if (r.canonical) { if (tab) rstdp_edge_kernel<true, true><<<grid, 256, 0, s>>>(p, r); else rstdp_edge_kernel<true, false><<<grid, 256, 0, s>>>(p, r); }
-    else { if (tab) rstdp_edge_kernel<false, true><<<grid, 256, 0, s>>>(p, r); else rstdp_edge_kernel<false, false><<<grid, 256, 0, s>>>(p, r); }
-    return cudaGetLastError();
+    if (r.canonical) return tab ? launch_pdl<PDL_EDGES>(rstdp_edge_kernel<true, true>, dim3(grid), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge_kernel<true, false>, dim3(grid), dim3(256), 0, s, p, r);
+    return tab ? launch_pdl<PDL_EDGES>(rstdp_edge_kernel<false, true>, dim3(grid), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge_kernel<false, false>, dim3(grid), dim3(256), 0, s, p, r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -670,6 +673,7 @@ cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaSt
 // Connecting edges OUT of such a lattice are refused by Engine::run (the reference looks them up with swapped end points and
 // panics).  One CTA per 32-row slice, one thread per edge, no ordering between edges.
 __global__ void __launch_bounds__(256) rstdp_net_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RnetParams r) {
+    pdl_wait();   // launch_pdl
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t slice = blockIdx.x;
     const uint32_t ln = slice * 32u + lane;
@@ -720,8 +724,7 @@ __global__ void __launch_bounds__(256) rstdp_net_edge_kernel(const __grid_consta
 
 cudaError_t launch_rstdp_net_edges(const StepParams &p, const RnetParams &r, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
-    rstdp_net_edge_kernel<<<(p.n_neurons + 31u) / 32u, 256, 0, s>>>(p, r);
-    return cudaGetLastError();
+    return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel, dim3((p.n_neurons + 31u) / 32u), dim3(256), 0, s, p, r);
 }
 
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s) {

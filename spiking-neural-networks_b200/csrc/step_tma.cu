@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kTmaThreads, tma_min_ctas<MODEL, CHEMG>()) ste
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)tp.stages * tp.stage_bytes);
     uint64_t *empty = full + tp.stages;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    pdl_wait();   // launch_pdl
     if (halo_failed(p)) return;
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < tp.stages; ++s) {
@@ -140,12 +141,12 @@ static cudaError_t launch_tma_3(const StepParams &p, const TmaParams &tp, bool s
         auto k = step_tma_kernel<MODEL, CHEMG, NTREL, true>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, kTmaThreads, smem, s>>>(p, tp);
+        return launch_pdl<PDL_STEP>(k, dim3(grid), dim3(kTmaThreads), smem, s, p, tp);
     } else {
         auto k = step_tma_kernel<MODEL, CHEMG, NTREL, false>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, kTmaThreads, smem, s>>>(p, tp);
+        return launch_pdl<PDL_STEP>(k, dim3(grid), dim3(kTmaThreads), smem, s, p, tp);
     }
     return cudaGetLastError();
 }

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(kWideWarps * 32) step_wide_kernel(const __grid
     extern __shared__ __align__(16) unsigned char wide_sm[];   // 2 x wide_buf_bytes(CHEMG): double-buffered chunk terms, then the node stage
     const uint32_t warp_global = blockIdx.x;   // one CTA per slice (terms pass: per slice and chunk)
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    pdl_wait();   // launch_pdl: the CTAs were scheduled while the previous pass / timestep was still draining
     if (blockIdx.x >= sp.n_slices) {
         // sum pass with fused spike trains: the CTAs past the last slice step 16 warps of trains each (accumulator row 0 only)
         if (NET && blockIdx.y == 0u) {
@@ -48,8 +49,7 @@ static cudaError_t launch_wide_3(const StepParams &p, bool stdp, unsigned char *
     static const TrainParams no_trains{};
     auto launch = [&](auto k, dim3 g, size_t smem, uint32_t stage, WideSplit sp) -> cudaError_t {
         if (smem > 48u * 1024u) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; }
-        k<<<g, kWideWarps * 32, smem, s>>>(p, stage, sp, (sp.mode == 2u && trains) ? *trains : no_trains);
-        return cudaGetLastError();
+        return launch_pdl<PDL_STEP>(k, g, dim3(kWideWarps * 32), smem, s, p, stage, sp, (sp.mode == 2u && trains) ? *trains : no_trains);
     };
     auto both = [&](dim3 g, size_t smem, uint32_t stage, WideSplit sp) -> cudaError_t {
         if (stdp) return launch(step_wide_kernel<MODEL, CHEMG, NTREL, true, NET>, g, smem, stage, sp);

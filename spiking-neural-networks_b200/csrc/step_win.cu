@@ -140,12 +140,6 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t)S * wp.stage_bytes);
     uint64_t *empty = full + S;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    if (halo_failed(p)) return;
-    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-        p.dbg[0] = (unsigned long long)clock64(); p.dbg[1] = gt;
-    }
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&full[s], kWinProducers);   // every producer warp announces its share of the bytes
@@ -154,6 +148,13 @@ step_win_kernel(const __grid_constant__ StepParams p, const __grid_constant__ Wi
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();   // everything above ran while the previous timestep's kernel was still draining (launch_pdl)
+    if (halo_failed(p)) return;
+    if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+        p.dbg[0] = (unsigned long long)clock64(); p.dbg[1] = gt;
+    }
 
     if (warp >= G * 8) {
         // ---- producers: kWinProducers warps fill every stage TOGETHER.  A cp.async.bulk costs its warp ~32 ns of issue
@@ -299,12 +300,12 @@ static cudaError_t launch_win_3(const StepParams &p, const WinParams &wp, bool s
         auto k = step_win_kernel<MODEL, CHEMG, NTREL, true, G>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, win_threads<G>(), smem, s>>>(p, wp);
+        return launch_pdl<PDL_STEP>(k, dim3(grid), dim3(win_threads<G>()), smem, s, p, wp);
     } else {
         auto k = step_win_kernel<MODEL, CHEMG, NTREL, false, G>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        k<<<grid, win_threads<G>(), smem, s>>>(p, wp);
+        return launch_pdl<PDL_STEP>(k, dim3(grid), dim3(win_threads<G>()), smem, s, p, wp);
     }
     return cudaGetLastError();
 }

@@ -356,12 +356,16 @@ struct RnetLat {
 };
 struct RnetParams {
     RnetLat lat[kMaxLattices];
-    // per post lattice: bit q set = the connecting block from presynaptic class q holds RewardModulatedWeight values (else Weight);
-    // q < kMaxLattices: neuron lattice q; q = kMaxLattices + t: spike-train lattice t
-    uint32_t conn_reward[kMaxLattices];
+    // per post lattice, 2 bits per presynaptic class q (q < kMaxLattices: neuron lattice q; q = kMaxLattices + t: spike-train lattice
+    // t): 0 leave the edge alone, 1 own graph (two modulator calls), 2 RewardModulatedWeight block (one call), 3 Weight block fed by
+    // a plain lattice (STDP with the input lattice's parameters)
+    uint64_t kinds[kMaxLattices];
+    uint32_t n_lat, nbase[kMaxLattices + 1];    // neuron lattice l covers local neuron numbers [nbase[l], nbase[l+1])
     uint32_t n_tl, tl_base[kMaxLattices + 1];   // spike-train lattice t covers node indices [train0 + tl_base[t], train0 + tl_base[t+1])
     uint32_t train0;
     uint8_t *counter; float *dw, *c;   // TraceRSTDP members next to StepParams::wgt (same element index)
+    uint32_t canonical;                // own-graph edges have counter == 0 and dw == 0 between timesteps (see the kernel)
+    const float *tab; uint32_t tab_n;  // per neuron lattice l, 2 * tab_n floats at tab + l * 2 * tab_n (layout of RstdpParams::tab); nullptr = formula
 };
 cudaError_t launch_rstdp_net_edges(const StepParams &p, const RnetParams &r, cudaStream_t s);
 cudaError_t launch_finalize(const StepParams &p, int model, const float *v_prev, cudaStream_t s);

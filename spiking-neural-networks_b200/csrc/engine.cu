@@ -68,6 +68,7 @@ Engine::~Engine() {
     if (halo_done_) cudaFree(halo_done_);
     if (multi_barrier_) cudaFree(multi_barrier_);
     if (rs_tab_) cudaFree(rs_tab_);
+    if (rnet_tab_) cudaFree(rnet_tab_);
     if (wide_scratch_) cudaFree(wide_scratch_);
     if (scratch_) cudaFree(scratch_);
     if (ev0_) cudaEventDestroy(ev0_);
@@ -1428,8 +1429,9 @@ int Engine::set_block_traces(uint64_t pre_id, uint64_t post_id, const float *wei
     for (uint64_t e = 0; e < nnz; ++e) {
         const size_t o = el[e];
         if (weight) { hw[o] = weight[e]; if (b->kind == Block::CSR) b->w[e] = weight[e]; }
-        if (counter) { hc[o] = (uint8_t)counter[e]; if (counter[e] != 0u) rs_canonical_ = false; }
-        if (dw) { hd[o] = dw[e]; if (dw[e] != 0.f) rs_canonical_ = false; }
+        // the canonical state concerns edges that get two calls per timestep: those of a reward-modulated lattice's own graph
+        if (counter) { hc[o] = (uint8_t)counter[e]; if (counter[e] != 0u && pre_id == post_id) rs_canonical_ = false; }
+        if (dw) { hd[o] = dw[e]; if (dw[e] != 0.f && pre_id == post_id) rs_canonical_ = false; }
         if (c) hcc[o] = c[e];
     }
     if (weight) CK(h2d_sync(wgt_, hw.data(), wel * 4, stream_), SNN_GPU_BUFFER_WRITE_ERROR);
@@ -2111,7 +2113,8 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             if (!B->is_reward && B->do_plasticity && A->is_reward)
                 return fail(SNN_UNSUPPORTED, "a plastic lattice fed by a reward-modulated lattice: the reference panics on it (neuron/mod.rs:4727-4731)");
         }
-        std::map<uint64_t, int> cls;   // lattice id -> presynaptic class of RnetParams::conn_reward
+        std::map<uint64_t, int> cls;   // lattice id -> presynaptic class of RnetParams::kinds
+        std::vector<const Lat *> nl;
         int kn = 0, kt = 0;
         for (auto &L : lats_) {
             if (L.is_train) { rnp.tl_base[kt] = (uint32_t)L.off; cls[L.id] = kMaxLattices + kt; ++kt; continue; }
@@ -2120,14 +2123,58 @@ int Engine::run(uint64_t iterations, float *elapsed_ms, uint64_t *launches, cons
             R.tau_plus = L.rstdp.tau_plus; R.tau_minus = L.rstdp.tau_minus; R.dt = L.rstdp.dt;
             R.flags = (L.is_reward ? 1u : 0u) | (L.is_reward && L.do_modulation ? 2u : 0u);
             net_rmod |= L.is_reward && L.do_modulation && L.n > 0;
+            rnp.nbase[kn] = (uint32_t)L.off;
+            nl.push_back(&L);
             cls[L.id] = kn++;
         }
+        rnp.n_lat = (uint32_t)kn; rnp.nbase[kn] = (uint32_t)n_neurons;
         rnp.n_tl = (uint32_t)kt; rnp.tl_base[kt] = (uint32_t)n_trains; rnp.train0 = train0_;
+        for (int post = 0; post < kn; ++post) {
+            if (!nl[post]->is_reward) continue;
+            uint64_t k = 1ull << (2 * post);                                 // own graph
+            for (int pre = 0; pre < kn; ++pre)
+                if (pre != post && !nl[pre]->is_reward) k |= 3ull << (2 * pre);   // Weight block fed by a plain lattice (the default kind)
+            rnp.kinds[post] = k;
+        }
         for (auto &kv : blocks_)
-            if (kv.second.reward_conn && kv.first.first != kv.first.second && cls.count(kv.first.first) && cls.count(kv.first.second))
-                rnp.conn_reward[cls[kv.first.second]] |= 1u << cls[kv.first.first];
+            if (kv.second.reward_conn && kv.first.first != kv.first.second && cls.count(kv.first.first) && cls.count(kv.first.second)) {
+                uint64_t &k = rnp.kinds[cls[kv.first.second]];
+                const int q = cls[kv.first.first];
+                k = (k & ~(3ull << (2 * q))) | (2ull << (2 * q));
+            }
         if (net_rmod) { int rr = ensure_reward_arrays(); if (rr) return rr; }
         rnp.counter = rs_counter_; rnp.dw = rs_dw_; rnp.c = rs_c_;
+        rnp.canonical = (rs_canonical_ && !getenv("SNN_B200_RNET_NOCANON")) ? 1u : 0u;
+        if (net_rmod && !getenv("SNN_B200_RSTDP_NOTAB")) {
+            // one difference table per neuron lattice: the modulator's STDP term for a reward-modulated lattice, the lattice's own
+            // STDP for a plain one (what Weight edges out of it use); long enough for every exponential to have underflowed
+            double reach = 0.0;
+            bool ok = true;
+            for (const Lat *L : nl) {
+                const float tp_ = L->is_reward ? L->rstdp.tau_plus : L->stdp.tau_plus, tm_ = L->is_reward ? L->rstdp.tau_minus : L->stdp.tau_minus;
+                const float dt_ = L->is_reward ? L->rstdp.dt : L->stdp.dt;
+                ok = ok && tp_ > 0.f && tm_ > 0.f && dt_ > 0.f;
+                reach = std::max(reach, 110.0 * std::max((double)tp_, (double)tm_) / std::max((double)dt_, 1e-30));
+            }
+            if (ok && reach > 0 && reach < 60000.0) {
+                const uint32_t tab_n = (uint32_t)reach + 8u;
+                const size_t need = (size_t)kn * 2u * tab_n;
+                if (rnet_tab_elems_ != need) {
+                    if (rnet_tab_) cudaFree(rnet_tab_);
+                    rnet_tab_ = nullptr; rnet_tab_elems_ = 0;
+                    CK(dev_alloc(&rnet_tab_, need), SNN_GPU_BUFFER_CREATE_ERROR);
+                    rnet_tab_elems_ = need;
+                }
+                for (int l = 0; l < kn; ++l) {   // the parameters may have changed since the last run
+                    const Lat &L = *nl[l];
+                    RstdpParams tpar{};
+                    if (L.is_reward) { tpar.a_plus = L.rstdp.a_plus; tpar.a_minus = L.rstdp.a_minus; tpar.tau_plus = L.rstdp.tau_plus; tpar.tau_minus = L.rstdp.tau_minus; tpar.dt = L.rstdp.dt; }
+                    else { tpar.a_plus = L.stdp.a_plus; tpar.a_minus = L.stdp.a_minus; tpar.tau_plus = L.stdp.tau_plus; tpar.tau_minus = L.stdp.tau_minus; tpar.dt = L.stdp.dt; }
+                    CK(launch_rstdp_table(tpar, rnet_tab_ + (size_t)l * 2u * tab_n, tab_n, stream_), SNN_GPU_QUEUE_FAILURE);
+                }
+                rnp.tab = rnet_tab_; rnp.tab_n = tab_n;
+            }
+        }
     }
     const bool lft_pp = stdp || rmod || net_rmod || (n_trains && electrical) || part_world > 1;
     const bool rmod_part = rmod && part_world > 1;

@@ -204,6 +204,7 @@ private:
     uint32_t *slice_off_ = nullptr, *col_ = nullptr; float *wgt_ = nullptr;
     // TraceRSTDP members next to wgt_ (same sliced-ELL positions), allocated on the first reward-modulated run
     uint8_t *rs_counter_ = nullptr; float *rs_dw_ = nullptr, *rs_c_ = nullptr; uint64_t rs_elems_ = 0;
+    float *rnet_tab_ = nullptr; size_t rnet_tab_elems_ = 0;   // per-lattice difference tables of a reward-modulated network (RnetParams::tab)
     float *rs_tab_ = nullptr; uint32_t rs_tab_n_ = 0;   // difference table of the reward-modulated STDP term (RstdpParams::tab)
     bool rs_canonical_ = true;   // counter == 0 and dw == 0 on every edge (TraceRSTDP::default, kept by two calls per timestep)
     int ensure_reward_arrays();

@@ -672,59 +672,127 @@ cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaSt
 //  - connecting edge, Weight: STDP::update_weight with the INPUT lattice's plasticity, only when the input is a plain Lattice.
 // Connecting edges OUT of such a lattice are refused by Engine::run (the reference looks them up with swapped end points and
 // panics).  One CTA per 32-row slice, one thread per edge, no ordering between edges.
+// U k-rows per thread and round: all col words first, then the spike-time gathers and trace loads they address, then the
+// arithmetic — U independent chains per thread hide the dependent round trips per edge.  The pass is instruction-bound before it
+// is bandwidth-bound (ncu, profiles/r2_rstdp_net_edge_v2_full.txt: 186 warp instructions per k-row with the exponentials
+// evaluated in place), hence:
+//  - TAB: the STDP term through per-lattice difference tables (RnetParams::tab, filled by rstdp_table_kernel with the very
+//    function the formula path calls — bit-identical while spike times are exact in f32);
+//  - the edge kind from a 2-bit-per-class mask per post lattice, lattice bounds from the kernel parameters (constant bank);
+//  - CANON: the edges of the lattices' own graphs enter every timestep with counter == 0 and dw == 0 (two calls per step return to
+//    that state; TraceRSTDP::default starts there), so neither array is read or written for them.
+template <bool CANON, bool TAB, int U>
 __global__ void __launch_bounds__(256) rstdp_net_edge_kernel(const __grid_constant__ StepParams p, const __grid_constant__ RnetParams r) {
     pdl_wait();   // launch_pdl
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t slice = blockIdx.x;
     const uint32_t ln = slice * 32u + lane;
     if (ln >= p.n_neurons) return;
-    const int lp = lat_index(p, ln);
+    int lp = 0;
+#pragma unroll 1
+    for (uint32_t q = 1; q < r.n_lat; ++q) if (ln >= r.nbase[q]) lp = (int)q;
     const RnetLat &P = r.lat[lp];
     if ((P.flags & 3u) != 3u) return;
     const uint32_t k0 = p.uniform_width ? slice * p.uniform_width : __ldg(p.slice_off + slice);
     const uint32_t k1 = p.uniform_width ? k0 + p.uniform_width : __ldg(p.slice_off + slice + 1);
     const int t_post = p.lft_out[p.own0 + ln];
     const float decay_c = expf(-P.dt / P.tau_c);
+    const uint64_t kinds = r.kinds[lp];
     RstdpParams m;
     m.dopamine = P.dopamine; m.tau_c = P.tau_c; m.a_plus = P.a_plus; m.a_minus = P.a_minus;
     m.tau_plus = P.tau_plus; m.tau_minus = P.tau_minus; m.dt = P.dt;
-    for (uint32_t k = k0 + warp; k < k1; k += 8u) {
-        const size_t e = (size_t)k * 32u + lane;
-        const uint32_t cw = __ldg(p.col + e);
-        if (cw == kColPad) continue;
-        const uint32_t j = cw & kColIdxMask;
-        const bool train = (cw & kColTrainBit) != 0u;
-        int t_pre, cls;
-        if (train) {
-            t_pre = p.lft_in[j];   // the trains step after this pass: their current value is still in the input buffer
-            const uint32_t tj = j - r.train0;
-            cls = 0;
-#pragma unroll 1
-            for (uint32_t t = 1; t < r.n_tl; ++t) if (tj >= r.tl_base[t]) cls = (int)t;
-            cls += kMaxLattices;
-        } else {
-            t_pre = p.lft_out[j];
-            cls = lat_index(p, j - p.own0);
+    m.tab = r.tab + (size_t)lp * 2u * r.tab_n; m.tab_n = r.tab_n;
+    // round trip 1 of a round: the col words together with the weights and the traces they will most likely need (these do not
+    // depend on the col word).  The loads of round t + 1 are issued before the stores of round t — the compiler cannot hoist them
+    // itself (the stores may alias) — so a thread always has the next round's first trip in flight.
+    uint32_t cw_n[U];
+    float c_n[U], w_n[U];
+    auto fetch = [&](uint32_t kb) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t k = kb + 8u * u;
+            const size_t e = (size_t)k * 32u + lane;
+            const bool in = k < k1;
+            cw_n[u] = in ? __ldg(p.col + e) : kColPad;
+            w_n[u] = in ? p.wgt[e] : 0.f;
+            c_n[u] = in ? r.c[e] : 0.f;
         }
-        const bool internal = !train && cls == lp;
-        if (internal || ((r.conn_reward[lp] >> cls) & 1u)) {
+    };
+    fetch(k0 + warp);
+    for (uint32_t kb = k0 + warp; kb < k1; kb += 8u * U) {
+        uint32_t cw[U];
+        float c[U], w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { cw[u] = cw_n[u]; c[u] = c_n[u]; w[u] = w_n[u]; }
+        if (kb + 8u * U < k1) fetch(kb + 8u * U);
+        // round trip 2: the presynaptic spike time the col word addresses, counter / dw where the edge kind needs them
+        int t_pre[U], cls[U];
+        uint32_t kind[U];   // 0 nothing, 1 own graph (two calls), 2 RewardModulatedWeight (one call), 3 Weight fed by a plain lattice
+        uint32_t cnt[U];
+        float dw[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            kind[u] = 0u; cnt[u] = 0u; dw[u] = 0.f; t_pre[u] = -1; cls[u] = 0;
+            if (cw[u] == kColPad) continue;
+            const size_t e = (size_t)(kb + 8u * u) * 32u + lane;
+            const uint32_t j = cw[u] & kColIdxMask;
+            int q0 = 0;
+            if (cw[u] & kColTrainBit) {
+                t_pre[u] = p.lft_in[j];   // the trains step after this pass: their current value is still in the input buffer
+                const uint32_t tj = j - r.train0;
+#pragma unroll 1
+                for (uint32_t q = 1; q < r.n_tl; ++q) if (tj >= r.tl_base[q]) q0 = (int)q;
+                q0 += kMaxLattices;
+            } else {
+                t_pre[u] = p.lft_out[j];
+                const uint32_t nj = j - p.own0;
+#pragma unroll 1
+                for (uint32_t q = 1; q < r.n_lat; ++q) if (nj >= r.nbase[q]) q0 = (int)q;
+            }
+            cls[u] = q0;
+            kind[u] = (uint32_t)(kinds >> (2 * q0)) & 3u;
+            if (kind[u] == 2u || (!CANON && kind[u] == 1u)) { cnt[u] = r.counter[e]; dw[u] = r.dw[e]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!kind[u]) continue;
+            const size_t e = (size_t)(kb + 8u * u) * 32u + lane;
+            const bool timed = t_pre[u] >= 0 && t_post >= 0 && t_pre[u] != t_post;
+            if (kind[u] == 3u) {
+                // STDP::update_weight with the INPUT lattice's parameters
+                float d = 0.f;
+                if (timed) {
+                    if (TAB) { RstdpParams s = m; s.tab = r.tab + (size_t)cls[u] * 2u * r.tab_n; d = rstdp_delta_tab(s, t_pre[u], t_post); }
+                    else d = stdp_delta(p.lat[cls[u]], t_pre[u], t_post);
+                }
+                if (d != 0.f) p.wgt[e] = w[u] + d;
+                continue;
+            }
             float delta_w = 0.f;
-            if (t_pre >= 0 && t_post >= 0 && t_pre != t_post) delta_w = rstdp_delta(m, t_pre, t_post);
-            uint32_t cnt = r.counter[e];
-            float dw = r.dw[e], c = r.c[e], w = p.wgt[e];
-            rstdp_call(m, delta_w, decay_c, cnt, dw, c, w);
-            if (internal) rstdp_call(m, delta_w, decay_c, cnt, dw, c, w);
-            r.counter[e] = (uint8_t)cnt; r.dw[e] = dw; r.c[e] = c; p.wgt[e] = w;
-        } else if (!train && !(r.lat[cls].flags & 1u)) {
-            const float d = stdp_delta(p.lat[cls], t_pre, t_post);
-            if (d != 0.f) p.wgt[e] = p.wgt[e] + d;
+            if (timed) delta_w = TAB ? rstdp_delta_tab(m, t_pre[u], t_post) : rstdp_delta(m, t_pre[u], t_post);
+            rstdp_call(m, delta_w, decay_c, cnt[u], dw[u], c[u], w[u]);
+            if (kind[u] == 1u) rstdp_call(m, delta_w, decay_c, cnt[u], dw[u], c[u], w[u]);
+            if (!(CANON && kind[u] == 1u)) { r.counter[e] = (uint8_t)cnt[u]; r.dw[e] = dw[u]; }
+            r.c[e] = c[u]; p.wgt[e] = w[u];
         }
     }
 }
 
+template <bool CANON, bool TAB>
+static cudaError_t launch_rnet_2(const StepParams &p, const RnetParams &r, cudaStream_t s) {
+    static const int u = getenv("SNN_B200_RNET_U") ? atoi(getenv("SNN_B200_RNET_U")) : 1;
+    const dim3 grid((p.n_neurons + 31u) / 32u);
+    if (u == 2) return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel<CANON, TAB, 2>, grid, dim3(256), 0, s, p, r);
+    if (u == 1) return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel<CANON, TAB, 1>, grid, dim3(256), 0, s, p, r);
+    return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel<CANON, TAB, 4>, grid, dim3(256), 0, s, p, r);
+}
+
 cudaError_t launch_rstdp_net_edges(const StepParams &p, const RnetParams &r, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
-    return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel, dim3((p.n_neurons + 31u) / 32u), dim3(256), 0, s, p, r);
+    // the tables stand for the formula while every spike time is exact in f32 (clock < 2^24)
+    const bool tab = r.tab != nullptr && p.clock < (1u << 24);
+    if (r.canonical) return tab ? launch_rnet_2<true, true>(p, r, s) : launch_rnet_2<true, false>(p, r, s);
+    return tab ? launch_rnet_2<false, true>(p, r, s) : launch_rnet_2<false, false>(p, r, s);
 }
 
 cudaError_t launch_flush_stdp(const StepParams &p, cudaStream_t s) {

@@ -580,8 +580,8 @@ static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((
 template <int MODEL, int CHEMG, bool NTREL, bool NET>
 static cudaError_t launch_step_3(const StepParams &p, bool stdp, cudaStream_t s) {
     const unsigned grid = blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256);
-    if (stdp) return launch_pdl<PDL_STEP>(step_kernel<MODEL, CHEMG, NTREL, true, NET>, dim3(grid), dim3(256), 0, s, p);
-    return launch_pdl<PDL_STEP>(step_kernel<MODEL, CHEMG, NTREL, false, NET>, dim3(grid), dim3(256), 0, s, p);
+    if (stdp) return launch_pdl<PDL_STEP>(pdl_ok(p), step_kernel<MODEL, CHEMG, NTREL, true, NET>, dim3(grid), dim3(256), 0, s, p);
+    return launch_pdl<PDL_STEP>(pdl_ok(p), step_kernel<MODEL, CHEMG, NTREL, false, NET>, dim3(grid), dim3(256), 0, s, p);
     return cudaGetLastError();
 }
 
@@ -617,7 +617,7 @@ cudaError_t launch_step(const StepParams &p, int model, int chemg, bool ntrel, b
 
 cudaError_t launch_trains(const TrainParams &p, cudaStream_t s) {
     if (p.n_trains == 0) return cudaSuccess;
-    return launch_pdl<PDL_TRAINS>(train_kernel, dim3(blocks_for((uint64_t)((p.n_trains + 31u) / 32u) * 32u, 256)), dim3(256), 0, s, p);
+    return launch_pdl<PDL_TRAINS>(pdl_ok(p), train_kernel, dim3(blocks_for((uint64_t)((p.n_trains + 31u) / 32u) * 32u, 256)), dim3(256), 0, s, p);
     return cudaGetLastError();
 }
 
@@ -636,7 +636,7 @@ cudaError_t launch_gpart_push(const StepParams &p, cudaStream_t s) {
 
 cudaError_t launch_bcm_edges(const StepParams &p, const BcmParams &b, cudaStream_t s) {
     if (p.n_neurons == 0) return cudaSuccess;
-    return launch_pdl<PDL_EDGES>(bcm_edge_kernel, dim3(blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256)), dim3(256), 0, s, p, b);
+    return launch_pdl<PDL_EDGES>(pdl_ok(p), bcm_edge_kernel, dim3(blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256)), dim3(256), 0, s, p, b);
     return cudaGetLastError();
 }
 
@@ -653,11 +653,11 @@ cudaError_t launch_rstdp_edges(const StepParams &p, const RstdpParams &r, cudaSt
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const unsigned pg = (unsigned)sms * (unsigned)SNN_RS_CTAS;
-        if (r.canonical) return tab ? launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<true, true>, dim3(pg), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<true, false>, dim3(pg), dim3(256), 0, s, p, r);
-        return tab ? launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<false, true>, dim3(pg), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge8_kernel<false, false>, dim3(pg), dim3(256), 0, s, p, r);
+        if (r.canonical) return tab ? launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge8_kernel<true, true>, dim3(pg), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge8_kernel<true, false>, dim3(pg), dim3(256), 0, s, p, r);
+        return tab ? launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge8_kernel<false, true>, dim3(pg), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge8_kernel<false, false>, dim3(pg), dim3(256), 0, s, p, r);
     }
-    if (r.canonical) return tab ? launch_pdl<PDL_EDGES>(rstdp_edge_kernel<true, true>, dim3(grid), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge_kernel<true, false>, dim3(grid), dim3(256), 0, s, p, r);
-    return tab ? launch_pdl<PDL_EDGES>(rstdp_edge_kernel<false, true>, dim3(grid), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(rstdp_edge_kernel<false, false>, dim3(grid), dim3(256), 0, s, p, r);
+    if (r.canonical) return tab ? launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge_kernel<true, true>, dim3(grid), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge_kernel<true, false>, dim3(grid), dim3(256), 0, s, p, r);
+    return tab ? launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge_kernel<false, true>, dim3(grid), dim3(256), 0, s, p, r) : launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_edge_kernel<false, false>, dim3(grid), dim3(256), 0, s, p, r);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -782,9 +782,9 @@ template <bool CANON, bool TAB>
 static cudaError_t launch_rnet_2(const StepParams &p, const RnetParams &r, cudaStream_t s) {
     static const int u = getenv("SNN_B200_RNET_U") ? atoi(getenv("SNN_B200_RNET_U")) : 1;
     const dim3 grid((p.n_neurons + 31u) / 32u);
-    if (u == 2) return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel<CANON, TAB, 2>, grid, dim3(256), 0, s, p, r);
-    if (u == 1) return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel<CANON, TAB, 1>, grid, dim3(256), 0, s, p, r);
-    return launch_pdl<PDL_EDGES>(rstdp_net_edge_kernel<CANON, TAB, 4>, grid, dim3(256), 0, s, p, r);
+    if (u == 2) return launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_net_edge_kernel<CANON, TAB, 2>, grid, dim3(256), 0, s, p, r);
+    if (u == 1) return launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_net_edge_kernel<CANON, TAB, 1>, grid, dim3(256), 0, s, p, r);
+    return launch_pdl<PDL_EDGES>(pdl_ok(p), rstdp_net_edge_kernel<CANON, TAB, 4>, grid, dim3(256), 0, s, p, r);
 }
 
 cudaError_t launch_rstdp_net_edges(const StepParams &p, const RnetParams &r, cudaStream_t s) {

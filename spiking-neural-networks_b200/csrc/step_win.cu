@@ -300,12 +300,12 @@ static cudaError_t launch_win_3(const StepParams &p, const WinParams &wp, bool s
         auto k = step_win_kernel<MODEL, CHEMG, NTREL, true, G>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return launch_pdl<PDL_STEP>(k, dim3(grid), dim3(win_threads<G>()), smem, s, p, wp);
+        return launch_pdl<PDL_STEP>(pdl_ok(p), k, dim3(grid), dim3(win_threads<G>()), smem, s, p, wp);
     } else {
         auto k = step_win_kernel<MODEL, CHEMG, NTREL, false, G>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        return launch_pdl<PDL_STEP>(k, dim3(grid), dim3(win_threads<G>()), smem, s, p, wp);
+        return launch_pdl<PDL_STEP>(pdl_ok(p), k, dim3(grid), dim3(win_threads<G>()), smem, s, p, wp);
     }
     return cudaGetLastError();
 }

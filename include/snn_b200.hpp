@@ -292,10 +292,101 @@ public:
     }
     snn_network_t *handle() { return h_; }
 
-private:
+protected:
     snn_network_t *h_ = nullptr;
     std::map<std::size_t, Position> dims_;
     void ck(int status) const { detail::check(status, h_ ? snn_network_last_error(h_) : nullptr); }
+};
+
+// RewardModulatedConnection<TraceRSTDP>, neuron/mod.rs:3418-3443: Weight(f32) or RewardModulatedWeight(TraceRSTDP{weight, ..default})
+struct RewardModulatedConnection {
+    float weight = 1.f;
+    bool reward_modulated = false;
+    static RewardModulatedConnection Weight(float w) { return {w, false}; }
+    static RewardModulatedConnection RewardModulatedWeight(float w) { return {w, true}; }
+};
+
+// RewardModulatedLatticeNetwork (neuron/mod.rs:3455-5455): plain, reward-modulated and spike-train lattices over one connecting
+// graph of RewardModulatedConnection values.  One connection kind per connecting block; the configurations on which the reference
+// panics make run_lattices* throw SNN_UNSUPPORTED (include/snn_b200.h).
+class RewardModulatedLatticeNetwork : public LatticeNetwork {
+public:
+    using LatticeNetwork::LatticeNetwork;
+
+    // add_reward_modulated_lattice, :3615-3634
+    void add_reward_modulated_lattice(std::size_t id, const BaseNeuron &base, std::size_t rows, std::size_t cols,
+                                      const RewardModulatedSTDP &modulator = RewardModulatedSTDP(), bool do_modulation = true) {
+        ck(snn_network_add_reward_modulated_lattice(h_, id, (uint32_t)rows, (uint32_t)cols));
+        dims_[id] = {rows, cols};
+        reward_ids_[id] = true;
+        for (auto &kv : base.fields) ck(snn_network_fill_field_f32(h_, id, kv.first.c_str(), kv.second));
+        set_reward_modulator(id, modulator, do_modulation);
+    }
+    void set_reward_modulator(std::size_t id, const RewardModulatedSTDP &r, bool do_modulation = true) {
+        const snn_rstdp_t m{r.dopamine, r.tau_d, r.tau_c, r.a_plus, r.a_minus, r.tau_plus, r.tau_minus, r.dt};
+        ck(snn_network_set_reward_modulator(h_, id, do_modulation, &m));
+    }
+    RewardModulatedSTDP reward_modulator(std::size_t id) {
+        snn_rstdp_t m{};
+        ck(snn_network_get_reward_modulator(h_, id, nullptr, &m));
+        RewardModulatedSTDP r;
+        r.dopamine = m.dopamine; r.tau_d = m.tau_d; r.tau_c = m.tau_c; r.a_plus = m.a_plus; r.a_minus = m.a_minus;
+        r.tau_plus = m.tau_plus; r.tau_minus = m.tau_minus; r.dt = m.dt;
+        return r;
+    }
+    // connect, :3836-3947: plain / spike-train lattices only (ConnectFunctionMustHaveNonRewardModulatedLattice otherwise); the
+    // checks that need the two lattice maps live here, the others in the library, in the reference's order
+    void connect(std::size_t pre_id, std::size_t post_id, const std::function<bool(Position, Position)> &cond,
+                 const std::function<float(Position, Position)> &weight = nullptr) {
+        const bool known_pre = dims_.count(pre_id) != 0;
+        if (known_pre && (reward_ids_.count(post_id) || (dims_.count(post_id) && reward_ids_.count(pre_id))))
+            detail::check(SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE,
+                          "Connect function must have non reward modulated lattices, connect with reward modulation instead");
+        LatticeNetwork::connect(pre_id, post_id, cond, weight);
+    }
+    // connect_reward_modulated_lattice_interally, :4393-4413 (IDNotFoundInLattices for anything but a reward-modulated lattice)
+    void connect_reward_modulated_lattice_interally(std::size_t id, const std::function<bool(Position, Position)> &cond,
+                                                    const std::function<float(Position, Position)> &weight = nullptr) {
+        if (!reward_ids_.count(id)) detail::check(SNN_NET_ID_NOT_FOUND_IN_LATTICES, ("Id not present in lattices, id: " + std::to_string(id)).c_str());
+        LatticeNetwork::connect(id, id, cond, weight);
+    }
+    // connect_with_reward_modulation, :4076-4209
+    void connect_with_reward_modulation(std::size_t pre_id, std::size_t post_id, const std::function<bool(Position, Position)> &cond,
+                                        const std::function<RewardModulatedConnection(Position, Position)> &weight_logic) {
+        const Position a = dims_.count(pre_id) ? dims_[pre_id] : Position{0, 0}, b = dims_.count(post_id) ? dims_[post_id] : Position{0, 0};
+        int kinds = 0;
+        const detail::Csr g = detail::evaluate(a.first, a.second, b.first, b.second, cond, [&](Position x, Position y) {
+            const RewardModulatedConnection c = weight_logic(x, y);
+            kinds |= c.reward_modulated ? 2 : 1;
+            return c.weight;
+        });
+        if (kinds == 3) detail::check(SNN_UNSUPPORTED, "one connecting block holds one kind of RewardModulatedConnection");
+        // the id checks in the reference's order (:4083-4107) before anything is changed; the block itself may not exist yet
+        const int pre_check = snn_network_set_connection_reward_modulated(h_, pre_id, post_id, kinds == 2);
+        if (pre_check != SNN_OK && pre_check != SNN_INVALID_ARGUMENT) ck(pre_check);
+        ck(snn_network_connect_csr(h_, pre_id, post_id, g.row_ptr.data(), g.pre.data(), g.w.data(), b.first * b.second, g.row_ptr.back()));
+        ck(snn_network_set_connection_reward_modulated(h_, pre_id, post_id, kinds == 2));
+    }
+    // run_lattices_with_reward, :5385-5392
+    void run_lattices_with_reward(float reward) {
+        ck(snn_network_set_option(h_, SNN_OPT_ELECTRICAL_SYNAPSE, electrical_synapse));
+        ck(snn_network_set_option(h_, SNN_OPT_CHEMICAL_SYNAPSE, chemical_synapse));
+        ck(snn_network_run_with_rewards(h_, &reward, 1));
+    }
+    std::vector<float> connection_weights(std::size_t pre_id, std::size_t post_id) {
+        uint64_t nnz = 0, n = 0;
+        ck(snn_network_connection_nnz(h_, pre_id, post_id, &nnz));
+        ck(snn_network_lattice_size(h_, post_id, &n));
+        std::vector<uint64_t> rp(n + 1);
+        std::vector<uint32_t> pre(nnz ? nnz : 1);
+        std::vector<float> w(nnz ? nnz : 1);
+        ck(snn_network_get_connection_csr(h_, pre_id, post_id, rp.data(), pre.data(), w.data(), n, nnz));
+        w.resize(nnz);
+        return w;
+    }
+
+private:
+    std::map<std::size_t, bool> reward_ids_;
 };
 
 // SpikeTrainLattice<N, T, U> on its own (neuron/mod.rs:1290-1428; RunSpikeTrainLattice :1419-1428): a network that holds just this lattice

@@ -125,6 +125,51 @@ int main(int argc, char **argv) {
     net.connect(0, 1, [](Position, Position) { return true; }, [](Position, Position) { return 0.5f; });
     net.run_lattices(50);
 
+    // ---- RewardModulatedLatticeNetwork in the shape of examples/lsm_architecture: trains -> liquid -> reward-modulated read-out ----
+    RewardModulatedLatticeNetwork lsm(SNN_MODEL_IZHIKEVICH, SNN_TRAIN_RATE);
+    const BaseNeuron cell = BaseNeuron(SNN_MODEL_IZHIKEVICH).with("gap_conductance", 10.f).with("c_m", 2.f).with("b", 0.3f);
+    lsm.add_spike_train_lattice(0, {{"rate", 7.f}, {"dt", 1.f}}, 2, 3);
+    lsm.add_lattice(1, cell, 4, 4);
+    RewardModulatedSTDP mod;
+    mod.tau_c = 0.1f; mod.a_plus = 0.002f; mod.a_minus = 0.002f;
+    lsm.add_reward_modulated_lattice(2, cell, 3, 3, mod);
+    const auto always = [](Position, Position) { return true; };
+    const auto apart = [](Position x, Position y) { return x != y; };
+    lsm.connect(1, 1, apart, [](Position, Position) { return 0.4f; });
+    lsm.connect_reward_modulated_lattice_interally(2, apart, [](Position, Position) { return 0.3f; });
+    lsm.connect(0, 1, always, [](Position, Position) { return 0.8f; });
+    lsm.connect_with_reward_modulation(0, 2, always, [](Position, Position) { return RewardModulatedConnection::RewardModulatedWeight(0.6f); });
+    lsm.connect_with_reward_modulation(1, 2, always, [](Position, Position) { return RewardModulatedConnection::Weight(0.5f); });
+    const struct { std::size_t pre, post; bool with_reward; int status; } refused[] = {
+        {1, 2, false, SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE},
+        {2, 1, false, SNN_NET_CONNECT_FUNCTION_MUST_HAVE_NON_REWARD_MODULATED_LATTICE},
+        {0, 1, true, SNN_NET_CANNOT_CONNECT_WITH_REWARD_MODULATED_CONNECTION},
+        {2, 2, true, SNN_NET_REWARD_MODULATED_CONNECTION_NOT_COMPATIBLE_INTERNALLY},
+        {2, 0, true, SNN_NET_POSTSYNAPTIC_LATTICE_CANNOT_BE_SPIKE_TRAIN},
+        {9, 2, true, SNN_NET_PRESYNAPTIC_ID_NOT_FOUND}};
+    for (const auto &c : refused) {
+        try {
+            if (c.with_reward) lsm.connect_with_reward_modulation(c.pre, c.post, always, [](Position, Position) { return RewardModulatedConnection::RewardModulatedWeight(1.f); });
+            else lsm.connect(c.pre, c.post, always);
+            REQUIRE(false);
+        } catch (const SpikingNeuralNetworksError &e) { REQUIRE(e.status == c.status); }
+    }
+    const std::vector<float> w02_before = lsm.connection_weights(0, 2), w22_before = lsm.connection_weights(2, 2);
+    for (int s = 0; s < 200; ++s) lsm.run_lattices_with_reward(s % 4 == 0 ? 0.004f : -0.001f);
+    lsm.run_lattices(20);
+    const std::vector<float> w02 = lsm.connection_weights(0, 2), w22 = lsm.connection_weights(2, 2), w01n = lsm.connection_weights(0, 1);
+    REQUIRE(w02.size() == 6 * 9 && w22.size() == 9 * 8);
+    std::size_t moved = 0;
+    for (std::size_t k = 0; k < w02.size(); ++k) moved += w02[k] != w02_before[k];
+    for (std::size_t k = 0; k < w22.size(); ++k) moved += w22[k] != w22_before[k];
+    REQUIRE(moved > 20 && lsm.reward_modulator(2).dopamine != 0.f);
+    for (float w : w01n) REQUIRE(w == 0.8f);   // plain lattice without do_plasticity: its in-edges stay
+    lsm.connect_with_reward_modulation(2, 1, [](Position x, Position y) { return x == y; }, [](Position, Position) { return RewardModulatedConnection::Weight(0.2f); });
+    try {
+        lsm.run_lattices(1);   // connecting edges out of a reward-modulated lattice with do_modulation: the reference panics
+        REQUIRE(false);
+    } catch (const SpikingNeuralNetworksError &e) { REQUIRE(e.status == SNN_UNSUPPORTED); }
+
     // ---- SpikeTrainLattice on its own: tests/rate_spike_train.rs:54-72 (rate 100, dt 1: a spike every 100th step) -----------
     SpikeTrainLattice trains(SNN_TRAIN_RATE, 4);
     trains.populate({{"rate", 100.f}, {"dt", 1.f}}, 2, 3);

@@ -307,3 +307,108 @@ def test_single_reward_lattice_network_and_do_modulation_off(oracle_lattice_fact
         ta, tb = a._be.connection_traces(4, 4), b._be.connection_traces(4, 4)
         assert (ta[0] == tb[0]).all() and (tb[0] == 0).all()
         SC.assert_close_robust(ta[2], tb[2], 2e-4, 1e-6, "c", max_abs=0.05)
+
+
+# ------------------------------------------------------------------ several lattices of every kind
+MANY_TRAINS, MANY_PLAIN, MANY_REWARD = (10, 11), (1, 5), (3, 7)
+MANY_BLOCKS = ((10, 1), (11, 5), (1, 5), (10, 3), (11, 3), (1, 3), (5, 3), (7, 3), (5, 7), (11, 7), (1, 1), (5, 5), (3, 3), (7, 7))
+MANY_RM = {(10, 3), (5, 3), (7, 3), (11, 7)}
+
+
+def build_many(lattice_factory, network_factory, seed=17):
+    """Two spike-train lattices, two plain lattices and two reward-modulated lattices with interleaved ids: every presynaptic
+    class index above 0 is exercised.  Lattice 7 does not modulate, so it may feed lattice 3."""
+    rng = np.random.default_rng(seed)
+    base = S.IzhikevichNeuron(gap_conductance=5.0, c_m=10.0)
+    shapes = {1: (3, 3), 5: (2, 4), 3: (3, 3), 7: (2, 3), 10: (2, 3), 11: (2, 2)}
+    lats = {}
+    for lid in MANY_PLAIN + MANY_REWARD:
+        cls_ = S.RewardModulatedLattice if lid in MANY_REWARD else S.Lattice
+        L = cls_(S.IzhikevichNeuron, id=lid, backend_factory=lattice_factory)
+        L.populate(base, *shapes[lid])
+        n = shapes[lid][0] * shapes[lid][1]
+        L.connect(lambda x, y: x != y and abs(x[0] - y[0]) + abs(x[1] - y[1]) <= 2, lambda x, y: 0.3 + 0.01 * lid)
+        L.set_field("current_voltage", rng.uniform(-65, 20, n).astype(f32))
+        L.set_field("b", rng.uniform(0.25, 0.33, n).astype(f32))
+        L.update_grid_history = L.update_spike_history = True
+        lats[lid] = L
+    lats[1].plasticity = S.STDP(a_plus=0.002, a_minus=0.0015, tau_plus=3.5)
+    lats[5].plasticity = S.STDP(a_plus=0.001, a_minus=0.003, tau_minus=6.0)
+    lats[3].reward_modulator = S.RewardModulatedSTDP(tau_c=0.1, a_plus=0.002, a_minus=0.0025, tau_plus=5.0, tau_minus=4.0)
+    lats[7].reward_modulator = S.RewardModulatedSTDP(tau_c=0.2, a_plus=0.004, a_minus=0.001)
+    lats[7].do_modulation = False
+    trains = {}
+    for tid in MANY_TRAINS:
+        st = S.SpikeTrainLattice(S.RateSpikeTrain, id=tid, network_backend_factory=network_factory)
+        st.populate(S.RateSpikeTrain(rate=2.0), *shapes[tid])
+        st.set_field("rate", rng.choice([1.5, 2.0, 3.0], shapes[tid][0] * shapes[tid][1]).astype(f32))
+        st.update_spike_history = True
+        trains[tid] = st
+    net = S.RewardModulatedLatticeNetwork.generate_network([lats[i] for i in MANY_PLAIN], [lats[i] for i in MANY_REWARD],
+                                                           [trains[i] for i in MANY_TRAINS], backend_factory=network_factory)
+    for pre, post in MANY_BLOCKS:
+        if pre == post:
+            continue
+        wmat = rng.uniform(0.1, 1.0, (8, 8)).astype(f32)
+        cond = lambda x, y, s=(pre + post): (x[0] + 2 * x[1] + y[0] + y[1] + s) % 3 != 0
+        wl = lambda x, y, m=wmat: float(m[(x[0] * 3 + x[1]) % 8, (y[0] * 3 + y[1]) % 8])
+        if post in MANY_REWARD or pre in MANY_REWARD:
+            kind = RMC.RewardModulatedWeight if (pre, post) in MANY_RM else RMC.Weight
+            net.connect_with_reward_modulation(pre, post, cond, lambda x, y, k=kind, f=wl:
+                                               k(S.TraceRSTDP(weight=f(x, y))) if k == RMC.RewardModulatedWeight else k(f(x, y)))
+        else:
+            net.connect(pre, post, cond, wl)
+    return net
+
+
+def _lat(net, lid):
+    return net.get_lattice(lid) or net.get_reward_modulated_lattice(lid) or net.get_spike_train_lattice(lid)
+
+
+def test_many_lattices_oracle_rules(oracle_lattice_factory, oracle_network_factory):
+    """Which blocks move and which stay, on the oracle: only edges INTO the modulating lattice 3 (its own graph,
+    RewardModulatedWeight blocks, Weight blocks fed by plain lattices) change."""
+    net = build_many(oracle_lattice_factory, oracle_network_factory)
+    be = net._be
+    w0 = {blk: be.get_connection_csr(*blk)[2].copy() for blk in MANY_BLOCKS}
+    net.run_lattices_with_rewards(rewards_for(150))
+    moved = {blk: bool((be.get_connection_csr(*blk)[2] != w0[blk]).any()) for blk in MANY_BLOCKS}
+    assert moved == {blk: blk in {(10, 3), (1, 3), (5, 3), (7, 3), (3, 3)} for blk in MANY_BLOCKS}
+    assert net.get_reward_modulated_lattice(7).reward_modulator.dopamine != 0.0   # every modulator takes the reward
+
+
+@pytest.mark.gpu
+def test_many_lattices_match_oracle(oracle_lattice_factory, oracle_network_factory):
+    a, b = build_many(None, None), build_many(oracle_lattice_factory, oracle_network_factory)
+    total, seg = 240, 40
+    rewards = rewards_for(total, seed=4)
+    for s0 in range(0, total, seg):
+        a.run_lattices_with_rewards(rewards[s0:s0 + seg]), b.run_lattices_with_rewards(rewards[s0:s0 + seg])
+        for lid in MANY_PLAIN + MANY_REWARD:
+            ga, gb = _lat(a, lid).grid_history.history, _lat(b, lid).grid_history.history
+            SC.assert_close_robust(ga[s0:s0 + seg], gb[s0:s0 + seg], 1e-4, 1e-3, f"voltages of lattice {lid}, steps {s0}..")
+            assert (_lat(a, lid).spike_history.history[s0:] == _lat(b, lid).spike_history.history[s0:]).mean() > 0.999
+        for tid in MANY_TRAINS:
+            assert (_lat(a, tid).spike_history.history == _lat(b, tid).spike_history.history).all()
+        for blk in MANY_BLOCKS:
+            wa, wb = a._be.get_connection_csr(*blk)[2], b._be.get_connection_csr(*blk)[2]
+            SC.assert_close_robust(wa, wb, 2e-4, 1e-5, f"weights of block {blk}, steps {s0}..", max_abs=0.05)
+            if blk[1] in MANY_REWARD:
+                ta, tb = a._be.connection_traces(*blk), b._be.connection_traces(*blk)
+                assert (ta[0] == tb[0]).all(), blk
+                SC.assert_close_robust(ta[1], tb[1], 2e-4, 1e-6, f"dw of block {blk}", max_abs=0.05)
+                SC.assert_close_robust(ta[2], tb[2], 2e-4, 1e-6, f"c of block {blk}", max_abs=0.05)
+        for lid in MANY_REWARD:
+            assert _lat(a, lid).reward_modulator.dopamine == pytest.approx(_lat(b, lid).reward_modulator.dopamine, rel=1e-5)
+        # re-synchronise a <- b
+        for lid in MANY_PLAIN + MANY_REWARD + MANY_TRAINS:
+            SC.copy_lattice_state(_lat(b, lid), _lat(a, lid), weights=False)
+        for blk in MANY_BLOCKS:
+            w = b._be.get_connection_csr(*blk)[2]
+            if blk[1] in MANY_REWARD:
+                cnt, dw, c = b._be.connection_traces(*blk)
+                a._be.set_connection_traces(w, cnt, dw, c, pre_id=blk[0], post_id=blk[1])
+            else:
+                a._be.set_connection_traces(w, None, None, None, pre_id=blk[0], post_id=blk[1])
+        for lid in MANY_REWARD:
+            _lat(a, lid).reward_modulator.dopamine = _lat(b, lid).reward_modulator.dopamine

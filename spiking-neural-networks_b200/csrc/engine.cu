@@ -1272,7 +1272,7 @@ int Engine::set_bcm_plasticity(bool enable, const snn_bcm_t *b) {
 int Engine::set_reward_modulator(bool enable, bool modulate, const snn_rstdp_t *m) {
     int n_neuron_lat = 0;
     for (auto &L : lats_) if (!L.is_train) n_neuron_lat++;
-    if (enable && (n_neuron_lat > 1 || n_trains > 0)) return fail(SNN_UNSUPPORTED, "reward-modulated lattice networks are not built yet");
+    if (enable && (n_neuron_lat > 1 || n_trains > 0)) return fail(SNN_UNSUPPORTED, "snn_lattice_set_reward_modulator is for single-lattice handles; networks add reward-modulated lattices with snn_network_add_reward_modulated_lattice");
     reward_mode = enable; do_modulation = modulate;
     if (m) rstdp = *m;
     if (!enable) free_reward_arrays();

@@ -27,7 +27,7 @@ namespace snn {
 // the fused step kernel, general form: every operand straight from HBM (any graph, networks, spike trains)
 // ------------------------------------------------------------------------------------------------
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
-__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p) {
+__device__ __forceinline__ void step_kernel_body(const StepParams &p) {
     pdl_wait();   // launch_pdl
     if (!NET && halo_failed(p)) return;
     uint32_t block = blockIdx.x;
@@ -58,6 +58,19 @@ __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepP
     neuron_step<MODEL, CHEMG, NTREL, STDP, NET>(p, src, warp_global, lane, ln, lnc, valid, export_lo, export_hi);
     if (!NET) halo_publish(p, warp_global, lane);
     if (!NET) gpart_export_publish(p, warp_global, lane, ln, valid);
+}
+
+template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
+__global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p) {
+    step_kernel_body<MODEL, CHEMG, NTREL, STDP, NET>(p);
+}
+// Networks without chemistry (rows of tens of in-edges from several lattices and spike trains): the kernel is latency-bound at the
+// four CTAs per SM that 64 registers allow (ncu, profiles/r2_step_kernel_net_full.txt: 47 % occupancy, 54 % long-scoreboard); five
+// resident CTAs (51 registers) measured 97 -> 89 us per step on the 1.1 M-neuron / 25 M-edge network of
+// tools/bench_reward_network.py, six were slower again (101 us).
+template <int MODEL, int CHEMG, bool NTREL, bool STDP>
+__global__ void __launch_bounds__(256, 5) step_net5_kernel(const __grid_constant__ StepParams p) {
+    step_kernel_body<MODEL, CHEMG, NTREL, STDP, true>(p);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -580,6 +593,10 @@ static inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((
 template <int MODEL, int CHEMG, bool NTREL, bool NET>
 static cudaError_t launch_step_3(const StepParams &p, bool stdp, cudaStream_t s) {
     const unsigned grid = blocks_for((uint64_t)((p.n_neurons + 31u) / 32u) * 32u, 256);
+    if constexpr (NET && !NTREL && MODEL != SNN_MODEL_HODGKIN_HUXLEY) {
+        if (stdp) return launch_pdl<PDL_STEP>(pdl_ok(p), step_net5_kernel<MODEL, CHEMG, NTREL, true>, dim3(grid), dim3(256), 0, s, p);
+        return launch_pdl<PDL_STEP>(pdl_ok(p), step_net5_kernel<MODEL, CHEMG, NTREL, false>, dim3(grid), dim3(256), 0, s, p);
+    }
     if (stdp) return launch_pdl<PDL_STEP>(pdl_ok(p), step_kernel<MODEL, CHEMG, NTREL, true, NET>, dim3(grid), dim3(256), 0, s, p);
     return launch_pdl<PDL_STEP>(pdl_ok(p), step_kernel<MODEL, CHEMG, NTREL, false, NET>, dim3(grid), dim3(256), 0, s, p);
     return cudaGetLastError();

@@ -60,6 +60,8 @@ __device__ __forceinline__ void step_kernel_body(const StepParams &p) {
     if (!NET) gpart_export_publish(p, warp_global, lane, ln, valid);
 }
 
+// (single lattices keep the compiler's choice of 64 registers: bounded to five / six resident CTAs the general-graph lattices of
+// tools/bench_general_graph.py got 10 % / 25 % slower — spills on the gather path)
 template <int MODEL, int CHEMG, bool NTREL, bool STDP, bool NET>
 __global__ void __launch_bounds__(256) step_kernel(const __grid_constant__ StepParams p) {
     step_kernel_body<MODEL, CHEMG, NTREL, STDP, NET>(p);
